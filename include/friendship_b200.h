@@ -1,0 +1,182 @@
+/* friendship_b200.h — C ABI of the B200-native renderer for libfriendship's effect tree.
+ *
+ * This header is the drop-in boundary for the reference's `Renderer` trait
+ * (reference: src/render/renderer.rs:6-17) and the `GraphWatcher` trait it inherits
+ * (reference: src/routing/graphwatcher.rs:4-9).  A Rust `impl Renderer for B200Renderer`
+ * (see INTEGRATION.md and rust/) binds exactly these entry points; tests/ and bench.py bind
+ * them through Python ctypes.  Plain pointers and sizes only; nothing throws across the ABI.
+ *
+ * Vocabulary follows the reference:
+ *   - node handle: u32, 0 == "toplevel" (the graph's own inputs/outputs), reference
+ *     src/routing/nullable_int.rs:27-31, src/routing/routegraph.rs:330-343.
+ *   - edge: {from, to, from_slot, to_slot}, reference src/routing/routegraph.rs:20-25,38-44.
+ *   - primitive effects: reference src/routing/effect.rs:86-112 (enum PrimitiveEffect).
+ *   - F32Constant's value is f32::from_bits(from_slot), reference src/render/reference.rs:217-220.
+ */
+#ifndef FRIENDSHIP_B200_H
+#define FRIENDSHIP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes (the reference's methods return () and panic; we return codes) ---- */
+#define FRB_OK                 0
+#define FRB_E_BAD_HANDLE      -1   /* unknown node / effect key (reference would panic: reference.rs:131,145,186) */
+#define FRB_E_INPUT_TOO_LONG  -2   /* input row longer than n_times (reference.rs:71 assert) */
+#define FRB_E_INPUT_GAP       -3   /* slot fed now but skipped earlier: len != idx (reference.rs:69 assert_eq) */
+#define FRB_E_BAD_SLOT        -4   /* from_slot != 0 on a single-output primitive (reference.rs:199,223,... assert) */
+#define FRB_E_CUDA            -5
+#define FRB_E_INVALID         -6   /* malformed arguments */
+#define FRB_E_UNSUPPORTED     -7   /* graph shape the device schedule cannot express */
+#define FRB_E_EXISTS          -8   /* handle / key already defined */
+#define FRB_E_NO_DEVICE       -9   /* no CUDA device: there is no CPU fallback */
+
+/* ---- node kinds ---- */
+/* the seven primitives of reference src/routing/effect.rs:86-112 */
+#define FRB_KIND_DELAY        0u
+#define FRB_KIND_F32CONSTANT  1u
+#define FRB_KIND_SUM2         2u
+#define FRB_KIND_MULTIPLY     3u
+#define FRB_KIND_DIVIDE       4u
+#define FRB_KIND_MODULO       5u
+#define FRB_KIND_MINIMUM      6u
+/* a nested effect (reference EffectData::RouteGraph, effect.rs:79-83); `key` names a definition */
+#define FRB_KIND_EFFECT       16u
+/* extension nodes named by the north star; NOT in the reference */
+#define FRB_KIND_OSCBANK      32u  /* 0 inputs, n_voices outputs; `key` names a bank definition */
+#define FRB_KIND_DIRECTFORM   33u  /* n_lanes inputs, n_lanes outputs; per-lane biquad (Direct Form I) */
+#define FRB_KIND_FBDELAY      34u  /* n_lanes inputs, n_lanes outputs; y[n] = x[n] + g*y[n-D] per lane */
+
+/* Edge, verbatim from reference src/routing/routegraph.rs:38-44 + :20-25 (handle 0 = toplevel). */
+typedef struct frb_edge {
+    uint32_t from;
+    uint32_t to;
+    uint32_t from_slot;
+    uint32_t to_slot;
+} frb_edge;
+
+/* One node of a nested effect definition (what RefRenderer::make_node walks, reference.rs:98-113). */
+typedef struct frb_node {
+    uint32_t handle;   /* non-zero */
+    uint32_t kind;     /* FRB_KIND_* */
+    uint64_t key;      /* definition key for EFFECT / OSCBANK / DIRECTFORM / FBDELAY, else 0 */
+} frb_node;
+
+typedef struct frb_config {
+    int32_t  device;          /* CUDA device ordinal */
+    uint32_t flags;           /* FRB_FLAG_* */
+    uint32_t osc_anchor;      /* oscillator re-anchor interval in samples (0 = default) */
+    uint32_t reserved;
+} frb_config;
+#define FRB_FLAG_SPARKLE_DELAY 1u  /* negative / NaN delay amounts yield 0.0 (reference sparkle.rs:525-542)
+                                      instead of clamping to delay 0 (reference.rs:205-210, the default) */
+
+/* Oscillator bank definition (extension).  Voice v owns partials [voice_offsets[v], voice_offsets[v+1]).
+ *   out_v(t) = sum_p amp_p * min(t/attack_p, 1) * exp(-t/tau_p) * sin(2*pi*freq_p*t/sample_rate + phase_p)
+ * attack_p <= 0 means no attack ramp; tau_p <= 0 or +inf means no decay.  t is the absolute sample index. */
+typedef struct frb_oscbank_desc {
+    uint32_t        n_voices;
+    uint32_t        reserved;
+    uint64_t        n_partials;
+    double          sample_rate;
+    const uint64_t* voice_offsets;   /* n_voices + 1 entries, non-decreasing, last == n_partials */
+    const double*   freq_hz;         /* n_partials */
+    const float*    amp;             /* n_partials */
+    const float*    phase;           /* n_partials, radians */
+    const float*    attack;          /* n_partials, samples */
+    const float*    tau;             /* n_partials, samples */
+} frb_oscbank_desc;
+
+/* Direct Form I biquad bank (extension): per lane
+ *   y[n] = b0 x[n] + b1 x[n-1] + b2 x[n-2] - a1 y[n-1] - a2 y[n-2],   x, y == 0 for n < 0. */
+typedef struct frb_directform_desc {
+    uint32_t     n_lanes;
+    uint32_t     reserved;
+    const float* b0; const float* b1; const float* b2; const float* a1; const float* a2;  /* n_lanes each */
+} frb_directform_desc;
+
+/* Feedback delay bank (extension): per lane  y[n] = x[n] + g * y[n - D],  D >= 1, y == 0 for n < 0. */
+typedef struct frb_fbdelay_desc {
+    uint32_t        n_lanes;
+    uint32_t        reserved;
+    const uint32_t* delay;   /* n_lanes, samples, >= 1 */
+    const float*    gain;    /* n_lanes */
+} frb_fbdelay_desc;
+
+typedef struct frb_renderer frb_renderer;
+
+/* ---- lifetime: replaces `SparkleRenderer::default()` moved into Dispatch::new (reference dispatch.rs:99-106) ---- */
+frb_renderer* frb_create(const frb_config* cfg);          /* NULL on failure; see frb_last_error(NULL) */
+void          frb_destroy(frb_renderer* r);
+const char*   frb_last_error(const frb_renderer* r);      /* r may be NULL for creation errors */
+
+/* ---- definitions consumed by on_add_node ---- */
+/* Nested effect body = EffectData::RouteGraph (reference effect.rs:79-83); children must be defined first.
+ * The definition is deep-copied into each node that instantiates it (reference.rs:98-113). */
+int frb_define_effect(frb_renderer* r, uint64_t key, const frb_node* nodes, uint32_t n_nodes,
+                      const frb_edge* edges, uint32_t n_edges);
+int frb_define_oscbank(frb_renderer* r, uint64_t key, const frb_oscbank_desc* desc);
+int frb_define_directform(frb_renderer* r, uint64_t key, const frb_directform_desc* desc);
+int frb_define_fbdelay(frb_renderer* r, uint64_t key, const frb_fbdelay_desc* desc);
+
+/* ---- GraphWatcher (reference src/routing/graphwatcher.rs:4-9; RefRenderer impl reference.rs:116-137) ---- */
+int frb_add_node(frb_renderer* r, uint32_t handle, uint32_t kind, uint64_t key);   /* on_add_node */
+int frb_del_node(frb_renderer* r, uint32_t handle);                                /* on_del_node */
+int frb_add_edge(frb_renderer* r, frb_edge e);                                     /* on_add_edge */
+int frb_del_edge(frb_renderer* r, frb_edge e);                                     /* on_del_edge */
+
+/* ---- Renderer::fill_buffer (reference src/render/renderer.rs:6-17; RefRenderer reference.rs:46-86) ----
+ * out: host, row-major [n_slots x n_times] f32 (what Dispatch allocates, dispatch.rs:149).
+ * inputs: jagged rows (Jagged2<f32>): row r feeds external-input slot r and occupies
+ *         in_data[in_row_offsets[r] .. in_row_offsets[r+1]); in_row_offsets has n_in_rows+1 entries.
+ * idx: absolute index of the first sample; idx != previous end is a seek (renderer.rs:12-15).
+ * Synchronous: on return `out` is filled. */
+int frb_fill_buffer(frb_renderer* r, float* out, uint32_t n_slots, uint64_t n_times, uint64_t idx,
+                    const float* in_data, const uint64_t* in_row_offsets, uint32_t n_in_rows);
+
+/* Same contract with `out` and `in_data` in DEVICE memory on the renderer's device (in_row_offsets stays on
+ * the host).  The call returns after enqueueing on the renderer's stream; frb_sync() waits.  Used to time the
+ * device-resident path and to hand the mixed block to a collective without a host round trip. */
+int frb_fill_buffer_device(frb_renderer* r, float* d_out, uint32_t n_slots, uint64_t n_times, uint64_t idx,
+                           const float* d_in_data, const uint64_t* in_row_offsets, uint32_t n_in_rows);
+int frb_sync(frb_renderer* r);
+void* frb_stream(frb_renderer* r);   /* the cudaStream_t the renderer launches on */
+
+/* ---- introspection for parity tests of routing order / buffer indexing / delay-line offsets ---- */
+/* Builds (if dirty) the device schedule for `n_slots` outputs and copies it out as u32 words:
+ * see libfriendship_b200/csrc/schedule.hpp for the record layout.  Returns the number of words the
+ * schedule needs (may exceed cap; nothing is written beyond cap), or a negative status. */
+int64_t frb_dump_schedule(frb_renderer* r, uint32_t n_slots, uint32_t* words, uint64_t cap);
+
+/* Counters since creation: kernel launches, bytes H2D, bytes D2H. */
+typedef struct frb_stats {
+    uint64_t kernel_launches;
+    uint64_t h2d_bytes;
+    uint64_t d2h_bytes;
+    uint64_t schedule_builds;
+    uint64_t osc_launches;
+    uint64_t interp_launches;
+    uint64_t scan_launches;
+    uint64_t reserved;
+} frb_stats;
+int frb_get_stats(const frb_renderer* r, frb_stats* out);
+
+/* Time (ms, CUDA events on the renderer's stream) the most recent fill spent in each kernel family. */
+typedef struct frb_timing {
+    float osc_ms;
+    float interp_ms;
+    float scan_ms;
+    float total_ms;
+} frb_timing;
+int frb_set_profiling(frb_renderer* r, int enabled);
+int frb_get_timing(const frb_renderer* r, frb_timing* out);
+
+const char* frb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRIENDSHIP_B200_H */

@@ -1,0 +1,84 @@
+"""libfriendship_b200 — B200-native renderer for libfriendship's effect tree.
+
+The product is the CUDA shared library `lib/libfriendship_b200.so` (C ABI: include/friendship_b200.h).  This
+package is the thin Python host mirror of the reference's `Renderer`/`GraphWatcher` interface used by tests/ and
+bench.py.  There is no CPU fallback: importing fails loudly if the library has not been built, and creating a
+renderer fails loudly without a CUDA device.
+"""
+import ctypes as _C
+import os as _os
+
+from . import _cabi
+from ._cabi import (  # noqa: F401
+    KIND_DELAY, KIND_F32CONSTANT, KIND_SUM2, KIND_MULTIPLY, KIND_DIVIDE, KIND_MODULO, KIND_MINIMUM, KIND_EFFECT,
+    KIND_OSCBANK, KIND_DIRECTFORM, KIND_FBDELAY, FLAG_SPARKLE_DELAY, RendererError,
+)
+
+LIB_PATH = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "lib", "libfriendship_b200.so")
+if not _os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: run `python __graft_entry__.py` (nvcc, sm_100a) first. "
+        "libfriendship_b200 has no CPU fallback.")
+_lib = _C.CDLL(LIB_PATH)
+_cabi.declare(_lib, "frb")
+_lib.frb_create.argtypes = [_C.POINTER(_cabi.frb_config)]
+_lib.frb_create.restype = _C.c_void_p
+_lib.frb_version.restype = _C.c_char_p
+
+
+def version():
+    return _lib.frb_version().decode()
+
+
+class B200Renderer(_cabi.CRendererBase):
+    """Drop-in for the reference's renderer object (`SparkleRenderer::default()` moved into `Dispatch::new`,
+    reference src/dispatch.rs:99-106), running on one B200.  device=-1 creates a planning-only instance (graph
+    mirror + schedule dumps); it cannot render."""
+
+    _lib = _lib
+    _prefix = "frb"
+
+    def __init__(self, device=0, flags=0, osc_anchor=0):
+        cfg = _cabi.frb_config(device, flags, osc_anchor, 0)
+        h = _lib.frb_create(_C.byref(cfg))
+        if not h:
+            msg = _lib.frb_last_error(None)
+            raise RendererError(_cabi.FRB_E_NO_DEVICE, msg.decode() if msg else "frb_create failed")
+        super().__init__(h)
+
+    # ---- device-resident path (inputs/outputs stay in HBM) ----
+    def fill_buffer_device(self, d_out_ptr, n_slots, n_times, idx, d_in_ptr=0, in_row_offsets=None):
+        import numpy as np
+        offs = np.ascontiguousarray(in_row_offsets if in_row_offsets is not None else [0], dtype=np.uint64)
+        n_rows = len(offs) - 1
+        self._check(_lib.frb_fill_buffer_device(self._h, d_out_ptr, n_slots, n_times, idx, d_in_ptr,
+                                                offs.ctypes.data_as(_C.POINTER(_C.c_uint64)), n_rows))
+
+    def sync(self):
+        self._check(_lib.frb_sync(self._h))
+
+    def stream(self):
+        return _lib.frb_stream(self._h)
+
+    def dump_schedule(self, n_slots):
+        import numpy as np
+        n = _lib.frb_dump_schedule(self._h, n_slots, None, 0)
+        if n < 0:
+            self._check(int(n))
+        w = np.zeros(n, dtype=np.uint32)
+        n2 = _lib.frb_dump_schedule(self._h, n_slots, w.ctypes.data_as(_C.POINTER(_C.c_uint32)), n)
+        assert n2 == n
+        return w
+
+    def stats(self):
+        s = _cabi.frb_stats()
+        self._check(_lib.frb_get_stats(self._h, _C.byref(s)))
+        return {n: getattr(s, n) for n, _ in s._fields_}
+
+    def set_profiling(self, on):
+        self._check(_lib.frb_set_profiling(self._h, 1 if on else 0))
+
+    def timing(self):
+        t = _cabi.frb_timing()
+        self._check(_lib.frb_get_timing(self._h, _C.byref(t)))
+        return {n: getattr(t, n) for n, _ in t._fields_}

@@ -1,0 +1,121 @@
+// capi.cu — extern "C" surface of libfriendship_b200.so (include/friendship_b200.h).
+// Each entry point cites the reference interface it replaces in the header.  Nothing throws across the ABI:
+// frb::Error becomes a status code + frb_last_error().
+#include <new>
+#include <string>
+
+#include "renderer.hpp"
+
+using frb::Error;
+using frb::Renderer;
+
+struct frb_renderer {
+    Renderer impl;
+    explicit frb_renderer(const frb_config& c) : impl(c) {}
+};
+
+static thread_local std::string g_create_error;
+
+template <typename F>
+static int guarded(frb_renderer* r, F f) {
+    if (!r) return FRB_E_INVALID;
+    try {
+        f();
+        return FRB_OK;
+    } catch (const Error& e) {
+        r->impl.last_error = e.msg;
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        r->impl.last_error = "out of host memory";
+        return FRB_E_INVALID;
+    } catch (const std::exception& e) {
+        r->impl.last_error = e.what();
+        return FRB_E_INVALID;
+    }
+}
+
+extern "C" {
+
+frb_renderer* frb_create(const frb_config* cfg) {
+    frb_config c{};
+    if (cfg) c = *cfg;
+    try {
+        return new frb_renderer(c);
+    } catch (const Error& e) {
+        g_create_error = e.msg;
+    } catch (const std::exception& e) {
+        g_create_error = e.what();
+    }
+    return nullptr;
+}
+
+void frb_destroy(frb_renderer* r) { delete r; }
+
+const char* frb_last_error(const frb_renderer* r) { return r ? r->impl.last_error.c_str() : g_create_error.c_str(); }
+
+int frb_define_effect(frb_renderer* r, uint64_t key, const frb_node* nodes, uint32_t n_nodes, const frb_edge* edges, uint32_t n_edges) {
+    return guarded(r, [&] { r->impl.define_effect(key, nodes, n_nodes, edges, n_edges); });
+}
+int frb_define_oscbank(frb_renderer* r, uint64_t key, const frb_oscbank_desc* d) {
+    return guarded(r, [&] { if (!d) throw Error{FRB_E_INVALID, "null desc"}; r->impl.define_oscbank(key, d); });
+}
+int frb_define_directform(frb_renderer* r, uint64_t key, const frb_directform_desc* d) {
+    return guarded(r, [&] { if (!d) throw Error{FRB_E_INVALID, "null desc"}; r->impl.define_directform(key, d); });
+}
+int frb_define_fbdelay(frb_renderer* r, uint64_t key, const frb_fbdelay_desc* d) {
+    return guarded(r, [&] { if (!d) throw Error{FRB_E_INVALID, "null desc"}; r->impl.define_fbdelay(key, d); });
+}
+
+int frb_add_node(frb_renderer* r, uint32_t handle, uint32_t kind, uint64_t key) {
+    return guarded(r, [&] { r->impl.add_node(handle, kind, key); });
+}
+int frb_del_node(frb_renderer* r, uint32_t handle) { return guarded(r, [&] { r->impl.del_node(handle); }); }
+int frb_add_edge(frb_renderer* r, frb_edge e) { return guarded(r, [&] { r->impl.add_edge(e); }); }
+int frb_del_edge(frb_renderer* r, frb_edge e) { return guarded(r, [&] { r->impl.del_edge(e); }); }
+
+int frb_fill_buffer(frb_renderer* r, float* out, uint32_t n_slots, uint64_t n_times, uint64_t idx,
+                    const float* in_data, const uint64_t* in_row_offsets, uint32_t n_in_rows) {
+    return guarded(r, [&] {
+        if (!out && (uint64_t)n_slots * n_times) throw Error{FRB_E_INVALID, "out is NULL"};
+        r->impl.fill(out, false, n_slots, n_times, idx, in_data, false, in_row_offsets, n_in_rows);
+    });
+}
+int frb_fill_buffer_device(frb_renderer* r, float* d_out, uint32_t n_slots, uint64_t n_times, uint64_t idx,
+                           const float* d_in_data, const uint64_t* in_row_offsets, uint32_t n_in_rows) {
+    return guarded(r, [&] {
+        if (!d_out && (uint64_t)n_slots * n_times) throw Error{FRB_E_INVALID, "d_out is NULL"};
+        r->impl.fill(d_out, true, n_slots, n_times, idx, d_in_data, true, in_row_offsets, n_in_rows);
+    });
+}
+int frb_sync(frb_renderer* r) { return guarded(r, [&] { r->impl.sync(); }); }
+void* frb_stream(frb_renderer* r) { return r ? (void*)r->impl.stream() : nullptr; }
+
+int64_t frb_dump_schedule(frb_renderer* r, uint32_t n_slots, uint32_t* words, uint64_t cap) {
+    int64_t n = 0;
+    int rc = guarded(r, [&] {
+        std::vector<uint32_t> w = r->impl.schedule(n_slots).dump();
+        n = (int64_t)w.size();
+        if (words) for (uint64_t i = 0; i < cap && i < w.size(); i++) words[i] = w[i];
+    });
+    return rc == FRB_OK ? n : (int64_t)rc;
+}
+
+int frb_get_stats(const frb_renderer* r, frb_stats* out) {
+    if (!r || !out) return FRB_E_INVALID;
+    *out = r->impl.stats;
+    return FRB_OK;
+}
+int frb_set_profiling(frb_renderer* r, int enabled) {
+    if (!r) return FRB_E_INVALID;
+    r->impl.profiling = enabled != 0;
+    return FRB_OK;
+}
+int frb_get_timing(const frb_renderer* r, frb_timing* out) {
+    if (!r || !out) return FRB_E_INVALID;
+    *out = r->impl.timing;
+    return FRB_OK;
+}
+
+const char* frb_version(void) { return "friendship_b200 0.1.0 (sm_100a)"; }
+
+}  // extern "C"

@@ -1,0 +1,448 @@
+// flatten.cc — routed effect tree -> topologically ordered schedule (see schedule.hpp).
+//
+// Semantics being flattened (reference src/render/reference.rs:178-266 and SURVEY.md Appendix A.5):
+//   * an edge from the toplevel of a nested effect reads the OUTER node's inbound edge of that slot (:189-193),
+//   * an edge from a nested-effect node reads the inner graph's output edge of that slot (:188-190),
+//   * a missing edge or out-of-range slot is 0.0f (:164-173),
+//   * every node is a pure function of (absolute time, inputs), so a shared sub-graph is evaluated once here
+//     (hash-consing) where the reference re-evaluates it per consumer: same values, less work.
+// Order: depth-first from output slot 0 upward, inbound slot 0 before slot 1 (Delay: source before frames) —
+// the deterministic counterpart of RouteGraph::iter_nodes_dep_first (routegraph.rs:105-126), whose own order
+// depends on HashMap iteration.
+#include "flatten.hpp"
+
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstring>
+#include <map>
+
+namespace frb {
+
+namespace {
+
+struct Ctx {
+    const Graph* g;
+    int parent;                 // context of the enclosing graph, -1 at the top
+    const GraphNode* pnode;     // the nested-effect node in the parent graph
+};
+
+struct Flattener {
+    const FlattenEnv& env;
+    Schedule& s;
+    std::vector<Ctx> ctxs;
+    std::map<std::pair<int, uint32_t>, int> child_ctx;              // (ctx, node handle) -> ctx
+    std::map<std::array<uint32_t, 4>, uint32_t> cons;               // hash-consing of values
+    std::map<std::array<uint32_t, 3>, uint32_t> edge_memo;          // (ctx, from, from_slot) -> value
+    std::map<std::pair<int, uint32_t>, uint32_t> ext_memo;          // (ctx, node handle) -> ext instance
+    int depth = 0;
+
+    Flattener(const FlattenEnv& e, Schedule& sch) : env(e), s(sch) {}
+
+    uint32_t mk(uint8_t op, uint32_t a, uint32_t b, uint32_t imm) {
+        std::array<uint32_t, 4> k{op, a, b, imm};
+        auto it = cons.find(k);
+        if (it != cons.end()) return it->second;
+        uint32_t id = (uint32_t)s.values.size();
+        s.values.push_back(Value{op, a, b, imm});
+        cons.emplace(k, id);
+        return id;
+    }
+    uint32_t zero() { return mk(V_ZERO, 0, 0, 0); }
+
+    uint32_t resolve_maybe(int ctx, const std::vector<std::optional<frb_edge>>& vec, size_t slot) {
+        if (slot < vec.size() && vec[slot].has_value()) return resolve(ctx, *vec[slot]);
+        return zero();
+    }
+
+    uint32_t resolve(int ctx, const frb_edge& e) {
+        if (++depth > 100000) throw Error{FRB_E_UNSUPPORTED, "graph too deep to flatten"};
+        struct Guard { int& d; ~Guard() { --d; } } guard{depth};
+        const Ctx c = ctxs[ctx];
+        if (e.from == 0) {
+            // reading an input of this graph level
+            if (c.parent < 0) {
+                s.n_input_slots = std::max(s.n_input_slots, e.from_slot + 1);
+                return mk(V_INPUT, 0, 0, e.from_slot);
+            }
+            return resolve_maybe(c.parent, c.pnode->inbound, e.from_slot);
+        }
+        std::array<uint32_t, 3> mk_key{(uint32_t)ctx, e.from, e.from_slot};
+        auto mit = edge_memo.find(mk_key);
+        if (mit != edge_memo.end()) return mit->second;
+
+        auto nit = c.g->nodes.find(e.from);
+        if (nit == c.g->nodes.end())
+            throw Error{FRB_E_BAD_HANDLE, "edge reads node " + std::to_string(e.from) + " which does not exist"};
+        const GraphNode& n = nit->second;
+        uint32_t v;
+        auto need_slot0 = [&](const char* what) {
+            if (e.from_slot != 0)
+                throw Error{FRB_E_BAD_SLOT, std::string(what) + ": from_slot must be 0 (reference.rs:199,223,230,237,244,251)"};
+        };
+        switch (n.kind) {
+            case FRB_KIND_F32CONSTANT: v = mk(V_CONST, 0, 0, e.from_slot); break;
+            case FRB_KIND_DELAY: {
+                need_slot0("Delay");
+                uint32_t src = resolve_maybe(ctx, n.inbound, 0);
+                uint32_t amt = resolve_maybe(ctx, n.inbound, 1);
+                // Delay of the constant-zero signal is zero at every t (exactly +0.0f either way).
+                v = (s.values[src].op == V_ZERO) ? src : mk(V_DELAY, src, amt, 0);
+                break;
+            }
+            case FRB_KIND_SUM2: case FRB_KIND_MULTIPLY: case FRB_KIND_DIVIDE: case FRB_KIND_MODULO: case FRB_KIND_MINIMUM: {
+                need_slot0("binary primitive");
+                uint32_t a = resolve_maybe(ctx, n.inbound, 0);
+                uint32_t b = resolve_maybe(ctx, n.inbound, 1);
+                uint8_t op = n.kind == FRB_KIND_SUM2 ? V_SUM2 : n.kind == FRB_KIND_MULTIPLY ? V_MUL
+                           : n.kind == FRB_KIND_DIVIDE ? V_DIV : n.kind == FRB_KIND_MODULO ? V_MOD : V_MIN;
+                v = mk(op, a, b, 0);
+                break;
+            }
+            case FRB_KIND_EFFECT: {
+                auto key = std::make_pair(ctx, e.from);
+                auto cit = child_ctx.find(key);
+                int child;
+                if (cit == child_ctx.end()) {
+                    child = (int)ctxs.size();
+                    ctxs.push_back(Ctx{n.body.get(), ctx, &n});
+                    child_ctx.emplace(key, child);
+                } else {
+                    child = cit->second;
+                }
+                v = resolve_maybe(child, n.body->output_edges, e.from_slot);
+                break;
+            }
+            case FRB_KIND_OSCBANK: case FRB_KIND_DIRECTFORM: case FRB_KIND_FBDELAY: {
+                auto key = std::make_pair(ctx, e.from);
+                auto xit = ext_memo.find(key);
+                uint32_t inst;
+                if (xit == ext_memo.end()) {
+                    int64_t lanes = env.ext_lanes(n.kind, n.key);
+                    if (lanes < 0) throw Error{FRB_E_BAD_HANDLE, "extension node with undefined key"};
+                    ExtInstance x;
+                    x.kind = n.kind == FRB_KIND_OSCBANK ? EXT_OSCBANK : n.kind == FRB_KIND_DIRECTFORM ? EXT_DIRECTFORM : EXT_FBDELAY;
+                    x.key = n.key;
+                    x.n_lanes = (uint32_t)lanes;
+                    if (x.kind != EXT_OSCBANK)
+                        for (uint32_t l = 0; l < x.n_lanes; l++) x.inputs.push_back(resolve_maybe(ctx, n.inbound, l));
+                    inst = (uint32_t)s.ext.size();
+                    s.ext.push_back(std::move(x));
+                    ext_memo.emplace(key, inst);
+                    // all lanes get consecutive value ids right after the instance's inputs
+                    for (uint32_t l = 0; l < s.ext[inst].n_lanes; l++) mk(V_EXT, inst, 0, l);
+                } else {
+                    inst = xit->second;
+                }
+                v = (e.from_slot < s.ext[inst].n_lanes) ? mk(V_EXT, inst, 0, e.from_slot) : zero();
+                break;
+            }
+            default: throw Error{FRB_E_INVALID, "unknown node kind " + std::to_string(n.kind)};
+        }
+        edge_memo.emplace(mk_key, v);
+        return v;
+    }
+};
+
+// Delay amount of a constant `frames` signal, with the clamps of reference.rs:200-212.
+// Returns false when the Delay can never read its source (frames >= 2^64).
+bool const_delay(uint32_t bits, uint64_t* out) {
+    float d;
+    std::memcpy(&d, &bits, 4);
+    if (d >= 18446744073709551616.0f) return false;
+    if (!(d >= 0.0f)) { *out = 0; return true; }   // negative or NaN -> delay 0
+    *out = (uint64_t)d;
+    return true;
+}
+
+uint64_t sat_add(uint64_t a, uint64_t b) {
+    if (a == LOOKBACK_FULL || b == LOOKBACK_FULL) return LOOKBACK_FULL;
+    uint64_t r = a + b;
+    if (r < a || r > (1ull << 40)) return LOOKBACK_FULL;
+    return r;
+}
+
+}  // namespace
+
+Schedule flatten(const Graph& top, uint32_t n_slots, const FlattenEnv& env) {
+    Schedule s;
+    Flattener f(env, s);
+    f.ctxs.push_back(Ctx{&top, -1, nullptr});
+    f.zero();   // value 0 is always the zero signal
+    for (uint32_t slot = 0; slot < n_slots; slot++) s.outputs.push_back(f.resolve_maybe(0, top.output_edges, slot));
+
+    const size_t nv = s.values.size();
+    auto& V = s.values;
+    auto is_leaf = [&](uint32_t v) { return V[v].op == V_ZERO || V[v].op == V_CONST || V[v].op == V_INPUT; };
+
+    // time-invariant values: constant expressions (no inputs, delays or extension outputs underneath)
+    std::vector<uint8_t> ti(nv, 0);
+    for (size_t v = 0; v < nv; v++) {
+        switch (V[v].op) {
+            case V_ZERO: case V_CONST: ti[v] = 1; break;
+            case V_SUM2: case V_MUL: case V_DIV: case V_MOD: case V_MIN: ti[v] = ti[V[v].a] && ti[V[v].b]; break;
+            default: ti[v] = 0;
+        }
+    }
+
+    // ---- stages ----
+    s.value_stage.assign(nv, 0);
+    auto& st = s.value_stage;
+    std::vector<uint8_t> ext_staged(s.ext.size(), 0);
+    for (size_t v = 0; v < nv; v++) {
+        const Value& x = V[v];
+        switch (x.op) {
+            case V_ZERO: case V_CONST: case V_INPUT: st[v] = 0; break;
+            case V_SUM2: case V_MUL: case V_DIV: case V_MOD: case V_MIN: st[v] = std::max(st[x.a], st[x.b]); break;
+            case V_DELAY: {
+                uint32_t sg = st[x.b];
+                if (!is_leaf(x.a) && !ti[x.a]) sg = std::max(sg, V[x.a].op == V_EXT ? st[x.a] : st[x.a] + 1);
+                st[v] = sg;
+                break;
+            }
+            case V_EXT: {
+                ExtInstance& inst = s.ext[x.a];
+                if (!ext_staged[x.a]) {
+                    uint32_t sg = 0;
+                    for (uint32_t in : inst.inputs) sg = std::max(sg, V[in].op == V_EXT ? st[in] : st[in] + 1);
+                    inst.stage = sg;
+                    ext_staged[x.a] = 1;
+                }
+                st[v] = inst.stage;
+                break;
+            }
+        }
+    }
+    uint32_t n_stages = 1;
+    for (size_t v = 0; v < nv; v++) n_stages = std::max(n_stages, st[v] + 1);
+    s.stages.resize(n_stages);
+    for (uint32_t i = 0; i < s.ext.size(); i++) s.stages[s.ext[i].stage].ext.push_back(i);
+
+    // ---- which values are materialised in HBM ----
+    std::vector<uint8_t> need_buf(nv, 0);
+    for (size_t v = 0; v < nv; v++) {
+        const Value& x = V[v];
+        if (x.op == V_EXT) { need_buf[v] = 1; continue; }
+        auto use = [&](uint32_t u) {
+            if (!is_leaf(u) && st[u] < st[v]) need_buf[u] = 1;          // consumed by a later stage
+        };
+        if (x.op == V_DELAY) {
+            if (!is_leaf(x.a) && !ti[x.a]) need_buf[x.a] = 1;           // Delay source becomes an indexed read
+            else use(x.a);                                              // constant expression from an earlier stage
+            use(x.b);
+        } else if (x.op >= V_SUM2 && x.op <= V_MIN) {
+            use(x.a); use(x.b);
+        }
+    }
+    for (auto& inst : s.ext)
+        for (uint32_t in : inst.inputs) need_buf[in] = 1;               // filters read planes (leaves included)
+
+    s.value_buffer.assign(nv, -1);
+    for (size_t v = 0; v < nv; v++) {
+        if (!need_buf[v]) continue;
+        s.value_buffer[v] = (int32_t)s.buffers.size();
+        BufferInfo b;
+        b.value = (uint32_t)v;
+        b.lookback = 0;
+        if (V[v].op == V_EXT) { b.ext = V[v].a; b.lane = V[v].imm; }
+        s.buffers.push_back(b);
+    }
+    for (uint32_t i = 0; i < s.ext.size(); i++) {
+        ExtInstance& inst = s.ext[i];
+        std::array<uint32_t, 4> k{V_EXT, i, 0, 0};
+        uint32_t v0 = f.cons.at(k);
+        inst.first_out_buf = (uint32_t)s.value_buffer[v0];
+        for (uint32_t in : inst.inputs) inst.in_bufs.push_back((uint32_t)s.value_buffer[in]);
+    }
+
+    // ---- lookback: how far before the block start each value must stay addressable ----
+    std::vector<uint64_t> L(nv, 0);
+    auto raise = [&](uint32_t v, uint64_t l) {
+        if (L[v] == LOOKBACK_FULL) return;
+        if (l == LOOKBACK_FULL || l > L[v]) L[v] = l;
+    };
+    std::vector<uint8_t> ext_done(s.ext.size(), 0);
+    for (size_t vi = nv; vi-- > 0;) {
+        const Value& x = V[vi];
+        switch (x.op) {
+            case V_SUM2: case V_MUL: case V_DIV: case V_MOD: case V_MIN: raise(x.a, L[vi]); raise(x.b, L[vi]); break;
+            case V_DELAY: {
+                raise(x.b, L[vi]);
+                uint64_t d = 0;
+                bool reads = true;
+                if (V[x.b].op == V_CONST) reads = const_delay(V[x.b].imm, &d);
+                else if (V[x.b].op == V_ZERO) d = 0;
+                else d = LOOKBACK_FULL;                                  // signal-driven delay (reference.rs:200)
+                if (reads) raise(x.a, sat_add(L[vi], d));
+                break;
+            }
+            case V_EXT: {
+                if (x.imm != 0) break;                                   // lanes are consecutive; lane 0 has the lowest id
+                ExtInstance& inst = s.ext[x.a];
+                uint64_t li = 0;
+                for (uint32_t l = 0; l < inst.n_lanes; l++) {
+                    uint64_t ll = L[vi + l];
+                    if (ll == LOOKBACK_FULL) li = LOOKBACK_FULL;
+                    else if (li != LOOKBACK_FULL) li = std::max(li, ll);
+                }
+                uint64_t own = li, in_l = li;
+                if (inst.kind == EXT_DIRECTFORM) {                       // needs x[n-1], x[n-2], y[n-1], y[n-2]
+                    own = (li == LOOKBACK_FULL) ? li : std::max<uint64_t>(li, 2);
+                    in_l = sat_add(li, 2);
+                }
+                if (inst.kind == EXT_FBDELAY) {
+                    uint64_t dmax = env.ext_max_delay ? env.ext_max_delay(inst.key) : 0;
+                    own = (li == LOOKBACK_FULL) ? li : std::max<uint64_t>(li, dmax);
+                }
+                for (uint32_t l = 0; l < inst.n_lanes; l++) L[vi + l] = own;
+                for (uint32_t in : inst.inputs) raise(in, in_l);
+                if (inst.kind != EXT_OSCBANK) s.from_zero = true;         // recurrences are defined from t = 0
+                break;
+            }
+            default: break;
+        }
+    }
+    for (size_t v = 0; v < nv; v++) {
+        if (L[v] == LOOKBACK_FULL) { s.full_history = true; s.from_zero = true; }
+        else s.max_lookback = std::max(s.max_lookback, L[v]);
+        if (s.value_buffer[v] >= 0) s.buffers[s.value_buffer[v]].lookback = L[v];
+    }
+
+    // ---- one register program per stage ----
+    std::vector<std::vector<uint32_t>> out_slots_of(nv);
+    for (uint32_t k = 0; k < s.outputs.size(); k++) out_slots_of[s.outputs[k]].push_back(k);
+
+    for (uint32_t sg = 0; sg < n_stages; sg++) {
+        struct VI { uint8_t op; uint32_t flags; uint32_t dst, a, b, aux; };   // with virtual registers
+        std::vector<VI> code;
+        std::vector<int64_t> vreg_of(nv, -1);
+        uint32_t n_vreg = 0;
+        auto new_vreg = [&]() { return n_vreg++; };
+        const uint32_t NOREG = 0xFFFFu;
+
+        // operand: immediate for constants, register otherwise (loading leaves / planes on first use)
+        auto operand = [&](uint32_t u, uint32_t imm_flag, uint32_t* flags) -> uint32_t {
+            if (V[u].op == V_ZERO) { *flags |= imm_flag; return 0u; }
+            if (V[u].op == V_CONST) { *flags |= imm_flag; return V[u].imm; }
+            if (vreg_of[u] >= 0) return (uint32_t)vreg_of[u];
+            uint32_t r = new_vreg();
+            if (V[u].op == V_INPUT) code.push_back(VI{I_LDIN, 0, r, 0, 0, V[u].imm});
+            else {
+                if (s.value_buffer[u] < 0) throw Error{FRB_E_UNSUPPORTED, "internal: value needed across stages has no buffer"};
+                code.push_back(VI{I_LDBUF, 0, r, 0, 0, (uint32_t)s.value_buffer[u]});
+            }
+            vreg_of[u] = r;
+            return r;
+        };
+        auto emit_sinks = [&](uint32_t v, uint32_t flags_a, uint32_t a) {
+            if (s.value_buffer[v] >= 0 && V[v].op != V_EXT)
+                code.push_back(VI{I_STBUF, flags_a, NOREG, a, 0, (uint32_t)s.value_buffer[v]});
+            for (uint32_t k : out_slots_of[v]) code.push_back(VI{I_STOUT, flags_a, NOREG, a, 0, k});
+        };
+
+        for (size_t v = 0; v < nv; v++) {
+            if (st[v] != sg) continue;
+            const Value& x = V[v];
+            if (is_leaf((uint32_t)v) || x.op == V_EXT) {
+                // leaves and extension outputs only appear in a program when they feed a sink directly
+                bool sink = !out_slots_of[v].empty() || (s.value_buffer[v] >= 0 && x.op != V_EXT);
+                if (!sink) continue;
+                uint32_t fl = 0;
+                uint32_t a = operand((uint32_t)v, IF_A_IMM, &fl);
+                emit_sinks((uint32_t)v, fl, a);
+                continue;
+            }
+            uint32_t fl = 0, dst;
+            if (x.op == V_DELAY) {
+                uint32_t amt = operand(x.b, IF_A_IMM, &fl);
+                const Value& src = V[x.a];
+                if (src.op == V_INPUT) {
+                    dst = new_vreg();
+                    code.push_back(VI{I_DLY_IN, fl, dst, amt, 0, src.imm});
+                } else if (ti[x.a]) {
+                    uint32_t b = operand(x.a, IF_B_IMM, &fl);
+                    dst = new_vreg();
+                    code.push_back(VI{I_DLY_TI, fl, dst, amt, b, 0});
+                } else {
+                    dst = new_vreg();
+                    code.push_back(VI{I_DLY_BUF, fl, dst, amt, 0, (uint32_t)s.value_buffer[x.a]});
+                }
+            } else {
+                uint32_t a = operand(x.a, IF_A_IMM, &fl);
+                uint32_t b = operand(x.b, IF_B_IMM, &fl);
+                dst = new_vreg();
+                uint8_t op = x.op == V_SUM2 ? I_ADD : x.op == V_MUL ? I_MUL : x.op == V_DIV ? I_DIV : x.op == V_MOD ? I_MOD : I_MIN;
+                code.push_back(VI{op, fl, dst, a, b, 0});
+            }
+            vreg_of[v] = dst;
+            emit_sinks((uint32_t)v, 0, dst);
+        }
+
+        // linear-scan register assignment over the straight-line program
+        std::vector<int64_t> last_use(n_vreg, -1);
+        for (size_t i = 0; i < code.size(); i++) {
+            const VI& c = code[i];
+            bool a_reg = !(c.flags & IF_A_IMM) && c.op != I_LDIN && c.op != I_LDBUF;
+            bool b_reg = !(c.flags & IF_B_IMM) && (c.op == I_ADD || c.op == I_MUL || c.op == I_DIV || c.op == I_MOD || c.op == I_MIN || c.op == I_DLY_TI);
+            if (a_reg) last_use[c.a] = (int64_t)i;
+            if (b_reg) last_use[c.b] = (int64_t)i;
+        }
+        std::vector<uint32_t> phys(n_vreg, NOREG), free_list;
+        uint32_t n_phys = 0;
+        Stage& stage = s.stages[sg];
+        for (size_t i = 0; i < code.size(); i++) {
+            VI c = code[i];
+            bool a_reg = !(c.flags & IF_A_IMM) && c.op != I_LDIN && c.op != I_LDBUF;
+            bool b_reg = !(c.flags & IF_B_IMM) && (c.op == I_ADD || c.op == I_MUL || c.op == I_DIV || c.op == I_MOD || c.op == I_MIN || c.op == I_DLY_TI);
+            uint32_t va = c.a, vb = c.b;
+            if (a_reg) c.a = phys[va];
+            if (b_reg) c.b = phys[vb];
+            if (a_reg && last_use[va] == (int64_t)i) free_list.push_back(phys[va]);
+            if (b_reg && last_use[vb] == (int64_t)i && !(a_reg && vb == va)) free_list.push_back(phys[vb]);
+            if (c.dst != NOREG) {
+                uint32_t vd = c.dst;
+                uint32_t p;
+                if (!free_list.empty()) { p = free_list.back(); free_list.pop_back(); }
+                else p = n_phys++;
+                phys[vd] = p;
+                c.dst = p;
+                if (last_use[vd] < 0) free_list.push_back(p);   // dead value (e.g. only its sinks were folded away)
+            }
+            stage.program.push_back(Instr::make(c.op, c.flags, c.dst, c.a, c.b, c.aux));
+        }
+        stage.program.push_back(Instr::make(I_END, 0, 0, 0, 0, 0));
+        stage.n_regs = n_phys;
+        if (n_phys > env.max_regs)
+            throw Error{FRB_E_UNSUPPORTED, "stage needs " + std::to_string(n_phys) + " live registers; limit " + std::to_string(env.max_regs)};
+    }
+    return s;
+}
+
+std::vector<uint32_t> Schedule::dump() const {
+    std::vector<uint32_t> w;
+    w.push_back(0x53425246u);   // 'FRBS'
+    w.push_back((uint32_t)values.size());
+    w.push_back((uint32_t)outputs.size());
+    w.push_back((uint32_t)buffers.size());
+    w.push_back((uint32_t)stages.size());
+    w.push_back((uint32_t)ext.size());
+    w.push_back(n_input_slots);
+    w.push_back((from_zero ? 1u : 0u) | (full_history ? 2u : 0u));
+    for (size_t v = 0; v < values.size(); v++) {
+        w.push_back(values[v].op); w.push_back(values[v].a); w.push_back(values[v].b); w.push_back(values[v].imm);
+        w.push_back(value_stage[v]); w.push_back((uint32_t)(value_buffer[v] + 1));
+    }
+    for (uint32_t o : outputs) w.push_back(o);
+    for (auto& b : buffers) {
+        w.push_back(b.value); w.push_back((uint32_t)(b.lookback & 0xFFFFFFFFu)); w.push_back((uint32_t)(b.lookback >> 32));
+        w.push_back(b.ext + 1); w.push_back(b.lane);
+    }
+    for (auto& sg : stages) {
+        w.push_back((uint32_t)sg.ext.size()); w.push_back((uint32_t)sg.program.size()); w.push_back(sg.n_regs);
+        for (uint32_t e : sg.ext) w.push_back(e);
+        for (auto& i : sg.program) { w.push_back(i.w0); w.push_back(i.a); w.push_back(i.b); w.push_back(i.aux); }
+    }
+    return w;
+}
+
+}  // namespace frb

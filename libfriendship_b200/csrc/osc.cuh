@@ -1,0 +1,31 @@
+// osc.cuh — K1 oscillator bank (extension node FRB_KIND_OSCBANK); see osc.cu
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/friendship_b200.h"
+#include "interp.cuh"
+
+namespace frb {
+
+struct OscBankDev;   // device-resident, preprocessed bank (defined in osc.cu)
+
+struct OscBankInfo {
+    uint32_t n_voices;
+    uint64_t n_partials;
+};
+
+// Uploads and preprocesses a bank (fp64 setup kernel).  Returns nullptr and sets *err on failure.
+std::shared_ptr<OscBankDev> osc_create(const frb_oscbank_desc* d, cudaStream_t stream, std::string* err);
+OscBankInfo osc_info(const OscBankDev& b);
+
+// Renders every voice of the bank over absolute times [lo, hi) into the voices' ring buffers
+// bufdesc[first_buf + v].  `anchor` = samples between exact re-anchors of each partial.
+cudaError_t launch_osc(const OscBankDev& b, const BufferDesc* d_bufdesc, uint32_t first_buf, uint64_t lo, uint64_t hi,
+                       uint32_t anchor, int sm_count, cudaStream_t stream, uint64_t* n_launches);
+
+}  // namespace frb

@@ -1,0 +1,480 @@
+// renderer.cu — B200Renderer host logic: graph mirror, external-input history in HBM, schedule upload,
+// block-wise rendering.  Follows the contract of Renderer::fill_buffer (reference src/render/renderer.rs:6-17)
+// and the bookkeeping of RefRenderer::fill_buffer (reference src/render/reference.rs:46-86).
+#include "renderer.hpp"
+
+#include <algorithm>
+#include <cstring>
+
+namespace frb {
+
+#define CU(expr)                                                                                    \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            throw Error{FRB_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)};            \
+    } while (0)
+
+static uint64_t pow2_ceil(uint64_t x) {
+    uint64_t p = 8;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+// pads data[start .. start+count) with data[last_pos], or 0 when has_last == 0 (reference.rs:72-73)
+__global__ void pad_kernel(float* data, unsigned long long start, unsigned long long count,
+                           unsigned long long last_pos, int has_last) {
+    const float v = has_last ? data[last_pos] : 0.0f;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+        data[start + i] = v;
+}
+
+Renderer::Renderer(const frb_config& cfg) : cfg_(cfg) {
+    if (cfg.device < 0) {
+        // planning-only instance: graph mirror + schedule dumps; rendering is refused (there is no CPU fallback)
+        host_only_ = true;
+        return;
+    }
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        throw Error{FRB_E_NO_DEVICE, std::string("no CUDA device available: ") + cudaGetErrorString(e)};
+    if (cfg.device >= n) throw Error{FRB_E_NO_DEVICE, "CUDA device ordinal out of range"};
+    device_ = cfg.device;
+    CU(cudaSetDevice(device_));
+    CU(cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, device_));
+    CU(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    for (auto& ev : ev_) CU(cudaEventCreate(&ev));
+}
+
+Renderer::~Renderer() {
+    if (host_only_) return;
+    cudaSetDevice(device_);
+    if (stream_) cudaStreamSynchronize(stream_);
+    free_device_schedule();
+    for (auto& s : inputs_) if (s.d_data) cudaFree(s.d_data);
+    if (d_indesc_) cudaFree(d_indesc_);
+    if (d_in_stage_) cudaFree(d_in_stage_);
+    if (d_out_) cudaFree(d_out_);
+    if (d_bufdesc_) cudaFree(d_bufdesc_);
+    for (auto& ev : ev_) if (ev) cudaEventDestroy(ev);
+    if (stream_) cudaStreamDestroy(stream_);
+}
+
+void Renderer::require_device() const {
+    if (host_only_) throw Error{FRB_E_NO_DEVICE, "renderer was created without a CUDA device (planning only); there is no CPU fallback"};
+}
+
+// ------------------------------------------------------------------------------------------------ definitions
+
+GraphNode Renderer::make_node(uint32_t kind, uint64_t key) const {
+    GraphNode n;
+    n.kind = kind;
+    n.key = key;
+    switch (kind) {
+        case FRB_KIND_DELAY: case FRB_KIND_F32CONSTANT: case FRB_KIND_SUM2: case FRB_KIND_MULTIPLY:
+        case FRB_KIND_DIVIDE: case FRB_KIND_MODULO: case FRB_KIND_MINIMUM:
+            break;
+        case FRB_KIND_EFFECT: {
+            auto it = effect_defs_.find(key);
+            if (it == effect_defs_.end()) throw Error{FRB_E_BAD_HANDLE, "unknown effect definition key"};
+            n.body = it->second->deep_copy();   // reference.rs:98-113: private copy per node
+            break;
+        }
+        case FRB_KIND_OSCBANK:
+            if (!osc_defs_.count(key)) throw Error{FRB_E_BAD_HANDLE, "unknown oscbank key"};
+            break;
+        case FRB_KIND_DIRECTFORM:
+            if (!df_defs_.count(key)) throw Error{FRB_E_BAD_HANDLE, "unknown directform key"};
+            break;
+        case FRB_KIND_FBDELAY:
+            if (!fb_defs_.count(key)) throw Error{FRB_E_BAD_HANDLE, "unknown fbdelay key"};
+            break;
+        default: throw Error{FRB_E_INVALID, "unknown node kind"};
+    }
+    return n;
+}
+
+void Renderer::define_effect(uint64_t key, const frb_node* nodes, uint32_t n_nodes, const frb_edge* edges, uint32_t n_edges) {
+    auto g = std::make_shared<Graph>();
+    for (uint32_t i = 0; i < n_nodes; i++) {
+        if (nodes[i].handle == 0) throw Error{FRB_E_INVALID, "node handle 0 is the toplevel"};
+        g->nodes[nodes[i].handle] = make_node(nodes[i].kind, nodes[i].key);
+    }
+    for (uint32_t i = 0; i < n_edges; i++)
+        if (!g->add_edge(edges[i])) throw Error{FRB_E_BAD_HANDLE, "effect definition: edge to unknown node"};
+    effect_defs_[key] = g;
+}
+
+void Renderer::define_oscbank(uint64_t key, const frb_oscbank_desc* d) {
+    require_device();
+    CU(cudaSetDevice(device_));
+    std::string err;
+    auto b = osc_create(d, stream_, &err);
+    if (!b) throw Error{FRB_E_INVALID, err};
+    stats.h2d_bytes += d->n_partials * (sizeof(double) + 4 * sizeof(float));
+    osc_defs_[key] = b;
+}
+void Renderer::define_directform(uint64_t key, const frb_directform_desc* d) {
+    require_device();
+    CU(cudaSetDevice(device_));
+    std::string err;
+    auto b = directform_create(d, stream_, &err);
+    if (!b) throw Error{FRB_E_INVALID, err};
+    df_defs_[key] = b;
+}
+void Renderer::define_fbdelay(uint64_t key, const frb_fbdelay_desc* d) {
+    require_device();
+    CU(cudaSetDevice(device_));
+    std::string err;
+    auto b = fbdelay_create(d, stream_, &err);
+    if (!b) throw Error{FRB_E_INVALID, err};
+    fb_defs_[key] = b;
+}
+
+// ------------------------------------------------------------------------------------------------ GraphWatcher
+
+void Renderer::add_node(uint32_t handle, uint32_t kind, uint64_t key) {   // reference.rs:117-120
+    if (handle == 0) throw Error{FRB_E_INVALID, "node handle 0 is the toplevel"};
+    graph_.nodes[handle] = make_node(kind, key);                          // HashMap::insert replaces
+    dirty_ = true;
+}
+void Renderer::del_node(uint32_t handle) {                                 // reference.rs:121-123
+    graph_.nodes.erase(handle);
+    dirty_ = true;
+}
+void Renderer::add_edge(const frb_edge& e) {                               // reference.rs:124-126
+    if (!graph_.add_edge(e)) throw Error{FRB_E_BAD_HANDLE, "add_edge: target node does not exist (reference.rs:145)"};
+    dirty_ = true;
+}
+void Renderer::del_edge(const frb_edge& e) {                               // reference.rs:127-136
+    if (!graph_.del_edge(e)) throw Error{FRB_E_BAD_HANDLE, "Attempt to delete edge, but it was never created! (reference.rs:131)"};
+    dirty_ = true;
+}
+
+// ------------------------------------------------------------------------------------------------ schedule
+
+void Renderer::free_device_schedule() {
+    for (auto p : d_programs_) if (p) cudaFree(p);
+    d_programs_.clear();
+    for (auto& b : h_bufdesc_) if (b.data) cudaFree(b.data);
+    h_bufdesc_.clear();
+    ring_cap_.clear();
+    for (auto p : d_ext_in_bufs_) if (p) cudaFree(p);
+    d_ext_in_bufs_.clear();
+}
+
+const Schedule& Renderer::schedule(uint32_t n_slots) {
+    if (dirty_ || sched_slots_ != n_slots) {
+        FlattenEnv env;
+        env.ext_lanes = [this](uint32_t kind, uint64_t key) -> int64_t {
+            if (kind == FRB_KIND_OSCBANK) { auto it = osc_defs_.find(key); return it == osc_defs_.end() ? -1 : (int64_t)osc_info(*it->second).n_voices; }
+            if (kind == FRB_KIND_DIRECTFORM) { auto it = df_defs_.find(key); return it == df_defs_.end() ? -1 : (int64_t)directform_lanes(*it->second); }
+            if (kind == FRB_KIND_FBDELAY) { auto it = fb_defs_.find(key); return it == fb_defs_.end() ? -1 : (int64_t)fbdelay_lanes(*it->second); }
+            return -1;
+        };
+        env.ext_max_delay = [this](uint64_t key) -> uint64_t {
+            auto it = fb_defs_.find(key);
+            return it == fb_defs_.end() ? 0 : fbdelay_max_delay(*it->second);
+        };
+        env.max_regs = 96;
+        Schedule s = flatten(graph_, n_slots, env);   // throws on malformed graphs; state unchanged then
+        if (!host_only_) {
+            CU(cudaSetDevice(device_));
+            CU(cudaStreamSynchronize(stream_));
+            free_device_schedule();
+        }
+        sched_ = std::move(s);
+        sched_slots_ = n_slots;
+        dirty_ = false;
+        cache_valid_ = false;
+        stats.schedule_builds++;
+        if (!host_only_) upload_schedule();
+    }
+    return sched_;
+}
+
+void Renderer::ensure_schedule(uint32_t n_slots) { (void)schedule(n_slots); }
+
+void Renderer::upload_schedule() {
+    d_programs_.assign(sched_.stages.size(), nullptr);
+    for (size_t i = 0; i < sched_.stages.size(); i++) {
+        auto& prog = sched_.stages[i].program;
+        size_t bytes = prog.size() * sizeof(Instr);
+        CU(cudaMalloc(&d_programs_[i], bytes));
+        CU(cudaMemcpyAsync(d_programs_[i], prog.data(), bytes, cudaMemcpyHostToDevice, stream_));
+        stats.h2d_bytes += bytes;
+    }
+    h_bufdesc_.assign(sched_.buffers.size(), BufferDesc{nullptr, 0});
+    ring_cap_.assign(sched_.buffers.size(), 0);
+    bufdesc_dirty_ = true;
+    d_ext_in_bufs_.assign(sched_.ext.size(), nullptr);
+    for (size_t i = 0; i < sched_.ext.size(); i++) {
+        auto& x = sched_.ext[i];
+        if (x.in_bufs.empty()) continue;
+        CU(cudaMalloc(&d_ext_in_bufs_[i], x.in_bufs.size() * sizeof(uint32_t)));
+        CU(cudaMemcpyAsync(d_ext_in_bufs_[i], x.in_bufs.data(), x.in_bufs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream_));
+    }
+    CU(cudaStreamSynchronize(stream_));   // host vectors above may go away
+}
+
+// Ring buffers: capacity = pow2 >= lookback + chunk (+ slack); LOOKBACK_FULL rings hold [0, t_end).
+void Renderer::ensure_rings(uint64_t t_end) {
+    for (size_t i = 0; i < sched_.buffers.size(); i++) {
+        const BufferInfo& b = sched_.buffers[i];
+        uint64_t need = (b.lookback == LOOKBACK_FULL) ? pow2_ceil(t_end + 8) : pow2_ceil(b.lookback + chunk_ + 8);
+        if (need <= ring_cap_[i]) continue;
+        float* nd = nullptr;
+        CU(cudaMalloc(&nd, need * sizeof(float)));
+        CU(cudaMemsetAsync(nd, 0, need * sizeof(float), stream_));
+        if (h_bufdesc_[i].data) {
+            if (b.lookback == LOOKBACK_FULL)   // index t & mask == t for t < old capacity: a prefix copy preserves history
+                CU(cudaMemcpyAsync(nd, h_bufdesc_[i].data, ring_cap_[i] * sizeof(float), cudaMemcpyDeviceToDevice, stream_));
+            else
+                cache_valid_ = false;
+            CU(cudaStreamSynchronize(stream_));
+            CU(cudaFree(h_bufdesc_[i].data));
+        }
+        h_bufdesc_[i].data = nd;
+        h_bufdesc_[i].mask = need - 1;
+        ring_cap_[i] = need;
+        bufdesc_dirty_ = true;
+    }
+    if (bufdesc_dirty_ && !h_bufdesc_.empty()) {
+        if (d_bufdesc_cap_ < h_bufdesc_.size()) {
+            if (d_bufdesc_) { CU(cudaStreamSynchronize(stream_)); CU(cudaFree(d_bufdesc_)); }
+            d_bufdesc_cap_ = h_bufdesc_.size() * 2;
+            CU(cudaMalloc(&d_bufdesc_, d_bufdesc_cap_ * sizeof(BufferDesc)));
+        }
+        CU(cudaMemcpyAsync(d_bufdesc_, h_bufdesc_.data(), h_bufdesc_.size() * sizeof(BufferDesc), cudaMemcpyHostToDevice, stream_));
+        CU(cudaStreamSynchronize(stream_));
+    }
+    bufdesc_dirty_ = false;
+}
+
+// ------------------------------------------------------------------------------------------------ inputs
+
+void Renderer::materialise_slot(size_t r) {
+    while (inputs_.size() <= r) {
+        size_t s = inputs_.size();
+        uint64_t base = 0;
+        for (auto& ep : epochs_) if (s < ep.first) { base = ep.second; break; }
+        InputSlot sl;
+        sl.base = base & ~3ull;
+        sl.end = base;               // `base` zeros so far; [sl.base, base) are explicit zeros once allocated
+        inputs_.push_back(sl);
+    }
+}
+
+void Renderer::grow_slot(InputSlot& s, uint64_t need_end) {
+    uint64_t need = need_end - s.base;
+    if (need <= s.cap) return;
+    uint64_t ncap = std::max<uint64_t>(pow2_ceil(need + 8), 1024);
+    float* nd = nullptr;
+    CU(cudaMalloc(&nd, ncap * sizeof(float)));
+    CU(cudaMemsetAsync(nd, 0, ncap * sizeof(float), stream_));
+    if (s.d_data) {
+        if (s.end > s.base) CU(cudaMemcpyAsync(nd, s.d_data, (s.end - s.base) * sizeof(float), cudaMemcpyDeviceToDevice, stream_));
+        CU(cudaStreamSynchronize(stream_));
+        CU(cudaFree(s.d_data));
+    }
+    s.d_data = nd;
+    s.cap = ncap;
+}
+
+// reference.rs:49-75
+void Renderer::ingest_inputs(uint32_t n_slots, uint64_t n_times, uint64_t idx, const float* in_data, bool in_on_device,
+                             const uint64_t* offs, uint32_t n_rows) {
+    const bool seek = idx != head_;
+    const uint64_t buff_len = (uint64_t)n_slots * n_times;                // ndarray len(): element count (:60)
+    const uint64_t n_vec_after = std::max(n_slot_vectors_, buff_len);
+    const size_t n_fed = (size_t)std::min<uint64_t>(n_rows, n_vec_after); // zip(rows, slots) stops at the shorter (:68)
+
+    // validate everything before touching state (the reference panics half-way; we refuse the call instead)
+    for (size_t r = 0; r < n_fed; r++) {
+        if (offs[r + 1] < offs[r]) throw Error{FRB_E_INVALID, "in_row_offsets must be non-decreasing"};
+        uint64_t row_len = offs[r + 1] - offs[r];
+        // length of the reference's slot vector r when the zip reaches it
+        uint64_t len_now = idx;                                           // after a seek (:52-58) or created now (:60-65)
+        if (!seek && r < n_slot_vectors_) {
+            if (r < inputs_.size()) len_now = inputs_[r].end;
+            else for (auto& ep : epochs_) if (r < ep.first) { len_now = ep.second; break; }
+        }
+        if (len_now != idx) throw Error{FRB_E_INPUT_GAP, "input slot " + std::to_string(r) + " has length " + std::to_string(len_now) + " != idx (reference.rs:69 assert_eq)"};
+        if (row_len > n_times) throw Error{FRB_E_INPUT_TOO_LONG, "cannot send inputs ahead of outputs (reference.rs:71 assert)"};
+    }
+
+    if (seek) {                                                            // :52-58
+        for (auto& s : inputs_) { s.base = idx & ~3ull; s.end = idx; if (s.d_data && s.cap) CU(cudaMemsetAsync(s.d_data, 0, std::min<uint64_t>(s.cap, 8) * sizeof(float), stream_)); }
+        epochs_.clear();
+        if (n_slot_vectors_ > inputs_.size()) epochs_.emplace_back(n_slot_vectors_, idx);
+        cache_valid_ = false;
+    }
+    if (n_slot_vectors_ < buff_len) {                                      // :60-65
+        epochs_.emplace_back(buff_len, idx);
+        n_slot_vectors_ = buff_len;
+    }
+    if (n_fed > 0) {
+        const float* d_rows = in_data;
+        uint64_t total = offs[n_fed] - offs[0];
+        if (!in_on_device && total > 0) {
+            if (d_in_stage_cap_ < total) {
+                if (d_in_stage_) { CU(cudaStreamSynchronize(stream_)); CU(cudaFree(d_in_stage_)); }
+                d_in_stage_cap_ = pow2_ceil(total);
+                CU(cudaMalloc(&d_in_stage_, d_in_stage_cap_ * sizeof(float)));
+            }
+            CU(cudaMemcpyAsync(d_in_stage_, in_data + offs[0], total * sizeof(float), cudaMemcpyHostToDevice, stream_));
+            stats.h2d_bytes += total * sizeof(float);
+            d_rows = d_in_stage_ - offs[0];
+        }
+        for (size_t r = 0; r < n_fed; r++) {
+            materialise_slot(r);
+            InputSlot& s = inputs_[r];
+            uint64_t row_len = offs[r + 1] - offs[r];
+            grow_slot(s, idx + n_times);
+            if (row_len) CU(cudaMemcpyAsync(s.d_data + (idx - s.base), d_rows + offs[r], row_len * sizeof(float), cudaMemcpyDeviceToDevice, stream_));
+            uint64_t filled_end = idx + row_len;
+            if (filled_end < idx + n_times) {                              // pad with the last value (:72-73)
+                // Vec::last of the slot after the extend: the row's last value, else the previous content's last
+                // value (explicit zeros count), else 0 for an empty vector.
+                // Times below s.base are implicit zeros, so a "last" there (or an empty vector) pads with 0.
+                int has_last = filled_end > s.base;
+                uint64_t last_pos = has_last ? filled_end - 1 - s.base : 0;
+                uint64_t count = idx + n_times - filled_end;
+                unsigned blocks = (unsigned)std::min<uint64_t>((count + 255) / 256, 1024);
+                pad_kernel<<<blocks, 256, 0, stream_>>>(s.d_data, filled_end - s.base, count, last_pos, has_last);
+                CU(cudaGetLastError());
+                stats.kernel_launches++;
+            }
+            s.end = idx + n_times;
+        }
+    }
+    // device table of input descriptors for the slots the schedule reads
+    // (built in fill() after the schedule is known)
+}
+
+// ------------------------------------------------------------------------------------------------ rendering
+
+void Renderer::run_range(uint64_t lo, uint64_t hi, float* d_out, uint64_t t0, uint64_t t1, uint64_t out_stride) {
+    if (hi <= lo) return;
+    const int out_vec_ok = d_out && (t0 % 4 == 0) && (out_stride % 4 == 0) && ((uintptr_t)d_out % 16 == 0);
+    uint64_t c0 = lo;
+    while (c0 < hi) {
+        uint64_t c1 = std::min(hi, (c0 / chunk_ + 1) * chunk_);
+        for (size_t sg = 0; sg < sched_.stages.size(); sg++) {
+            const Stage& st = sched_.stages[sg];
+            for (uint32_t xi : st.ext) {
+                const ExtInstance& x = sched_.ext[xi];
+                uint64_t nl = 0;
+                if (x.kind == EXT_OSCBANK) {
+                    if (profiling) CU(cudaEventRecord(ev_[2], stream_));
+                    CU(launch_osc(*osc_defs_.at(x.key), d_bufdesc_, x.first_out_buf, c0, c1, cfg_.osc_anchor, sm_count_, stream_, &nl));
+                    if (profiling) { CU(cudaEventRecord(ev_[3], stream_)); CU(cudaEventSynchronize(ev_[3])); float ms = 0; CU(cudaEventElapsedTime(&ms, ev_[2], ev_[3])); timing.osc_ms += ms; }
+                    stats.osc_launches += nl;
+                } else if (x.kind == EXT_DIRECTFORM) {
+                    if (profiling) CU(cudaEventRecord(ev_[2], stream_));
+                    CU(launch_directform(*df_defs_.at(x.key), d_bufdesc_, d_ext_in_bufs_[xi], x.first_out_buf, c0, c1, sm_count_, stream_, &nl));
+                    if (profiling) { CU(cudaEventRecord(ev_[3], stream_)); CU(cudaEventSynchronize(ev_[3])); float ms = 0; CU(cudaEventElapsedTime(&ms, ev_[2], ev_[3])); timing.scan_ms += ms; }
+                    stats.scan_launches += nl;
+                } else {
+                    if (profiling) CU(cudaEventRecord(ev_[2], stream_));
+                    CU(launch_fbdelay(*fb_defs_.at(x.key), d_bufdesc_, d_ext_in_bufs_[xi], x.first_out_buf, c0, c1, sm_count_, stream_, &nl));
+                    if (profiling) { CU(cudaEventRecord(ev_[3], stream_)); CU(cudaEventSynchronize(ev_[3])); float ms = 0; CU(cudaEventElapsedTime(&ms, ev_[2], ev_[3])); timing.scan_ms += ms; }
+                    stats.scan_launches += nl;
+                }
+                stats.kernel_launches += nl;
+            }
+            if (st.program.size() <= 1) continue;   // only I_END
+            InterpParams p;
+            p.program = d_programs_[sg];
+            p.inputs = d_indesc_;
+            p.buffers = d_bufdesc_;
+            p.out = d_out;
+            p.out_stride = out_stride;
+            p.t_begin = c0 & ~3ull;
+            p.n_groups = ((c1 + 3) / 4) - (c0 / 4);
+            p.t0 = t0;
+            p.t1 = d_out ? t1 : t0;                  // warm-up ranges write no output
+            p.out_vec_ok = out_vec_ok;
+            p.sparkle_delay = (cfg_.flags & FRB_FLAG_SPARKLE_DELAY) ? 1 : 0;
+            if (profiling) CU(cudaEventRecord(ev_[2], stream_));
+            CU(launch_interp(p, st.n_regs, sm_count_, stream_));
+            if (profiling) { CU(cudaEventRecord(ev_[3], stream_)); CU(cudaEventSynchronize(ev_[3])); float ms = 0; CU(cudaEventElapsedTime(&ms, ev_[2], ev_[3])); timing.interp_ms += ms; }
+            stats.kernel_launches++;
+            stats.interp_launches++;
+        }
+        c0 = c1;
+    }
+}
+
+void Renderer::fill(float* out, bool out_on_device, uint32_t n_slots, uint64_t n_times, uint64_t idx,
+                    const float* in_data, bool in_on_device, const uint64_t* offs, uint32_t n_rows) {
+    require_device();
+    CU(cudaSetDevice(device_));
+    if (n_rows && !offs) throw Error{FRB_E_INVALID, "in_row_offsets is NULL"};
+    if (idx + n_times < idx) throw Error{FRB_E_INVALID, "idx + n_times overflows"};
+    ensure_schedule(n_slots);            // may throw on a malformed graph, before any state changes
+    if (profiling) { timing = frb_timing{}; CU(cudaEventRecord(ev_[0], stream_)); }
+    ingest_inputs(n_slots, n_times, idx, in_data, in_on_device, offs, n_rows);
+
+    const uint64_t t1 = idx + n_times;
+    if (n_times > 0 && n_slots > 0) {
+        // input descriptor table for the slots the schedule reads
+        uint32_t nin = sched_.n_input_slots;
+        if (nin) {
+            std::vector<InputDesc> h(nin);
+            for (uint32_t s = 0; s < nin; s++) {
+                if (s < inputs_.size() && inputs_[s].d_data) h[s] = InputDesc{inputs_[s].d_data, inputs_[s].base, inputs_[s].end};
+                else h[s] = InputDesc{nullptr, 0, 0};
+            }
+            if (d_indesc_cap_ < nin) {
+                if (d_indesc_) { CU(cudaStreamSynchronize(stream_)); CU(cudaFree(d_indesc_)); }
+                d_indesc_cap_ = std::max<size_t>(nin * 2, 16);
+                CU(cudaMalloc(&d_indesc_, d_indesc_cap_ * sizeof(InputDesc)));
+            }
+            CU(cudaMemcpyAsync(d_indesc_, h.data(), nin * sizeof(InputDesc), cudaMemcpyHostToDevice, stream_));
+            CU(cudaStreamSynchronize(stream_));
+        }
+        ensure_rings(t1);
+
+        float* d_out = out;
+        const uint64_t n_out = (uint64_t)n_slots * n_times;
+        if (!out_on_device) {
+            if (d_out_cap_ < n_out) {
+                if (d_out_) { CU(cudaStreamSynchronize(stream_)); CU(cudaFree(d_out_)); }
+                d_out_cap_ = n_out;
+                CU(cudaMalloc(&d_out_, d_out_cap_ * sizeof(float)));
+            }
+            d_out = d_out_;
+        }
+        if (!(cache_valid_ && cache_head_ == idx)) {
+            // seek, graph edit or first call: rebuild the rings the block depends on (SURVEY.md A.3 trap T1:
+            // constants and input history before idx are live, only the external inputs were zeroed by a seek)
+            uint64_t start = sched_.from_zero ? 0 : (idx > sched_.max_lookback ? idx - sched_.max_lookback : 0);
+            run_range(start & ~3ull, idx, nullptr, idx, idx, 0);
+        }
+        run_range(idx, t1, d_out, idx, t1, n_times);
+        cache_valid_ = true;
+        cache_head_ = t1;
+        if (!out_on_device) {
+            CU(cudaMemcpyAsync(out, d_out, n_out * sizeof(float), cudaMemcpyDeviceToHost, stream_));
+            stats.d2h_bytes += n_out * sizeof(float);
+        }
+    }
+    head_ = t1;                           // reference.rs:84
+    if (profiling) {
+        CU(cudaEventRecord(ev_[1], stream_));
+        CU(cudaEventSynchronize(ev_[1]));
+        CU(cudaEventElapsedTime(&timing.total_ms, ev_[0], ev_[1]));
+    }
+    if (!out_on_device) CU(cudaStreamSynchronize(stream_));
+}
+
+void Renderer::sync() {
+    if (host_only_) return;
+    CU(cudaSetDevice(device_));
+    CU(cudaStreamSynchronize(stream_));
+}
+
+}  // namespace frb

@@ -1,0 +1,117 @@
+// renderer.hpp — B200Renderer: the host object behind the C ABI (include/friendship_b200.h).
+// Mirrors the reference's RefRenderer state (reference src/render/reference.rs:20-29): graph mirror, full
+// external-input history, playhead — with the history and every sample buffer resident in HBM.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "flatten.hpp"
+#include "graph.hpp"
+#include "interp.cuh"
+#include "osc.cuh"
+#include "scan.cuh"
+#include "schedule.hpp"
+
+namespace frb {
+
+struct InputSlot {
+    // values for absolute times [base, end); zeros before base; reads at >= end are 0 (reference.rs:90-96)
+    uint64_t base = 0;       // multiple of 4
+    uint64_t end = 0;        // == the reference's slot vector length
+    float* d_data = nullptr;
+    uint64_t cap = 0;        // floats allocated
+};
+
+class Renderer {
+public:
+    explicit Renderer(const frb_config& cfg);
+    ~Renderer();
+    Renderer(const Renderer&) = delete;
+
+    // definitions
+    void define_effect(uint64_t key, const frb_node* nodes, uint32_t n_nodes, const frb_edge* edges, uint32_t n_edges);
+    void define_oscbank(uint64_t key, const frb_oscbank_desc* d);
+    void define_directform(uint64_t key, const frb_directform_desc* d);
+    void define_fbdelay(uint64_t key, const frb_fbdelay_desc* d);
+    // GraphWatcher
+    void add_node(uint32_t handle, uint32_t kind, uint64_t key);
+    void del_node(uint32_t handle);
+    void add_edge(const frb_edge& e);
+    void del_edge(const frb_edge& e);
+    // Renderer::fill_buffer
+    void fill(float* out, bool out_on_device, uint32_t n_slots, uint64_t n_times, uint64_t idx,
+              const float* in_data, bool in_on_device, const uint64_t* in_row_offsets, uint32_t n_in_rows);
+    void sync();
+
+    const Schedule& schedule(uint32_t n_slots);   // (re)builds if needed
+    cudaStream_t stream() const { return stream_; }
+
+    std::string last_error;
+    frb_stats stats{};
+    frb_timing timing{};
+    bool profiling = false;
+
+private:
+    GraphNode make_node(uint32_t kind, uint64_t key) const;
+    void require_device() const;
+    void ensure_schedule(uint32_t n_slots);
+    void upload_schedule();
+    void ensure_rings(uint64_t t_end);
+    void ingest_inputs(uint32_t n_slots, uint64_t n_times, uint64_t idx, const float* in_data, bool in_on_device,
+                       const uint64_t* offs, uint32_t n_rows);
+    void materialise_slot(size_t r);
+    void grow_slot(InputSlot& s, uint64_t need_end);
+    void run_range(uint64_t lo, uint64_t hi, float* d_out, uint64_t t0, uint64_t t1, uint64_t out_stride);
+    void free_device_schedule();
+
+    frb_config cfg_;
+    int device_ = -1;
+    bool host_only_ = false;
+    int sm_count_ = 148;
+    cudaStream_t stream_ = nullptr;
+    cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
+
+    Graph graph_;
+    std::map<uint64_t, std::shared_ptr<Graph>> effect_defs_;
+    std::map<uint64_t, std::shared_ptr<OscBankDev>> osc_defs_;
+    std::map<uint64_t, std::shared_ptr<DirectFormDev>> df_defs_;
+    std::map<uint64_t, std::shared_ptr<FbDelayDev>> fb_defs_;
+
+    bool dirty_ = true;
+    Schedule sched_;
+    uint32_t sched_slots_ = ~0u;
+
+    // device-resident schedule
+    std::vector<uint32_t*> d_programs_;         // per stage
+    std::vector<uint32_t*> d_ext_in_bufs_;      // per extension instance: input ring ids per lane
+    std::vector<BufferDesc> h_bufdesc_;
+    std::vector<uint64_t> ring_cap_;
+    BufferDesc* d_bufdesc_ = nullptr;
+    size_t d_bufdesc_cap_ = 0;
+    bool bufdesc_dirty_ = true;
+    uint64_t chunk_ = 1ull << 16;
+
+    // external-input history
+    std::vector<InputSlot> inputs_;
+    uint64_t n_slot_vectors_ = 0;                                  // reference's self.inputs.len()
+    std::vector<std::pair<uint64_t, uint64_t>> epochs_;            // (slot upper bound, base) for never-fed slots
+    uint64_t head_ = 0;                                            // reference.rs:26-28
+    InputDesc* d_indesc_ = nullptr;
+    size_t d_indesc_cap_ = 0;
+    float* d_in_stage_ = nullptr;
+    size_t d_in_stage_cap_ = 0;
+
+    // output staging
+    float* d_out_ = nullptr;
+    size_t d_out_cap_ = 0;
+
+    // cached rings are valid for a fill that starts exactly at cache_head_
+    bool cache_valid_ = false;
+    uint64_t cache_head_ = 0;
+};
+
+}  // namespace frb

@@ -1,0 +1,35 @@
+"""ctypes binding of the CPU oracle (oracle/_build/liboracle.so) — TEST INFRASTRUCTURE ONLY.
+
+Same Python surface as libfriendship_b200.B200Renderer so parity tests drive both with the same calls.
+"""
+import ctypes as C
+import os
+
+from libfriendship_b200 import _cabi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_LIB_PATH = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
+_lib = C.CDLL(_LIB_PATH)
+_cabi.declare(_lib, "orc")
+_lib.orc_create.restype = C.c_void_p
+_lib.orc_set_ext_mode.argtypes = [C.c_void_p, C.c_int]
+_lib.orc_fill_buffer_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32,
+                                    C.POINTER(C.c_double)]
+_lib.orc_fill_buffer_mt.restype = C.c_int
+
+
+class OracleRenderer(_cabi.CRendererBase):
+    _lib = _lib
+    _prefix = "orc"
+
+    def __init__(self, ext_mode="fp64", **_ignored):
+        super().__init__(_lib.orc_create())
+        _lib.orc_set_ext_mode(self._h, 0 if ext_mode == "fp64" else 1)
+
+    def fill_buffer_mt(self, n_slots, n_times, idx, n_threads):
+        """CPU-baseline helper: multi-threaded evaluation of the current graph (inputs already fed)."""
+        import numpy as np
+        out = np.zeros((n_slots, n_times), dtype=np.float32)
+        sec = C.c_double(0)
+        self._check(_lib.orc_fill_buffer_mt(self._h, out.ctypes.data, n_slots, n_times, idx, n_threads, C.byref(sec)))
+        return out, sec.value

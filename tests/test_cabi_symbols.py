@@ -1,0 +1,58 @@
+"""CPU: the C-ABI library loads and exports every symbol include/friendship_b200.h declares; no compute calls."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "friendship_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(frb_[a-z_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported():
+    import libfriendship_b200 as L
+    lib = ctypes.CDLL(L.LIB_PATH)
+    syms = declared_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in the header but not exported"
+    assert set(L._cabi.EXPORTS) == set(syms)
+
+
+def test_no_cpu_fallback_without_device():
+    """Without a GPU frb_create(device >= 0) must fail loudly; a planning-only handle must refuse to render."""
+    import numpy as np
+    import libfriendship_b200 as L
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if not has_gpu:
+        try:
+            L.B200Renderer(device=0)
+            raise AssertionError("creating a renderer without a GPU must fail")
+        except L.RendererError as e:
+            assert e.code == L._cabi.FRB_E_NO_DEVICE
+    r = L.B200Renderer(device=-1)
+    try:
+        r.fill_buffer(1, 4, 0)
+        raise AssertionError("planning-only renderer must not render")
+    except L.RendererError as e:
+        assert e.code == L._cabi.FRB_E_NO_DEVICE
+
+
+def test_product_does_not_link_or_import_oracle():
+    import subprocess
+    import libfriendship_b200 as L
+    out = subprocess.run(["ldd", L.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
+    assert "oracle" not in out
+    pkg = os.path.join(ROOT, "libfriendship_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cc", ".hpp", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle/" not in src and "liboracle" not in src and "ref_renderer" not in src, f

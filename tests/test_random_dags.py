@@ -1,0 +1,112 @@
+"""GPU parity proper: seeded random effect graphs (all 7 primitives, nested effects, constant and signal-driven
+Delay amounts, NaN/inf/huge/negative constants, unconnected inputs, multi-slot outputs) rendered through the
+C ABI on the B200 and by the CPU oracle — bit-exact, over several consecutive fill_buffer calls including
+ragged inputs, seeks and graph edits between calls."""
+import numpy as np
+import pytest
+
+from oracle_binding import OracleRenderer
+from randgraph import random_graph, random_inputs
+from replay import assert_same_bits
+
+pytestmark = pytest.mark.gpu
+
+
+def both():
+    from libfriendship_b200 import B200Renderer
+    return B200Renderer(), OracleRenderer()
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_graph_consecutive_calls(seed):
+    gpu, orc = both()
+    rec = random_graph(seed, n_inputs=2, n_nodes=10 + seed % 9, n_outputs=2, nested_levels=1 + seed % 2)
+    rec.apply(gpu)
+    rec.apply(orc)
+    rng = np.random.RandomState(1000 + seed)
+    idx = 0
+    for call in range(3):
+        n = int(rng.choice([1, 3, 4, 7, 64, 130, 257]))
+        rows = random_inputs(rng, 2, n)
+        a = gpu.fill_buffer(2, n, idx, rows)
+        b = orc.fill_buffer(2, n, idx, rows)
+        assert_same_bits(a, b, f"seed {seed} call {call} idx {idx} n {n}")
+        idx += n
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_graph_seek_and_edit(seed):
+    gpu, orc = both()
+    rec = random_graph(500 + seed, n_inputs=2, n_nodes=14, n_outputs=3, nested_levels=2)
+    rec.apply(gpu)
+    rec.apply(orc)
+    rng = np.random.RandomState(7 + seed)
+    plan = [(0, 33), (33, 31), (200, 16), (216, 8), (5, 40)]       # contiguous, contiguous, seek, contiguous, seek back
+    for i, (idx, n) in enumerate(plan):
+        rows = random_inputs(rng, 2, n)
+        if i == 2:
+            # graph edit between calls: rewire output 0 to a delayed copy of input 0 (retroactive)
+            for r in (gpu, orc):
+                r.on_add_node(9001, 0)                              # Delay
+                r.on_add_node(9002, 1)                              # F32Constant
+                r.on_add_edge((0, 9001, 0, 0))
+                r.on_add_edge((9002, 9001, 0x40400000, 1))          # 3.0 frames
+                r.on_add_edge((9001, 0, 0, 0))
+        if i == 4:
+            for r in (gpu, orc):
+                r.on_del_edge((9001, 0, 0, 0))
+        a = gpu.fill_buffer(3, n, idx, rows)
+        b = orc.fill_buffer(3, n, idx, rows)
+        assert_same_bits(a, b, f"seed {seed} step {i}")
+
+
+def test_cfg1_one_call_equals_blocks():
+    """BASELINE configs[0]: 440 Hz sine through Multiply/Sum/Delay, 48 kHz x 1 s — one call and 94 x 512-sample
+    calls are identical, and both equal the oracle bit for bit."""
+    from graphs import build_cfg1_graph, cfg1_input
+    n = 48000
+    x = cfg1_input(n)
+    gpu, orc = both()
+    build_cfg1_graph(gpu)
+    build_cfg1_graph(orc)
+    whole = gpu.fill_buffer(2, n, 0, [x])
+    ref = orc.fill_buffer(2, n, 0, [x])
+    assert_same_bits(whole, ref, "cfg1 whole")
+    from libfriendship_b200 import B200Renderer
+    g2 = B200Renderer()
+    build_cfg1_graph(g2)
+    parts = []
+    for s in range(0, n, 512):
+        m = min(512, n - s)
+        parts.append(g2.fill_buffer(2, m, s, [x[s:s + m]]))
+    assert_same_bits(np.concatenate(parts, axis=1), ref, "cfg1 blocks")
+
+
+def test_warmup_after_seek_constants_are_live():
+    """SURVEY.md A.3 trap T1: C(0.5) -> Delay(2) rendered over 100..104 right after a seek is 0.5 x 4."""
+    gpu, orc = both()
+    for r in (gpu, orc):
+        r.on_add_node(1, 0)
+        r.on_add_node(2, 1)
+        r.on_add_edge((2, 1, 0x3f000000, 0))
+        r.on_add_edge((2, 1, 0x40000000, 1))
+        r.on_add_edge((1, 0, 0, 0))
+    a = gpu.fill_buffer(1, 4, 100)
+    b = orc.fill_buffer(1, 4, 100)
+    assert_same_bits(a, b)
+    assert (a == 0.5).all()
+
+
+def test_input_contract_errors():
+    from libfriendship_b200 import RendererError
+    gpu, orc = both()
+    for r in (gpu, orc):
+        r.on_add_edge((0, 0, 0, 0))
+        r.on_add_edge((0, 0, 1, 1))
+        r.fill_buffer(2, 4, 0, [[1, 2, 3, 4]])                     # slot 1 not fed: stays at length 0
+        with pytest.raises(RendererError) as e:
+            r.fill_buffer(2, 4, 4, [[1, 2], [5, 6]])               # slot 1 fed later: len 0 != idx 4 (reference.rs:69)
+        assert e.value.code == -3
+        with pytest.raises(RendererError) as e:
+            r.fill_buffer(2, 2, 4, [[1, 2, 3]])                    # row longer than n_times (reference.rs:71)
+        assert e.value.code == -2
