@@ -1,15 +1,403 @@
-// osc.cu — placeholder until K1 lands (next commit): definitions are recorded, launches are refused.
+// osc.cu — K1: oscillator bank for sm_100a (extension node FRB_KIND_OSCBANK; not in the reference).
+//
+//   out_v(t) = sum_p amp_p * min(t/A_p, 1) * exp(-t/tau_p) * sin(2 pi f_p t / sr + phi_p)
+//
+// Bound: the FP32 FMA pipe (128 lanes/clk/SM; measured 125 on B200 with tools/microbench/fma_peak.cu).
+// There is no dense contraction here, so tensor cores are not used.
+//
+// Design (measured choices: tools/microbench/osc_loop.cu, profiles/):
+//  * One thread owns one time SEGMENT of L consecutive samples of one voice, and walks through all partials of
+//    that voice in groups of K.  Lanes of a warp therefore differ in time, not in partial: the per-partial
+//    coefficients are warp-uniform, there is no cross-lane reduction at all (no shuffles, no barriers), and the
+//    K recurrences of a group give the scheduler K independent FMA chains per thread.
+//  * Each partial is a damped two-state resonator in lifting form, 3 FFMA + 1 FADD per partial-sample:
+//        x <- x - a*y ;  y <- (1+cm1)*y + b*x ;  acc += y          (cos w >= 0)
+//        x <- a*y - x ;  y <- b*x - (1+cm1)*y ;  acc += y          (cos w <  0: the same resonator at pi - w, negated,
+//                                                                    which keeps a*b small and well conditioned)
+//    with a*b = (1-rho)^2 + 4 rho sin^2(w'/2), cm1 = rho^2 - 1: the eigenvalues are rho*exp(+-i w), so y is exactly
+//    amp * rho^n * sin(w n + phi) in exact arithmetic; the exponential decay costs nothing extra.
+//  * State is re-anchored exactly at the start of every segment (segments are aligned to absolute time, so the
+//    result does not depend on how a render is cut into blocks): phase = inc*n + phase0 in 64-bit fixed-point
+//    turns (exact range reduction by integer wrap-around), sin/cos by MUFU, envelope by ex2 of an fp64 product.
+//    With L = 128 the worst single-partial error is ~6e-6 of its amplitude (tools/osc_math_check.py).
+//  * Coefficients come from an fp64 setup kernel at definition time.
+//  * The attack ramp min(t/A,1) only matters for t < max(A): a warp-uniform branch selects a slower loop there.
+//  * Per-thread accumulators for the L samples live in shared memory as float4 columns (conflict-free),
+//    read-modify-written once per 4 samples per group: 2 LSU instructions per 16*K FMA-pipe instructions.
 #include "osc.cuh"
 
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
 namespace frb {
-struct OscBankDev { uint32_t n_voices; uint64_t n_partials; };
-std::shared_ptr<OscBankDev> osc_create(const frb_oscbank_desc* d, cudaStream_t, std::string*) {
+
+constexpr int OSC_K = 8;            // partials per group (independent FMA chains per thread)
+constexpr int OSC_THREADS = 128;    // threads (= time segments) per CTA
+constexpr int OSC_LMAX = 256;       // max segment length (shared memory: L * THREADS * 4 B)
+
+struct OscBankDev {
+    uint32_t n_voices = 0;
+    uint64_t n_partials = 0;        // as defined by the user
+    uint64_t n_records = 0;         // after per-(voice, class) padding to multiples of OSC_K
+    double sample_rate = 48000.0;
+    float max_attack = 0.0f;
+    uint32_t max_groups = 0;        // largest number of groups in one voice
+    uint32_t split = 1;             // partial-range split per voice (fixed per bank: keeps the summation order fixed)
+    float4* d_hot = nullptr;        // {a, b, cm1, k1}
+    float4* d_anc = nullptr;        // {k2, amp, kappa, invA}
+    uint4* d_ph = nullptr;          // {inc_lo, inc_hi, ph0_lo, ph0_hi}
+    uint32_t* d_grp_begin = nullptr;   // per voice: first group
+    uint32_t* d_n_grp0 = nullptr;      // per voice: groups of class 0
+    uint32_t* d_n_grp = nullptr;       // per voice: groups in total
+    mutable float* d_planes = nullptr; // scratch for split > 1: [split][n_voices][plane_len]
+    mutable uint64_t planes_cap = 0;
+    ~OscBankDev() {
+        cudaFree(d_hot); cudaFree(d_anc); cudaFree(d_ph);
+        cudaFree(d_grp_begin); cudaFree(d_n_grp0); cudaFree(d_n_grp); cudaFree(d_planes);
+    }
+};
+
+OscBankInfo osc_info(const OscBankDev& b) { return OscBankInfo{b.n_voices, b.n_partials}; }
+
+// ------------------------------------------------------------------------------------------------------------------
+// setup: raw partial parameters (already grouped by voice and class, padded with amp = 0) -> resonator records
+__global__ void osc_setup_kernel(uint64_t n, double sample_rate, const double* __restrict__ freq,
+                                 const float* __restrict__ amp, const float* __restrict__ phase,
+                                 const float* __restrict__ attack, const float* __restrict__ tau,
+                                 float4* __restrict__ hot, float4* __restrict__ anc, uint4* __restrict__ ph) {
+    const double PI = 3.14159265358979323846;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const float am = amp[i];
+        if (am == 0.0f) {   // padding or silent partial: a resonator that stays at 0
+            hot[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            anc[i] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
+            ph[i] = make_uint4(0u, 0u, 0u, 0u);
+            continue;
+        }
+        double fr = freq[i] / sample_rate;
+        fr -= floor(fr);                                    // turns per sample in [0, 1)
+        const bool cls1 = fr > 0.25 && fr < 0.75;           // cos w < 0
+        double wp;                                          // w' in [-pi/2, pi/2]
+        if (cls1) wp = PI - 2.0 * PI * fr;
+        else wp = (fr <= 0.25) ? 2.0 * PI * fr : 2.0 * PI * (fr - 1.0);
+        const float tf = tau[i];
+        const bool decays = tf > 0.0f && isfinite(tf);
+        const double one_m_rho = decays ? -expm1(-1.0 / (double)tf) : 0.0;
+        const double rho = 1.0 - one_m_rho;
+        const double sh = sin(0.5 * wp);
+        const double ab = one_m_rho * one_m_rho + 4.0 * rho * sh * sh;
+        float a32 = 0.f, b32 = 0.f, k1 = 0.f, k2 = 0.f;
+        if (ab > 0.0) {
+            // a = b = sqrt(ab) up to rounding; try neighbours of a so that fl(a)*fl(b) is as close to ab as possible
+            // (the product sets the realised frequency: its rounding error is the systematic phase drift).
+            const float a0 = (float)sqrt(ab);
+            double best = 1e300;
+            for (int d = -3; d <= 3; d++) {
+                float ac = __int_as_float(__float_as_int(a0) + d);
+                if (!(ac > 0.f)) continue;
+                float bc = (float)(ab / (double)ac);
+                double err = fabs((double)ac * (double)bc - ab);
+                if (err < best) { best = err; a32 = ac; b32 = bc; }
+            }
+            const double bd = (double)b32;
+            k1 = (float)((one_m_rho + 2.0 * rho * sh * sh) / bd);          // (1 - rho cos w') / b
+            k2 = (float)((cls1 ? -1.0 : 1.0) * rho * sin(wp) / bd);
+        }
+        const float cm1 = (float)(-(one_m_rho) * (1.0 + rho));             // rho^2 - 1
+        hot[i] = make_float4(a32, b32, cm1, k1);
+        const float kappa = decays ? (float)(1.4426950408889634 / (double)tf) : 0.0f;
+        const float at = attack[i];
+        const float invA = (at > 0.0f) ? 1.0f / at : __int_as_float(0x7f800000);
+        anc[i] = make_float4(k2, am, kappa, invA);
+        const unsigned long long inc = __double2ull_rn(fr * 18446744073709551616.0);
+        double p0 = (double)phase[i] / (2.0 * PI);
+        p0 -= floor(p0);
+        const unsigned long long ph0 = __double2ull_rn(p0 * 18446744073709551616.0);
+        ph[i] = make_uint4((unsigned)(inc & 0xffffffffull), (unsigned)(inc >> 32), (unsigned)(ph0 & 0xffffffffull), (unsigned)(ph0 >> 32));
+    }
+}
+
+std::shared_ptr<OscBankDev> osc_create(const frb_oscbank_desc* d, cudaStream_t stream, std::string* err) {
+    auto fail = [&](const std::string& m) { if (err) *err = m; return std::shared_ptr<OscBankDev>(); };
+    if (!d->voice_offsets || (d->n_partials && (!d->freq_hz || !d->amp || !d->phase || !d->attack || !d->tau)))
+        return fail("oscbank: null array");
+    if (!(d->sample_rate > 0.0)) return fail("oscbank: sample_rate must be positive");
+    if (d->voice_offsets[0] != 0 || d->voice_offsets[d->n_voices] != d->n_partials) return fail("oscbank: voice_offsets must span [0, n_partials]");
     auto b = std::make_shared<OscBankDev>();
-    b->n_voices = d->n_voices; b->n_partials = d->n_partials;
+    b->n_voices = d->n_voices;
+    b->n_partials = d->n_partials;
+    b->sample_rate = d->sample_rate;
+
+    // group by (voice, class), pad every class segment to a multiple of K with silent partials
+    std::vector<uint32_t> grp_begin(d->n_voices), n_grp0(d->n_voices), n_grp(d->n_voices);
+    std::vector<uint64_t> order;            // source index per record, ~0 = padding
+    order.reserve(d->n_partials + (uint64_t)d->n_voices * 2 * OSC_K);
+    float max_attack = 0.f;
+    for (uint32_t v = 0; v < d->n_voices; v++) {
+        uint64_t lo = d->voice_offsets[v], hi = d->voice_offsets[v + 1];
+        if (hi < lo) return fail("oscbank: voice_offsets must be non-decreasing");
+        grp_begin[v] = (uint32_t)(order.size() / OSC_K);
+        for (int cls = 0; cls < 2; cls++) {
+            for (uint64_t p = lo; p < hi; p++) {
+                double fr = d->freq_hz[p] / d->sample_rate;
+                fr -= std::floor(fr);
+                bool c1 = fr > 0.25 && fr < 0.75;
+                if ((int)c1 == cls) order.push_back(p);
+            }
+            while (order.size() % OSC_K) order.push_back(~0ull);
+            if (cls == 0) n_grp0[v] = (uint32_t)(order.size() / OSC_K) - grp_begin[v];
+        }
+        n_grp[v] = (uint32_t)(order.size() / OSC_K) - grp_begin[v];
+        b->max_groups = std::max(b->max_groups, n_grp[v]);
+    }
+    for (uint64_t p = 0; p < d->n_partials; p++)
+        if (d->attack[p] > 0.f && d->amp[p] != 0.f) max_attack = std::max(max_attack, d->attack[p]);
+    b->max_attack = max_attack;
+    const uint64_t n = order.size();
+    b->n_records = n;
+    // Partial-range split: enough CTAs to balance 148 SMs when a voice has many groups.  Fixed per bank so the
+    // order of summation (and hence the result) never depends on the block size of a render.
+    {
+        uint32_t s = 1;
+        while (s < 64 && b->max_groups / (s * 2) >= 256 && (uint64_t)d->n_voices * s < 4096) s *= 2;
+        b->split = s;
+    }
+
+    std::vector<double> h_freq(n, 0.0);
+    std::vector<float> h_amp(n, 0.f), h_phase(n, 0.f), h_attack(n, 0.f), h_tau(n, 0.f);
+    for (uint64_t i = 0; i < n; i++) {
+        uint64_t p = order[i];
+        if (p == ~0ull) continue;
+        h_freq[i] = d->freq_hz[p]; h_amp[i] = d->amp[p]; h_phase[i] = d->phase[p];
+        h_attack[i] = d->attack[p]; h_tau[i] = d->tau[p];
+    }
+#define OC(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(std::string("oscbank: ") + cudaGetErrorString(e_)); } while (0)
+    double* d_freq = nullptr; float *d_amp = nullptr, *d_phase = nullptr, *d_attack = nullptr, *d_tau = nullptr;
+    const uint64_t nn = std::max<uint64_t>(n, 1);
+    OC(cudaMalloc(&d_freq, nn * sizeof(double)));
+    OC(cudaMalloc(&d_amp, nn * sizeof(float))); OC(cudaMalloc(&d_phase, nn * sizeof(float)));
+    OC(cudaMalloc(&d_attack, nn * sizeof(float))); OC(cudaMalloc(&d_tau, nn * sizeof(float)));
+    OC(cudaMalloc(&b->d_hot, nn * sizeof(float4))); OC(cudaMalloc(&b->d_anc, nn * sizeof(float4))); OC(cudaMalloc(&b->d_ph, nn * sizeof(uint4)));
+    const uint32_t nv = std::max<uint32_t>(d->n_voices, 1);
+    OC(cudaMalloc(&b->d_grp_begin, nv * sizeof(uint32_t))); OC(cudaMalloc(&b->d_n_grp0, nv * sizeof(uint32_t))); OC(cudaMalloc(&b->d_n_grp, nv * sizeof(uint32_t)));
+    if (n) {
+        OC(cudaMemcpyAsync(d_freq, h_freq.data(), n * sizeof(double), cudaMemcpyHostToDevice, stream));
+        OC(cudaMemcpyAsync(d_amp, h_amp.data(), n * sizeof(float), cudaMemcpyHostToDevice, stream));
+        OC(cudaMemcpyAsync(d_phase, h_phase.data(), n * sizeof(float), cudaMemcpyHostToDevice, stream));
+        OC(cudaMemcpyAsync(d_attack, h_attack.data(), n * sizeof(float), cudaMemcpyHostToDevice, stream));
+        OC(cudaMemcpyAsync(d_tau, h_tau.data(), n * sizeof(float), cudaMemcpyHostToDevice, stream));
+    }
+    if (d->n_voices) {
+        OC(cudaMemcpyAsync(b->d_grp_begin, grp_begin.data(), d->n_voices * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+        OC(cudaMemcpyAsync(b->d_n_grp0, n_grp0.data(), d->n_voices * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+        OC(cudaMemcpyAsync(b->d_n_grp, n_grp.data(), d->n_voices * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    }
+    if (n) {
+        unsigned blocks = (unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 8);
+        osc_setup_kernel<<<blocks, 256, 0, stream>>>(n, d->sample_rate, d_freq, d_amp, d_phase, d_attack, d_tau, b->d_hot, b->d_anc, b->d_ph);
+        OC(cudaGetLastError());
+    }
+    OC(cudaStreamSynchronize(stream));
+    cudaFree(d_freq); cudaFree(d_amp); cudaFree(d_phase); cudaFree(d_attack); cudaFree(d_tau);
+#undef OC
     return b;
 }
-OscBankInfo osc_info(const OscBankDev& b) { return OscBankInfo{b.n_voices, b.n_partials}; }
-cudaError_t launch_osc(const OscBankDev&, const BufferDesc*, uint32_t, uint64_t, uint64_t, uint32_t, int, cudaStream_t, uint64_t*) {
-    return cudaErrorNotSupported;
+
+// ------------------------------------------------------------------------------------------------------------------
+struct OscLaunch {
+    const float4* hot; const float4* anc; const uint4* ph;
+    const uint32_t* grp_begin; const uint32_t* n_grp0; const uint32_t* n_grp;
+    const BufferDesc* bufdesc; uint32_t first_buf;
+    unsigned long long lo, hi;       // absolute output window [lo, hi)
+    unsigned long long seg0;         // absolute index (t / L) of the first segment
+    unsigned nseg;                   // segments per voice
+    int L;                           // segment length, multiple of 4
+    unsigned split;                  // partial-range split
+    float* planes;                   // split > 1: [split][n_voices][plane_len], plane time 0 == seg0 * L
+    unsigned long long plane_len;
+    unsigned n_voices;
+    float max_attack;
+};
+
+// One group of K partials over one segment.  CLS1: resonator at pi - w (negated).  ATTACK: apply min(t*invA, 1).
+template <int K, bool CLS1, bool ATTACK>
+__device__ __forceinline__ void osc_group(const float4* __restrict__ hot, const float4* __restrict__ anc,
+                                          const uint4* __restrict__ ph, unsigned long long n0, int L,
+                                          float4* s_acc, unsigned nthr) {
+    float x[K], y[K], a[K], b[K], cm1[K], invA[K];
+    const float nf = (float)n0;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const float4 h = __ldg(hot + k);
+        const float4 an = __ldg(anc + k);
+        const uint4 p = __ldg(ph + k);
+        a[k] = h.x; b[k] = h.y; cm1[k] = h.z;
+        invA[k] = an.w;
+        // exact phase: 64-bit fixed-point turns, wrap-around == range reduction
+        const unsigned long long inc = ((unsigned long long)p.y << 32) | p.x;
+        const unsigned long long ph0 = ((unsigned long long)p.w << 32) | p.z;
+        const unsigned long long turns = inc * n0 + ph0;
+        const float th = (float)(int)(turns >> 32) * 1.4629180792671596e-9f;      // * 2 pi / 2^32, in [-pi, pi)
+        float s, c;
+        __sincosf(th, &s, &c);
+        const float e = an.y * exp2f((float)(-(double)an.z * (double)n0));        // amp * exp(-n/tau)
+        y[k] = e * s;
+        x[k] = e * fmaf(h.w, s, an.x * c);
+    }
+    for (int j4 = 0; j4 < L / 4; j4++) {
+        float4 acc = s_acc[j4 * nthr];
+        float r[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            float sum = r[u];
+            float tf = 0.f;
+            if (ATTACK) tf = nf + (float)(j4 * 4 + u);
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                if (ATTACK) sum = fmaf(fminf(tf * invA[k], 1.0f), y[k], sum);
+                else sum += y[k];
+                if (!CLS1) {
+                    x[k] = fmaf(-a[k], y[k], x[k]);
+                    const float t = fmaf(cm1[k], y[k], y[k]);
+                    y[k] = fmaf(b[k], x[k], t);
+                } else {
+                    x[k] = fmaf(a[k], y[k], -x[k]);
+                    const float t = fmaf(cm1[k], y[k], y[k]);
+                    y[k] = fmaf(b[k], x[k], -t);
+                }
+            }
+            r[u] = sum;
+        }
+        s_acc[j4 * nthr] = make_float4(r[0], r[1], r[2], r[3]);
+    }
 }
+
+template <int K>
+__global__ void __launch_bounds__(OSC_THREADS) osc_kernel(OscLaunch p) {
+    extern __shared__ float4 s_acc_all[];
+    const unsigned nthr = blockDim.x;
+    float4* s_acc = s_acc_all + threadIdx.x;                 // column of this thread: s_acc[j4 * nthr]
+    const unsigned seg = blockIdx.x * nthr + threadIdx.x;
+    const unsigned v = blockIdx.y;
+    const unsigned sp = blockIdx.z;
+    if (seg >= p.nseg) return;                               // no barriers in this kernel: early exit is safe
+    const int L = p.L;
+    const unsigned long long n0 = (p.seg0 + seg) * (unsigned long long)L;
+    for (int j4 = 0; j4 < L / 4; j4++) s_acc[j4 * nthr] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    const unsigned ng = p.n_grp[v], ng0 = p.n_grp0[v], gb = p.grp_begin[v];
+    const unsigned g_lo = (unsigned)((unsigned long long)ng * sp / p.split);
+    const unsigned g_hi = (unsigned)((unsigned long long)ng * (sp + 1) / p.split);
+    // warp-uniform: the attack ramp is only live below max_attack (first lane of the warp has the earliest time)
+    const unsigned long long warp_n0 = (p.seg0 + (seg & ~31u)) * (unsigned long long)L;
+    const bool attack = (float)warp_n0 < p.max_attack;
+    for (unsigned g = g_lo; g < g_hi; g++) {
+        const size_t r = (size_t)(gb + g) * K;
+        if (g < ng0) {
+            if (attack) osc_group<K, false, true>(p.hot + r, p.anc + r, p.ph + r, n0, L, s_acc, nthr);
+            else osc_group<K, false, false>(p.hot + r, p.anc + r, p.ph + r, n0, L, s_acc, nthr);
+        } else {
+            if (attack) osc_group<K, true, true>(p.hot + r, p.anc + r, p.ph + r, n0, L, s_acc, nthr);
+            else osc_group<K, true, false>(p.hot + r, p.anc + r, p.ph + r, n0, L, s_acc, nthr);
+        }
+    }
+    if (p.split == 1) {
+        const BufferDesc bd = p.bufdesc[p.first_buf + v];
+        for (int j4 = 0; j4 < L / 4; j4++) {
+            const unsigned long long t = n0 + 4ull * j4;
+            const float4 acc = s_acc[j4 * nthr];
+            if (t >= p.lo && t + 4 <= p.hi) {
+                *reinterpret_cast<float4*>(bd.data + (t & bd.mask)) = acc;
+            } else {
+                const float r[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (t + u >= p.lo && t + u < p.hi) bd.data[(t + u) & bd.mask] = r[u];
+            }
+        }
+    } else {
+        float* plane = p.planes + ((size_t)sp * p.n_voices + v) * p.plane_len + (size_t)seg * L;
+        for (int j4 = 0; j4 < L / 4; j4++) *reinterpret_cast<float4*>(plane + 4 * j4) = s_acc[j4 * nthr];
+    }
+}
+
+// sums the split planes in fixed order into the voices' rings
+__global__ void osc_reduce_kernel(OscLaunch p) {
+    const unsigned v = blockIdx.y;
+    const BufferDesc bd = p.bufdesc[p.first_buf + v];
+    const unsigned long long base = p.seg0 * (unsigned long long)p.L;
+    const unsigned long long n4 = p.plane_len / 4;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        float4 s = *reinterpret_cast<const float4*>(p.planes + (size_t)v * p.plane_len + 4 * i);
+        for (unsigned sp = 1; sp < p.split; sp++) {
+            const float4 q = *reinterpret_cast<const float4*>(p.planes + ((size_t)sp * p.n_voices + v) * p.plane_len + 4 * i);
+            s.x += q.x; s.y += q.y; s.z += q.z; s.w += q.w;
+        }
+        const unsigned long long t = base + 4 * i;
+        if (t >= p.lo && t + 4 <= p.hi) {
+            *reinterpret_cast<float4*>(bd.data + (t & bd.mask)) = s;
+        } else {
+            const float r[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (t + u >= p.lo && t + u < p.hi) bd.data[(t + u) & bd.mask] = r[u];
+        }
+    }
+}
+
+cudaError_t launch_osc(const OscBankDev& b, const BufferDesc* d_bufdesc, uint32_t first_buf, uint64_t lo, uint64_t hi,
+                       uint32_t anchor, int sm_count, cudaStream_t stream, uint64_t* n_launches) {
+    if (n_launches) *n_launches = 0;
+    if (hi <= lo || b.n_voices == 0) return cudaSuccess;
+    int L = anchor ? (int)anchor : 128;
+    L = std::max(4, std::min(OSC_LMAX, (L / 4) * 4));
+    OscLaunch p;
+    p.hot = b.d_hot; p.anc = b.d_anc; p.ph = b.d_ph;
+    p.grp_begin = b.d_grp_begin; p.n_grp0 = b.d_n_grp0; p.n_grp = b.d_n_grp;
+    p.bufdesc = d_bufdesc; p.first_buf = first_buf;
+    p.lo = lo; p.hi = hi;
+    p.L = L;
+    p.seg0 = lo / L;
+    p.nseg = (unsigned)((hi + L - 1) / L - p.seg0);
+    p.split = b.split;
+    p.n_voices = b.n_voices;
+    p.max_attack = b.max_attack;
+    p.plane_len = (unsigned long long)p.nseg * L;
+    p.planes = nullptr;
+    if (p.split > 1) {
+        uint64_t need = (uint64_t)p.split * b.n_voices * p.plane_len;
+        if (need > b.planes_cap) {
+            if (b.d_planes) { cudaStreamSynchronize(stream); cudaFree(b.d_planes); b.d_planes = nullptr; }
+            cudaError_t e = cudaMalloc(&b.d_planes, need * sizeof(float));
+            if (e != cudaSuccess) return e;
+            b.planes_cap = need;
+        }
+        p.planes = b.d_planes;
+    }
+    const unsigned threads = OSC_THREADS;
+    const size_t smem = (size_t)L * threads * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(osc_kernel<OSC_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, OSC_LMAX * OSC_THREADS * (int)sizeof(float));
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    dim3 grid((p.nseg + threads - 1) / threads, b.n_voices, p.split);
+    osc_kernel<OSC_K><<<grid, threads, smem, stream>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (n_launches) (*n_launches)++;
+    if (p.split > 1) {
+        unsigned long long n4 = p.plane_len / 4;
+        unsigned bx = (unsigned)std::min<unsigned long long>((n4 + 255) / 256, (unsigned long long)sm_count * 4);
+        osc_reduce_kernel<<<dim3(bx, b.n_voices), 256, 0, stream>>>(p);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        if (n_launches) (*n_launches)++;
+    }
+    return cudaSuccess;
+}
+
 }  // namespace frb

@@ -395,11 +395,15 @@ public:
             epochs.emplace_back(buff_len, idx);
             n_slot_vectors = buff_len;
         }
-        for (size_t r = 0; r < rows.size() && r < n_slot_vectors; r++) {        // :66-74 zip(rows, slots)
+        // The reference panics (process abort) in the middle of the zip below; a library cannot, so the two
+        // asserts are evaluated for every row first and the call is refused with the state left as it was.
+        for (size_t r = 0; r < rows.size() && r < n_slot_vectors; r++) {
             materialise_upto(r);
-            InputSlot& dest = inputs[r];
-            if (dest.len() != idx) throw Panic(-3, "input slot length != idx (reference.rs:69 assert_eq)");
+            if (inputs[r].len() != idx) throw Panic(-3, "input slot length != idx (reference.rs:69 assert_eq)");
             if (rows[r].size() > n_times) throw Panic(-2, "cannot send inputs ahead of outputs (reference.rs:71 assert)");
+        }
+        for (size_t r = 0; r < rows.size() && r < n_slot_vectors; r++) {        // :66-74 zip(rows, slots)
+            InputSlot& dest = inputs[r];
             dest.data.insert(dest.data.end(), rows[r].begin(), rows[r].end());
             float pad_val = dest.last_or_zero();                                // :72
             dest.data.resize(idx + n_times - dest.base, pad_val);               // :73
