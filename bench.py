@@ -1,0 +1,269 @@
+#!/usr/bin/env python
+"""bench.py — rendered partial-samples/s on BASELINE.json configs[3]:
+65,536 detuned partials x 64 voices with envelopes and a per-voice delay effect, 48 kHz x 10 s,
+sharded by voice over N GPUs with one NCCL reduce of the mixed output.
+
+One "step" = one full 10 s render of the whole graph (2.013e12 partial-samples over all voices).
+  value : device-resident throughput (output block stays in HBM; reduce included), CUDA-timed, max over ranks
+  e2e   : the same through the host-facing call (device->host copy of the mixed block on rank 0 inside the timed region)
+  roofline : dominant kernel (K1 osc_kernel) against the FP32 FMA pipe
+  cpu_baseline : the CPU oracle (restatement of the reference's per-sample renderer) on the box's host cores
+`--impl reference` times that CPU implementation alone on the same metric/config (bounded sample).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np
+
+SR = 48000.0
+N_VOICES = 64
+N_PARTIALS = 65536
+N_SAMPLES = 480000
+FMA_SLOTS_PER_PARTIAL_SAMPLE = 6      # rotation 4 + accumulate 1 + envelope 1 (algorithmic)
+EXECUTED_OPS_PER_PARTIAL_SAMPLE = 4   # what K1 issues: 3 FFMA + 1 FADD
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, device):
+        super().__init__(daemon=True)
+        self.device, self.stop_flag, self.samples, self.reasons, self.max_mhz = device, False, [], set(), None
+
+    def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.device)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            names = {
+                getattr(pynvml, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+                getattr(pynvml, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                getattr(pynvml, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                getattr(pynvml, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            }
+            while not self.stop_flag:
+                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                try:
+                    bits = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    bits = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if bits & bit:
+                        self.reasons.add(name)
+                time.sleep(0.05)
+        except Exception as e:      # pragma: no cover
+            self.reasons.add(f"sampler_error:{type(e).__name__}")
+
+    def result(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def cpu_baseline(n_threads=None, budget_s=12.0):
+    """The CPU oracle (reference-style f32 per-sample evaluation, as RefRenderer would do it) on a bounded sample of
+    the same workload: voice 0, its first `p` partials, `n` samples, through the same per-voice delay/mix graph."""
+    from banks import build_voice_mix_graph, detuned_bank
+    from oracle_binding import OracleRenderer
+    n_threads = n_threads or os.cpu_count() or 1
+    p, n = 4096, 2400
+    bank, ids = detuned_bank(1, p)
+    r = OracleRenderer(ext_mode="f32")
+    build_voice_mix_graph(r, bank, ids)
+    r.fill_buffer(1, 0, 0)
+    # calibrate on a short run, then size the sample for ~budget_s of CPU work
+    _, sec = r.fill_buffer_mt(1, n, 0, n_threads)
+    per = sec / (p * n * 2)      # the Delay re-evaluates the voice at t-d: 2 evaluations per output sample
+    n2 = int(min(48000, max(n, budget_s / max(per * p * 2, 1e-12))))
+    _, sec = r.fill_buffer_mt(1, n2, 4800, n_threads)     # start after the delay so both taps are live
+    value = p * n2 / sec
+    _, sec1 = r.fill_buffer_mt(1, max(n2 // n_threads, 64), 4800, 1)
+    value1 = p * max(n2 // n_threads, 64) / sec1
+    return {"value": value, "unit": "partial-samples/s", "cores": n_threads, "kind": "port",
+            "sample": f"1 voice x {p} partials x {n2} samples of the cfg4 graph (per-voice delay+mix), oracle f32 per-sample "
+                      f"evaluation (sinf/expf per partial-sample, as RefRenderer would), time axis split over {n_threads} threads",
+            "value_1thread": value1}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    vals = []
+    cb = None
+    for i in range(args.warmup + args.steps):
+        cb = cpu_baseline(budget_s=6.0)
+        if i >= args.warmup:
+            vals.append(cb["value"])
+    v = float(np.mean(vals))
+    cb["value"] = v
+    line = {
+        "impl": "reference", "metric": "rendered partial-samples/sec", "value": v, "unit": "partial-samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * (N_VOICES * N_PARTIALS * N_SAMPLES) / v, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": cb,
+        "e2e": {"value": v, "unit": "partial-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "the reference (Rust 2017-nightly + LLVM 3.8) cannot be built here; this is the C++ restatement of its "
+                "per-sample renderer (oracle/), all host threads, bounded sample extrapolated linearly",
+    }
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus):
+    return {"workload": "cfg4: 65,536 detuned partials x 64 voices, envelopes + per-voice Delay/mix, 48 kHz x 10 s "
+                        "(BASELINE.json configs[3])",
+            "voices": N_VOICES, "partials_per_voice": N_PARTIALS, "samples": N_SAMPLES, "sample_rate": SR,
+            "partial_samples_per_step": N_VOICES * N_PARTIALS * N_SAMPLES,
+            "sharding": f"voices round-robin over {n_gpus} GPU(s), one NCCL reduce of the [1 x 480000] mix per step",
+            "cache": "compute-bound; per-step parameter stream 201 MB/GPU-shard-of-64 > 126 MB L2, re-read every 64k-sample block",
+            "inputs": "none per step (synthesis): bank parameters are uploaded once from host arrays through "
+                      "frb_define_oscbank, outside the timed region (SURVEY.md §8d)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--voices", type=int, default=N_VOICES, help="debug: shrink the workload (invalidates the number)")
+    ap.add_argument("--partials", type=int, default=N_PARTIALS)
+    ap.add_argument("--samples", type=int, default=N_SAMPLES)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from banks import build_voice_mix_graph, detuned_bank
+    from libfriendship_b200.sharded import ShardedRenderer
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    n_voices, n_partials, n_samples = args.voices, args.partials, args.samples
+    sr = ShardedRenderer(rank=rank, world_size=world, device=local_rank)
+    my_voices = sr.voices_of_rank(n_voices)
+    bank, ids = detuned_bank(n_voices, n_partials, voices=my_voices)
+    build_voice_mix_graph(sr.r, bank, ids)
+    total_ps = n_voices * n_partials * n_samples
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        barrier()
+        # the renderer runs on its own stream and every step ends with a host sync on it, so the wall clock of the
+        # synchronized loop is the device time of the steps; take the larger of the two clocks
+        ms = max(ev0.elapsed_time(ev1), wall * 1e3)
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    step_dev = lambda: sr.fill_buffer_device(1, n_samples, 0)
+    step_e2e = lambda: sr.fill_buffer(1, n_samples, 0)
+    for _ in range(args.warmup):
+        step_dev()
+    s0 = sr.r.stats()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_dev = timed(step_dev, args.steps)
+    s1 = sr.r.stats()
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    sampler.stop_flag = True
+
+    # dominant kernel: K1, timed live with CUDA events on the renderer's stream (frb_set_profiling)
+    sr.r.set_profiling(True)
+    step_dev()
+    tim = sr.r.timing()
+    sr.r.set_profiling(False)
+    osc_ms = torch.tensor([tim["osc_ms"]], dtype=torch.float64, device="cuda")
+    tot_ms = torch.tensor([tim["total_ms"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(osc_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot_ms, op=dist.ReduceOp.MAX)
+
+    if rank == 0:
+        peaks = measured_peaks()
+        sm_max = peaks.get("sm_max_mhz", 1965.0)
+        n_sm = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        peak_fma = n_sm * 128 * sm_max * 1e6                  # FP32 FMA lanes/s (derived; microbench measured 97% of it)
+        ps_per_gpu = len(my_voices) * n_partials * n_samples  # rank 0's share (the largest shard)
+        osc_s = float(osc_ms.item()) * 1e-3
+        n_osc_launches = max(1, (s1["osc_launches"] - s0["osc_launches"]) // args.steps)
+        achieved = ps_per_gpu * FMA_SLOTS_PER_PARTIAL_SAMPLE * 2 / osc_s / 1e12
+        peak_tf = peak_fma * 2 / 1e12
+        value = total_ps * args.steps / (ms_dev * 1e-3)
+        e2e_v = total_ps * args.steps / (ms_e2e * 1e-3)
+        line = {
+            "metric": "rendered partial-samples/sec", "value": value, "unit": "partial-samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(world),
+            "e2e": {"value": e2e_v, "unit": "partial-samples/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 4 * n_samples, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(s1["kernel_launches"] - s0["kernel_launches"]),
+            "clocks": sampler.result(),
+            "roofline": {
+                "kernel": "osc_kernel<8> (K1)", "bound": "fp32_fma", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": achieved / peak_tf, "traffic": None,
+                "peak_source": f"derived {n_sm} SM x 128 lanes x 2 x sm_max_mhz {sm_max} (MEASURED_PEAKS.json); "
+                               "tools/microbench/fma_peak.cu measured 3.60e13 FMA/s = 97% of it on this pool",
+                "algorithmic": "6 FMA-pipe slots (12 flop) per partial-sample x partial-samples per launch (BASELINE.md §3)",
+                "executed_frac": ps_per_gpu * EXECUTED_OPS_PER_PARTIAL_SAMPLE / osc_s / peak_fma,
+                "launches_per_step": int(n_osc_launches), "avg_launch_ms": float(osc_ms.item()) / n_osc_launches,
+                "kernel_share_of_step": float(osc_ms.item()) / float(tot_ms.item()),
+            },
+        }
+        if not (args.voices == N_VOICES and args.partials == N_PARTIALS and args.samples == N_SAMPLES):
+            line["config"]["workload"] = f"DEBUG reduced workload {n_voices}x{n_partials}x{n_samples}: not a valid bench number"
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -212,26 +212,34 @@ struct OscLaunch {
     unsigned long long lo, hi;       // absolute output window [lo, hi)
     unsigned long long seg0;         // absolute index (t / L) of the first segment
     unsigned nseg;                   // segments per voice
-    int L;                           // segment length, multiple of 4
+    int L;                           // segment length, multiple of 16
     unsigned split;                  // partial-range split
     float* planes;                   // split > 1: [split][n_voices][plane_len], plane time 0 == seg0 * L
     unsigned long long plane_len;
+    unsigned long long plane_off;    // offset of this launch's first segment inside a plane
     unsigned n_voices;
     float max_attack;
 };
 
-// One group of K partials over one segment.  CLS1: resonator at pi - w (negated).  ATTACK: apply min(t*invA, 1).
-template <int K, bool CLS1, bool ATTACK>
-__device__ __forceinline__ void osc_group(const float4* __restrict__ hot, const float4* __restrict__ anc,
-                                          const uint4* __restrict__ ph, unsigned long long n0, int L,
-                                          float4* s_acc, unsigned nthr) {
+// One group of K partials over one segment.  ATTACK: apply min(t*invA, 1).
+// Both resonator classes run this same recurrence: for a class-1 partial (cos w < 0) the variables
+// x_p[n] = (-1)^n x[n], y_p[n] = (-1)^n y[n] obey exactly the class-0 update with the same (a, b, cm1), and segments
+// start at even n, so the anchor state needs no change; the kernel flips the sign of the odd samples of the
+// accumulator column between the class-0 and class-1 groups instead (osc_kernel).  One instance of the hot loop
+// per kernel matters: ptxas' uniform-register budget is per function (2 instances -> 75% promoted, 4 -> none).
+// The records come from shared memory at warp-uniform addresses: the compiler keeps a, b, cm1 in uniform
+// registers, so the hot loop's FFMAs read two vector registers each instead of three (register-file read
+// bandwidth, not the FMA pipe, was the limiter with per-thread coefficient registers: 27% dispatch stalls).
+template <int K, bool ATTACK>
+__device__ __forceinline__ void osc_group(const float4* hot, const float4* anc, const uint4* ph,
+                                          unsigned long long n0, int L, float4* s_acc, unsigned nthr) {
     float x[K], y[K], a[K], b[K], cm1[K], invA[K];
     const float nf = (float)n0;
 #pragma unroll
     for (int k = 0; k < K; k++) {
-        const float4 h = __ldg(hot + k);
-        const float4 an = __ldg(anc + k);
-        const uint4 p = __ldg(ph + k);
+        const float4 h = hot[k];
+        const float4 an = anc[k];
+        const uint4 p = ph[k];
         a[k] = h.x; b[k] = h.y; cm1[k] = h.z;
         invA[k] = an.w;
         // exact phase: 64-bit fixed-point turns, wrap-around == range reduction
@@ -245,63 +253,88 @@ __device__ __forceinline__ void osc_group(const float4* __restrict__ hot, const 
         y[k] = e * s;
         x[k] = e * fmaf(h.w, s, an.x * c);
     }
-    for (int j4 = 0; j4 < L / 4; j4++) {
-        float4 acc = s_acc[j4 * nthr];
-        float r[4] = {acc.x, acc.y, acc.z, acc.w};
+    // 16 samples per loop iteration.  ptxas only moves the loop-invariant, warp-uniform coefficients into uniform
+    // registers when each is used often enough per iteration (measured on the SASS: 4 samples/iteration -> none,
+    // 8 -> about half, 16 -> all of a, b, cm1).  With uniform-register coefficients every hot FFMA reads two vector
+    // registers instead of three; the register-file read ports, not the FMA pipe, were the limiter before
+    // (27% dispatch stalls, 61% FMA-pipe utilisation in profiles/ncu_osc_r1a_summary.txt).
+    constexpr int NV = 4;
+    for (int jb = 0; jb < L / (4 * NV); jb++) {
+        float4 av[NV];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            float sum = r[u];
-            float tf = 0.f;
-            if (ATTACK) tf = nf + (float)(j4 * 4 + u);
+        for (int q = 0; q < NV; q++) av[q] = s_acc[(NV * jb + q) * nthr];
 #pragma unroll
-            for (int k = 0; k < K; k++) {
-                if (ATTACK) sum = fmaf(fminf(tf * invA[k], 1.0f), y[k], sum);
-                else sum += y[k];
-                if (!CLS1) {
+        for (int q = 0; q < NV; q++) {
+            float r[4] = {av[q].x, av[q].y, av[q].z, av[q].w};
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                float sum = r[u];
+                float tf = 0.f;
+                if (ATTACK) tf = nf + (float)(jb * 4 * NV + q * 4 + u);
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                    if (ATTACK) sum = fmaf(fminf(tf * invA[k], 1.0f), y[k], sum);
+                    else sum += y[k];
                     x[k] = fmaf(-a[k], y[k], x[k]);
                     const float t = fmaf(cm1[k], y[k], y[k]);
                     y[k] = fmaf(b[k], x[k], t);
-                } else {
-                    x[k] = fmaf(a[k], y[k], -x[k]);
-                    const float t = fmaf(cm1[k], y[k], y[k]);
-                    y[k] = fmaf(b[k], x[k], -t);
                 }
+                r[u] = sum;
             }
-            r[u] = sum;
+            av[q] = make_float4(r[0], r[1], r[2], r[3]);
         }
-        s_acc[j4 * nthr] = make_float4(r[0], r[1], r[2], r[3]);
+#pragma unroll
+        for (int q = 0; q < NV; q++) s_acc[(NV * jb + q) * nthr] = av[q];
     }
 }
 
 template <int K>
+struct OscStage {            // one group's records, staged in shared memory (double buffered)
+    float4 hot[K];
+    float4 anc[K];
+    uint4 ph[K];
+};
+
+template <int K, bool ATTACK>
 __global__ void __launch_bounds__(OSC_THREADS) osc_kernel(OscLaunch p) {
     extern __shared__ float4 s_acc_all[];
+    __shared__ OscStage<K> stage;                            // static: constant addresses -> uniform-register loads
     const unsigned nthr = blockDim.x;
+    const int L = p.L;
     float4* s_acc = s_acc_all + threadIdx.x;                 // column of this thread: s_acc[j4 * nthr]
     const unsigned seg = blockIdx.x * nthr + threadIdx.x;
     const unsigned v = blockIdx.y;
     const unsigned sp = blockIdx.z;
-    if (seg >= p.nseg) return;                               // no barriers in this kernel: early exit is safe
-    const int L = p.L;
+    const bool live = seg < p.nseg;                          // dead threads compute too (dropped at the end)
     const unsigned long long n0 = (p.seg0 + seg) * (unsigned long long)L;
     for (int j4 = 0; j4 < L / 4; j4++) s_acc[j4 * nthr] = make_float4(0.f, 0.f, 0.f, 0.f);
 
     const unsigned ng = p.n_grp[v], ng0 = p.n_grp0[v], gb = p.grp_begin[v];
     const unsigned g_lo = (unsigned)((unsigned long long)ng * sp / p.split);
     const unsigned g_hi = (unsigned)((unsigned long long)ng * (sp + 1) / p.split);
-    // warp-uniform: the attack ramp is only live below max_attack (first lane of the warp has the earliest time)
-    const unsigned long long warp_n0 = (p.seg0 + (seg & ~31u)) * (unsigned long long)L;
-    const bool attack = (float)warp_n0 < p.max_attack;
-    for (unsigned g = g_lo; g < g_hi; g++) {
-        const size_t r = (size_t)(gb + g) * K;
-        if (g < ng0) {
-            if (attack) osc_group<K, false, true>(p.hot + r, p.anc + r, p.ph + r, n0, L, s_acc, nthr);
-            else osc_group<K, false, false>(p.hot + r, p.anc + r, p.ph + r, n0, L, s_acc, nthr);
-        } else {
-            if (attack) osc_group<K, true, true>(p.hot + r, p.anc + r, p.ph + r, n0, L, s_acc, nthr);
-            else osc_group<K, true, false>(p.hot + r, p.anc + r, p.ph + r, n0, L, s_acc, nthr);
+    const unsigned g_mid = min(max(ng0, g_lo), g_hi);        // first class-1 group of this split
+
+    auto flip_odd = [&]() {                                  // acc[j] *= (-1)^j
+        for (int j4 = 0; j4 < L / 4; j4++) {
+            float4 a4 = s_acc[j4 * nthr];
+            a4.y = -a4.y; a4.w = -a4.w;
+            s_acc[j4 * nthr] = a4;
         }
+    };
+    for (unsigned g = g_lo; g < g_hi; g++) {
+        __syncthreads();                                     // everyone is done with the previous group's records
+        if (threadIdx.x < K) {                               // threads 0..K-1 stage one record each
+            const size_t r = (size_t)(gb + g) * K + threadIdx.x;
+            stage.hot[threadIdx.x] = __ldg(p.hot + r);
+            stage.anc[threadIdx.x] = __ldg(p.anc + r);
+            stage.ph[threadIdx.x] = __ldg(p.ph + r);
+        }
+        if (g == g_mid) flip_odd();                          // class-0 sums -> alternating-sign domain
+        __syncthreads();
+        osc_group<K, ATTACK>(stage.hot, stage.anc, stage.ph, n0, L, s_acc, nthr);
     }
+    if (g_mid < g_hi) flip_odd();                            // back: out[j] = acc0[j] + (-1)^j acc1[j]
+    if (!live) return;
     if (p.split == 1) {
         const BufferDesc bd = p.bufdesc[p.first_buf + v];
         for (int j4 = 0; j4 < L / 4; j4++) {
@@ -317,7 +350,7 @@ __global__ void __launch_bounds__(OSC_THREADS) osc_kernel(OscLaunch p) {
             }
         }
     } else {
-        float* plane = p.planes + ((size_t)sp * p.n_voices + v) * p.plane_len + (size_t)seg * L;
+        float* plane = p.planes + ((size_t)sp * p.n_voices + v) * p.plane_len + p.plane_off + (size_t)seg * L;
         for (int j4 = 0; j4 < L / 4; j4++) *reinterpret_cast<float4*>(plane + 4 * j4) = s_acc[j4 * nthr];
     }
 }
@@ -352,7 +385,7 @@ cudaError_t launch_osc(const OscBankDev& b, const BufferDesc* d_bufdesc, uint32_
     if (n_launches) *n_launches = 0;
     if (hi <= lo || b.n_voices == 0) return cudaSuccess;
     int L = anchor ? (int)anchor : 128;
-    L = std::max(4, std::min(OSC_LMAX, (L / 4) * 4));
+    L = std::max(16, std::min(OSC_LMAX, (L / 16) * 16));
     OscLaunch p;
     p.hot = b.d_hot; p.anc = b.d_anc; p.ph = b.d_ph;
     p.grp_begin = b.d_grp_begin; p.n_grp0 = b.d_n_grp0; p.n_grp = b.d_n_grp;
@@ -366,6 +399,7 @@ cudaError_t launch_osc(const OscBankDev& b, const BufferDesc* d_bufdesc, uint32_
     p.max_attack = b.max_attack;
     p.plane_len = (unsigned long long)p.nseg * L;
     p.planes = nullptr;
+    p.plane_off = 0;
     if (p.split > 1) {
         uint64_t need = (uint64_t)p.split * b.n_voices * p.plane_len;
         if (need > b.planes_cap) {
@@ -380,15 +414,41 @@ cudaError_t launch_osc(const OscBankDev& b, const BufferDesc* d_bufdesc, uint32_
     const size_t smem = (size_t)L * threads * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(osc_kernel<OSC_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, OSC_LMAX * OSC_THREADS * (int)sizeof(float));
+        const int mx = OSC_LMAX * OSC_THREADS * (int)sizeof(float);
+        cudaError_t e = cudaFuncSetAttribute(osc_kernel<OSC_K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(osc_kernel<OSC_K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    dim3 grid((p.nseg + threads - 1) / threads, b.n_voices, p.split);
-    osc_kernel<OSC_K><<<grid, threads, smem, stream>>>(p);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    if (n_launches) (*n_launches)++;
+    // Segments that start below max_attack need the attack ramp: they get their own (slower) kernel so that each
+    // kernel contains exactly one instance of the hot loop.
+    unsigned n_att = 0;
+    if (b.max_attack > 0.f) {
+        unsigned long long first_plain = ((unsigned long long)std::ceil((double)b.max_attack) + L - 1) / L;   // first segment with n0 >= max_attack
+        if (first_plain > p.seg0) n_att = (unsigned)std::min<unsigned long long>(first_plain - p.seg0, p.nseg);
+    }
+    const unsigned nseg_total = p.nseg;
+    if (n_att) {
+        OscLaunch q = p;
+        q.nseg = n_att;
+        dim3 grid((n_att + threads - 1) / threads, b.n_voices, p.split);
+        osc_kernel<OSC_K, true><<<grid, threads, smem, stream>>>(q);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        if (n_launches) (*n_launches)++;
+    }
+    if (nseg_total > n_att) {
+        OscLaunch q = p;
+        q.seg0 = p.seg0 + n_att;
+        q.nseg = nseg_total - n_att;
+        q.plane_off = (unsigned long long)n_att * L;
+        dim3 grid((q.nseg + threads - 1) / threads, b.n_voices, p.split);
+        osc_kernel<OSC_K, false><<<grid, threads, smem, stream>>>(q);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        if (n_launches) (*n_launches)++;
+    }
+    cudaError_t e = cudaSuccess;
     if (p.split > 1) {
         unsigned long long n4 = p.plane_len / 4;
         unsigned bx = (unsigned)std::min<unsigned long long>((n4 + 255) / 256, (unsigned long long)sm_count * 4);
