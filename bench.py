@@ -148,6 +148,7 @@ def main():
     ap.add_argument("--partials", type=int, default=N_PARTIALS)
     ap.add_argument("--samples", type=int, default=N_SAMPLES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--osc-anchor", type=int, default=0, help="debug: K1 segment length / re-anchor interval")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -166,7 +167,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     n_voices, n_partials, n_samples = args.voices, args.partials, args.samples
-    sr = ShardedRenderer(rank=rank, world_size=world, device=local_rank)
+    sr = ShardedRenderer(rank=rank, world_size=world, device=local_rank, osc_anchor=args.osc_anchor)
     my_voices = sr.voices_of_rank(n_voices)
     bank, ids = detuned_bank(n_voices, n_partials, voices=my_voices)
     build_voice_mix_graph(sr.r, bank, ids)

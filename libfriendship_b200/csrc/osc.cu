@@ -33,7 +33,7 @@
 namespace frb {
 
 constexpr int OSC_K = 8;            // partials per group (independent FMA chains per thread)
-constexpr int OSC_THREADS = 128;    // threads (= time segments) per CTA
+constexpr int OSC_THREADS = 32;     // threads (= time segments) per CTA: one warp, so the per-group barrier couples no warps
 constexpr int OSC_LMAX = 256;       // max segment length (shared memory: L * THREADS * 4 B)
 
 struct OscBankDev {
@@ -243,13 +243,17 @@ __device__ __forceinline__ void osc_group(const float4* hot, const float4* anc, 
         a[k] = h.x; b[k] = h.y; cm1[k] = h.z;
         invA[k] = an.w;
         // exact phase: 64-bit fixed-point turns, wrap-around == range reduction
-        const unsigned long long inc = ((unsigned long long)p.y << 32) | p.x;
-        const unsigned long long ph0 = ((unsigned long long)p.w << 32) | p.z;
-        const unsigned long long turns = inc * n0 + ph0;
-        const float th = (float)(int)(turns >> 32) * 1.4629180792671596e-9f;      // * 2 pi / 2^32, in [-pi, pi)
+        // top 32 bits of (inc * n0 + ph0) mod 2^64; the carry out of the low words is dropped (<= 2^-32 turns)
+        const unsigned n0_lo = (unsigned)n0, n0_hi = (unsigned)(n0 >> 32);
+        const unsigned turns_hi = __umulhi(p.x, n0_lo) + p.y * n0_lo + p.x * n0_hi + p.w;
+        const float th = (float)(int)turns_hi * 1.4629180792671596e-9f;           // * 2 pi / 2^32, in [-pi, pi)
         float s, c;
         __sincosf(th, &s, &c);
-        const float e = an.y * exp2f((float)(-(double)an.z * (double)n0));        // amp * exp(-n/tau)
+        // amp * exp(-n/tau) = amp * 2^(-kappa n).  f32 product: the exponent's rounding error X*6e-8 (X = kappa n)
+        // gives a relative error X*4e-8 of an envelope that is itself 2^-X of the amplitude — far below 1e-5.
+        float e;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-an.z * nf));
+        e *= an.y;
         y[k] = e * s;
         x[k] = e * fmaf(h.w, s, an.x * c);
     }
@@ -271,10 +275,22 @@ __device__ __forceinline__ void osc_group(const float4* hot, const float4* anc, 
                 float sum = r[u];
                 float tf = 0.f;
                 if (ATTACK) tf = nf + (float)(jb * 4 * NV + q * 4 + u);
+                if (ATTACK) {
+#pragma unroll
+                    for (int k = 0; k < K; k++) sum = fmaf(fminf(tf * invA[k], 1.0f), y[k], sum);
+                } else {
+                    // pairwise tree over the K partials (fixed order): dependency depth log2(K)+1 instead of K
+                    float part[K];
+#pragma unroll
+                    for (int k = 0; k < K; k++) part[k] = y[k];
+#pragma unroll
+                    for (int w = 1; w < K; w *= 2)
+#pragma unroll
+                        for (int k = 0; k + w < K; k += 2 * w) part[k] += part[k + w];
+                    sum += part[0];
+                }
 #pragma unroll
                 for (int k = 0; k < K; k++) {
-                    if (ATTACK) sum = fmaf(fminf(tf * invA[k], 1.0f), y[k], sum);
-                    else sum += y[k];
                     x[k] = fmaf(-a[k], y[k], x[k]);
                     const float t = fmaf(cm1[k], y[k], y[k]);
                     y[k] = fmaf(b[k], x[k], t);
