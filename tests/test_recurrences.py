@@ -1,0 +1,128 @@
+"""GPU: K4 Direct-Form recurrences (extension nodes; PARITY UNPINNED by any reference test) against the fp64
+sequential oracle (tolerance from BASELINE.json: <= 1e-4 of full scale for feedback recurrences) and, for the
+feedback delay, bit-exact against the sequential f32 evaluation."""
+import numpy as np
+import pytest
+
+from filters import build_cfg3_graph, cfg3_filters, rbj_lowpass
+from oracle_binding import OracleRenderer
+from replay import assert_same_bits
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_cls():
+    from libfriendship_b200 import B200Renderer
+    return B200Renderer
+
+
+def noise(n_rows, n, seed=0):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    return [rng.uniform(-1, 1, n).astype(np.float32) for _ in range(n_rows)]
+
+
+def test_fbdelay_bit_exact_vs_sequential_f32():
+    from libfriendship_b200 import KIND_FBDELAY
+    lanes, n = 5, 3000
+    delay = np.array([1, 2, 7, 100, 999], dtype=np.uint32)
+    gain = np.array([0.5, -0.9, 0.7, 0.99, 0.3], dtype=np.float32)
+    x = noise(lanes, n)
+    outs = []
+    for r in (gpu_cls()(), OracleRenderer(ext_mode="f32")):
+        r.define_fbdelay(3, delay, gain)
+        r.on_add_node(1, KIND_FBDELAY, 3)
+        for l in range(lanes):
+            r.on_add_edge((0, 1, l, l))
+            r.on_add_edge((1, 0, l, l))
+        outs.append(r.fill_buffer(lanes, n, 0, x))
+    assert_same_bits(outs[0], outs[1], "fbdelay")
+
+
+def test_directform_vs_fp64_and_block_continuity():
+    from libfriendship_b200 import KIND_DIRECTFORM
+    lanes, n = 6, 9000
+    fc = np.array([50.0, 200.0, 1000.0, 4000.0, 8000.0, 15000.0])
+    q = np.array([0.707, 4.0, 2.0, 0.9, 3.0, 1.0])
+    coefs = rbj_lowpass(fc, q)
+    x = noise(lanes, n, seed=5)
+
+    def build(r):
+        r.define_directform(3, *coefs)
+        r.on_add_node(1, KIND_DIRECTFORM, 3)
+        for l in range(lanes):
+            r.on_add_edge((0, 1, l, l))
+            r.on_add_edge((1, 0, l, l))
+
+    g, o = gpu_cls()(), OracleRenderer()
+    build(g)
+    build(o)
+    a = g.fill_buffer(lanes, n, 0, x)
+    b = o.fill_buffer(lanes, n, 0, x)
+    scale = np.abs(b).max()
+    # f32 Direct Form I is itself noisy for poles near z = 1 (50 Hz low-pass): the bound is the north star's 1e-4 of
+    # full scale, and the scan must not be meaningfully worse than a sequential f32 evaluation of the same recurrence
+    o32 = OracleRenderer(ext_mode="f32")
+    build(o32)
+    err_seq = np.abs(o32.fill_buffer(lanes, n, 0, x).astype(np.float64) - b).max()
+    err = np.abs(a.astype(np.float64) - b).max()
+    assert err <= 1e-4 * scale and err <= max(1e-5 * scale, 4 * err_seq), (err, err_seq, scale)
+    # ragged consecutive blocks continue exactly from the rings (state = last two samples of x and y)
+    g2 = gpu_cls()()
+    build(g2)
+    parts, idx = [], 0
+    for m in (1, 2, 5, 2047, 2048, 2049, 2848):
+        parts.append(g2.fill_buffer(lanes, m, idx, [row[idx:idx + m] for row in x]))
+        idx += m
+    c = np.concatenate(parts, axis=1)
+    err_c = np.abs(c.astype(np.float64) - b).max()
+    assert err_c <= 1e-4 * scale and err_c <= max(1e-5 * scale, 4 * err_seq), (err_c, err_seq)
+
+
+def test_cfg3_shape_small_chain_and_seek():
+    """cfg3 at test scale: per voice biquad -> feedback delay; whole render, then a render that starts at idx > 0
+    with no history (the recurrences are defined from t = 0: the renderer re-runs [0, idx) before the block)."""
+    n_voices, n = 8, 6000
+    x = noise(n_voices, n, seed=9)
+    g, o = gpu_cls()(), OracleRenderer()
+    build_cfg3_graph(g, n_voices)
+    build_cfg3_graph(o, n_voices)
+    a = g.fill_buffer(n_voices, n, 0, x)
+    b = o.fill_buffer(n_voices, n, 0, x)
+    scale = np.abs(b).max()
+    assert np.abs(a.astype(np.float64) - b).max() <= 1e-4 * scale
+    # seek: inputs before idx are zero after a seek (renderer.rs:12-15), so feed the block only
+    g2, o2 = gpu_cls()(), OracleRenderer()
+    build_cfg3_graph(g2, n_voices)
+    build_cfg3_graph(o2, n_voices)
+    blk = [row[:500] for row in x]
+    a2 = g2.fill_buffer(n_voices, 500, 4000, blk)
+    b2 = o2.fill_buffer(n_voices, 500, 4000, blk)
+    assert np.abs(a2.astype(np.float64) - b2).max() <= 1e-4 * max(np.abs(b2).max(), 1e-3)
+
+
+def test_ten_seconds_feedback_chain_error_bound():
+    """'<= 1e-4 after 10 s for feedback recurrences': 2 voices, 480,000 samples, in 64k-sample blocks."""
+    n_voices, n = 2, 480000
+    x = noise(n_voices, n, seed=11)
+    g, o = gpu_cls()(), OracleRenderer()
+    build_cfg3_graph(g, n_voices)
+    build_cfg3_graph(o, n_voices)
+    a = g.fill_buffer(n_voices, n, 0, x)
+    b = o.fill_buffer(n_voices, n, 0, x)
+    scale = np.abs(b).max()
+    err = np.abs(a.astype(np.float64) - b)
+    assert err.max() <= 1e-4 * scale, (err.max(), scale)
+    assert err[:, -48000:].max() <= 1e-4 * scale
+
+
+def test_osc_excited_chain_mixed_to_one_slot():
+    from banks import detuned_bank
+    n_voices, n = 4, 2500
+    bank, _ = detuned_bank(n_voices, 32, seed=3)
+    outs = []
+    for cls in (gpu_cls(), OracleRenderer):
+        r = cls()
+        build_cfg3_graph(r, n_voices, excitation="osc", bank=bank, mix_to_one=True)
+        outs.append(r.fill_buffer(1, n, 0))
+    scale = np.abs(outs[1]).max()
+    assert np.abs(outs[0].astype(np.float64) - outs[1]).max() <= 1e-4 * scale
