@@ -83,13 +83,13 @@ GraphNode Renderer::make_node(uint32_t kind, uint64_t key) const {
             break;
         }
         case FRB_KIND_OSCBANK:
-            if (!osc_defs_.count(key)) throw Error{FRB_E_BAD_HANDLE, "unknown oscbank key"};
+            if (!osc_defs_.count(key) && !meta_lanes_.count({kind, key})) throw Error{FRB_E_BAD_HANDLE, "unknown oscbank key"};
             break;
         case FRB_KIND_DIRECTFORM:
-            if (!df_defs_.count(key)) throw Error{FRB_E_BAD_HANDLE, "unknown directform key"};
+            if (!df_defs_.count(key) && !meta_lanes_.count({kind, key})) throw Error{FRB_E_BAD_HANDLE, "unknown directform key"};
             break;
         case FRB_KIND_FBDELAY:
-            if (!fb_defs_.count(key)) throw Error{FRB_E_BAD_HANDLE, "unknown fbdelay key"};
+            if (!fb_defs_.count(key) && !meta_lanes_.count({kind, key})) throw Error{FRB_E_BAD_HANDLE, "unknown fbdelay key"};
             break;
         default: throw Error{FRB_E_INVALID, "unknown node kind"};
     }
@@ -108,6 +108,7 @@ void Renderer::define_effect(uint64_t key, const frb_node* nodes, uint32_t n_nod
 }
 
 void Renderer::define_oscbank(uint64_t key, const frb_oscbank_desc* d) {
+    if (host_only_) { meta_lanes_[{FRB_KIND_OSCBANK, key}] = {d->n_voices, 0}; return; }   // planning only: shape
     require_device();
     CU(cudaSetDevice(device_));
     std::string err;
@@ -117,6 +118,7 @@ void Renderer::define_oscbank(uint64_t key, const frb_oscbank_desc* d) {
     osc_defs_[key] = b;
 }
 void Renderer::define_directform(uint64_t key, const frb_directform_desc* d) {
+    if (host_only_) { meta_lanes_[{FRB_KIND_DIRECTFORM, key}] = {d->n_lanes, 0}; return; }
     require_device();
     CU(cudaSetDevice(device_));
     std::string err;
@@ -125,6 +127,15 @@ void Renderer::define_directform(uint64_t key, const frb_directform_desc* d) {
     df_defs_[key] = b;
 }
 void Renderer::define_fbdelay(uint64_t key, const frb_fbdelay_desc* d) {
+    if (host_only_) {
+        uint64_t mx = 0;
+        for (uint32_t i = 0; i < d->n_lanes; i++) {
+            if (d->delay[i] < 1) throw Error{FRB_E_INVALID, "fbdelay: delay must be >= 1"};
+            mx = std::max<uint64_t>(mx, d->delay[i]);
+        }
+        meta_lanes_[{FRB_KIND_FBDELAY, key}] = {d->n_lanes, mx};
+        return;
+    }
     require_device();
     CU(cudaSetDevice(device_));
     std::string err;
@@ -169,12 +180,16 @@ const Schedule& Renderer::schedule(uint32_t n_slots) {
     if (dirty_ || sched_slots_ != n_slots) {
         FlattenEnv env;
         env.ext_lanes = [this](uint32_t kind, uint64_t key) -> int64_t {
+            auto mit = meta_lanes_.find({kind, key});
+            if (mit != meta_lanes_.end()) return (int64_t)mit->second.first;
             if (kind == FRB_KIND_OSCBANK) { auto it = osc_defs_.find(key); return it == osc_defs_.end() ? -1 : (int64_t)osc_info(*it->second).n_voices; }
             if (kind == FRB_KIND_DIRECTFORM) { auto it = df_defs_.find(key); return it == df_defs_.end() ? -1 : (int64_t)directform_lanes(*it->second); }
             if (kind == FRB_KIND_FBDELAY) { auto it = fb_defs_.find(key); return it == fb_defs_.end() ? -1 : (int64_t)fbdelay_lanes(*it->second); }
             return -1;
         };
         env.ext_max_delay = [this](uint64_t key) -> uint64_t {
+            auto mit = meta_lanes_.find({FRB_KIND_FBDELAY, key});
+            if (mit != meta_lanes_.end()) return mit->second.second;
             auto it = fb_defs_.find(key);
             return it == fb_defs_.end() ? 0 : fbdelay_max_delay(*it->second);
         };

@@ -80,6 +80,8 @@ private:
     std::map<uint64_t, std::shared_ptr<OscBankDev>> osc_defs_;
     std::map<uint64_t, std::shared_ptr<DirectFormDev>> df_defs_;
     std::map<uint64_t, std::shared_ptr<FbDelayDev>> fb_defs_;
+    // planning-only handles keep just the shape of extension definitions: (kind, key) -> (lanes, max delay)
+    std::map<std::pair<uint32_t, uint64_t>, std::pair<uint32_t, uint64_t>> meta_lanes_;
 
     bool dirty_ = true;
     Schedule sched_;

@@ -1,0 +1,103 @@
+"""CPU (host logic, no device): routing order, buffer indexing and delay-line offsets of the device schedule are
+bit-exact against an independent restatement of the flattening rules (tests/pyflatten.py), on seeded random graphs
+with nested effects, shared sub-graphs, constant and signal-driven delays and extension nodes."""
+import numpy as np
+import pytest
+
+from pyflatten import FULL, PyGraph, flatten, parse_dump
+from randgraph import random_graph
+
+
+def planner():
+    from libfriendship_b200 import B200Renderer
+    return B200Renderer(device=-1)
+
+
+def check(rec, n_slots):
+    r, g = planner(), PyGraph()
+    rec.apply(r)
+    rec.apply(g)
+    got = parse_dump(r.dump_schedule(n_slots))
+    want = flatten(g, n_slots)
+    assert got["values"] == [tuple(v) for v in want["values"]]            # routing order (dependency first)
+    assert got["outputs"] == want["outputs"]
+    assert got["stage"] == want["stage"]
+    assert got["buffer"] == want["buffer"]                                # buffer indexing
+    assert [b["lookback"] for b in got["buffers"]] == [want["lookback"][v] for v in range(len(want["values"])) if want["buffer"][v] >= 0]
+    assert got["n_inputs"] == want["n_inputs"]
+    assert got["from_zero"] == want["from_zero"] and got["full_history"] == want["full_history"]
+    return got, want
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_schedule_matches_python_restatement(seed):
+    rec = random_graph(seed, n_inputs=3, n_nodes=8 + seed % 17, n_outputs=3, nested_levels=1 + seed % 3)
+    check(rec, 3)
+
+
+def test_delay_line_offsets_and_stage_cut():
+    """in0 -> *0.5 -> Delay(12000) -> ... : the Delay source is a computed signal, so it is materialised with a
+    lookback of exactly 12000 samples and the Delay lands in the next stage."""
+    from graphs import build_cfg1_graph
+    from randgraph import Recorder
+    rec = Recorder()
+    build_cfg1_graph(rec)
+    got, want = check(rec, 2)
+    lbs = sorted(b["lookback"] for b in got["buffers"])
+    assert lbs == [12000]
+    assert max(got["stage"]) == 1
+
+
+def test_signal_driven_delay_needs_full_history():
+    from randgraph import Recorder
+    rec = Recorder()
+    rec.on_add_node(1, 0)          # Delay
+    rec.on_add_node(2, 3)          # Multiply (computed source)
+    rec.on_add_node(3, 1)          # const
+    rec.on_add_edge((0, 2, 0, 0))
+    rec.on_add_edge((3, 2, 0x3f000000, 1))
+    rec.on_add_edge((2, 1, 0, 0))
+    rec.on_add_edge((0, 1, 1, 1))  # frames driven by input 1
+    rec.on_add_edge((1, 0, 0, 0))
+    got, _ = check(rec, 1)
+    assert got["full_history"] and got["from_zero"]
+    assert [b["lookback"] for b in got["buffers"]] == [FULL]
+
+
+def test_extension_nodes_lanes_and_lookbacks():
+    from randgraph import Recorder
+    rec = Recorder()
+    rec.define_oscbank(5, 48000.0, [0, 2, 4, 6], [1.0] * 6, [1.0] * 6, [0.0] * 6, [0.0] * 6, [0.0] * 6)
+    rec.define_directform(6, [1.0] * 3, [0.0] * 3, [0.0] * 3, [0.0] * 3, [0.0] * 3)
+    rec.define_fbdelay(7, [10, 200, 30], [0.5] * 3)
+    rec.on_add_node(1, 32, 5)
+    rec.on_add_node(2, 33, 6)
+    rec.on_add_node(3, 34, 7)
+    for l in range(3):
+        rec.on_add_edge((1, 2, l, l))
+        rec.on_add_edge((2, 3, l, l))
+        rec.on_add_edge((3, 0, l, l))
+    got, want = check(rec, 3)
+    by_ext = {}
+    for b in got["buffers"]:
+        by_ext.setdefault(b["ext"], []).append(b["lookback"])
+    assert by_ext[0] == [2, 2, 2]          # OscBank lanes feed the biquad: x[n-1], x[n-2] must stay addressable
+    assert by_ext[1] == [2, 2, 2]          # biquad output keeps y[n-1], y[n-2]
+    assert by_ext[2] == [200, 200, 200]    # feedback delay keeps its longest delay line
+    assert got["from_zero"]
+
+
+def test_shared_subgraph_is_evaluated_once():
+    from randgraph import Recorder
+    rec = Recorder()
+    rec.on_add_node(1, 1)
+    rec.on_add_node(2, 3)
+    rec.on_add_node(3, 2)
+    rec.on_add_edge((0, 2, 0, 0))
+    rec.on_add_edge((1, 2, 0x40000000, 1))
+    rec.on_add_edge((2, 3, 0, 0))
+    rec.on_add_edge((2, 3, 0, 1))        # Sum2(m, m): m shared
+    rec.on_add_edge((3, 0, 0, 0))
+    rec.on_add_edge((2, 0, 0, 1))        # and also an output
+    got, _ = check(rec, 2)
+    assert sum(1 for v in got["values"] if v[0] == 5) == 1
