@@ -4,41 +4,58 @@ mixed output blocks onto rank 0.  The feed-forward effect tree is linear in its 
 per-rank mixes equals the single-GPU render up to f32 summation order.
 
 PyTorch is plumbing here: device tensors for the output block, torch.distributed for the reduce."""
-import numpy as np
 import torch
 
 from . import B200Renderer
 
 
+def voices_of_rank(n_voices, rank, world_size):
+    """voices v with v mod world_size == rank (round-robin shard)."""
+    return list(range(rank, n_voices, world_size))
+
+
 class ShardedRenderer:
-    def __init__(self, rank=0, world_size=1, device=0, **kw):
+    """`renderer` defaults to a B200Renderer on `device`.  Tests inject another object with the renderer interface
+    (host path: fill_buffer) to exercise the shard/reduce logic over gloo without a GPU."""
+
+    def __init__(self, rank=0, world_size=1, device=0, renderer=None, **kw):
         self.rank, self.world_size, self.device = rank, world_size, device
-        self.r = B200Renderer(device=device, **kw)
+        self.on_gpu = renderer is None
+        self.r = B200Renderer(device=device, **kw) if renderer is None else renderer
         self._out = None
         self._host = None
 
     def voices_of_rank(self, n_voices):
-        """voices v with v mod world_size == rank (round-robin shard)."""
-        return list(range(self.rank, n_voices, self.world_size))
+        return voices_of_rank(n_voices, self.rank, self.world_size)
 
-    def _device_out(self, n_slots, n_times):
+    def _block(self, n_slots, n_times):
+        dev = f"cuda:{self.device}" if self.on_gpu else "cpu"
         if self._out is None or tuple(self._out.shape) != (n_slots, n_times):
-            self._out = torch.empty((n_slots, n_times), dtype=torch.float32, device=f"cuda:{self.device}")
+            self._out = torch.empty((n_slots, n_times), dtype=torch.float32, device=dev)
         return self._out
 
-    def fill_buffer_device(self, n_slots, n_times, idx):
-        """Renders this rank's shard and reduces onto rank 0.  Returns the device tensor (valid on rank 0)."""
-        out = self._device_out(n_slots, n_times)
-        self.r.fill_buffer_device(out.data_ptr(), n_slots, n_times, idx)
-        self.r.sync()                                   # renderer stream -> visible to the collective's stream
+    def _reduce(self, out):
         if self.world_size > 1:
             import torch.distributed as dist
-            dist.reduce(out, dst=0, op=dist.ReduceOp.SUM)
+            dist.reduce(out, dst=0, op=dist.ReduceOp.SUM)   # the path's single exchange step
         return out
 
-    def fill_buffer(self, n_slots, n_times, idx):
+    def fill_buffer_device(self, n_slots, n_times, idx, inputs=None):
+        """Renders this rank's shard and reduces onto rank 0.  Returns the block tensor (valid on rank 0)."""
+        out = self._block(n_slots, n_times)
+        if self.on_gpu:
+            assert not inputs, "device path: feed external inputs through B200Renderer.fill_buffer_device directly"
+            self.r.fill_buffer_device(out.data_ptr(), n_slots, n_times, idx)
+            self.r.sync()                               # renderer stream -> visible to the collective's stream
+        else:
+            out.copy_(torch.from_numpy(self.r.fill_buffer(n_slots, n_times, idx, inputs)))
+        return self._reduce(out)
+
+    def fill_buffer(self, n_slots, n_times, idx, inputs=None):
         """End-to-end: host ndarray on rank 0 (None elsewhere); includes the device->host copy."""
-        out = self.fill_buffer_device(n_slots, n_times, idx)
+        out = self.fill_buffer_device(n_slots, n_times, idx, inputs)
+        if not self.on_gpu:
+            return out.numpy().copy() if self.rank == 0 else None
         if self.rank != 0:
             torch.cuda.synchronize(self.device)
             return None
