@@ -312,6 +312,32 @@ Schedule flatten(const Graph& top, uint32_t n_slots, const FlattenEnv& env) {
     std::vector<std::vector<uint32_t>> out_slots_of(nv);
     for (uint32_t k = 0; k < s.outputs.size(); k++) out_slots_of[s.outputs[k]].push_back(k);
 
+    // Sum2 chains over consecutive lanes of an extension node — the "voices summed to one slot" mix,
+    // ((x0 + x1) + x2) + ... — become ONE fold instruction with the same left-to-right order (bit-exact), so a
+    // 4,096-voice mix is a streaming loop over planes instead of 8,192 interpreted instructions per thread.
+    std::vector<uint32_t> n_uses(nv, 0);
+    for (size_t v = 0; v < nv; v++) {
+        if (V[v].op == V_DELAY || (V[v].op >= V_SUM2 && V[v].op <= V_MIN)) { n_uses[V[v].a]++; n_uses[V[v].b]++; }
+    }
+    for (uint32_t o : s.outputs) n_uses[o]++;
+    for (auto& inst : s.ext) for (uint32_t in : inst.inputs) n_uses[in]++;
+    std::vector<uint32_t> fold_first(nv, 0), fold_len(nv, 0);
+    std::vector<uint8_t> absorbed(nv, 0);
+    for (size_t v = 0; v < nv; v++) {
+        const Value& x = V[v];
+        if (x.op != V_SUM2 || V[x.b].op != V_EXT || st[x.b] > st[v]) continue;
+        const uint32_t bb = (uint32_t)s.value_buffer[x.b];
+        if (V[x.a].op == V_EXT && V[x.a].a == V[x.b].a && st[x.a] <= st[v] && (uint32_t)s.value_buffer[x.a] + 1 == bb) {
+            fold_first[v] = (uint32_t)s.value_buffer[x.a];
+            fold_len[v] = 2;
+        } else if (fold_len[x.a] > 0 && fold_first[x.a] + fold_len[x.a] == bb && s.buffers[fold_first[x.a]].ext == V[x.b].a && n_uses[x.a] == 1 &&
+                   s.value_buffer[x.a] < 0 && st[x.a] == st[v]) {
+            fold_first[v] = fold_first[x.a];
+            fold_len[v] = fold_len[x.a] + 1;
+            absorbed[x.a] = 1;
+        }
+    }
+
     for (uint32_t sg = 0; sg < n_stages; sg++) {
         struct VI { uint8_t op; uint32_t flags; uint32_t dst, a, b, aux; };   // with virtual registers
         std::vector<VI> code;
@@ -341,8 +367,15 @@ Schedule flatten(const Graph& top, uint32_t n_slots, const FlattenEnv& env) {
         };
 
         for (size_t v = 0; v < nv; v++) {
-            if (st[v] != sg) continue;
+            if (st[v] != sg || absorbed[v]) continue;
             const Value& x = V[v];
+            if (fold_len[v] >= 3) {
+                uint32_t dst = new_vreg();
+                code.push_back(VI{I_FOLD, 0, dst, fold_first[v], fold_len[v], 0});
+                vreg_of[v] = dst;
+                emit_sinks((uint32_t)v, 0, dst);
+                continue;
+            }
             if (is_leaf((uint32_t)v) || x.op == V_EXT) {
                 // leaves and extension outputs only appear in a program when they feed a sink directly
                 bool sink = !out_slots_of[v].empty() || (s.value_buffer[v] >= 0 && x.op != V_EXT);
@@ -382,7 +415,7 @@ Schedule flatten(const Graph& top, uint32_t n_slots, const FlattenEnv& env) {
         std::vector<int64_t> last_use(n_vreg, -1);
         for (size_t i = 0; i < code.size(); i++) {
             const VI& c = code[i];
-            bool a_reg = !(c.flags & IF_A_IMM) && c.op != I_LDIN && c.op != I_LDBUF;
+            bool a_reg = !(c.flags & IF_A_IMM) && c.op != I_LDIN && c.op != I_LDBUF && c.op != I_FOLD;
             bool b_reg = !(c.flags & IF_B_IMM) && (c.op == I_ADD || c.op == I_MUL || c.op == I_DIV || c.op == I_MOD || c.op == I_MIN || c.op == I_DLY_TI);
             if (a_reg) last_use[c.a] = (int64_t)i;
             if (b_reg) last_use[c.b] = (int64_t)i;
@@ -392,7 +425,7 @@ Schedule flatten(const Graph& top, uint32_t n_slots, const FlattenEnv& env) {
         Stage& stage = s.stages[sg];
         for (size_t i = 0; i < code.size(); i++) {
             VI c = code[i];
-            bool a_reg = !(c.flags & IF_A_IMM) && c.op != I_LDIN && c.op != I_LDBUF;
+            bool a_reg = !(c.flags & IF_A_IMM) && c.op != I_LDIN && c.op != I_LDBUF && c.op != I_FOLD;
             bool b_reg = !(c.flags & IF_B_IMM) && (c.op == I_ADD || c.op == I_MUL || c.op == I_DIV || c.op == I_MOD || c.op == I_MIN || c.op == I_DLY_TI);
             uint32_t va = c.a, vb = c.b;
             if (a_reg) c.a = phys[va];
@@ -411,6 +444,7 @@ Schedule flatten(const Graph& top, uint32_t n_slots, const FlattenEnv& env) {
             stage.program.push_back(Instr::make(c.op, c.flags, c.dst, c.a, c.b, c.aux));
         }
         stage.program.push_back(Instr::make(I_END, 0, 0, 0, 0, 0));
+        stage.program.push_back(Instr::make(I_END, 0, 0, 0, 0, 0));   // pad: the kernel prefetches one instruction ahead
         stage.n_regs = n_phys;
         if (n_phys > env.max_regs)
             throw Error{FRB_E_UNSUPPORTED, "stage needs " + std::to_string(n_phys) + " live registers; limit " + std::to_string(env.max_regs)};

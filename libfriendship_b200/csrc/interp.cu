@@ -42,18 +42,27 @@ interp_kernel(InterpParams p) {
     extern __shared__ float4 s_regs[];
     const unsigned tid = threadIdx.x;
     const unsigned nthr = blockDim.x;
-    const uint4* __restrict__ prog = reinterpret_cast<const uint4*>(p.program);
+    // the program is staged in shared memory behind the register columns when it fits (broadcast LDS instead of
+    // a dependent global load per interpreted instruction)
+    const uint4* prog = reinterpret_cast<const uint4*>(p.program);
+    if (p.prog_in_smem) {
+        uint4* s_prog = reinterpret_cast<uint4*>(s_regs + (size_t)p.n_regs * nthr);
+        for (unsigned i = tid; i < p.n_instr; i += nthr) s_prog[i] = __ldg(prog + i);
+        __syncthreads();
+        prog = s_prog;
+    }
 
     for (unsigned long long g = (unsigned long long)blockIdx.x * nthr + tid; g < p.n_groups;
          g += (unsigned long long)gridDim.x * nthr) {
         const unsigned long long t = p.t_begin + 4ull * g;        // absolute time of element 0; multiple of 4
 #define REG(r) s_regs[(r) * nthr + tid]
+        uint4 ins = prog[0];
         for (unsigned pc = 0;; pc++) {
-            const uint4 ins = __ldg(prog + pc);
+            const uint4 nxt = prog[pc + 1];                       // prefetch (programs end with two I_ENDs)
             const unsigned op = ins.x & 0xFFu, flags = (ins.x >> 8) & 0xFFu, dst = ins.x >> 16;
             if (op == I_END) break;
             float4 a, b;
-            if (op != I_LDIN && op != I_LDBUF) {
+            if (op != I_LDIN && op != I_LDBUF && op != I_FOLD) {
                 if (flags & IF_A_IMM) { float v = __uint_as_float(ins.y); a = make_float4(v, v, v, v); }
                 else a = REG(ins.y);
             }
@@ -85,6 +94,32 @@ interp_kernel(InterpParams p) {
                 case I_LDBUF: {
                     const BufferDesc bd = p.buffers[ins.w];
                     REG(dst) = *reinterpret_cast<const float4*>(bd.data + (t & bd.mask));
+                    break;
+                }
+                case I_FOLD: {
+                    // left fold of ins.z consecutive planes starting at buffer ins.y: the Sum2 chain's own order
+                    // the lanes of one extension instance are one allocation: plane i = base + i * stride
+                    const BufferDesc b0 = p.buffers[ins.y];
+                    const unsigned long long stride = (unsigned long long)(p.buffers[ins.y + 1].data - b0.data);
+                    const float* base = b0.data + (t & b0.mask);
+                    float4 acc = *reinterpret_cast<const float4*>(base);
+                    unsigned i = 1;
+                    for (; i + 16 <= ins.z; i += 16) {             // 16 independent plane loads in flight, then the ordered adds
+                        float4 v[16];
+#pragma unroll
+                        for (int q = 0; q < 16; q++) v[q] = *reinterpret_cast<const float4*>(base + (unsigned long long)(i + q) * stride);
+#pragma unroll
+                        for (int q = 0; q < 16; q++) {
+                            acc.x = __fadd_rn(acc.x, v[q].x); acc.y = __fadd_rn(acc.y, v[q].y);
+                            acc.z = __fadd_rn(acc.z, v[q].z); acc.w = __fadd_rn(acc.w, v[q].w);
+                        }
+                    }
+                    for (; i < ins.z; i++) {
+                        const float4 v = *reinterpret_cast<const float4*>(base + (unsigned long long)i * stride);
+                        acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y);
+                        acc.z = __fadd_rn(acc.z, v.z); acc.w = __fadd_rn(acc.w, v.w);
+                    }
+                    REG(dst) = acc;
                     break;
                 }
                 case I_STBUF: {
@@ -145,27 +180,33 @@ interp_kernel(InterpParams p) {
                 }
                 default: break;
             }
+            ins = nxt;
         }
 #undef REG
     }
 }
 
-cudaError_t launch_interp(const InterpParams& p, unsigned n_regs, int sm_count, cudaStream_t stream) {
-    if (p.n_groups == 0) return cudaSuccess;
+cudaError_t launch_interp(const InterpParams& p_in, unsigned n_regs, int sm_count, cudaStream_t stream) {
+    if (p_in.n_groups == 0) return cudaSuccess;
+    InterpParams p = p_in;
     const unsigned threads = INTERP_THREADS;
-    size_t smem = (size_t)(n_regs ? n_regs : 1) * threads * sizeof(float4);
+    p.n_regs = n_regs ? n_regs : 1;
+    size_t smem = (size_t)p.n_regs * threads * sizeof(float4);
+    const size_t prog_bytes = (size_t)p.n_instr * sizeof(uint4);
+    p.prog_in_smem = (prog_bytes <= 48 * 1024 && smem + prog_bytes <= 200 * 1024) ? 1u : 0u;
+    if (p.prog_in_smem) smem += prog_bytes;
     unsigned long long blocks = (p.n_groups + threads - 1) / threads;
     // persistent-style grid: a multiple of the SM count, enough CTAs per SM to cover latency
     unsigned long long per_sm = 227ull * 1024ull / (smem + 1024);
-    if (per_sm > 8) per_sm = 8;
+    if (per_sm > 12) per_sm = 12;
     if (per_sm < 1) per_sm = 1;
     unsigned long long cap = (unsigned long long)sm_count * per_sm;
     if (blocks > cap) blocks = cap;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    static bool configured = false;
+    if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(interp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
         if (e != cudaSuccess) return e;
-        configured = 227 * 1024;
+        configured = true;
     }
     interp_kernel<<<(unsigned)blocks, threads, smem, stream>>>(p);
     return cudaGetLastError();

@@ -25,6 +25,9 @@ struct BufferDesc {
 
 struct InterpParams {
     const uint32_t* program;        // device: Instr words
+    unsigned n_instr;               // including the trailing I_END pair
+    unsigned n_regs;                // set by launch_interp: float4 register columns per thread
+    unsigned prog_in_smem;          // set by launch_interp: the program is staged in shared memory
     const InputDesc* inputs;        // device table, indexed by external input slot
     const BufferDesc* buffers;      // device table, indexed by buffer id
     float* out;                     // device: [n_slots x out_stride], column 0 == time t0

@@ -396,10 +396,27 @@ __global__ void osc_reduce_kernel(OscLaunch p) {
     }
 }
 
+static cudaError_t launch_osc_range(const OscBankDev& b, const BufferDesc* d_bufdesc, uint32_t first_buf, uint64_t lo, uint64_t hi,
+                                    uint32_t anchor, int sm_count, cudaStream_t stream, uint64_t* n_launches);
+
 cudaError_t launch_osc(const OscBankDev& b, const BufferDesc* d_bufdesc, uint32_t first_buf, uint64_t lo, uint64_t hi,
                        uint32_t anchor, int sm_count, cudaStream_t stream, uint64_t* n_launches) {
     if (n_launches) *n_launches = 0;
     if (hi <= lo || b.n_voices == 0) return cudaSuccess;
+    // split banks stage their partial-range planes in scratch: bound it by rendering 64 Ki samples at a time
+    if (b.split == 1) return launch_osc_range(b, d_bufdesc, first_buf, lo, hi, anchor, sm_count, stream, n_launches);
+    const uint64_t sub = 1ull << 16;
+    for (uint64_t c0 = lo; c0 < hi;) {
+        const uint64_t c1 = std::min(hi, (c0 / sub + 1) * sub);
+        cudaError_t e = launch_osc_range(b, d_bufdesc, first_buf, c0, c1, anchor, sm_count, stream, n_launches);
+        if (e != cudaSuccess) return e;
+        c0 = c1;
+    }
+    return cudaSuccess;
+}
+
+static cudaError_t launch_osc_range(const OscBankDev& b, const BufferDesc* d_bufdesc, uint32_t first_buf, uint64_t lo, uint64_t hi,
+                                    uint32_t anchor, int sm_count, cudaStream_t stream, uint64_t* n_launches) {
     int L = anchor ? (int)anchor : 128;
     L = std::max(16, std::min(OSC_LMAX, (L / 16) * 16));
     OscLaunch p;

@@ -169,9 +169,9 @@ void Renderer::del_edge(const frb_edge& e) {                               // re
 void Renderer::free_device_schedule() {
     for (auto p : d_programs_) if (p) cudaFree(p);
     d_programs_.clear();
-    for (auto& b : h_bufdesc_) if (b.data) cudaFree(b.data);
+    for (auto& g : ring_groups_) if (g.data) cudaFree(g.data);
+    ring_groups_.clear();
     h_bufdesc_.clear();
-    ring_cap_.clear();
     for (auto p : d_ext_in_bufs_) if (p) cudaFree(p);
     d_ext_in_bufs_.clear();
 }
@@ -221,8 +221,15 @@ void Renderer::upload_schedule() {
         CU(cudaMemcpyAsync(d_programs_[i], prog.data(), bytes, cudaMemcpyHostToDevice, stream_));
         stats.h2d_bytes += bytes;
     }
+    // Block length: as long as the rings allow (more samples per launch = more parallelism for the stage kernels),
+    // with the ring memory (<= 2 x block x 4 B per ring) kept under ~8 GB.
+    {
+        const uint64_t nb = std::max<uint64_t>(sched_.buffers.size(), 1);
+        uint64_t c = 1ull << 20;
+        while (c > (1ull << 14) && 2 * c * nb > (1ull << 31)) c >>= 1;
+        chunk_ = c;
+    }
     h_bufdesc_.assign(sched_.buffers.size(), BufferDesc{nullptr, 0});
-    ring_cap_.assign(sched_.buffers.size(), 0);
     bufdesc_dirty_ = true;
     d_ext_in_bufs_.assign(sched_.ext.size(), nullptr);
     for (size_t i = 0; i < sched_.ext.size(); i++) {
@@ -234,26 +241,46 @@ void Renderer::upload_schedule() {
     CU(cudaStreamSynchronize(stream_));   // host vectors above may go away
 }
 
-// Ring buffers: capacity = pow2 >= lookback + chunk (+ slack); LOOKBACK_FULL rings hold [0, t_end).
+// Ring buffers: capacity = pow2 >= lookback + block (+ slack); LOOKBACK_FULL rings hold [0, t_end).
+// The lanes of one extension instance share one allocation, lane l at base + l * capacity (they have the same
+// lookback), so a fold over consecutive lanes needs no per-plane descriptor.
 void Renderer::ensure_rings(uint64_t t_end) {
-    for (size_t i = 0; i < sched_.buffers.size(); i++) {
-        const BufferInfo& b = sched_.buffers[i];
-        uint64_t need = (b.lookback == LOOKBACK_FULL) ? pow2_ceil(t_end + 8) : pow2_ceil(b.lookback + chunk_ + 8);
-        if (need <= ring_cap_[i]) continue;
-        float* nd = nullptr;
-        CU(cudaMalloc(&nd, need * sizeof(float)));
-        CU(cudaMemsetAsync(nd, 0, need * sizeof(float), stream_));
-        if (h_bufdesc_[i].data) {
-            if (b.lookback == LOOKBACK_FULL)   // index t & mask == t for t < old capacity: a prefix copy preserves history
-                CU(cudaMemcpyAsync(nd, h_bufdesc_[i].data, ring_cap_[i] * sizeof(float), cudaMemcpyDeviceToDevice, stream_));
-            else
-                cache_valid_ = false;
-            CU(cudaStreamSynchronize(stream_));
-            CU(cudaFree(h_bufdesc_[i].data));
+    if (ring_groups_.empty() && !sched_.buffers.empty()) {
+        for (size_t i = 0; i < sched_.buffers.size();) {
+            size_t n = 1;
+            if (sched_.buffers[i].ext != ~0u)
+                while (i + n < sched_.buffers.size() && sched_.buffers[i + n].ext == sched_.buffers[i].ext) n++;
+            ring_groups_.push_back(RingGroup{(uint32_t)i, (uint32_t)n, nullptr, 0});
+            i += n;
         }
-        h_bufdesc_[i].data = nd;
-        h_bufdesc_[i].mask = need - 1;
-        ring_cap_[i] = need;
+    }
+    for (auto& g : ring_groups_) {
+        const BufferInfo& b = sched_.buffers[g.first];
+        const bool full = b.lookback == LOOKBACK_FULL;
+        uint64_t need = full ? pow2_ceil(t_end + 8) : pow2_ceil(b.lookback + chunk_ + 8);
+        if (need <= g.cap) continue;
+        // lane stride = capacity + 96 floats: consecutive lanes must not sit at the same power-of-two offset (the
+        // fold reads the same time index of every lane back to back)
+        const uint64_t lstride = need + (g.count > 1 ? 96 : 0);
+        float* nd = nullptr;
+        CU(cudaMalloc(&nd, (size_t)g.count * lstride * sizeof(float)));
+        CU(cudaMemsetAsync(nd, 0, (size_t)g.count * lstride * sizeof(float), stream_));
+        if (g.data) {
+            if (full) {   // index t & mask == t for t < old capacity: a prefix copy per lane preserves the history
+                for (uint32_t l = 0; l < g.count; l++)
+                    CU(cudaMemcpyAsync(nd + (size_t)l * lstride, g.data + (size_t)l * (g.cap + 96), g.cap * sizeof(float), cudaMemcpyDeviceToDevice, stream_));
+            } else {
+                cache_valid_ = false;
+            }
+            CU(cudaStreamSynchronize(stream_));
+            CU(cudaFree(g.data));
+        }
+        g.data = nd;
+        g.cap = need;
+        for (uint32_t l = 0; l < g.count; l++) {
+            h_bufdesc_[g.first + l].data = nd + (size_t)l * lstride;
+            h_bufdesc_[g.first + l].mask = need - 1;
+        }
         bufdesc_dirty_ = true;
     }
     if (bufdesc_dirty_ && !h_bufdesc_.empty()) {
@@ -400,9 +427,10 @@ void Renderer::run_range(uint64_t lo, uint64_t hi, float* d_out, uint64_t t0, ui
                 }
                 stats.kernel_launches += nl;
             }
-            if (st.program.size() <= 1) continue;   // only I_END
+            if (st.program.size() <= 2) continue;   // only I_END (+ pad)
             InterpParams p;
             p.program = d_programs_[sg];
+            p.n_instr = (unsigned)st.program.size();
             p.inputs = d_indesc_;
             p.buffers = d_bufdesc_;
             p.out = d_out;

@@ -91,7 +91,8 @@ private:
     std::vector<uint32_t*> d_programs_;         // per stage
     std::vector<uint32_t*> d_ext_in_bufs_;      // per extension instance: input ring ids per lane
     std::vector<BufferDesc> h_bufdesc_;
-    std::vector<uint64_t> ring_cap_;
+    struct RingGroup { uint32_t first, count; float* data; uint64_t cap; };   // consecutive buffers in one allocation
+    std::vector<RingGroup> ring_groups_;
     BufferDesc* d_bufdesc_ = nullptr;
     size_t d_bufdesc_cap_ = 0;
     bool bufdesc_dirty_ = true;

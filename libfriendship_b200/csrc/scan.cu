@@ -24,9 +24,10 @@
 
 namespace frb {
 
-constexpr int DF_THREADS = 256;
+constexpr int FB_THREADS = 128;
+constexpr int DF_CTA_THREADS = 128;   // 4 lanes per CTA, one warp each
 constexpr int DF_PER_THREAD = 8;
-constexpr int DF_LEVELS = 8;      // log2(DF_THREADS)
+constexpr int DF_LEVELS = 8;      // stored powers A^(8*2^k), k < 8 (the warp scan uses k < 5)
 
 struct DirectFormDev {
     uint32_t n_lanes = 0;
@@ -102,31 +103,45 @@ __device__ __forceinline__ float ring_at(const BufferDesc& b, long long t) {
     return t >= 0 ? b.data[(unsigned long long)t & b.mask] : 0.0f;    // every signal is 0 before t = 0
 }
 
-__global__ void __launch_bounds__(DF_THREADS)
+// One WARP per lane (4 lanes per CTA): tiles of 32 threads x 8 samples, warp-level scan only, no block barriers.
+__global__ void __launch_bounds__(DF_CTA_THREADS)
 directform_kernel(const float* __restrict__ coef, const float* __restrict__ pw, const BufferDesc* __restrict__ bufdesc,
-                  const uint32_t* __restrict__ in_bufs, uint32_t first_out_buf, unsigned long long lo, unsigned long long hi) {
-    const unsigned lane = blockIdx.x;
-    const unsigned tid = threadIdx.x, wl = tid & 31, wid = tid >> 5;
+                  const uint32_t* __restrict__ in_bufs, uint32_t first_out_buf, unsigned n_lanes,
+                  unsigned long long lo, unsigned long long hi) {
+    const unsigned wl = threadIdx.x & 31;
+    const unsigned lane = blockIdx.x * (DF_CTA_THREADS / 32) + (threadIdx.x >> 5);
+    if (lane >= n_lanes) return;                                   // whole warp exits together
     const BufferDesc xin = bufdesc[in_bufs[lane]];
     const BufferDesc yout = bufdesc[first_out_buf + lane];
     const float b0 = coef[lane * 5 + 0], b1 = coef[lane * 5 + 1], b2 = coef[lane * 5 + 2];
     const float a1 = coef[lane * 5 + 3], a2 = coef[lane * 5 + 4];
-    const float* P = pw + (size_t)lane * DF_LEVELS * 4;
-    __shared__ float2 s_warp[DF_THREADS / 32];     // end state of each warp's span (zero initial state)
-    __shared__ float2 s_carry;                     // (y[t-1], y[t-2]) at the start of the tile
-
-    // carry into the first tile: the last two outputs before lo, re-read from the output ring
-    float y1c = ring_at(yout, (long long)lo - 1), y2c = ring_at(yout, (long long)lo - 2);
-    constexpr int TILE = DF_THREADS * DF_PER_THREAD;
-    for (unsigned long long tb = lo; tb < hi; tb += TILE) {
-        const unsigned long long t0 = tb + (unsigned long long)tid * DF_PER_THREAD;
-        // x[t0-2 .. t0+7]: the thread's 8 samples plus two of history (coalesced: 32 B per thread, contiguous per warp)
-        float x[DF_PER_THREAD + 2];
+    // A^(8*2^k), k = 0..5, in registers (warp-uniform)
+    float P[6][4];
 #pragma unroll
-        for (int j = 0; j < DF_PER_THREAD + 2; j++) {
-            const long long t = (long long)t0 - 2 + j;
-            x[j] = (t >= 0 && (unsigned long long)t < hi) ? xin.data[(unsigned long long)t & xin.mask] : 0.0f;
+    for (int k = 0; k < 6; k++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) P[k][j] = pw[((size_t)lane * DF_LEVELS + k) * 4 + j];
+
+    // carries: the last two outputs and inputs before the tile
+    float y1c = ring_at(yout, (long long)lo - 1), y2c = ring_at(yout, (long long)lo - 2);
+    float x1c = ring_at(xin, (long long)lo - 1), x2c = ring_at(xin, (long long)lo - 2);
+    const bool vec = (lo % 4 == 0);                                // 128-bit accesses when the block start is aligned
+    constexpr int TILE = 32 * DF_PER_THREAD;
+    for (unsigned long long tb = lo; tb < hi; tb += TILE) {
+        const unsigned long long t0 = tb + (unsigned long long)wl * DF_PER_THREAD;
+        float x[DF_PER_THREAD + 2];
+        if (vec && t0 + DF_PER_THREAD <= hi) {
+            const float4 v0 = *reinterpret_cast<const float4*>(xin.data + (t0 & xin.mask));
+            const float4 v1 = *reinterpret_cast<const float4*>(xin.data + ((t0 + 4) & xin.mask));
+            x[2] = v0.x; x[3] = v0.y; x[4] = v0.z; x[5] = v0.w; x[6] = v1.x; x[7] = v1.y; x[8] = v1.z; x[9] = v1.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < DF_PER_THREAD; j++) x[2 + j] = (t0 + j < hi) ? xin.data[(t0 + j) & xin.mask] : 0.0f;
         }
+        // two samples of history from the previous thread (lane 0: from the carry)
+        const float px1 = __shfl_up_sync(0xffffffffu, x[9], 1), px2 = __shfl_up_sync(0xffffffffu, x[8], 1);
+        x[1] = wl ? px1 : x1c;
+        x[0] = wl ? px2 : x2c;
         float u[DF_PER_THREAD];
 #pragma unroll
         for (int j = 0; j < DF_PER_THREAD; j++) u[j] = fmaf(b2, x[j], fmaf(b1, x[j + 1], b0 * x[j + 2]));
@@ -137,77 +152,81 @@ directform_kernel(const float* __restrict__ coef, const float* __restrict__ pw, 
             const float y = fmaf(-a2, e2, fmaf(-a1, e1, u[j]));
             e2 = e1; e1 = y;
         }
-        // inclusive scan within the warp: v_i <- v_i + A^(8*2^k) v_(i-2^k)
+        // inclusive scan over the warp: v_i <- v_i + A^(8*2^k) v_(i-2^k)
         float v1 = e1, v2 = e2;
 #pragma unroll
         for (int k = 0; k < 5; k++) {
             const float o1 = __shfl_up_sync(0xffffffffu, v1, 1u << k), o2 = __shfl_up_sync(0xffffffffu, v2, 1u << k);
             if (wl >= (1u << k)) {
-                v1 += P[k * 4 + 0] * o1 + P[k * 4 + 1] * o2;
-                v2 += P[k * 4 + 2] * o1 + P[k * 4 + 3] * o2;
+                v1 += P[k][0] * o1 + P[k][1] * o2;
+                v2 += P[k][2] * o1 + P[k][3] * o2;
             }
         }
-        if (wl == 31) s_warp[wid] = make_float2(v1, v2);
-        if (tid == 0) s_carry = make_float2(y1c, y2c);
-        __syncthreads();
-        // state entering this warp = A^(256 * wid) carry + sum over earlier warps, built sequentially (8 warps)
-        float w1 = s_carry.x, w2 = s_carry.y;          // state at the tile start
-        for (unsigned w = 0; w < wid; w++) {
-            // advance one warp span (256 samples = A^(8*32) = level 5) and add that warp's zero-state end
-            const float n1 = P[5 * 4 + 0] * w1 + P[5 * 4 + 1] * w2 + s_warp[w].x;
-            const float n2 = P[5 * 4 + 2] * w1 + P[5 * 4 + 3] * w2 + s_warp[w].y;
-            w1 = n1; w2 = n2;
-        }
-        // state entering this thread = A^(8 * wl) (warp entry state) + exclusive warp prefix
+        // state entering this thread = A^(8*wl) carry + exclusive prefix
         float p1 = __shfl_up_sync(0xffffffffu, v1, 1), p2 = __shfl_up_sync(0xffffffffu, v2, 1);
         if (wl == 0) { p1 = 0.f; p2 = 0.f; }
-        // A^(8*wl) w: apply the binary decomposition of wl with the precomputed powers
-        float h1 = w1, h2 = w2;
+        float h1 = y1c, h2 = y2c;
 #pragma unroll
         for (int k = 0; k < 5; k++) {
             if (wl & (1u << k)) {
-                const float n1 = P[k * 4 + 0] * h1 + P[k * 4 + 1] * h2;
-                const float n2 = P[k * 4 + 2] * h1 + P[k * 4 + 3] * h2;
+                const float n1 = P[k][0] * h1 + P[k][1] * h2;
+                const float n2 = P[k][2] * h1 + P[k][3] * h2;
                 h1 = n1; h2 = n2;
             }
         }
-        float y1 = h1 + p1, y2 = h2 + p2;               // (y[t0-1], y[t0-2])
-        // the thread's 8 samples from the true state
+        float y1 = h1 + p1, y2 = h2 + p2;                           // (y[t0-1], y[t0-2])
         float yv[DF_PER_THREAD];
 #pragma unroll
         for (int j = 0; j < DF_PER_THREAD; j++) {
             const float y = fmaf(-a2, y2, fmaf(-a1, y1, u[j]));
             yv[j] = y; y2 = y1; y1 = y;
         }
+        if (vec && t0 + DF_PER_THREAD <= hi) {
+            *reinterpret_cast<float4*>(yout.data + (t0 & yout.mask)) = make_float4(yv[0], yv[1], yv[2], yv[3]);
+            *reinterpret_cast<float4*>(yout.data + ((t0 + 4) & yout.mask)) = make_float4(yv[4], yv[5], yv[6], yv[7]);
+        } else {
 #pragma unroll
-        for (int j = 0; j < DF_PER_THREAD; j++)
-            if (t0 + j < hi) yout.data[(t0 + j) & yout.mask] = yv[j];
-        // carry to the next tile = state after the last thread
-        __syncthreads();
-        if (tid == DF_THREADS - 1) s_carry = make_float2(y1, y2);
-        __syncthreads();
-        y1c = s_carry.x; y2c = s_carry.y;
-        __syncthreads();
+            for (int j = 0; j < DF_PER_THREAD; j++)
+                if (t0 + j < hi) yout.data[(t0 + j) & yout.mask] = yv[j];
+        }
+        // carries for the next tile come from the last thread
+        y1c = __shfl_sync(0xffffffffu, y1, 31); y2c = __shfl_sync(0xffffffffu, y2, 31);
+        x1c = __shfl_sync(0xffffffffu, x[9], 31); x2c = __shfl_sync(0xffffffffu, x[8], 31);
     }
 }
 
-__global__ void __launch_bounds__(256)
+// Phase j of the delay line (t = lo + j + k D) only ever depends on itself, so one thread carries y[t - D] in a
+// register and walks k; the D phases of a lane run in parallel with no barrier at all.  Loads of x are independent of
+// the recurrence and are issued four steps ahead.
+__global__ void __launch_bounds__(FB_THREADS)
 fbdelay_kernel(const uint32_t* __restrict__ delay, const float* __restrict__ gain, const BufferDesc* __restrict__ bufdesc,
                const uint32_t* __restrict__ in_bufs, uint32_t first_out_buf, unsigned long long lo, unsigned long long hi) {
-    const unsigned lane = blockIdx.x;
+    const unsigned lane = blockIdx.y;
     const BufferDesc xin = bufdesc[in_bufs[lane]];
     const BufferDesc yout = bufdesc[first_out_buf + lane];
     const unsigned long long D = delay[lane];
     const float g = gain[lane];
-    for (unsigned long long base = lo; base < hi; base += D) {
-        const unsigned long long n = min(D, hi - base);
-        for (unsigned long long j = threadIdx.x; j < n; j += blockDim.x) {
-            const unsigned long long t = base + j;
-            const float yd = (t >= D) ? yout.data[(t - D) & yout.mask] : 0.0f;
-            // two roundings, like a sequential f32 evaluation: x + (g * y[n-D])
-            yout.data[t & yout.mask] = __fadd_rn(xin.data[t & xin.mask], __fmul_rn(g, yd));
+    for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < D;
+         j += (unsigned long long)gridDim.x * blockDim.x) {
+        unsigned long long t = lo + j;
+        if (t >= hi) break;
+        float yp = (t >= D) ? yout.data[(t - D) & yout.mask] : 0.0f;
+        for (; t + 3 * D < hi; t += 4 * D) {
+            const float x0 = xin.data[t & xin.mask], x1 = xin.data[(t + D) & xin.mask];
+            const float x2 = xin.data[(t + 2 * D) & xin.mask], x3 = xin.data[(t + 3 * D) & xin.mask];
+            // two roundings per step, like a sequential f32 evaluation: x + (g * y[n-D])
+            const float y0 = __fadd_rn(x0, __fmul_rn(g, yp));
+            const float y1 = __fadd_rn(x1, __fmul_rn(g, y0));
+            const float y2 = __fadd_rn(x2, __fmul_rn(g, y1));
+            const float y3 = __fadd_rn(x3, __fmul_rn(g, y2));
+            yout.data[t & yout.mask] = y0; yout.data[(t + D) & yout.mask] = y1;
+            yout.data[(t + 2 * D) & yout.mask] = y2; yout.data[(t + 3 * D) & yout.mask] = y3;
+            yp = y3;
         }
-        __syncthreads();    // writes of this step are read D samples later by other threads of this CTA
+        for (; t < hi; t += D) {
+            yp = __fadd_rn(xin.data[t & xin.mask], __fmul_rn(g, yp));
+            yout.data[t & yout.mask] = yp;
+        }
     }
 }
 
@@ -215,7 +234,8 @@ cudaError_t launch_directform(const DirectFormDev& f, const BufferDesc* d_bufdes
                               uint32_t first_out_buf, uint64_t lo, uint64_t hi, int, cudaStream_t stream, uint64_t* n_launches) {
     if (n_launches) *n_launches = 0;
     if (hi <= lo || f.n_lanes == 0) return cudaSuccess;
-    directform_kernel<<<f.n_lanes, DF_THREADS, 0, stream>>>(f.d_coef, f.d_pow, d_bufdesc, d_in_bufs, first_out_buf, lo, hi);
+    const unsigned per_cta = DF_CTA_THREADS / 32;
+    directform_kernel<<<(f.n_lanes + per_cta - 1) / per_cta, DF_CTA_THREADS, 0, stream>>>(f.d_coef, f.d_pow, d_bufdesc, d_in_bufs, first_out_buf, f.n_lanes, lo, hi);
     if (n_launches) *n_launches = 1;
     return cudaGetLastError();
 }
@@ -224,7 +244,8 @@ cudaError_t launch_fbdelay(const FbDelayDev& f, const BufferDesc* d_bufdesc, con
                            uint32_t first_out_buf, uint64_t lo, uint64_t hi, int, cudaStream_t stream, uint64_t* n_launches) {
     if (n_launches) *n_launches = 0;
     if (hi <= lo || f.n_lanes == 0) return cudaSuccess;
-    fbdelay_kernel<<<f.n_lanes, 256, 0, stream>>>(f.d_delay, f.d_gain, d_bufdesc, d_in_bufs, first_out_buf, lo, hi);
+    const unsigned bx = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((f.max_delay + FB_THREADS - 1) / FB_THREADS, 64));
+    fbdelay_kernel<<<dim3(bx, f.n_lanes), FB_THREADS, 0, stream>>>(f.d_delay, f.d_gain, d_bufdesc, d_in_bufs, first_out_buf, lo, hi);
     if (n_launches) *n_launches = 1;
     return cudaGetLastError();
 }

@@ -59,6 +59,7 @@ enum InstrOp : uint8_t {
     I_STBUF = 11,    // buffer[aux](t) = a
     I_STOUT = 12,    // out[aux](t - t0) = a
     I_MOV = 13,      // dst = a
+    I_FOLD = 14,     // dst = ((buffer[a] + buffer[a+1]) + ...) + buffer[a+b-1]   left fold of b consecutive planes (a Sum2 chain)
 };
 constexpr uint32_t IF_A_IMM = 1u;   // a is an immediate f32 bit pattern, not a register
 constexpr uint32_t IF_B_IMM = 2u;

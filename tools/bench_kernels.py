@@ -1,0 +1,103 @@
+"""GPU-box helper: measures the HBM-bound kernels (K2/K3 fused elementwise + Delay, K4 recurrences) against the
+measured HBM peak, device-resident, CUDA-event timed through frb_set_profiling.  Prints one JSON line per case."""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np
+import torch
+
+from libfriendship_b200 import (B200Renderer, KIND_DELAY, KIND_F32CONSTANT, KIND_MULTIPLY, KIND_SUM2)
+from graphs import GraphBuilder, f32_bits
+
+HBM = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6535.7) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6535.7
+
+
+def timed_fill(r, d_out, n_slots, n, idx, d_in=0, offs=None, reps=5):
+    for _ in range(2):
+        r.fill_buffer_device(d_out.data_ptr(), n_slots, n, 0, d_in, offs)   # idx 0 every time = seek: full recompute
+    r.sync()
+    r.set_profiling(True)
+    best = None
+    for _ in range(reps):
+        r.fill_buffer_device(d_out.data_ptr(), n_slots, n, 0, d_in, offs)
+        r.sync()
+        t = r.timing()
+        if best is None or t["total_ms"] < best["total_ms"]:
+            best = t
+    r.set_profiling(False)
+    return best
+
+
+def case_elementwise(n_slots=64, n=1 << 22):
+    """out_s = 0.5*in_s + 0.35*Delay(0.5*in_s, 12000)  for s in slots: reads one input plane, writes one output plane
+    (+ the materialised delay source: one ring write + one ring read).  Algorithmic: 8 B/sample (in + out)."""
+    r = B200Renderer()
+    g = GraphBuilder(r)
+    for s in range(n_slots):
+        x = g.input(s)
+        gain = g.node(KIND_MULTIPLY, x, g.const(0.5))
+        d = g.node(KIND_DELAY, gain, g.const(12000.0))
+        e = g.node(KIND_MULTIPLY, d, g.const(0.35))
+        g.output(s, g.node(KIND_SUM2, gain, e))
+    x = torch.rand((n_slots, n), dtype=torch.float32, device="cuda")
+    out = torch.empty((n_slots, n), dtype=torch.float32, device="cuda")
+    offs = np.arange(n_slots + 1, dtype=np.uint64) * n
+    t = timed_fill(r, out, n_slots, n, 0, x.data_ptr(), offs)
+    alg = 8.0 * n_slots * n
+    return {"case": "K2/K3 fused elementwise+Delay", "slots": n_slots, "samples": n, "ms": t["total_ms"], "interp_ms": t["interp_ms"],
+            "algorithmic_GBs": alg / t["interp_ms"] / 1e6, "peak_GBs": HBM, "frac": alg / t["interp_ms"] / 1e6 / HBM,
+            "note": "total_ms includes the D2D ingest of the input rows into the history buffers"}
+
+
+def case_pure_elementwise(n_slots=64, n=1 << 22):
+    """out_s = (in_s * 0.5 + 0.25) min in_s : no Delay, single stage; 8 B/sample."""
+    from libfriendship_b200 import KIND_MINIMUM
+    r = B200Renderer()
+    g = GraphBuilder(r)
+    for s in range(n_slots):
+        x = g.input(s)
+        a = g.node(KIND_MULTIPLY, x, g.const(0.5))
+        b = g.node(KIND_SUM2, a, g.const(0.25))
+        g.output(s, g.node(KIND_MINIMUM, b, x))
+    x = torch.rand((n_slots, n), dtype=torch.float32, device="cuda")
+    out = torch.empty((n_slots, n), dtype=torch.float32, device="cuda")
+    offs = np.arange(n_slots + 1, dtype=np.uint64) * n
+    t = timed_fill(r, out, n_slots, n, 0, x.data_ptr(), offs)
+    alg = 8.0 * n_slots * n
+    return {"case": "K2 pure elementwise (3 nodes/slot)", "slots": n_slots, "samples": n, "ms": t["total_ms"], "interp_ms": t["interp_ms"],
+            "algorithmic_GBs": alg / t["interp_ms"] / 1e6, "peak_GBs": HBM, "frac": alg / t["interp_ms"] / 1e6 / HBM}
+
+
+def case_cfg3(n_voices=4096, n=480000):
+    """cfg3: per voice 1-partial oscillator -> biquad -> feedback delay, mixed to one slot.  K4 algorithmic traffic:
+    8 B per voice-sample per node (2 nodes)."""
+    from banks import detuned_bank
+    from filters import build_cfg3_graph
+    r = B200Renderer()
+    bank, _ = detuned_bank(n_voices, 1, seed=5)
+    build_cfg3_graph(r, n_voices, excitation="osc", bank=bank, mix_to_one=True)
+    out = torch.empty((1, n), dtype=torch.float32, device="cuda")
+    t = timed_fill(r, out, 1, n, 0, reps=3)
+    alg = 16.0 * n_voices * n
+    return {"case": "cfg3 osc->DirectForm->FbDelay->mix", "voices": n_voices, "samples": n, "ms": t["total_ms"], "scan_ms": t["scan_ms"],
+            "osc_ms": t["osc_ms"], "interp_ms": t["interp_ms"], "K4_algorithmic_GBs": alg / t["scan_ms"] / 1e6, "peak_GBs": HBM,
+            "K4_frac": alg / t["scan_ms"] / 1e6 / HBM, "voice_samples_per_s": n_voices * n / (t["total_ms"] * 1e-3)}
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["pure", "elementwise", "cfg3"]
+    for w in which:
+        fn = {"pure": case_pure_elementwise, "elementwise": case_elementwise, "cfg3": case_cfg3}[w]
+        t0 = time.time()
+        try:
+            res = fn()
+        except Exception as e:
+            res = {"case": w, "error": repr(e)}
+        res["wall_s"] = time.time() - t0
+        print(json.dumps(res), flush=True)
