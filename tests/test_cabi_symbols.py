@@ -6,10 +6,10 @@ import re
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def declared_symbols():
-    text = open(os.path.join(ROOT, "include", "friendship_b200.h")).read()
+def declared_symbols(header="friendship_b200.h", prefix="frb"):
+    text = open(os.path.join(ROOT, "include", header)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(frb_[a-z_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(%s_[a-z0-9_]+)\s*\(" % prefix, text)))
 
 
 def test_every_declared_symbol_is_exported():
@@ -20,6 +20,10 @@ def test_every_declared_symbol_is_exported():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in the header but not exported"
     assert set(L._cabi.EXPORTS) == set(syms)
+    dsyms = declared_symbols("friendship_dispatch.h", "frd")
+    assert len(dsyms) >= 14
+    for s in dsyms:
+        assert hasattr(lib, s), f"{s} declared in friendship_dispatch.h but not exported"
 
 
 def test_no_cpu_fallback_without_device():
