@@ -179,20 +179,23 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    rstream = sr.render_stream()
+
     def timed(fn, steps):
+        # CUDA events on the stream the kernels are launched on (the renderer's own stream); every step ends with a
+        # device sync (renderer stream, and the collective's stream for N > 1), so the bracket covers all the work.
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
-        ev0.record()
+        ev0.record(rstream)
         t0 = time.perf_counter()
         for _ in range(steps):
             fn()
-        ev1.record()
+        ev1.record(rstream)
+        ev1.synchronize()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         barrier()
-        # the renderer runs on its own stream and every step ends with a host sync on it, so the wall clock of the
-        # synchronized loop is the device time of the steps; take the larger of the two clocks
-        ms = max(ev0.elapsed_time(ev1), wall * 1e3)
+        ms = max(ev0.elapsed_time(ev1), wall * 1e3)      # wall clock of the synchronized loop as a cross-check
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -32,7 +32,7 @@
 
 namespace frb {
 
-constexpr int OSC_K = 8;            // partials per group (independent FMA chains per thread)
+constexpr int OSC_K = 16;           // partials per group (independent FMA chains per thread)
 constexpr int OSC_THREADS = 32;     // threads (= time segments) per CTA: one warp, so the per-group barrier couples no warps
 constexpr int OSC_LMAX = 256;       // max segment length (shared memory: L * THREADS * 4 B)
 

@@ -38,7 +38,14 @@ class ShardedRenderer:
         if self.world_size > 1:
             import torch.distributed as dist
             dist.reduce(out, dst=0, op=dist.ReduceOp.SUM)   # the path's single exchange step
+            if self.on_gpu:
+                # the next render (renderer stream) overwrites this block: the collective must have read it first
+                torch.cuda.current_stream(self.device).synchronize()
         return out
+
+    def render_stream(self):
+        """The CUDA stream the renderer launches on, as a torch stream (for CUDA-event timing)."""
+        return torch.cuda.ExternalStream(self.r.stream(), device=f"cuda:{self.device}")
 
     def fill_buffer_device(self, n_slots, n_times, idx, inputs=None):
         """Renders this rank's shard and reduces onto rank 0.  Returns the block tensor (valid on rank 0)."""
