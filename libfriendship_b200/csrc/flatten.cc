@@ -370,10 +370,21 @@ Schedule flatten(const Graph& top, uint32_t n_slots, const FlattenEnv& env) {
             if (st[v] != sg || absorbed[v]) continue;
             const Value& x = V[v];
             if (fold_len[v] >= 3) {
-                uint32_t dst = new_vreg();
-                code.push_back(VI{I_FOLD, 0, dst, fold_first[v], fold_len[v], 0});
-                vreg_of[v] = dst;
-                emit_sinks((uint32_t)v, 0, dst);
+                // the fold kernel materialises the chain's value; the program only routes it to its sinks
+                if (s.value_buffer[v] < 0) {
+                    s.value_buffer[v] = (int32_t)s.buffers.size();
+                    BufferInfo b;
+                    b.value = (uint32_t)v;
+                    b.lookback = L[v];
+                    s.buffers.push_back(b);
+                }
+                s.stages[sg].folds.push_back(FoldJob{fold_first[v], fold_len[v], (uint32_t)s.value_buffer[v]});
+                if (!out_slots_of[v].empty()) {
+                    uint32_t dst = new_vreg();
+                    code.push_back(VI{I_LDBUF, 0, dst, 0, 0, (uint32_t)s.value_buffer[v]});
+                    vreg_of[v] = dst;
+                    for (uint32_t k : out_slots_of[v]) code.push_back(VI{I_STOUT, 0, NOREG, dst, 0, k});
+                }
                 continue;
             }
             if (is_leaf((uint32_t)v) || x.op == V_EXT) {
@@ -415,7 +426,7 @@ Schedule flatten(const Graph& top, uint32_t n_slots, const FlattenEnv& env) {
         std::vector<int64_t> last_use(n_vreg, -1);
         for (size_t i = 0; i < code.size(); i++) {
             const VI& c = code[i];
-            bool a_reg = !(c.flags & IF_A_IMM) && c.op != I_LDIN && c.op != I_LDBUF && c.op != I_FOLD;
+            bool a_reg = !(c.flags & IF_A_IMM) && c.op != I_LDIN && c.op != I_LDBUF;
             bool b_reg = !(c.flags & IF_B_IMM) && (c.op == I_ADD || c.op == I_MUL || c.op == I_DIV || c.op == I_MOD || c.op == I_MIN || c.op == I_DLY_TI);
             if (a_reg) last_use[c.a] = (int64_t)i;
             if (b_reg) last_use[c.b] = (int64_t)i;
@@ -425,7 +436,7 @@ Schedule flatten(const Graph& top, uint32_t n_slots, const FlattenEnv& env) {
         Stage& stage = s.stages[sg];
         for (size_t i = 0; i < code.size(); i++) {
             VI c = code[i];
-            bool a_reg = !(c.flags & IF_A_IMM) && c.op != I_LDIN && c.op != I_LDBUF && c.op != I_FOLD;
+            bool a_reg = !(c.flags & IF_A_IMM) && c.op != I_LDIN && c.op != I_LDBUF;
             bool b_reg = !(c.flags & IF_B_IMM) && (c.op == I_ADD || c.op == I_MUL || c.op == I_DIV || c.op == I_MOD || c.op == I_MIN || c.op == I_DLY_TI);
             uint32_t va = c.a, vb = c.b;
             if (a_reg) c.a = phys[va];

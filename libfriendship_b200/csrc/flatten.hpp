@@ -12,7 +12,7 @@ struct FlattenEnv {
     std::function<int64_t(uint32_t kind, uint64_t key)> ext_lanes;
     // largest per-lane delay of a feedback-delay definition
     std::function<uint64_t(uint64_t key)> ext_max_delay;
-    uint32_t max_regs = 96;   // float4 registers per thread the interpreter kernel can hold in shared memory
+    uint32_t max_regs = 48;   // registers (8 samples each) per thread the interpreter kernel can hold in shared memory
 };
 
 // Throws frb::Error.

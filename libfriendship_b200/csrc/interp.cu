@@ -37,16 +37,19 @@ __device__ __forceinline__ float op_mod(float a, float b) {
     return (r < 0.0f) ? __fadd_rn(r, b) : r;                       // reference.rs:255-261
 }
 
+// Each thread owns INTERP_VW float4 (= 8 consecutive samples): one decoded instruction is applied to both, which
+// halves the interpretive overhead per byte moved (the kernel is instruction-issue bound, not HBM bound, otherwise).
 __global__ void __launch_bounds__(INTERP_THREADS)
 interp_kernel(InterpParams p) {
     extern __shared__ float4 s_regs[];
     const unsigned tid = threadIdx.x;
     const unsigned nthr = blockDim.x;
+    constexpr int VW = INTERP_VW;
     // the program is staged in shared memory behind the register columns when it fits (broadcast LDS instead of
     // a dependent global load per interpreted instruction)
     const uint4* prog = reinterpret_cast<const uint4*>(p.program);
     if (p.prog_in_smem) {
-        uint4* s_prog = reinterpret_cast<uint4*>(s_regs + (size_t)p.n_regs * nthr);
+        uint4* s_prog = reinterpret_cast<uint4*>(s_regs + (size_t)p.n_regs * VW * nthr);
         for (unsigned i = tid; i < p.n_instr; i += nthr) s_prog[i] = __ldg(prog + i);
         __syncthreads();
         prog = s_prog;
@@ -54,128 +57,121 @@ interp_kernel(InterpParams p) {
 
     for (unsigned long long g = (unsigned long long)blockIdx.x * nthr + tid; g < p.n_groups;
          g += (unsigned long long)gridDim.x * nthr) {
-        const unsigned long long t = p.t_begin + 4ull * g;        // absolute time of element 0; multiple of 4
-#define REG(r) s_regs[(r) * nthr + tid]
+        const unsigned long long t0g = p.t_begin + (unsigned long long)(4 * VW) * g;   // absolute time of element 0; multiple of 8
+#define REG(r, w) s_regs[((r) * VW + (w)) * nthr + tid]
         uint4 ins = prog[0];
         for (unsigned pc = 0;; pc++) {
             const uint4 nxt = prog[pc + 1];                       // prefetch (programs end with two I_ENDs)
             const unsigned op = ins.x & 0xFFu, flags = (ins.x >> 8) & 0xFFu, dst = ins.x >> 16;
             if (op == I_END) break;
-            float4 a, b;
-            if (op != I_LDIN && op != I_LDBUF && op != I_FOLD) {
-                if (flags & IF_A_IMM) { float v = __uint_as_float(ins.y); a = make_float4(v, v, v, v); }
-                else a = REG(ins.y);
+            float4 a[VW], b[VW];
+            if (op != I_LDIN && op != I_LDBUF) {
+                if (flags & IF_A_IMM) {
+                    const float v = __uint_as_float(ins.y);
+#pragma unroll
+                    for (int w = 0; w < VW; w++) a[w] = make_float4(v, v, v, v);
+                } else {
+#pragma unroll
+                    for (int w = 0; w < VW; w++) a[w] = REG(ins.y, w);
+                }
+            }
+            if (op <= I_MIN || op == I_DLY_TI) {
+                if (flags & IF_B_IMM) {
+                    const float v = __uint_as_float(ins.z);
+#pragma unroll
+                    for (int w = 0; w < VW; w++) b[w] = make_float4(v, v, v, v);
+                } else {
+#pragma unroll
+                    for (int w = 0; w < VW; w++) b[w] = REG(ins.z, w);
+                }
             }
             switch (op) {
-                case I_ADD: case I_MUL: case I_DIV: case I_MOD: case I_MIN: {
-                    if (flags & IF_B_IMM) { float v = __uint_as_float(ins.z); b = make_float4(v, v, v, v); }
-                    else b = REG(ins.z);
-                    float4 r;
-                    if (op == I_ADD) r = make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w));
-                    else if (op == I_MUL) r = make_float4(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y), __fmul_rn(a.z, b.z), __fmul_rn(a.w, b.w));
-                    else if (op == I_DIV) r = make_float4(__fdiv_rn(a.x, b.x), __fdiv_rn(a.y, b.y), __fdiv_rn(a.z, b.z), __fdiv_rn(a.w, b.w));
-                    else if (op == I_MOD) r = make_float4(op_mod(a.x, b.x), op_mod(a.y, b.y), op_mod(a.z, b.z), op_mod(a.w, b.w));
-                    else r = make_float4(fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z), fminf(a.w, b.w));
-                    REG(dst) = r;
+                case I_ADD:
+#pragma unroll
+                    for (int w = 0; w < VW; w++) REG(dst, w) = make_float4(__fadd_rn(a[w].x, b[w].x), __fadd_rn(a[w].y, b[w].y), __fadd_rn(a[w].z, b[w].z), __fadd_rn(a[w].w, b[w].w));
                     break;
-                }
-                case I_MOV: REG(dst) = a; break;
+                case I_MUL:
+#pragma unroll
+                    for (int w = 0; w < VW; w++) REG(dst, w) = make_float4(__fmul_rn(a[w].x, b[w].x), __fmul_rn(a[w].y, b[w].y), __fmul_rn(a[w].z, b[w].z), __fmul_rn(a[w].w, b[w].w));
+                    break;
+                case I_DIV:
+#pragma unroll
+                    for (int w = 0; w < VW; w++) REG(dst, w) = make_float4(__fdiv_rn(a[w].x, b[w].x), __fdiv_rn(a[w].y, b[w].y), __fdiv_rn(a[w].z, b[w].z), __fdiv_rn(a[w].w, b[w].w));
+                    break;
+                case I_MOD:
+#pragma unroll
+                    for (int w = 0; w < VW; w++) REG(dst, w) = make_float4(op_mod(a[w].x, b[w].x), op_mod(a[w].y, b[w].y), op_mod(a[w].z, b[w].z), op_mod(a[w].w, b[w].w));
+                    break;
+                case I_MIN:
+#pragma unroll
+                    for (int w = 0; w < VW; w++) REG(dst, w) = make_float4(fminf(a[w].x, b[w].x), fminf(a[w].y, b[w].y), fminf(a[w].z, b[w].z), fminf(a[w].w, b[w].w));
+                    break;
+                case I_MOV:
+#pragma unroll
+                    for (int w = 0; w < VW; w++) REG(dst, w) = a[w];
+                    break;
                 case I_LDIN: {
                     const InputDesc in = p.inputs[ins.w];
-                    float4 r;
-                    if (t >= in.base_time && t + 4 <= in.end_time) {
-                        r = *reinterpret_cast<const float4*>(in.data + (t - in.base_time));   // base_time % 4 == 0
-                    } else {
-                        r = make_float4(load_input(in, t), load_input(in, t + 1), load_input(in, t + 2), load_input(in, t + 3));
+#pragma unroll
+                    for (int w = 0; w < VW; w++) {
+                        const unsigned long long t = t0g + 4 * w;
+                        float4 r;
+                        if (t >= in.base_time && t + 4 <= in.end_time) {
+                            r = *reinterpret_cast<const float4*>(in.data + (t - in.base_time));   // base_time % 4 == 0
+                        } else {
+                            r = make_float4(load_input(in, t), load_input(in, t + 1), load_input(in, t + 2), load_input(in, t + 3));
+                        }
+                        REG(dst, w) = r;
                     }
-                    REG(dst) = r;
                     break;
                 }
                 case I_LDBUF: {
                     const BufferDesc bd = p.buffers[ins.w];
-                    REG(dst) = *reinterpret_cast<const float4*>(bd.data + (t & bd.mask));
-                    break;
-                }
-                case I_FOLD: {
-                    // left fold of ins.z consecutive planes starting at buffer ins.y: the Sum2 chain's own order
-                    // the lanes of one extension instance are one allocation: plane i = base + i * stride
-                    const BufferDesc b0 = p.buffers[ins.y];
-                    const unsigned long long stride = (unsigned long long)(p.buffers[ins.y + 1].data - b0.data);
-                    const float* base = b0.data + (t & b0.mask);
-                    float4 acc = *reinterpret_cast<const float4*>(base);
-                    unsigned i = 1;
-                    for (; i + 16 <= ins.z; i += 16) {             // 16 independent plane loads in flight, then the ordered adds
-                        float4 v[16];
 #pragma unroll
-                        for (int q = 0; q < 16; q++) v[q] = *reinterpret_cast<const float4*>(base + (unsigned long long)(i + q) * stride);
-#pragma unroll
-                        for (int q = 0; q < 16; q++) {
-                            acc.x = __fadd_rn(acc.x, v[q].x); acc.y = __fadd_rn(acc.y, v[q].y);
-                            acc.z = __fadd_rn(acc.z, v[q].z); acc.w = __fadd_rn(acc.w, v[q].w);
-                        }
-                    }
-                    for (; i < ins.z; i++) {
-                        const float4 v = *reinterpret_cast<const float4*>(base + (unsigned long long)i * stride);
-                        acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y);
-                        acc.z = __fadd_rn(acc.z, v.z); acc.w = __fadd_rn(acc.w, v.w);
-                    }
-                    REG(dst) = acc;
+                    for (int w = 0; w < VW; w++) REG(dst, w) = *reinterpret_cast<const float4*>(bd.data + ((t0g + 4 * w) & bd.mask));
                     break;
                 }
                 case I_STBUF: {
                     const BufferDesc bd = p.buffers[ins.w];
-                    *reinterpret_cast<float4*>(bd.data + (t & bd.mask)) = a;
+#pragma unroll
+                    for (int w = 0; w < VW; w++) *reinterpret_cast<float4*>(bd.data + ((t0g + 4 * w) & bd.mask)) = a[w];
                     break;
                 }
                 case I_STOUT: {
                     // out[slot][t - t0], only for t0 <= t < t1
                     float* row = p.out + (unsigned long long)ins.w * p.out_stride;
-                    const float v[4] = {a.x, a.y, a.z, a.w};
-                    if (t >= p.t0 && t + 4 <= p.t1 && p.out_vec_ok) {
-                        *reinterpret_cast<float4*>(row + (t - p.t0)) = a;
-                    } else {
 #pragma unroll
-                        for (int i = 0; i < 4; i++)
-                            if (t + i >= p.t0 && t + i < p.t1) row[t + i - p.t0] = v[i];
+                    for (int w = 0; w < VW; w++) {
+                        const unsigned long long t = t0g + 4 * w;
+                        if (t >= p.t0 && t + 4 <= p.t1 && p.out_vec_ok) {
+                            *reinterpret_cast<float4*>(row + (t - p.t0)) = a[w];
+                        } else {
+                            const float v[4] = {a[w].x, a[w].y, a[w].z, a[w].w};
+#pragma unroll
+                            for (int i = 0; i < 4; i++)
+                                if (t + i >= p.t0 && t + i < p.t1) row[t + i - p.t0] = v[i];
+                        }
                     }
                     break;
                 }
-                case I_DLY_IN: {
-                    const InputDesc in = p.inputs[ins.w];
-                    const float d[4] = {a.x, a.y, a.z, a.w};
-                    float r[4];
+                case I_DLY_IN: case I_DLY_BUF: case I_DLY_TI: {
+                    const InputDesc in = (op == I_DLY_IN) ? p.inputs[ins.w] : InputDesc{nullptr, 0, 0};
+                    const BufferDesc bd = (op == I_DLY_BUF) ? p.buffers[ins.w] : BufferDesc{nullptr, 0};
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        unsigned long long o;
-                        r[i] = delay_origin(d[i], t + i, p.sparkle_delay, &o) ? load_input(in, o) : 0.0f;
-                    }
-                    REG(dst) = make_float4(r[0], r[1], r[2], r[3]);
-                    break;
-                }
-                case I_DLY_BUF: {
-                    const BufferDesc bd = p.buffers[ins.w];
-                    const float d[4] = {a.x, a.y, a.z, a.w};
-                    float r[4];
+                    for (int w = 0; w < VW; w++) {
+                        const float d[4] = {a[w].x, a[w].y, a[w].z, a[w].w};
+                        const float sv[4] = {b[w].x, b[w].y, b[w].z, b[w].w};
+                        float r[4];
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        unsigned long long o;
-                        r[i] = delay_origin(d[i], t + i, p.sparkle_delay, &o) ? bd.data[o & bd.mask] : 0.0f;
+                        for (int i = 0; i < 4; i++) {
+                            unsigned long long o;
+                            const bool live = delay_origin(d[i], t0g + 4 * w + i, p.sparkle_delay, &o);
+                            float v = 0.0f;
+                            if (live) v = (op == I_DLY_IN) ? load_input(in, o) : (op == I_DLY_BUF) ? bd.data[o & bd.mask] : sv[i];
+                            r[i] = v;
+                        }
+                        REG(dst, w) = make_float4(r[0], r[1], r[2], r[3]);
                     }
-                    REG(dst) = make_float4(r[0], r[1], r[2], r[3]);
-                    break;
-                }
-                case I_DLY_TI: {
-                    if (flags & IF_B_IMM) { float v = __uint_as_float(ins.z); b = make_float4(v, v, v, v); }
-                    else b = REG(ins.z);
-                    const float d[4] = {a.x, a.y, a.z, a.w};
-                    const float s[4] = {b.x, b.y, b.z, b.w};
-                    float r[4];
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        unsigned long long o;
-                        r[i] = delay_origin(d[i], t + i, p.sparkle_delay, &o) ? s[i] : 0.0f;
-                    }
-                    REG(dst) = make_float4(r[0], r[1], r[2], r[3]);
                     break;
                 }
                 default: break;
@@ -186,12 +182,46 @@ interp_kernel(InterpParams p) {
     }
 }
 
+// Left fold of `count` consecutive planes (lanes of one extension instance: plane i = base + i * stride) into one
+// ring, one sample per thread, 32 independent plane loads in flight per thread, adds in the chain's own order.
+__global__ void __launch_bounds__(256)
+fold_kernel(const BufferDesc* __restrict__ bufs, unsigned first, unsigned count, unsigned out_buf,
+            unsigned long long lo, unsigned long long hi) {
+    const BufferDesc b0 = bufs[first];
+    const BufferDesc ob = bufs[out_buf];
+    const unsigned long long stride = (unsigned long long)(bufs[first + 1].data - b0.data);
+    for (unsigned long long t = lo + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < hi;
+         t += (unsigned long long)gridDim.x * blockDim.x) {
+        const float* base = b0.data + (t & b0.mask);
+        float acc = base[0];
+        unsigned i = 1;
+        for (; i + 32 <= count; i += 32) {
+            float v[32];
+#pragma unroll
+            for (int q = 0; q < 32; q++) v[q] = base[(unsigned long long)(i + q) * stride];
+#pragma unroll
+            for (int q = 0; q < 32; q++) acc = __fadd_rn(acc, v[q]);
+        }
+        for (; i < count; i++) acc = __fadd_rn(acc, base[(unsigned long long)i * stride]);
+        ob.data[t & ob.mask] = acc;
+    }
+}
+
+cudaError_t launch_fold(const BufferDesc* d_bufdesc, unsigned first, unsigned count, unsigned out_buf,
+                        unsigned long long lo, unsigned long long hi, int sm_count, cudaStream_t stream) {
+    if (hi <= lo) return cudaSuccess;
+    unsigned long long blocks = (hi - lo + 255) / 256;
+    if (blocks > (unsigned long long)sm_count * 8) blocks = (unsigned long long)sm_count * 8;
+    fold_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_bufdesc, first, count, out_buf, lo, hi);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_interp(const InterpParams& p_in, unsigned n_regs, int sm_count, cudaStream_t stream) {
     if (p_in.n_groups == 0) return cudaSuccess;
     InterpParams p = p_in;
     const unsigned threads = INTERP_THREADS;
     p.n_regs = n_regs ? n_regs : 1;
-    size_t smem = (size_t)p.n_regs * threads * sizeof(float4);
+    size_t smem = (size_t)p.n_regs * INTERP_VW * threads * sizeof(float4);
     const size_t prog_bytes = (size_t)p.n_instr * sizeof(uint4);
     p.prog_in_smem = (prog_bytes <= 48 * 1024 && smem + prog_bytes <= 200 * 1024) ? 1u : 0u;
     if (p.prog_in_smem) smem += prog_bytes;

@@ -8,6 +8,7 @@
 namespace frb {
 
 constexpr unsigned INTERP_THREADS = 128;
+constexpr int INTERP_VW = 2;           // float4 per thread per register: 8 consecutive samples
 
 // External-input history of one slot, device resident: values for absolute times [base_time, end_time),
 // zeros elsewhere (reference src/render/reference.rs:22-25, :90-96).  base_time is a multiple of 4.
@@ -32,13 +33,15 @@ struct InterpParams {
     const BufferDesc* buffers;      // device table, indexed by buffer id
     float* out;                     // device: [n_slots x out_stride], column 0 == time t0
     unsigned long long out_stride;
-    unsigned long long t_begin;     // first absolute time evaluated (multiple of 4)
-    unsigned long long n_groups;    // number of 4-sample groups evaluated
+    unsigned long long t_begin;     // first absolute time evaluated (multiple of 8)
+    unsigned long long n_groups;    // number of 8-sample groups evaluated
     unsigned long long t0, t1;      // output window [t0, t1)
     int out_vec_ok;                 // rows and t0 are 16-byte aligned: 128-bit output stores allowed
     int sparkle_delay;              // FRB_FLAG_SPARKLE_DELAY
 };
 
+cudaError_t launch_fold(const BufferDesc* d_bufdesc, unsigned first, unsigned count, unsigned out_buf,
+                        unsigned long long lo, unsigned long long hi, int sm_count, cudaStream_t stream);
 cudaError_t launch_interp(const InterpParams& p, unsigned n_regs, int sm_count, cudaStream_t stream);
 
 }  // namespace frb

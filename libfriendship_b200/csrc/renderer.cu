@@ -193,7 +193,7 @@ const Schedule& Renderer::schedule(uint32_t n_slots) {
             auto it = fb_defs_.find(key);
             return it == fb_defs_.end() ? 0 : fbdelay_max_delay(*it->second);
         };
-        env.max_regs = 96;
+        env.max_regs = 48;
         Schedule s = flatten(graph_, n_slots, env);   // throws on malformed graphs; state unchanged then
         if (!host_only_) {
             CU(cudaSetDevice(device_));
@@ -427,6 +427,13 @@ void Renderer::run_range(uint64_t lo, uint64_t hi, float* d_out, uint64_t t0, ui
                 }
                 stats.kernel_launches += nl;
             }
+            for (const FoldJob& fj : st.folds) {
+                if (profiling) CU(cudaEventRecord(ev_[2], stream_));
+                CU(launch_fold(d_bufdesc_, fj.first_buf, fj.count, fj.out_buf, c0, c1, sm_count_, stream_));
+                if (profiling) { CU(cudaEventRecord(ev_[3], stream_)); CU(cudaEventSynchronize(ev_[3])); float ms = 0; CU(cudaEventElapsedTime(&ms, ev_[2], ev_[3])); timing.interp_ms += ms; }
+                stats.kernel_launches++;
+                stats.interp_launches++;
+            }
             if (st.program.size() <= 2) continue;   // only I_END (+ pad)
             InterpParams p;
             p.program = d_programs_[sg];
@@ -435,8 +442,8 @@ void Renderer::run_range(uint64_t lo, uint64_t hi, float* d_out, uint64_t t0, ui
             p.buffers = d_bufdesc_;
             p.out = d_out;
             p.out_stride = out_stride;
-            p.t_begin = c0 & ~3ull;
-            p.n_groups = ((c1 + 3) / 4) - (c0 / 4);
+            p.t_begin = c0 & ~7ull;
+            p.n_groups = ((c1 + 7) / 8) - (c0 / 8);
             p.t0 = t0;
             p.t1 = d_out ? t1 : t0;                  // warm-up ranges write no output
             p.out_vec_ok = out_vec_ok;
@@ -495,7 +502,7 @@ void Renderer::fill(float* out, bool out_on_device, uint32_t n_slots, uint64_t n
             // seek, graph edit or first call: rebuild the rings the block depends on (SURVEY.md A.3 trap T1:
             // constants and input history before idx are live, only the external inputs were zeroed by a seek)
             uint64_t start = sched_.from_zero ? 0 : (idx > sched_.max_lookback ? idx - sched_.max_lookback : 0);
-            run_range(start & ~3ull, idx, nullptr, idx, idx, 0);
+            run_range(start & ~7ull, idx, nullptr, idx, idx, 0);
         }
         run_range(idx, t1, d_out, idx, t1, n_times);
         cache_valid_ = true;

@@ -59,7 +59,6 @@ enum InstrOp : uint8_t {
     I_STBUF = 11,    // buffer[aux](t) = a
     I_STOUT = 12,    // out[aux](t - t0) = a
     I_MOV = 13,      // dst = a
-    I_FOLD = 14,     // dst = ((buffer[a] + buffer[a+1]) + ...) + buffer[a+b-1]   left fold of b consecutive planes (a Sum2 chain)
 };
 constexpr uint32_t IF_A_IMM = 1u;   // a is an immediate f32 bit pattern, not a register
 constexpr uint32_t IF_B_IMM = 2u;
@@ -80,8 +79,15 @@ struct BufferInfo {
     uint32_t lane = 0;
 };
 
+// A Sum2 chain over consecutive lanes of one extension instance, ((x0 + x1) + x2) + ... : evaluated by a dedicated
+// streaming kernel (same left-to-right order, so bit-exact) into its own ring before the stage's program runs.
+struct FoldJob {
+    uint32_t first_buf, count, out_buf;
+};
+
 struct Stage {
     std::vector<uint32_t> ext;      // extension instances launched at the start of this stage (creation order)
+    std::vector<FoldJob> folds;     // run after the extension instances, before the program
     std::vector<Instr> program;     // register program of the interpreter pass (may be just I_END)
     uint32_t n_regs = 0;
 };
