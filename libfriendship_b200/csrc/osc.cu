@@ -52,7 +52,12 @@ struct OscBankDev {
     uint32_t* d_n_grp = nullptr;       // per voice: groups in total
     mutable float* d_planes = nullptr; // scratch for split > 1: [split][n_voices][plane_len]
     mutable uint64_t planes_cap = 0;
+    mutable cudaStream_t side = nullptr;   // the (tiny, slow) attack-ramp kernel runs beside the main kernel
+    mutable cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     ~OscBankDev() {
+        if (side) cudaStreamDestroy(side);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
         cudaFree(d_hot); cudaFree(d_anc); cudaFree(d_ph);
         cudaFree(d_grp_begin); cudaFree(d_n_grp0); cudaFree(d_n_grp); cudaFree(d_planes);
     }
@@ -461,11 +466,24 @@ static cudaError_t launch_osc_range(const OscBankDev& b, const BufferDesc* d_buf
         if (first_plain > p.seg0) n_att = (unsigned)std::min<unsigned long long>(first_plain - p.seg0, p.nseg);
     }
     const unsigned nseg_total = p.nseg;
+    const bool fork = n_att && nseg_total > n_att;
+    if (fork && !b.side) {
+        cudaError_t e = cudaStreamCreateWithFlags(&b.side, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b.ev_fork, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b.ev_join, cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+    }
     if (n_att) {
         OscLaunch q = p;
         q.nseg = n_att;
+        cudaStream_t st = stream;
+        if (fork) {   // a handful of warps walking every partial: overlap it with the main kernel instead of serialising
+            cudaEventRecord(b.ev_fork, stream);
+            cudaStreamWaitEvent(b.side, b.ev_fork, 0);
+            st = b.side;
+        }
         dim3 grid((n_att + threads - 1) / threads, b.n_voices, p.split);
-        osc_kernel<OSC_K, true><<<grid, threads, smem, stream>>>(q);
+        osc_kernel<OSC_K, true><<<grid, threads, smem, st>>>(q);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         if (n_launches) (*n_launches)++;
@@ -480,6 +498,10 @@ static cudaError_t launch_osc_range(const OscBankDev& b, const BufferDesc* d_buf
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         if (n_launches) (*n_launches)++;
+    }
+    if (fork) {
+        cudaEventRecord(b.ev_join, b.side);
+        cudaStreamWaitEvent(stream, b.ev_join, 0);
     }
     cudaError_t e = cudaSuccess;
     if (p.split > 1) {
