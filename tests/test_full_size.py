@@ -120,3 +120,47 @@ def test_cfg3_full_voice_count_selected_voices_vs_fp64():
     assert np.abs(out[1:].astype(np.float64) - want).max() <= 1e-4 * scale
     # the mix slot is the left fold of all 4,096 voices: at least bounded and consistent with the picked voices' scale
     assert np.abs(out[0]).max() <= 4096 * scale
+
+
+def test_cfg5_shape_one_voice_of_a_million_partials_at_the_end_of_a_minute():
+    """cfg5: 2^20 partials per voice, 192 kHz, sample index ~11.5 M (60 s).  One voice, a 48-sample window at the
+    very end of the render: exercises the exact fixed-point phase at large t and a 48 MB coefficient stream."""
+    from libfriendship_b200 import KIND_OSCBANK
+    sr, n_partials = 192000.0, 1 << 20
+    rng = np.random.Generator(np.random.PCG64(2))
+    k = np.arange(1, n_partials + 1, dtype=np.float64)
+    f = 55.0 * k * (1.0 + rng.uniform(-0.002, 0.002, n_partials))
+    f = np.where(f >= sr / 2, np.mod(f, sr / 2 * 0.98) + 20.0, f)
+    bank = dict(sample_rate=sr, voice_offsets=np.array([0, n_partials], dtype=np.uint64), freq_hz=f,
+                amp=(1.0 / k).astype(np.float32), phase=np.zeros(n_partials, dtype=np.float32),
+                attack=(192.0 * (1 + (k.astype(np.int64) % 7))).astype(np.float32),
+                tau=(sr * (20.0 + 200.0 / k)).astype(np.float32))       # slow decay: still audible after 60 s
+    idx, n = 11_520_000 - 48, 48
+    outs = []
+    for cls in (gpu().__class__, OracleRenderer):
+        r = cls()
+        r.define_oscbank(5, **bank)
+        r.on_add_node(1, KIND_OSCBANK, 5)
+        r.on_add_edge((1, 0, 0, 0))
+        outs.append(r.fill_buffer(1, n, idx))
+    fs = full_scale(bank)
+    assert np.abs(outs[1]).max() > 1e-3 * fs          # the signal is alive there
+    assert np.abs(outs[0].astype(np.float64) - outs[1]).max() <= TOL * fs
+
+
+def test_device_resident_inputs_and_outputs_match_the_host_path():
+    """frb_fill_buffer_device: inputs and outputs stay in HBM (what bench.py's `value` times)."""
+    import torch
+    from graphs import build_cfg1_graph, cfg1_input
+    n = 20000
+    x = cfg1_input(n)
+    host = gpu()
+    build_cfg1_graph(host)
+    want = host.fill_buffer(2, n, 0, [x])
+    dev = gpu()
+    build_cfg1_graph(dev)
+    d_in = torch.from_numpy(x).cuda()
+    d_out = torch.empty((2, n), dtype=torch.float32, device="cuda")
+    dev.fill_buffer_device(d_out.data_ptr(), 2, n, 0, d_in.data_ptr(), [0, n])
+    dev.sync()
+    assert_same_bits(d_out.cpu().numpy(), want, "device path")
