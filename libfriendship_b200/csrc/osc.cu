@@ -161,11 +161,13 @@ std::shared_ptr<OscBankDev> osc_create(const frb_oscbank_desc* d, cudaStream_t s
     b->max_attack = max_attack;
     const uint64_t n = order.size();
     b->n_records = n;
-    // Partial-range split: enough CTAs to balance 148 SMs when a voice has many groups.  Fixed per bank so the
-    // order of summation (and hence the result) never depends on the block size of a render.
+    // Partial-range split: one CTA is one warp working through (groups / split) groups for 32 segments.  All CTAs of a
+    // launch cost the same, so the only imbalance is the partially filled last wave (148 SMs x ~12 resident CTAs):
+    // aim for voices x split >= 4096 (>= 30 waves per 64 Ki-sample block) while keeping >= 8 groups per CTA.
+    // Fixed per bank, so the order of summation (and hence the result) never depends on the block size of a render.
     {
         uint32_t s = 1;
-        while (s < 64 && b->max_groups / (s * 2) >= 256 && (uint64_t)d->n_voices * s < 4096) s *= 2;
+        while (s < 512 && (uint64_t)d->n_voices * s < 4096 && b->max_groups / (s * 2) >= 8) s *= 2;
         b->split = s;
     }
 
@@ -410,7 +412,9 @@ cudaError_t launch_osc(const OscBankDev& b, const BufferDesc* d_bufdesc, uint32_
     if (hi <= lo || b.n_voices == 0) return cudaSuccess;
     // split banks stage their partial-range planes in scratch: bound it by rendering 64 Ki samples at a time
     if (b.split == 1) return launch_osc_range(b, d_bufdesc, first_buf, lo, hi, anchor, sm_count, stream, n_launches);
-    const uint64_t sub = 1ull << 16;
+    // ... in sub-blocks whose planes stay under 1 GiB (at least 64 Ki samples)
+    uint64_t sub = 1ull << 20;
+    while (sub > (1ull << 16) && sub * b.split * b.n_voices > (1ull << 28)) sub >>= 1;
     for (uint64_t c0 = lo; c0 < hi;) {
         const uint64_t c1 = std::min(hi, (c0 / sub + 1) * sub);
         cudaError_t e = launch_osc_range(b, d_bufdesc, first_buf, c0, c1, anchor, sm_count, stream, n_launches);
