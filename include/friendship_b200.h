@@ -73,6 +73,8 @@ typedef struct frb_config {
 } frb_config;
 #define FRB_FLAG_SPARKLE_DELAY 1u  /* negative / NaN delay amounts yield 0.0 (reference sparkle.rs:525-542)
                                       instead of clamping to delay 0 (reference.rs:205-210, the default) */
+#define FRB_FLAG_NO_JIT        2u  /* always interpret stage programs; never compile them (see frb_jit_cubin_size) */
+#define FRB_FLAG_JIT_EAGER     4u  /* compile a stage program the first time it runs (default: once it is hot) */
 
 /* Oscillator bank definition (extension).  Voice v owns partials [voice_offsets[v], voice_offsets[v+1]).
  *   out_v(t) = sum_p amp_p * min(t/attack_p, 1) * exp(-t/tau_p) * sin(2*pi*freq_p*t/sample_rate + phase_p)
@@ -151,6 +153,13 @@ void* frb_stream(frb_renderer* r);   /* the cudaStream_t the renderer launches o
  * schedule needs (may exceed cap; nothing is written beyond cap), or a negative status. */
 int64_t frb_dump_schedule(frb_renderer* r, uint32_t n_slots, uint32_t* words, uint64_t cap);
 
+/* The stage JIT (the B200 counterpart of the reference's LLVM JIT, src/render/sparkle.rs): CUDA source generated for
+ * stage `stage` of the schedule for `n_slots` outputs, and the size of the sm_100a cubin NVRTC builds from it
+ * (negative status on failure; needs no GPU).  frb_jit_source writes at most cap bytes (NUL-terminated) and returns
+ * the length needed. */
+int64_t frb_jit_source(frb_renderer* r, uint32_t n_slots, uint32_t stage, char* out, uint64_t cap);
+int64_t frb_jit_cubin_size(frb_renderer* r, uint32_t n_slots, uint32_t stage);
+
 /* Counters since creation: kernel launches, bytes H2D, bytes D2H. */
 typedef struct frb_stats {
     uint64_t kernel_launches;
@@ -160,7 +169,7 @@ typedef struct frb_stats {
     uint64_t osc_launches;
     uint64_t interp_launches;
     uint64_t scan_launches;
-    uint64_t reserved;
+    uint64_t jit_launches;      /* stage launches that ran a JIT-compiled kernel instead of the interpreter */
 } frb_stats;
 int frb_get_stats(const frb_renderer* r, frb_stats* out);
 

@@ -11,7 +11,7 @@ import os as _os
 from . import _cabi
 from ._cabi import (  # noqa: F401
     KIND_DELAY, KIND_F32CONSTANT, KIND_SUM2, KIND_MULTIPLY, KIND_DIVIDE, KIND_MODULO, KIND_MINIMUM, KIND_EFFECT,
-    KIND_OSCBANK, KIND_DIRECTFORM, KIND_FBDELAY, FLAG_SPARKLE_DELAY, RendererError,
+    KIND_OSCBANK, KIND_DIRECTFORM, KIND_FBDELAY, FLAG_SPARKLE_DELAY, FLAG_NO_JIT, FLAG_JIT_EAGER, RendererError,
 )
 
 LIB_PATH = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "lib", "libfriendship_b200.so")
@@ -69,6 +69,22 @@ class B200Renderer(_cabi.CRendererBase):
         n2 = _lib.frb_dump_schedule(self._h, n_slots, w.ctypes.data_as(_C.POINTER(_C.c_uint32)), n)
         assert n2 == n
         return w
+
+    def jit_source(self, n_slots, stage):
+        """CUDA source the stage JIT generates for `stage` (see csrc/jit.cc)."""
+        n = _lib.frb_jit_source(self._h, n_slots, stage, None, 0)
+        if n < 0:
+            self._check(int(n))
+        buf = _C.create_string_buffer(n + 1)
+        _lib.frb_jit_source(self._h, n_slots, stage, buf, n + 1)
+        return buf.value.decode()
+
+    def jit_cubin_size(self, n_slots, stage):
+        """Compiles the stage with NVRTC for sm_100a (no GPU needed) and returns the cubin size."""
+        n = _lib.frb_jit_cubin_size(self._h, n_slots, stage)
+        if n < 0:
+            self._check(int(n))
+        return int(n)
 
     def stats(self):
         s = _cabi.frb_stats()

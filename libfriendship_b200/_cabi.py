@@ -33,6 +33,8 @@ KIND_DIRECTFORM = 33
 KIND_FBDELAY = 34
 
 FLAG_SPARKLE_DELAY = 1
+FLAG_NO_JIT = 2
+FLAG_JIT_EAGER = 4
 
 
 class frb_edge(C.Structure):
@@ -68,7 +70,7 @@ class frb_fbdelay_desc(C.Structure):
 
 class frb_stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("kernel_launches", "h2d_bytes", "d2h_bytes", "schedule_builds",
-                                           "osc_launches", "interp_launches", "scan_launches", "reserved")]
+                                           "osc_launches", "interp_launches", "scan_launches", "jit_launches")]
 
 
 class frb_timing(C.Structure):
@@ -80,7 +82,7 @@ EXPORTS = [
     "frb_create", "frb_destroy", "frb_last_error", "frb_define_effect", "frb_define_oscbank",
     "frb_define_directform", "frb_define_fbdelay", "frb_add_node", "frb_del_node", "frb_add_edge", "frb_del_edge",
     "frb_fill_buffer", "frb_fill_buffer_device", "frb_sync", "frb_stream", "frb_dump_schedule", "frb_get_stats",
-    "frb_set_profiling", "frb_get_timing", "frb_version",
+    "frb_set_profiling", "frb_get_timing", "frb_version", "frb_jit_source", "frb_jit_cubin_size",
 ]
 
 
@@ -106,6 +108,8 @@ def declare(lib, prefix):
         "get_stats": ([vp, C.POINTER(frb_stats)], C.c_int),
         "set_profiling": ([vp, C.c_int], C.c_int),
         "get_timing": ([vp, C.POINTER(frb_timing)], C.c_int),
+        "jit_source": ([vp, C.c_uint32, C.c_uint32, C.c_char_p, C.c_uint64], C.c_int64),
+        "jit_cubin_size": ([vp, C.c_uint32, C.c_uint32], C.c_int64),
     }
     for name, (args, res) in sig.items():
         fn = getattr(lib, f"{prefix}_{name}", None)

@@ -4,6 +4,10 @@
 #include <new>
 #include <string>
 
+#include <algorithm>
+#include <cstring>
+
+#include "jit.hpp"
 #include "renderer.hpp"
 
 using frb::Error;
@@ -96,6 +100,34 @@ int64_t frb_dump_schedule(frb_renderer* r, uint32_t n_slots, uint32_t* words, ui
         std::vector<uint32_t> w = r->impl.schedule(n_slots).dump();
         n = (int64_t)w.size();
         if (words) for (uint64_t i = 0; i < cap && i < w.size(); i++) words[i] = w[i];
+    });
+    return rc == FRB_OK ? n : (int64_t)rc;
+}
+
+int64_t frb_jit_source(frb_renderer* r, uint32_t n_slots, uint32_t stage, char* out, uint64_t cap) {
+    int64_t n = 0;
+    int rc = guarded(r, [&] {
+        const frb::Schedule& s = r->impl.schedule(n_slots);
+        if (stage >= s.stages.size()) throw Error{FRB_E_INVALID, "no such stage"};
+        std::string src = frb::jit_generate_source(s.stages[stage]);
+        n = (int64_t)src.size();
+        if (out && cap) {
+            size_t m = std::min<size_t>(src.size(), cap - 1);
+            memcpy(out, src.data(), m);
+            out[m] = 0;
+        }
+    });
+    return rc == FRB_OK ? n : (int64_t)rc;
+}
+int64_t frb_jit_cubin_size(frb_renderer* r, uint32_t n_slots, uint32_t stage) {
+    int64_t n = 0;
+    int rc = guarded(r, [&] {
+        const frb::Schedule& s = r->impl.schedule(n_slots);
+        if (stage >= s.stages.size()) throw Error{FRB_E_INVALID, "no such stage"};
+        std::string cubin, log;
+        if (!frb::jit_compile_to_cubin(frb::jit_generate_source(s.stages[stage]), &cubin, &log))
+            throw Error{FRB_E_UNSUPPORTED, "NVRTC: " + log};
+        n = (int64_t)cubin.size();
     });
     return rc == FRB_OK ? n : (int64_t)rc;
 }

@@ -15,6 +15,7 @@
 #include <array>
 #include <cmath>
 #include <cstring>
+#include <functional>
 #include <map>
 
 namespace frb {
@@ -422,43 +423,89 @@ Schedule flatten(const Graph& top, uint32_t n_slots, const FlattenEnv& env) {
             emit_sinks((uint32_t)v, 0, dst);
         }
 
-        // linear-scan register assignment over the straight-line program
-        std::vector<int64_t> last_use(n_vreg, -1);
-        for (size_t i = 0; i < code.size(); i++) {
-            const VI& c = code[i];
-            bool a_reg = !(c.flags & IF_A_IMM) && c.op != I_LDIN && c.op != I_LDBUF;
-            bool b_reg = !(c.flags & IF_B_IMM) && (c.op == I_ADD || c.op == I_MUL || c.op == I_DIV || c.op == I_MOD || c.op == I_MIN || c.op == I_DLY_TI);
-            if (a_reg) last_use[c.a] = (int64_t)i;
-            if (b_reg) last_use[c.b] = (int64_t)i;
+        // ---- strands: independent sub-programs (connected components over registers) run as separate thread
+        // blocks (grid.y), so a stage that drives 64 unrelated output slots exposes 64x the memory-level
+        // parallelism of one long straight-line program; each strand gets its own register assignment.
+        auto uses_a = [](const VI& c) { return !(c.flags & IF_A_IMM) && c.op != I_LDIN && c.op != I_LDBUF; };
+        auto uses_b = [](const VI& c) {
+            return !(c.flags & IF_B_IMM) && (c.op == I_ADD || c.op == I_MUL || c.op == I_DIV || c.op == I_MOD || c.op == I_MIN || c.op == I_DLY_TI);
+        };
+        std::vector<uint32_t> parent(n_vreg);
+        for (uint32_t i = 0; i < n_vreg; i++) parent[i] = i;
+        std::function<uint32_t(uint32_t)> find = [&](uint32_t x) { while (parent[x] != x) x = parent[x] = parent[parent[x]]; return x; };
+        auto unite = [&](uint32_t a, uint32_t b) { a = find(a); b = find(b); if (a != b) parent[std::max(a, b)] = std::min(a, b); };
+        for (const VI& c : code) {
+            uint32_t anchor = c.dst != NOREG ? c.dst : (uses_a(c) ? c.a : NOREG);
+            if (anchor == NOREG) continue;
+            if (uses_a(c)) unite(anchor, c.a);
+            if (uses_b(c)) unite(anchor, c.b);
         }
-        std::vector<uint32_t> phys(n_vreg, NOREG), free_list;
-        uint32_t n_phys = 0;
-        Stage& stage = s.stages[sg];
-        for (size_t i = 0; i < code.size(); i++) {
-            VI c = code[i];
-            bool a_reg = !(c.flags & IF_A_IMM) && c.op != I_LDIN && c.op != I_LDBUF;
-            bool b_reg = !(c.flags & IF_B_IMM) && (c.op == I_ADD || c.op == I_MUL || c.op == I_DIV || c.op == I_MOD || c.op == I_MIN || c.op == I_DLY_TI);
-            uint32_t va = c.a, vb = c.b;
-            if (a_reg) c.a = phys[va];
-            if (b_reg) c.b = phys[vb];
-            if (a_reg && last_use[va] == (int64_t)i) free_list.push_back(phys[va]);
-            if (b_reg && last_use[vb] == (int64_t)i && !(a_reg && vb == va)) free_list.push_back(phys[vb]);
-            if (c.dst != NOREG) {
-                uint32_t vd = c.dst;
-                uint32_t p;
-                if (!free_list.empty()) { p = free_list.back(); free_list.pop_back(); }
-                else p = n_phys++;
-                phys[vd] = p;
-                c.dst = p;
-                if (last_use[vd] < 0) free_list.push_back(p);   // dead value (e.g. only its sinks were folded away)
+        constexpr uint32_t MAX_STRANDS = 4096;
+        std::map<uint32_t, uint32_t> strand_of_root;          // component root -> strand (in order of first appearance)
+        std::vector<std::vector<VI>> strands;
+        std::vector<VI> immediates_only;                      // sinks of immediates (e.g. an unconnected output slot)
+        for (const VI& c : code) {
+            uint32_t anchor = c.dst != NOREG ? c.dst : (uses_a(c) ? c.a : NOREG);
+            if (anchor == NOREG) { immediates_only.push_back(c); continue; }
+            uint32_t root = find(anchor);
+            auto it = strand_of_root.find(root);
+            if (it == strand_of_root.end()) {
+                uint32_t id = (uint32_t)strand_of_root.size() % MAX_STRANDS;
+                it = strand_of_root.emplace(root, id).first;
+                if (id >= strands.size()) strands.emplace_back();
             }
-            stage.program.push_back(Instr::make(c.op, c.flags, c.dst, c.a, c.b, c.aux));
+            strands[it->second].push_back(c);
         }
-        stage.program.push_back(Instr::make(I_END, 0, 0, 0, 0, 0));
-        stage.program.push_back(Instr::make(I_END, 0, 0, 0, 0, 0));   // pad: the kernel prefetches one instruction ahead
-        stage.n_regs = n_phys;
-        if (n_phys > env.max_regs)
-            throw Error{FRB_E_UNSUPPORTED, "stage needs " + std::to_string(n_phys) + " live registers; limit " + std::to_string(env.max_regs)};
+        if (!immediates_only.empty()) {
+            if (strands.empty()) strands.emplace_back();
+            strands[0].insert(strands[0].end(), immediates_only.begin(), immediates_only.end());
+        }
+
+        Stage& stage = s.stages[sg];
+        uint32_t max_phys = 0;
+        for (auto& sc : strands) {
+            stage.strand_offsets.push_back((uint32_t)stage.program.size());
+            // linear-scan register assignment over the strand's straight-line program
+            std::map<uint32_t, int64_t> last_use;
+            for (size_t i = 0; i < sc.size(); i++) {
+                if (uses_a(sc[i])) last_use[sc[i].a] = (int64_t)i;
+                if (uses_b(sc[i])) last_use[sc[i].b] = (int64_t)i;
+            }
+            std::map<uint32_t, uint32_t> phys;
+            std::vector<uint32_t> free_list;
+            uint32_t n_phys = 0;
+            for (size_t i = 0; i < sc.size(); i++) {
+                VI c = sc[i];
+                const bool a_reg = uses_a(c), b_reg = uses_b(c);
+                const uint32_t va = c.a, vb = c.b;
+                if (a_reg) c.a = phys.at(va);
+                if (b_reg) c.b = phys.at(vb);
+                if (a_reg && last_use[va] == (int64_t)i) free_list.push_back(phys.at(va));
+                if (b_reg && last_use[vb] == (int64_t)i && !(a_reg && vb == va)) free_list.push_back(phys.at(vb));
+                if (c.dst != NOREG) {
+                    const uint32_t vd = c.dst;
+                    uint32_t pr;
+                    if (!free_list.empty()) { pr = free_list.back(); free_list.pop_back(); }
+                    else pr = n_phys++;
+                    phys[vd] = pr;
+                    c.dst = pr;
+                    if (!last_use.count(vd)) free_list.push_back(pr);   // dead value
+                }
+                stage.program.push_back(Instr::make(c.op, c.flags, c.dst, c.a, c.b, c.aux));
+            }
+            stage.program.push_back(Instr::make(I_END, 0, 0, 0, 0, 0));
+            stage.program.push_back(Instr::make(I_END, 0, 0, 0, 0, 0));   // pad: the kernel prefetches one instruction ahead
+            max_phys = std::max(max_phys, n_phys);
+        }
+        if (strands.empty()) {
+            stage.strand_offsets.push_back(0);
+            stage.program.push_back(Instr::make(I_END, 0, 0, 0, 0, 0));
+            stage.program.push_back(Instr::make(I_END, 0, 0, 0, 0, 0));
+        }
+        stage.strand_offsets.push_back((uint32_t)stage.program.size());
+        stage.n_regs = max_phys;
+        if (max_phys > env.max_regs)
+            throw Error{FRB_E_UNSUPPORTED, "stage needs " + std::to_string(max_phys) + " live registers; limit " + std::to_string(env.max_regs)};
     }
     return s;
 }

@@ -12,31 +12,6 @@
 
 namespace frb {
 
-__device__ __forceinline__ float load_input(const InputDesc& in, unsigned long long t) {
-    // value of external input at absolute time t; 0 outside the stored history (reference.rs:90-96)
-    return (t >= in.base_time && t < in.end_time) ? in.data[t - in.base_time] : 0.0f;
-}
-
-// Delay clamps, reference.rs:200-212.  Returns false when the output is 0 without reading the source.
-__device__ __forceinline__ bool delay_origin(float d, unsigned long long t, bool sparkle, unsigned long long* origin) {
-    if (d >= 18446744073709551616.0f) return false;               // >= 2^64: indexing negative time
-    unsigned long long di;
-    if (!(d >= 0.0f)) {                                            // negative or NaN
-        if (sparkle) return false;                                 // sparkle.rs:525-542 returns 0.0
-        di = 0ull;                                                 // reference.rs:206-207 (NaN: saturating cast -> 0)
-    } else {
-        di = __float2ull_rz(d);                                    // truncation toward zero (:208-210)
-    }
-    if (t < di) return false;                                      // checked_sub -> None -> 0 (:212)
-    *origin = t - di;
-    return true;
-}
-
-__device__ __forceinline__ float op_mod(float a, float b) {
-    float r = fmodf(a, b);                                         // Rust `%` on f32
-    return (r < 0.0f) ? __fadd_rn(r, b) : r;                       // reference.rs:255-261
-}
-
 // Each thread owns INTERP_VW float4 (= 8 consecutive samples): one decoded instruction is applied to both, which
 // halves the interpretive overhead per byte moved (the kernel is instruction-issue bound, not HBM bound, otherwise).
 __global__ void __launch_bounds__(INTERP_THREADS)
@@ -47,10 +22,11 @@ interp_kernel(InterpParams p) {
     constexpr int VW = INTERP_VW;
     // the program is staged in shared memory behind the register columns when it fits (broadcast LDS instead of
     // a dependent global load per interpreted instruction)
-    const uint4* prog = reinterpret_cast<const uint4*>(p.program);
+    const unsigned s_lo = __ldg(p.program + blockIdx.y), s_hi = __ldg(p.program + blockIdx.y + 1);   // this block's strand
+    const uint4* prog = reinterpret_cast<const uint4*>(p.program + p.prog_base) + s_lo;
     if (p.prog_in_smem) {
         uint4* s_prog = reinterpret_cast<uint4*>(s_regs + (size_t)p.n_regs * VW * nthr);
-        for (unsigned i = tid; i < p.n_instr; i += nthr) s_prog[i] = __ldg(prog + i);
+        for (unsigned i = tid; i < s_hi - s_lo; i += nthr) s_prog[i] = __ldg(prog + i);
         __syncthreads();
         prog = s_prog;
     }
@@ -230,7 +206,8 @@ cudaError_t launch_interp(const InterpParams& p_in, unsigned n_regs, int sm_coun
     unsigned long long per_sm = 227ull * 1024ull / (smem + 1024);
     if (per_sm > 12) per_sm = 12;
     if (per_sm < 1) per_sm = 1;
-    unsigned long long cap = (unsigned long long)sm_count * per_sm;
+    unsigned long long cap = ((unsigned long long)sm_count * per_sm + p.n_strands - 1) / p.n_strands;
+    if (cap < 1) cap = 1;
     if (blocks > cap) blocks = cap;
     static bool configured = false;
     if (!configured) {
@@ -238,7 +215,7 @@ cudaError_t launch_interp(const InterpParams& p_in, unsigned n_regs, int sm_coun
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    interp_kernel<<<(unsigned)blocks, threads, smem, stream>>>(p);
+    interp_kernel<<<dim3((unsigned)blocks, p.n_strands), threads, smem, stream>>>(p);
     return cudaGetLastError();
 }
 

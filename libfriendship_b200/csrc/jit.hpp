@@ -1,0 +1,23 @@
+// jit.hpp — see jit.cc
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "interp.cuh"
+#include "schedule.hpp"
+
+namespace frb {
+
+struct JitKernel;
+
+// CUDA source of the fused kernel for one stage program (thread = 8 consecutive samples, like the interpreter).
+std::string jit_generate_source(const Stage& st);
+// NVRTC: source -> sm_100a cubin.  Needs no GPU.  Returns false (and the compiler log) on failure.
+bool jit_compile_to_cubin(const std::string& source, std::string* cubin, std::string* log);
+// compile + load into the current context; nullptr on failure
+JitKernel* jit_build(const Stage& st, std::string* err);
+void jit_free(JitKernel* k);
+bool jit_launch(JitKernel* k, const InterpParams& p, int sm_count, cudaStream_t stream);
+
+}  // namespace frb

@@ -169,6 +169,8 @@ void Renderer::del_edge(const frb_edge& e) {                               // re
 void Renderer::free_device_schedule() {
     for (auto p : d_programs_) if (p) cudaFree(p);
     d_programs_.clear();
+    for (auto& j : stage_jit_) jit_free(j.k);
+    stage_jit_.clear();
     for (auto& g : ring_groups_) if (g.data) cudaFree(g.data);
     ring_groups_.clear();
     h_bufdesc_.clear();
@@ -214,11 +216,16 @@ void Renderer::ensure_schedule(uint32_t n_slots) { (void)schedule(n_slots); }
 
 void Renderer::upload_schedule() {
     d_programs_.assign(sched_.stages.size(), nullptr);
+    stage_jit_.assign(sched_.stages.size(), StageJit{});
     for (size_t i = 0; i < sched_.stages.size(); i++) {
-        auto& prog = sched_.stages[i].program;
-        size_t bytes = prog.size() * sizeof(Instr);
+        // device layout: [strand offsets, padded to a multiple of 4 words][instructions]
+        const Stage& stg = sched_.stages[i];
+        std::vector<uint32_t> words(stg.strand_offsets);
+        while (words.size() % 4) words.push_back(0);
+        for (const Instr& in : stg.program) { words.push_back(in.w0); words.push_back(in.a); words.push_back(in.b); words.push_back(in.aux); }
+        size_t bytes = words.size() * sizeof(uint32_t);
         CU(cudaMalloc(&d_programs_[i], bytes));
-        CU(cudaMemcpyAsync(d_programs_[i], prog.data(), bytes, cudaMemcpyHostToDevice, stream_));
+        CU(cudaMemcpy(d_programs_[i], words.data(), bytes, cudaMemcpyHostToDevice));
         stats.h2d_bytes += bytes;
     }
     // Block length: as long as the rings allow (more samples per launch = more parallelism for the stage kernels),
@@ -437,7 +444,11 @@ void Renderer::run_range(uint64_t lo, uint64_t hi, float* d_out, uint64_t t0, ui
             if (st.program.size() <= 2) continue;   // only I_END (+ pad)
             InterpParams p;
             p.program = d_programs_[sg];
-            p.n_instr = (unsigned)st.program.size();
+            p.n_strands = (unsigned)st.strand_offsets.size() - 1;
+            p.prog_base = (unsigned)((st.strand_offsets.size() + 3) / 4 * 4);
+            p.n_instr = 0;
+            for (size_t k = 0; k + 1 < st.strand_offsets.size(); k++)
+                p.n_instr = std::max(p.n_instr, st.strand_offsets[k + 1] - st.strand_offsets[k]);   // longest strand
             p.inputs = d_indesc_;
             p.buffers = d_bufdesc_;
             p.out = d_out;
@@ -449,7 +460,23 @@ void Renderer::run_range(uint64_t lo, uint64_t hi, float* d_out, uint64_t t0, ui
             p.out_vec_ok = out_vec_ok;
             p.sparkle_delay = (cfg_.flags & FRB_FLAG_SPARKLE_DELAY) ? 1 : 0;
             if (profiling) CU(cudaEventRecord(ev_[2], stream_));
-            CU(launch_interp(p, st.n_regs, sm_count_, stream_));
+            // Tiered like the reference's JIT renderer (sparkle.rs:271-288 compiles lazily at the next render): a stage
+            // program is interpreted until it is hot (4th launch, or a block of >= 256 Ki samples), then compiled
+            // once by NVRTC into a fused kernel.  A stage that fails to compile stays on the interpreter.
+            StageJit& sj = stage_jit_[sg];
+            sj.uses++;
+            if (sj.state == 0 && !(cfg_.flags & FRB_FLAG_NO_JIT) && st.program.size() <= 4096 &&   // bound the compile time
+                ((cfg_.flags & FRB_FLAG_JIT_EAGER) || sj.uses >= 4 || p.n_groups >= (1ull << 15))) {
+                std::string jerr;
+                sj.k = jit_build(st, &jerr);
+                sj.state = sj.k ? 1 : 2;
+                if (!sj.k) last_jit_error = jerr;
+            }
+            if (sj.state == 1 && jit_launch(sj.k, p, sm_count_, stream_)) {
+                stats.jit_launches++;
+            } else {
+                CU(launch_interp(p, st.n_regs, sm_count_, stream_));
+            }
             if (profiling) { CU(cudaEventRecord(ev_[3], stream_)); CU(cudaEventSynchronize(ev_[3])); float ms = 0; CU(cudaEventElapsedTime(&ms, ev_[2], ev_[3])); timing.interp_ms += ms; }
             stats.kernel_launches++;
             stats.interp_launches++;

@@ -12,6 +12,7 @@
 #include "flatten.hpp"
 #include "graph.hpp"
 #include "interp.cuh"
+#include "jit.hpp"
 #include "osc.cuh"
 #include "scan.cuh"
 #include "schedule.hpp"
@@ -51,6 +52,7 @@ public:
     cudaStream_t stream() const { return stream_; }
 
     std::string last_error;
+    std::string last_jit_error;
     frb_stats stats{};
     frb_timing timing{};
     bool profiling = false;
@@ -89,6 +91,8 @@ private:
 
     // device-resident schedule
     std::vector<uint32_t*> d_programs_;         // per stage
+    struct StageJit { JitKernel* k = nullptr; int state = 0; uint64_t uses = 0; };   // state: 0 untried, 1 ready, 2 failed
+    std::vector<StageJit> stage_jit_;
     std::vector<uint32_t*> d_ext_in_bufs_;      // per extension instance: input ring ids per lane
     std::vector<BufferDesc> h_bufdesc_;
     struct RingGroup { uint32_t first, count; float* data; uint64_t cap; };   // consecutive buffers in one allocation

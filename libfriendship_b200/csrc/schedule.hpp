@@ -88,7 +88,9 @@ struct FoldJob {
 struct Stage {
     std::vector<uint32_t> ext;      // extension instances launched at the start of this stage (creation order)
     std::vector<FoldJob> folds;     // run after the extension instances, before the program
-    std::vector<Instr> program;     // register program of the interpreter pass (may be just I_END)
+    std::vector<Instr> program;     // register programs of the stage's strands, each ended by two I_ENDs
+    std::vector<uint32_t> strand_offsets;   // first instruction of every strand, then program.size(); strands are
+                                            // independent sub-programs run by separate thread blocks (grid.y)
     uint32_t n_regs = 0;
 };
 
