@@ -51,6 +51,68 @@ struct Flattener {
     }
     uint32_t zero() { return mk(V_ZERO, 0, 0, 0); }
 
+    // ---- Delay of a cheap, purely elementwise source: re-evaluate the source at the shifted time ----
+    // Delay(src, d)(t) = (t >= d) ? src(t - d) : 0.  When src is a small expression over stored signals (external
+    // inputs, extension lanes), constants and constant Delays, src(t - d) is the same expression over those signals
+    // read at t - d: same operations on the same operands, hence bit-identical, and no ring write + read of src.
+    static constexpr uint32_t CLONE_MAX_OPS = 8;
+    static uint64_t shift_of(const Value& x) { return ((uint64_t)x.b << 32) | x.imm; }
+    uint32_t mk64(uint8_t op, uint32_t a, uint64_t v) { return mk(op, a, (uint32_t)(v >> 32), (uint32_t)(v & 0xffffffffu)); }
+
+    // number of operations a shifted copy of v would add, or UINT32_MAX if v cannot be shifted
+    uint32_t clone_cost(uint32_t v, uint32_t budget) {
+        const Value x = s.values[v];
+        switch (x.op) {
+            case V_ZERO: case V_CONST: return 0;
+            case V_INPUT: case V_EXT: case V_TAP: return 0;
+            case V_GATE: return clone_cost(x.a, budget);
+            case V_SUM2: case V_MUL: case V_DIV: case V_MOD: case V_MIN: {
+                if (budget == 0) return UINT32_MAX;
+                uint32_t ca = clone_cost(x.a, budget - 1);
+                if (ca == UINT32_MAX) return ca;
+                uint32_t cb = clone_cost(x.b, budget - 1 - std::min(ca, budget - 1));
+                if (cb == UINT32_MAX || 1 + ca + cb > budget) return UINT32_MAX;
+                return 1 + ca + cb;
+            }
+            case V_DELAY: {
+                // a Delay that stayed a Delay has a leaf / constant-expression source or a signal-driven amount
+                const Value amt = s.values[x.b];
+                if (amt.op != V_CONST && amt.op != V_ZERO) return UINT32_MAX;
+                const uint8_t sop = s.values[x.a].op;
+                if (sop != V_INPUT && sop != V_EXT && !is_time_invariant(x.a)) return UINT32_MAX;
+                return 0;
+            }
+            default: return UINT32_MAX;
+        }
+    }
+    static bool const_delay_of(const Value& amt, uint64_t* d);   // defined below
+    uint32_t clone_shifted(uint32_t v, uint64_t shift) {
+        const Value x = s.values[v];
+        switch (x.op) {
+            case V_ZERO: case V_CONST: return v;
+            case V_INPUT: case V_EXT: return mk64(V_TAP, v, shift);
+            case V_TAP: return mk64(V_TAP, x.a, shift_of(x) + shift);
+            case V_GATE: return mk64(V_GATE, clone_shifted(x.a, shift), shift_of(x) + shift);
+            case V_DELAY: {
+                uint64_t d = 0;
+                if (!const_delay_of(s.values[x.b], &d)) return zero();          // never reads its source
+                if (is_time_invariant(x.a)) return mk64(V_GATE, x.a, shift + d);  // a constant expression is the same at any time
+                return mk64(V_GATE, mk64(V_TAP, x.a, shift + d), shift + d);
+            }
+            default: {
+                uint32_t a = clone_shifted(x.a, shift), b = clone_shifted(x.b, shift);
+                return mk(x.op, a, b, 0);
+            }
+        }
+    }
+
+    bool is_time_invariant(uint32_t v) {
+        const Value x = s.values[v];
+        if (x.op == V_ZERO || x.op == V_CONST) return true;
+        if (x.op >= V_SUM2 && x.op <= V_MIN) return is_time_invariant(x.a) && is_time_invariant(x.b);
+        return false;
+    }
+
     uint32_t resolve_maybe(int ctx, const std::vector<std::optional<frb_edge>>& vec, size_t slot) {
         if (slot < vec.size() && vec[slot].has_value()) return resolve(ctx, *vec[slot]);
         return zero();
@@ -88,7 +150,19 @@ struct Flattener {
                 uint32_t src = resolve_maybe(ctx, n.inbound, 0);
                 uint32_t amt = resolve_maybe(ctx, n.inbound, 1);
                 // Delay of the constant-zero signal is zero at every t (exactly +0.0f either way).
-                v = (s.values[src].op == V_ZERO) ? src : mk(V_DELAY, src, amt, 0);
+                if (s.values[src].op == V_ZERO) { v = src; break; }
+                {
+                    const uint8_t sop = s.values[src].op;
+                    const bool computed = (sop >= V_SUM2 && sop <= V_MIN) || sop == V_GATE;
+                    uint64_t d = 0;
+                    const Value amtv = s.values[amt];
+                    if (computed && (amtv.op == V_CONST || amtv.op == V_ZERO) && const_delay_of(amtv, &d) && d < (1ull << 40) &&
+                        clone_cost(src, CLONE_MAX_OPS) != UINT32_MAX && !is_time_invariant(src)) {
+                        v = mk64(V_GATE, clone_shifted(src, d), d);
+                        break;
+                    }
+                }
+                v = mk(V_DELAY, src, amt, 0);
                 break;
             }
             case FRB_KIND_SUM2: case FRB_KIND_MULTIPLY: case FRB_KIND_DIVIDE: case FRB_KIND_MODULO: case FRB_KIND_MINIMUM: {
@@ -144,6 +218,13 @@ struct Flattener {
         return v;
     }
 };
+
+bool const_delay(uint32_t bits, uint64_t* out);
+
+bool Flattener::const_delay_of(const Value& amt, uint64_t* d) {
+    if (amt.op == V_ZERO) { *d = 0; return true; }
+    return const_delay(amt.imm, d);
+}
 
 // Delay amount of a constant `frames` signal, with the clamps of reference.rs:200-212.
 // Returns false when the Delay can never read its source (frames >= 2^64).
@@ -201,6 +282,7 @@ Schedule flatten(const Graph& top, uint32_t n_slots, const FlattenEnv& env) {
                 st[v] = sg;
                 break;
             }
+            case V_TAP: case V_GATE: st[v] = st[x.a]; break;
             case V_EXT: {
                 ExtInstance& inst = s.ext[x.a];
                 if (!ext_staged[x.a]) {
@@ -233,6 +315,8 @@ Schedule flatten(const Graph& top, uint32_t n_slots, const FlattenEnv& env) {
             use(x.b);
         } else if (x.op >= V_SUM2 && x.op <= V_MIN) {
             use(x.a); use(x.b);
+        } else if (x.op == V_GATE) {
+            use(x.a);
         }
     }
     for (auto& inst : s.ext)
@@ -277,6 +361,8 @@ Schedule flatten(const Graph& top, uint32_t n_slots, const FlattenEnv& env) {
                 if (reads) raise(x.a, sat_add(L[vi], d));
                 break;
             }
+            case V_GATE: raise(x.a, L[vi]); break;
+            case V_TAP: raise(x.a, sat_add(L[vi], Flattener::shift_of(x))); break;
             case V_EXT: {
                 if (x.imm != 0) break;                                   // lanes are consecutive; lane 0 has the lowest id
                 ExtInstance& inst = s.ext[x.a];
@@ -319,6 +405,7 @@ Schedule flatten(const Graph& top, uint32_t n_slots, const FlattenEnv& env) {
     std::vector<uint32_t> n_uses(nv, 0);
     for (size_t v = 0; v < nv; v++) {
         if (V[v].op == V_DELAY || (V[v].op >= V_SUM2 && V[v].op <= V_MIN)) { n_uses[V[v].a]++; n_uses[V[v].b]++; }
+        if (V[v].op == V_TAP || V[v].op == V_GATE) n_uses[V[v].a]++;
     }
     for (uint32_t o : s.outputs) n_uses[o]++;
     for (auto& inst : s.ext) for (uint32_t in : inst.inputs) n_uses[in]++;
@@ -398,7 +485,15 @@ Schedule flatten(const Graph& top, uint32_t n_slots, const FlattenEnv& env) {
                 continue;
             }
             uint32_t fl = 0, dst;
-            if (x.op == V_DELAY) {
+            if (x.op == V_TAP) {
+                dst = new_vreg();
+                if (V[x.a].op == V_INPUT) code.push_back(VI{I_TAP_IN, 0, dst, x.imm, x.b, V[x.a].imm});
+                else code.push_back(VI{I_TAP_BUF, 0, dst, x.imm, x.b, (uint32_t)s.value_buffer[x.a]});
+            } else if (x.op == V_GATE) {
+                uint32_t a = operand(x.a, IF_A_IMM, &fl);
+                dst = new_vreg();
+                code.push_back(VI{I_GATE, fl, dst, a, x.imm, x.b});
+            } else if (x.op == V_DELAY) {
                 uint32_t amt = operand(x.b, IF_A_IMM, &fl);
                 const Value& src = V[x.a];
                 if (src.op == V_INPUT) {
@@ -426,7 +521,7 @@ Schedule flatten(const Graph& top, uint32_t n_slots, const FlattenEnv& env) {
         // ---- strands: independent sub-programs (connected components over registers) run as separate thread
         // blocks (grid.y), so a stage that drives 64 unrelated output slots exposes 64x the memory-level
         // parallelism of one long straight-line program; each strand gets its own register assignment.
-        auto uses_a = [](const VI& c) { return !(c.flags & IF_A_IMM) && c.op != I_LDIN && c.op != I_LDBUF; };
+        auto uses_a = [](const VI& c) { return !(c.flags & IF_A_IMM) && c.op != I_LDIN && c.op != I_LDBUF && c.op != I_TAP_IN && c.op != I_TAP_BUF; };
         auto uses_b = [](const VI& c) {
             return !(c.flags & IF_B_IMM) && (c.op == I_ADD || c.op == I_MUL || c.op == I_DIV || c.op == I_MOD || c.op == I_MIN || c.op == I_DLY_TI);
         };

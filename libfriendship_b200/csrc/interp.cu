@@ -41,7 +41,7 @@ interp_kernel(InterpParams p) {
             const unsigned op = ins.x & 0xFFu, flags = (ins.x >> 8) & 0xFFu, dst = ins.x >> 16;
             if (op == I_END) break;
             float4 a[VW], b[VW];
-            if (op != I_LDIN && op != I_LDBUF) {
+            if (op != I_LDIN && op != I_LDBUF && op != I_TAP_IN && op != I_TAP_BUF) {
                 if (flags & IF_A_IMM) {
                     const float v = __uint_as_float(ins.y);
 #pragma unroll
@@ -105,6 +105,26 @@ interp_kernel(InterpParams p) {
                     const BufferDesc bd = p.buffers[ins.w];
 #pragma unroll
                     for (int w = 0; w < VW; w++) REG(dst, w) = *reinterpret_cast<const float4*>(bd.data + ((t0g + 4 * w) & bd.mask));
+                    break;
+                }
+                case I_TAP_IN: {
+                    const InputDesc in = p.inputs[ins.w];
+                    const unsigned long long shift = ((unsigned long long)ins.z << 32) | ins.y;
+#pragma unroll
+                    for (int w = 0; w < VW; w++) REG(dst, w) = f4tap_in(in, t0g + 4 * w, shift);
+                    break;
+                }
+                case I_TAP_BUF: {
+                    const BufferDesc bd = p.buffers[ins.w];
+                    const unsigned long long shift = ((unsigned long long)ins.z << 32) | ins.y;
+#pragma unroll
+                    for (int w = 0; w < VW; w++) REG(dst, w) = f4tap_buf(bd, t0g + 4 * w, shift);
+                    break;
+                }
+                case I_GATE: {
+                    const unsigned long long thr = ((unsigned long long)ins.w << 32) | ins.z;
+#pragma unroll
+                    for (int w = 0; w < VW; w++) REG(dst, w) = f4gate(a[w], t0g + 4 * w, thr);
                     break;
                 }
                 case I_STBUF: {

@@ -129,6 +129,9 @@ std::string jit_generate_source(const Stage& st) {
                     case I_LDBUF: o << reg(dst, w) << " = f4ld_buf(p.buffers[" << in.aux << "], " << t << ");"; break;
                     case I_STBUF: o << "f4st_buf(p.buffers[" << in.aux << "], " << t << ", " << a << ");"; break;
                     case I_STOUT: o << "f4st_out(p, " << in.aux << "u, " << t << ", " << a << ");"; break;
+                    case I_TAP_IN: o << reg(dst, w) << " = f4tap_in(p.inputs[" << in.aux << "], " << t << ", " << ((((unsigned long long)in.b) << 32) | in.a) << "ull);"; break;
+                    case I_TAP_BUF: o << reg(dst, w) << " = f4tap_buf(p.buffers[" << in.aux << "], " << t << ", " << ((((unsigned long long)in.b) << 32) | in.a) << "ull);"; break;
+                    case I_GATE: o << reg(dst, w) << " = f4gate(" << a << ", " << t << ", " << ((((unsigned long long)in.aux) << 32) | in.b) << "ull);"; break;
                     case I_DLY_IN: o << reg(dst, w) << " = f4delay<0>(p.inputs[" << in.aux << "], no_buf, " << a << ", z4, " << t << ", p.sparkle_delay);"; break;
                     case I_DLY_BUF: o << reg(dst, w) << " = f4delay<1>(no_in, p.buffers[" << in.aux << "], " << a << ", z4, " << t << ", p.sparkle_delay);"; break;
                     case I_DLY_TI: o << reg(dst, w) << " = f4delay<2>(no_in, no_buf, " << a << ", " << b << ", " << t << ", p.sparkle_delay);"; break;

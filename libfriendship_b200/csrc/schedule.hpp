@@ -26,6 +26,10 @@ enum ValueOp : uint8_t {
     V_MOD = 7,      // true modulo (reference.rs:249-262)
     V_MIN = 8,      // minNum
     V_EXT = 9,      // output imm of extension instance a
+    V_TAP = 10,     // stored signal a (an external input or an extension lane) read at t - shift, 0 for t < shift;
+                    // shift = (b << 32) | imm.  Produced by re-evaluating a cheap Delay source at the shifted time
+                    // instead of materialising it (flatten.cc)
+    V_GATE = 11,    // (t >= threshold) ? a : 0 ; threshold = (b << 32) | imm : the "0 before t = d" of a Delay
 };
 
 struct Value {
@@ -59,6 +63,9 @@ enum InstrOp : uint8_t {
     I_STBUF = 11,    // buffer[aux](t) = a
     I_STOUT = 12,    // out[aux](t - t0) = a
     I_MOV = 13,      // dst = a
+    I_TAP_IN = 14,   // dst = input[aux](t - shift), shift = (b << 32) | a, 0 for t < shift
+    I_TAP_BUF = 15,  // dst = buffer[aux](t - shift)
+    I_GATE = 16,     // dst = (t >= threshold) ? a : 0, threshold = (aux << 32) | b
 };
 constexpr uint32_t IF_A_IMM = 1u;   // a is an immediate f32 bit pattern, not a register
 constexpr uint32_t IF_B_IMM = 2u;

@@ -5,7 +5,8 @@ Semantics follow reference src/render/reference.rs:158-266 (see SURVEY.md Append
 import copy
 import struct
 
-V_ZERO, V_CONST, V_INPUT, V_DELAY, V_SUM2, V_MUL, V_DIV, V_MOD, V_MIN, V_EXT = range(10)
+V_ZERO, V_CONST, V_INPUT, V_DELAY, V_SUM2, V_MUL, V_DIV, V_MOD, V_MIN, V_EXT, V_TAP, V_GATE = range(12)
+CLONE_MAX_OPS = 8
 KIND_TO_OP = {2: V_SUM2, 3: V_MUL, 4: V_DIV, 5: V_MOD, 6: V_MIN}
 FULL = (1 << 64) - 1
 
@@ -87,6 +88,71 @@ def flatten(top, n_slots):
             values.append(k)
         return cons[k]
 
+    def mk64(op, a, v):
+        return mk(op, a, v >> 32, v & 0xFFFFFFFF)
+
+    def shift_of(x):
+        return (x[2] << 32) | x[3]
+
+    def is_ti(v):
+        o, a, b, _ = values[v]
+        if o in (V_ZERO, V_CONST):
+            return True
+        if V_SUM2 <= o <= V_MIN:
+            return is_ti(a) and is_ti(b)
+        return False
+
+    def const_delay_of(amt):
+        """(reads, d) for a constant `frames` value"""
+        if values[amt][0] == V_ZERO:
+            return 0
+        return const_delay(values[amt][3])
+
+    def clone_cost(v, budget):
+        o, a, b, _ = values[v]
+        if o in (V_ZERO, V_CONST, V_INPUT, V_EXT, V_TAP):
+            return 0
+        if o == V_GATE:
+            return clone_cost(a, budget)
+        if V_SUM2 <= o <= V_MIN:
+            if budget == 0:
+                return None
+            ca = clone_cost(a, budget - 1)
+            if ca is None:
+                return None
+            cb = clone_cost(b, budget - 1 - min(ca, budget - 1))
+            if cb is None or 1 + ca + cb > budget:
+                return None
+            return 1 + ca + cb
+        if o == V_DELAY:
+            if values[b][0] not in (V_CONST, V_ZERO):
+                return None
+            if values[a][0] not in (V_INPUT, V_EXT) and not is_ti(a):
+                return None
+            return 0
+        return None
+
+    def clone_shifted(v, shift):
+        o, a, b, imm = values[v]
+        if o in (V_ZERO, V_CONST):
+            return v
+        if o in (V_INPUT, V_EXT):
+            return mk64(V_TAP, v, shift)
+        if o == V_TAP:
+            return mk64(V_TAP, a, shift_of(values[v]) + shift)
+        if o == V_GATE:
+            return mk64(V_GATE, clone_shifted(a, shift), shift_of(values[v]) + shift)
+        if o == V_DELAY:
+            d = const_delay_of(b)
+            if d is None:
+                return mk(V_ZERO)
+            if is_ti(a):
+                return mk64(V_GATE, a, shift + d)
+            return mk64(V_GATE, mk64(V_TAP, a, shift + d), shift + d)
+        ca = clone_shifted(a, shift)
+        cb = clone_shifted(b, shift)
+        return mk(o, ca, cb)
+
     def maybe(ctx, vec, slot):
         if slot < len(vec) and vec[slot] is not None:
             return resolve(ctx, vec[slot])
@@ -112,7 +178,18 @@ def flatten(top, n_slots):
             assert from_slot == 0
             src = maybe(ctx, n["inbound"], 0)
             amt = maybe(ctx, n["inbound"], 1)
-            v = src if values[src][0] == V_ZERO else mk(V_DELAY, src, amt)
+            if values[src][0] == V_ZERO:
+                v = src
+            else:
+                sop = values[src][0]
+                computed = (V_SUM2 <= sop <= V_MIN) or sop == V_GATE
+                v = None
+                if computed and values[amt][0] in (V_CONST, V_ZERO):
+                    d = const_delay_of(amt)
+                    if d is not None and d < (1 << 40) and clone_cost(src, CLONE_MAX_OPS) is not None and not is_ti(src):
+                        v = mk64(V_GATE, clone_shifted(src, d), d)
+                if v is None:
+                    v = mk(V_DELAY, src, amt)
         elif kind in KIND_TO_OP:
             assert from_slot == 0
             a = maybe(ctx, n["inbound"], 0)
@@ -158,6 +235,8 @@ def flatten(top, n_slots):
             if not is_leaf(a) and not ti[a]:
                 s = max(s, st[a] if op[a] == V_EXT else st[a] + 1)
             st[v] = s
+        elif o in (V_TAP, V_GATE):
+            st[v] = st[a]
         elif o == V_EXT:
             x = ext[a]
             if "stage" not in x:
@@ -182,6 +261,8 @@ def flatten(top, n_slots):
         elif V_SUM2 <= o <= V_MIN:
             use(a)
             use(b)
+        elif o == V_GATE:
+            use(a)
     for x in ext:
         for i in x["inputs"]:
             need[i] = True
@@ -214,6 +295,10 @@ def flatten(top, n_slots):
                 d = FULL
             if d is not None:
                 raise_(a, sat_add(L[v], d))
+        elif o == V_GATE:
+            raise_(a, L[v])
+        elif o == V_TAP:
+            raise_(a, sat_add(L[v], (b << 32) | imm))
         elif o == V_EXT and imm == 0:
             x = ext[a]
             li = 0

@@ -43,8 +43,28 @@ def test_delay_line_offsets_and_stage_cut():
     rec = Recorder()
     build_cfg1_graph(rec)
     got, want = check(rec, 2)
-    lbs = sorted(b["lookback"] for b in got["buffers"])
-    assert lbs == [12000]
+    # the Delay source (in0 * 0.5) is a cheap elementwise expression: it is re-evaluated at t - 12000 from the input
+    # history (V_TAP + V_GATE) instead of being written to a ring and read back, so there is no buffer and one stage
+    assert got["buffers"] == [] and max(got["stage"]) == 0
+    taps = [v for v in got["values"] if v[0] == 10]
+    gates = [v for v in got["values"] if v[0] == 11]
+    assert [(v[2] << 32) | v[3] for v in taps] == [12000] and [(v[2] << 32) | v[3] for v in gates] == [12000]
+
+
+def test_expensive_delay_source_is_materialised_with_exact_lookback():
+    """A Delay source with more than 8 operations is materialised: ring lookback = the delay, Delay in the next stage."""
+    from graphs import GraphBuilder
+    from randgraph import Recorder
+    from libfriendship_b200 import KIND_DELAY, KIND_MULTIPLY, KIND_SUM2
+    rec = Recorder()
+    g = GraphBuilder(rec)
+    x = g.input(0)
+    for k in range(10):
+        x = g.node(KIND_SUM2 if k % 2 else KIND_MULTIPLY, x, g.input(1 + k % 3))
+    d = g.node(KIND_DELAY, x, g.const(777.0))
+    g.output(0, g.node(KIND_SUM2, d, x))
+    got, _ = check(rec, 1)
+    assert sorted(b["lookback"] for b in got["buffers"]) == [777]
     assert max(got["stage"]) == 1
 
 

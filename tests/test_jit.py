@@ -9,16 +9,25 @@ from replay import assert_same_bits, load_golden, replay
 
 
 def test_generated_source_compiles_for_sm_100a_without_a_gpu():
-    """CPU: codegen + NVRTC (--gpu-architecture=sm_100a --fmad=false) for both stages of the cfg1 graph."""
-    from libfriendship_b200 import B200Renderer
+    """CPU: codegen + NVRTC (--gpu-architecture=sm_100a --fmad=false): the cfg1 graph (single stage: the Delay
+    source is re-evaluated at t - 12000) and a graph whose Delay source is materialised (two stages)."""
+    from graphs import GraphBuilder
+    from libfriendship_b200 import B200Renderer, KIND_DELAY, KIND_MULTIPLY, KIND_SUM2
     r = B200Renderer(device=-1)
     build_cfg1_graph(r)
     src0 = r.jit_source(2, 0)
-    src1 = r.jit_source(2, 1)
-    assert "frb_stage" in src0 and "f4st_buf" in src0            # stage 0 materialises the Delay source
-    assert "f4delay<1>" in src1 and "f4st_out" in src1           # stage 1 reads it back at t - 12000
+    assert "frb_stage" in src0 and "f4tap_in" in src0 and "f4gate" in src0 and "f4st_out" in src0
     assert r.jit_cubin_size(2, 0) > 1000
-    assert r.jit_cubin_size(2, 1) > 1000
+    r2 = B200Renderer(device=-1)
+    g = GraphBuilder(r2)
+    x = g.input(0)
+    for k in range(10):
+        x = g.node(KIND_SUM2 if k % 2 else KIND_MULTIPLY, x, g.input(1 + k % 3))
+    g.output(0, g.node(KIND_SUM2, g.node(KIND_DELAY, x, g.const(777.0)), x))
+    s0, s1 = r2.jit_source(1, 0), r2.jit_source(1, 1)
+    assert "f4st_buf" in s0                                        # stage 0 materialises the Delay source
+    assert "f4delay<1>" in s1 and "f4st_out" in s1                 # stage 1 reads it back at t - 777
+    assert r2.jit_cubin_size(1, 0) > 1000 and r2.jit_cubin_size(1, 1) > 1000
 
 
 @pytest.mark.parametrize("seed", range(8))
