@@ -84,65 +84,125 @@ std::string reg(uint32_t r, int w) { return "r" + std::to_string(r) + "_" + std:
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------------------------
+// Strands with the same SHAPE (same operations on the same registers; only slot / buffer indices, immediates, shifts
+// and thresholds differ) share one code body; what differs comes from a per-strand row of a constant table.  A stage
+// that applies the same chain to 64 slots compiles one body, not 64.
 std::string jit_generate_source(const Stage& st) {
-    std::ostringstream o;
-    o << kInterpDeviceSource << "\n";
-    o << "extern \"C\" __global__ void __launch_bounds__(128) frb_stage(const InterpParams p) {\n";
-    o << "  const InputDesc no_in = {nullptr, 0ull, 0ull};\n  const BufferDesc no_buf = {nullptr, 0ull};\n";
-    o << "  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);\n";
-    o << "  (void)no_in; (void)no_buf; (void)z4;\n";
-    o << "  switch (blockIdx.y) {\n";
-    for (size_t sd = 0; sd + 1 < st.strand_offsets.size(); sd++) {
-        o << "  case " << sd << ": {\n";
-        o << "  for (unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; g < p.n_groups;\n"
-             "       g += (unsigned long long)gridDim.x * blockDim.x) {\n";
-        o << "    const unsigned long long t_0 = p.t_begin + 8ull * g, t_1 = t_0 + 4ull;\n";
-        uint32_t nreg = 0;
+    const size_t n_strands = st.strand_offsets.empty() ? 0 : st.strand_offsets.size() - 1;
+    struct Shape { std::string key; std::vector<uint32_t> strands; };
+    std::vector<Shape> shapes;
+    std::vector<uint32_t> shape_of(n_strands), idx_of(n_strands);
+    for (size_t sd = 0; sd < n_strands; sd++) {
+        std::string key;
         for (uint32_t i = st.strand_offsets[sd]; i < st.strand_offsets[sd + 1]; i++) {
             const Instr& in = st.program[i];
-            const uint32_t op = in.w0 & 0xFFu;
+            const uint32_t op = in.w0 & 0xFFu, flags = (in.w0 >> 8) & 0xFFu;
             if (op == I_END) break;
-            if (op != I_STBUF && op != I_STOUT) nreg = std::max(nreg, (in.w0 >> 16) + 1);
+            const bool a_reg = !(flags & IF_A_IMM) && op != I_LDIN && op != I_LDBUF && op != I_TAP_IN && op != I_TAP_BUF;
+            const bool b_reg = !(flags & IF_B_IMM) && (op <= I_MIN || op == I_DLY_TI);
+            char buf[64];
+            snprintf(buf, sizeof buf, "%x.%x.%x.%x;", in.w0, a_reg ? in.a : 0xffffu, b_reg ? in.b : 0xffffu, 0u);
+            key += buf;
         }
-        for (uint32_t r = 0; r < nreg; r++) o << "    float4 " << reg(r, 0) << ", " << reg(r, 1) << ";\n";
-        for (uint32_t i = st.strand_offsets[sd]; i < st.strand_offsets[sd + 1]; i++) {
-            const Instr& in = st.program[i];
+        size_t k = 0;
+        for (; k < shapes.size(); k++) if (shapes[k].key == key) break;
+        if (k == shapes.size()) shapes.push_back(Shape{key, {}});
+        shape_of[sd] = (uint32_t)k;
+        idx_of[sd] = (uint32_t)shapes[k].strands.size();
+        shapes[k].strands.push_back((uint32_t)sd);
+    }
+
+    std::ostringstream o, tables;
+    o << kInterpDeviceSource << "\n";
+    std::ostringstream body;
+    body << "extern \"C\" __global__ void __launch_bounds__(128) frb_stage(const InterpParams p) {\n";
+    body << "  const InputDesc no_in = {nullptr, 0ull, 0ull};\n  const BufferDesc no_buf = {nullptr, 0ull};\n";
+    body << "  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);\n";
+    body << "  (void)no_in; (void)no_buf; (void)z4;\n";
+    body << "  const unsigned strand = blockIdx.y;\n";
+    body << "  switch (frb_shape_of[strand]) {\n";
+    for (size_t k = 0; k < shapes.size(); k++) {
+        // the varying words of every strand of this shape, in instruction order
+        std::vector<std::vector<uint32_t>> rows(shapes[k].strands.size());
+        const uint32_t rep = shapes[k].strands[0];
+        body << "  case " << k << ": {\n";
+        body << "  const unsigned* q = frb_tab" << k << "[frb_idx_of[strand]];\n  (void)q;\n";
+        body << "  for (unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; g < p.n_groups;\n"
+                "       g += (unsigned long long)gridDim.x * blockDim.x) {\n";
+        body << "    const unsigned long long t_0 = p.t_begin + 8ull * g, t_1 = t_0 + 4ull;\n";
+        uint32_t nreg = 0;
+        for (uint32_t i = st.strand_offsets[rep]; i < st.strand_offsets[rep + 1]; i++) {
+            const uint32_t op = st.program[i].w0 & 0xFFu;
+            if (op == I_END) break;
+            if (op != I_STBUF && op != I_STOUT) nreg = std::max(nreg, (st.program[i].w0 >> 16) + 1);
+        }
+        for (uint32_t r = 0; r < nreg; r++) body << "    float4 " << reg(r, 0) << ", " << reg(r, 1) << ";\n";
+        uint32_t n_words = 0;
+        const uint32_t len = st.strand_offsets[rep + 1] - st.strand_offsets[rep];
+        for (uint32_t j = 0; j < len; j++) {
+            const Instr& in = st.program[st.strand_offsets[rep] + j];
             const uint32_t op = in.w0 & 0xFFu, flags = (in.w0 >> 8) & 0xFFu, dst = in.w0 >> 16;
             if (op == I_END) break;
+            // table words for this instruction: [a if immediate / shift-lo][b if immediate / shift-hi][aux]
+            auto word = [&](int which) {   // 0: a, 1: b, 2: aux
+                for (size_t m = 0; m < rows.size(); m++) {
+                    const Instr& im = st.program[st.strand_offsets[shapes[k].strands[m]] + j];
+                    rows[m].push_back(which == 0 ? im.a : which == 1 ? im.b : im.aux);
+                }
+                return "q[" + std::to_string(n_words++) + "]";
+            };
+            const bool tap = op == I_TAP_IN || op == I_TAP_BUF;
+            std::string wa, wb, wx;
+            if ((flags & IF_A_IMM) || tap) wa = word(0);
+            if ((flags & IF_B_IMM) || tap || op == I_GATE) wb = word(1);
+            if (op == I_LDIN || op == I_LDBUF || op == I_STBUF || op == I_STOUT || op == I_DLY_IN || op == I_DLY_BUF || tap || op == I_GATE) wx = word(2);
             for (int w = 0; w < 2; w++) {
                 const std::string t = "t_" + std::to_string(w);
-                auto opnd = [&](uint32_t v, bool imm) {
-                    char buf[48];
-                    if (imm) { snprintf(buf, sizeof buf, "f4splat(0x%08xu)", v); return std::string(buf); }
-                    return reg(v, w);
-                };
-                const std::string a = opnd(in.a, flags & IF_A_IMM), b = opnd(in.b, flags & IF_B_IMM);
-                o << "    ";
+                const std::string a = (flags & IF_A_IMM) ? "f4splat(" + wa + ")" : reg(in.a, w);
+                const std::string b = (flags & IF_B_IMM) ? "f4splat(" + wb + ")" : reg(in.b, w);
+                const std::string sh = "(((unsigned long long)" + wb + " << 32) | " + wa + ")";
+                body << "    ";
                 switch (op) {
-                    case I_ADD: o << reg(dst, w) << " = f4add(" << a << ", " << b << ");"; break;
-                    case I_MUL: o << reg(dst, w) << " = f4mul(" << a << ", " << b << ");"; break;
-                    case I_DIV: o << reg(dst, w) << " = f4div(" << a << ", " << b << ");"; break;
-                    case I_MOD: o << reg(dst, w) << " = f4mod(" << a << ", " << b << ");"; break;
-                    case I_MIN: o << reg(dst, w) << " = f4min(" << a << ", " << b << ");"; break;
-                    case I_MOV: o << reg(dst, w) << " = " << a << ";"; break;
-                    case I_LDIN: o << reg(dst, w) << " = f4ld_in(p.inputs[" << in.aux << "], " << t << ");"; break;
-                    case I_LDBUF: o << reg(dst, w) << " = f4ld_buf(p.buffers[" << in.aux << "], " << t << ");"; break;
-                    case I_STBUF: o << "f4st_buf(p.buffers[" << in.aux << "], " << t << ", " << a << ");"; break;
-                    case I_STOUT: o << "f4st_out(p, " << in.aux << "u, " << t << ", " << a << ");"; break;
-                    case I_TAP_IN: o << reg(dst, w) << " = f4tap_in(p.inputs[" << in.aux << "], " << t << ", " << ((((unsigned long long)in.b) << 32) | in.a) << "ull);"; break;
-                    case I_TAP_BUF: o << reg(dst, w) << " = f4tap_buf(p.buffers[" << in.aux << "], " << t << ", " << ((((unsigned long long)in.b) << 32) | in.a) << "ull);"; break;
-                    case I_GATE: o << reg(dst, w) << " = f4gate(" << a << ", " << t << ", " << ((((unsigned long long)in.aux) << 32) | in.b) << "ull);"; break;
-                    case I_DLY_IN: o << reg(dst, w) << " = f4delay<0>(p.inputs[" << in.aux << "], no_buf, " << a << ", z4, " << t << ", p.sparkle_delay);"; break;
-                    case I_DLY_BUF: o << reg(dst, w) << " = f4delay<1>(no_in, p.buffers[" << in.aux << "], " << a << ", z4, " << t << ", p.sparkle_delay);"; break;
-                    case I_DLY_TI: o << reg(dst, w) << " = f4delay<2>(no_in, no_buf, " << a << ", " << b << ", " << t << ", p.sparkle_delay);"; break;
-                    default: o << "/* unknown op " << op << " */"; break;
+                    case I_ADD: body << reg(dst, w) << " = f4add(" << a << ", " << b << ");"; break;
+                    case I_MUL: body << reg(dst, w) << " = f4mul(" << a << ", " << b << ");"; break;
+                    case I_DIV: body << reg(dst, w) << " = f4div(" << a << ", " << b << ");"; break;
+                    case I_MOD: body << reg(dst, w) << " = f4mod(" << a << ", " << b << ");"; break;
+                    case I_MIN: body << reg(dst, w) << " = f4min(" << a << ", " << b << ");"; break;
+                    case I_MOV: body << reg(dst, w) << " = " << a << ";"; break;
+                    case I_LDIN: body << reg(dst, w) << " = f4ld_in(p.inputs[" << wx << "], " << t << ");"; break;
+                    case I_LDBUF: body << reg(dst, w) << " = f4ld_buf(p.buffers[" << wx << "], " << t << ");"; break;
+                    case I_STBUF: body << "f4st_buf(p.buffers[" << wx << "], " << t << ", " << a << ");"; break;
+                    case I_STOUT: body << "f4st_out(p, " << wx << ", " << t << ", " << a << ");"; break;
+                    case I_TAP_IN: body << reg(dst, w) << " = f4tap_in(p.inputs[" << wx << "], " << t << ", " << sh << ");"; break;
+                    case I_TAP_BUF: body << reg(dst, w) << " = f4tap_buf(p.buffers[" << wx << "], " << t << ", " << sh << ");"; break;
+                    case I_GATE: body << reg(dst, w) << " = f4gate(" << a << ", " << t << ", (((unsigned long long)" << wx << " << 32) | " << wb << "));"; break;
+                    case I_DLY_IN: body << reg(dst, w) << " = f4delay<0>(p.inputs[" << wx << "], no_buf, " << a << ", z4, " << t << ", p.sparkle_delay);"; break;
+                    case I_DLY_BUF: body << reg(dst, w) << " = f4delay<1>(no_in, p.buffers[" << wx << "], " << a << ", z4, " << t << ", p.sparkle_delay);"; break;
+                    case I_DLY_TI: body << reg(dst, w) << " = f4delay<2>(no_in, no_buf, " << a << ", " << b << ", " << t << ", p.sparkle_delay);"; break;
+                    default: body << "/* unknown op " << op << " */"; break;
                 }
-                o << "\n";
+                body << "\n";
             }
         }
-        o << "  }\n  } break;\n";
+        body << "  }\n  } break;\n";
+        tables << "__device__ const unsigned frb_tab" << k << "[" << rows.size() << "][" << std::max<uint32_t>(n_words, 1) << "] = {";
+        for (size_t m = 0; m < rows.size(); m++) {
+            tables << (m ? ",{" : "{");
+            if (rows[m].empty()) tables << "0u";
+            for (size_t j = 0; j < rows[m].size(); j++) tables << (j ? "," : "") << rows[m][j] << "u";
+            tables << "}";
+        }
+        tables << "};\n";
     }
-    o << "  default: break;\n  }\n}\n";
+    body << "  default: break;\n  }\n}\n";
+    tables << "__device__ const unsigned frb_shape_of[" << std::max<size_t>(n_strands, 1) << "] = {";
+    for (size_t sd = 0; sd < n_strands; sd++) tables << (sd ? "," : "") << shape_of[sd] << "u";
+    if (!n_strands) tables << "0u";
+    tables << "};\n__device__ const unsigned frb_idx_of[" << std::max<size_t>(n_strands, 1) << "] = {";
+    for (size_t sd = 0; sd < n_strands; sd++) tables << (sd ? "," : "") << idx_of[sd] << "u";
+    if (!n_strands) tables << "0u";
+    tables << "};\n";
+    o << tables.str() << body.str();
     return o.str();
 }
 

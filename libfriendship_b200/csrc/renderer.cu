@@ -465,7 +465,7 @@ void Renderer::run_range(uint64_t lo, uint64_t hi, float* d_out, uint64_t t0, ui
             // once by NVRTC into a fused kernel.  A stage that fails to compile stays on the interpreter.
             StageJit& sj = stage_jit_[sg];
             sj.uses++;
-            if (sj.state == 0 && !(cfg_.flags & FRB_FLAG_NO_JIT) && st.program.size() <= 4096 &&   // bound the compile time
+            if (sj.state == 0 && !(cfg_.flags & FRB_FLAG_NO_JIT) && st.program.size() <= 65536 &&   // bound the generated source
                 ((cfg_.flags & FRB_FLAG_JIT_EAGER) || sj.uses >= 4 || p.n_groups >= (1ull << 15))) {
                 std::string jerr;
                 sj.k = jit_build(st, &jerr);
