@@ -239,6 +239,10 @@ struct JitKernel {
 JitKernel* jit_build(const Stage& st, std::string* err) {
     std::string cubin, log;
     if (!jit_compile_to_cubin(jit_generate_source(st), &cubin, &log)) { if (err) *err = "NVRTC: " + log; return nullptr; }
+    return jit_load(cubin, err);
+}
+
+JitKernel* jit_load(const std::string& cubin, std::string* err) {
     Api& a = api(true);
     if (!a.ok) { if (err) *err = a.why; return nullptr; }
     auto* k = new JitKernel();

@@ -17,6 +17,8 @@ std::string jit_generate_source(const Stage& st);
 bool jit_compile_to_cubin(const std::string& source, std::string* cubin, std::string* log);
 // compile + load into the current context; nullptr on failure
 JitKernel* jit_build(const Stage& st, std::string* err);
+// load an already compiled cubin (jit_compile_to_cubin) into the current context
+JitKernel* jit_load(const std::string& cubin, std::string* err);
 void jit_free(JitKernel* k);
 bool jit_launch(JitKernel* k, const InterpParams& p, int sm_count, cudaStream_t stream);
 

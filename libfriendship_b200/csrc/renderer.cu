@@ -4,6 +4,7 @@
 #include "renderer.hpp"
 
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 
 namespace frb {
@@ -169,7 +170,10 @@ void Renderer::del_edge(const frb_edge& e) {                               // re
 void Renderer::free_device_schedule() {
     for (auto p : d_programs_) if (p) cudaFree(p);
     d_programs_.clear();
-    for (auto& j : stage_jit_) jit_free(j.k);
+    for (auto& j : stage_jit_) {
+        if (j.state == 3 && j.cubin.valid()) j.cubin.wait();   // never leave a compile thread behind
+        jit_free(j.k);
+    }
     stage_jit_.clear();
     for (auto& g : ring_groups_) if (g.data) cudaFree(g.data);
     ring_groups_.clear();
@@ -216,7 +220,7 @@ void Renderer::ensure_schedule(uint32_t n_slots) { (void)schedule(n_slots); }
 
 void Renderer::upload_schedule() {
     d_programs_.assign(sched_.stages.size(), nullptr);
-    stage_jit_.assign(sched_.stages.size(), StageJit{});
+    stage_jit_ = std::vector<StageJit>(sched_.stages.size());   // StageJit holds a future: not copyable
     for (size_t i = 0; i < sched_.stages.size(); i++) {
         // device layout: [strand offsets, padded to a multiple of 4 words][instructions]
         const Stage& stg = sched_.stages[i];
@@ -467,10 +471,28 @@ void Renderer::run_range(uint64_t lo, uint64_t hi, float* d_out, uint64_t t0, ui
             sj.uses++;
             if (sj.state == 0 && !(cfg_.flags & FRB_FLAG_NO_JIT) && st.program.size() <= 65536 &&   // bound the generated source
                 ((cfg_.flags & FRB_FLAG_JIT_EAGER) || sj.uses >= 4 || p.n_groups >= (1ull << 15))) {
+                if ((cfg_.flags & FRB_FLAG_JIT_EAGER) || p.n_groups >= (1ull << 15)) {
+                    // a long block (or an explicit request) pays for the ~0.2 s of NVRTC right away
+                    std::string jerr;
+                    sj.k = jit_build(st, &jerr);
+                    sj.state = sj.k ? 1 : 2;
+                    if (!sj.k) last_jit_error = jerr;
+                } else {
+                    // streaming in short blocks: compile beside the render loop, never stall a block for it
+                    const std::string src = jit_generate_source(st);
+                    sj.cubin = std::async(std::launch::async, [src]() {
+                        std::string cubin, log;
+                        return jit_compile_to_cubin(src, &cubin, &log) ? cubin : std::string();
+                    });
+                    sj.state = 3;
+                }
+            }
+            if (sj.state == 3 && sj.cubin.wait_for(std::chrono::seconds(0)) == std::future_status::ready) {
+                const std::string cubin = sj.cubin.get();
                 std::string jerr;
-                sj.k = jit_build(st, &jerr);
+                sj.k = cubin.empty() ? nullptr : jit_load(cubin, &jerr);
                 sj.state = sj.k ? 1 : 2;
-                if (!sj.k) last_jit_error = jerr;
+                if (!sj.k) last_jit_error = cubin.empty() ? "NVRTC compile failed" : jerr;
             }
             if (sj.state == 1 && jit_launch(sj.k, p, sm_count_, stream_)) {
                 stats.jit_launches++;

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <future>
 #include <map>
 #include <memory>
 #include <string>
@@ -91,7 +92,8 @@ private:
 
     // device-resident schedule
     std::vector<uint32_t*> d_programs_;         // per stage
-    struct StageJit { JitKernel* k = nullptr; int state = 0; uint64_t uses = 0; };   // state: 0 untried, 1 ready, 2 failed
+    // state: 0 untried, 1 ready, 2 failed, 3 compiling in the background (the stage keeps being interpreted meanwhile)
+    struct StageJit { JitKernel* k = nullptr; int state = 0; uint64_t uses = 0; std::future<std::string> cubin; };
     std::vector<StageJit> stage_jit_;
     std::vector<uint32_t*> d_ext_in_bufs_;      // per extension instance: input ring ids per lane
     std::vector<BufferDesc> h_bufdesc_;

@@ -90,10 +90,39 @@ def case_cfg3(n_voices=4096, n=480000):
             "K4_frac": alg / t["scan_ms"] / 1e6 / HBM, "voice_samples_per_s": n_voices * n / (t["total_ms"] * 1e-3)}
 
 
+def case_cfg1():
+    """cfg1: 440 Hz sine through Multiply/Sum/Delay (+ Min/Mod/Div side chain), 48 kHz x 1 s, host in/out through
+    frb_fill_buffer: one call, and 94 x 512-sample streaming calls.  Latency-bound: reported as us per block."""
+    from graphs import build_cfg1_graph, cfg1_input
+    n = 48000
+    x = cfg1_input(n)
+    r = B200Renderer()
+    build_cfg1_graph(r)
+    for _ in range(3):
+        r.fill_buffer(2, n, 0, [x])
+    t0 = time.perf_counter()
+    for _ in range(10):
+        r.fill_buffer(2, n, 0, [x])
+    whole_us = (time.perf_counter() - t0) / 10 * 1e6
+    out = np.zeros((2, 512), dtype=np.float32)
+    def stream():
+        for s0 in range(0, n, 512):
+            m = min(512, n - s0)
+            r.fill_buffer(2, m, s0, [x[s0:s0 + m]], out=out[:, :m] if m == 512 else None)
+    stream()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        stream()
+    blk_us = (time.perf_counter() - t0) / 3 / 94 * 1e6
+    return {"case": "cfg1 render_prim-style graph, 48 kHz x 1 s, host buffers", "one_call_us": whole_us,
+            "us_per_512_sample_block": blk_us, "realtime_factor_streaming": (512 / 48000 * 1e6) / blk_us,
+            "jit_launches": r.stats()["jit_launches"]}
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["pure", "elementwise", "cfg3"]
     for w in which:
-        fn = {"pure": case_pure_elementwise, "elementwise": case_elementwise, "cfg3": case_cfg3}[w]
+        fn = {"pure": case_pure_elementwise, "elementwise": case_elementwise, "cfg3": case_cfg3, "cfg1": case_cfg1}[w]
         t0 = time.time()
         try:
             res = fn()
