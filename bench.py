@@ -127,12 +127,12 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
-def workload_config(n_gpus):
+def workload_config(n_gpus, exchange="NCCL reduce"):
     return {"workload": "cfg4: 65,536 detuned partials x 64 voices, envelopes + per-voice Delay/mix, 48 kHz x 10 s "
                         "(BASELINE.json configs[3])",
             "voices": N_VOICES, "partials_per_voice": N_PARTIALS, "samples": N_SAMPLES, "sample_rate": SR,
             "partial_samples_per_step": N_VOICES * N_PARTIALS * N_SAMPLES,
-            "sharding": f"voices round-robin over {n_gpus} GPU(s), one NCCL reduce of the [1 x 480000] mix per step",
+            "sharding": f"voices round-robin over {n_gpus} GPU(s), one {exchange} exchange of the [1 x 480000] mix per step",
             "cache": "compute-bound; per-step parameter stream 201 MB/GPU-shard-of-64 > 126 MB L2, re-read every 64k-sample block",
             "inputs": "none per step (synthesis): bank parameters are uploaded once from host arrays through "
                       "frb_define_oscbank, outside the timed region (SURVEY.md §8d)"}
@@ -149,6 +149,9 @@ def main():
     ap.add_argument("--samples", type=int, default=N_SAMPLES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--osc-anchor", type=int, default=0, help="debug: K1 segment length / re-anchor interval")
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "p2p"],
+                    help="N > 1: nccl = one NCCL reduce of the mix blocks (default); p2p = K5, the stage kernel stores its "
+                         "block into rank 0's slab over NVLink (CUDA IPC) and rank 0 sums the rows in rank order")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -167,7 +170,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     n_voices, n_partials, n_samples = args.voices, args.partials, args.samples
-    sr = ShardedRenderer(rank=rank, world_size=world, device=local_rank, osc_anchor=args.osc_anchor)
+    sr = ShardedRenderer(rank=rank, world_size=world, device=local_rank, osc_anchor=args.osc_anchor, exchange=args.exchange)
     my_voices = sr.voices_of_rank(n_voices)
     bank, ids = detuned_bank(n_voices, n_partials, voices=my_voices)
     build_voice_mix_graph(sr.r, bank, ids)
@@ -251,7 +254,7 @@ def main():
             "metric": "rendered partial-samples/sec", "value": value, "unit": "partial-samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(world),
+            "config": workload_config(world, "NCCL reduce" if args.exchange == "nccl" else "P2P-store + rank-ordered sum (K5)"),
             "e2e": {"value": e2e_v, "unit": "partial-samples/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 4 * n_samples, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(s1["kernel_launches"] - s0["kernel_launches"]),

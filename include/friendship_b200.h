@@ -147,6 +147,22 @@ int frb_fill_buffer_device(frb_renderer* r, float* d_out, uint32_t n_slots, uint
 int frb_sync(frb_renderer* r);
 void* frb_stream(frb_renderer* r);   /* the cudaStream_t the renderer launches on */
 
+/* ---- K5: cross-GPU mix without a separate collective ----
+ * One process per GPU.  Rank 0 owns a slab [world x n_slots x n_times] in its HBM; every rank renders its shard of
+ * the voices with frb_fill_buffer_device pointing at ITS row of that slab (the stage kernel's output stores go
+ * straight over NVLink through a CUDA-IPC mapping: the mix epilogue and the transfer are one kernel), and after a
+ * barrier rank 0 sums the rows in rank order (deterministic, unlike a tree reduce) with frb_sum_rows.
+ * frb_ipc_export / frb_ipc_open wrap cudaIpcGetMemHandle / cudaIpcOpenMemHandle (64-byte opaque handle). */
+/* plain cudaMalloc / cudaFree on the renderer's device: an IPC handle names a whole allocation, so the slab must not
+ * be a sub-block of a pooling allocator */
+int frb_device_alloc(frb_renderer* r, uint64_t bytes, void** d_ptr_out);
+int frb_device_free(frb_renderer* r, void* d_ptr);
+int frb_ipc_export(frb_renderer* r, const void* d_ptr, unsigned char handle[64]);
+int frb_ipc_open(frb_renderer* r, const unsigned char handle[64], void** d_ptr_out);
+int frb_ipc_close(frb_renderer* r, void* d_ptr);
+/* d_out[i] = ((rows[0][i] + rows[1][i]) + ...) + rows[n_rows-1][i], rows contiguous with stride row_stride floats */
+int frb_sum_rows(frb_renderer* r, float* d_out, const float* d_rows, uint32_t n_rows, uint64_t row_stride, uint64_t n);
+
 /* ---- introspection for parity tests of routing order / buffer indexing / delay-line offsets ---- */
 /* Builds (if dirty) the device schedule for `n_slots` outputs and copies it out as u32 words:
  * see libfriendship_b200/csrc/schedule.hpp for the record layout.  Returns the number of words the

@@ -24,6 +24,12 @@ _cabi.declare(_lib, "frb")
 _lib.frb_create.argtypes = [_C.POINTER(_cabi.frb_config)]
 _lib.frb_create.restype = _C.c_void_p
 _lib.frb_version.restype = _C.c_char_p
+_lib.frb_device_alloc.argtypes = [_C.c_void_p, _C.c_uint64, _C.POINTER(_C.c_void_p)]
+_lib.frb_device_free.argtypes = [_C.c_void_p, _C.c_void_p]
+_lib.frb_ipc_export.argtypes = [_C.c_void_p, _C.c_void_p, _C.POINTER(_C.c_ubyte)]
+_lib.frb_ipc_open.argtypes = [_C.c_void_p, _C.POINTER(_C.c_ubyte), _C.POINTER(_C.c_void_p)]
+_lib.frb_ipc_close.argtypes = [_C.c_void_p, _C.c_void_p]
+_lib.frb_sum_rows.argtypes = [_C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_uint32, _C.c_uint64, _C.c_uint64]
 
 
 def version():
@@ -85,6 +91,32 @@ class B200Renderer(_cabi.CRendererBase):
         if n < 0:
             self._check(int(n))
         return int(n)
+
+    # ---- K5: CUDA-IPC plumbing for the cross-GPU mix (see include/friendship_b200.h) ----
+    def device_alloc(self, nbytes):
+        out = _C.c_void_p()
+        self._check(_lib.frb_device_alloc(self._h, nbytes, _C.byref(out)))
+        return out.value
+
+    def device_free(self, d_ptr):
+        self._check(_lib.frb_device_free(self._h, _C.c_void_p(d_ptr)))
+
+    def ipc_export(self, d_ptr):
+        h = (_C.c_ubyte * 64)()
+        self._check(_lib.frb_ipc_export(self._h, _C.c_void_p(d_ptr), h))
+        return bytes(h)
+
+    def ipc_open(self, handle):
+        out = _C.c_void_p()
+        h = (_C.c_ubyte * 64).from_buffer_copy(handle)
+        self._check(_lib.frb_ipc_open(self._h, h, _C.byref(out)))
+        return out.value
+
+    def ipc_close(self, d_ptr):
+        self._check(_lib.frb_ipc_close(self._h, _C.c_void_p(d_ptr)))
+
+    def sum_rows(self, d_out, d_rows, n_rows, row_stride, n):
+        self._check(_lib.frb_sum_rows(self._h, _C.c_void_p(d_out), _C.c_void_p(d_rows), n_rows, row_stride, n))
 
     def stats(self):
         s = _cabi.frb_stats()

@@ -94,6 +94,46 @@ int frb_fill_buffer_device(frb_renderer* r, float* d_out, uint32_t n_slots, uint
 int frb_sync(frb_renderer* r) { return guarded(r, [&] { r->impl.sync(); }); }
 void* frb_stream(frb_renderer* r) { return r ? (void*)r->impl.stream() : nullptr; }
 
+int frb_device_alloc(frb_renderer* r, uint64_t bytes, void** d_ptr_out) {
+    return guarded(r, [&] {
+        cudaError_t e = cudaMalloc(d_ptr_out, bytes);
+        if (e == cudaSuccess) e = cudaMemset(*d_ptr_out, 0, bytes);
+        if (e != cudaSuccess) throw Error{FRB_E_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e)};
+    });
+}
+int frb_device_free(frb_renderer* r, void* d_ptr) {
+    return guarded(r, [&] {
+        cudaError_t e = cudaFree(d_ptr);
+        if (e != cudaSuccess) throw Error{FRB_E_CUDA, std::string("cudaFree: ") + cudaGetErrorString(e)};
+    });
+}
+int frb_ipc_export(frb_renderer* r, const void* d_ptr, unsigned char handle[64]) {
+    return guarded(r, [&] {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        cudaIpcMemHandle_t h;
+        cudaError_t e = cudaIpcGetMemHandle(&h, const_cast<void*>(d_ptr));
+        if (e != cudaSuccess) throw Error{FRB_E_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)};
+        memcpy(handle, &h, 64);
+    });
+}
+int frb_ipc_open(frb_renderer* r, const unsigned char handle[64], void** d_ptr_out) {
+    return guarded(r, [&] {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handle, 64);
+        cudaError_t e = cudaIpcOpenMemHandle(d_ptr_out, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) throw Error{FRB_E_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e)};
+    });
+}
+int frb_ipc_close(frb_renderer* r, void* d_ptr) {
+    return guarded(r, [&] {
+        cudaError_t e = cudaIpcCloseMemHandle(d_ptr);
+        if (e != cudaSuccess) throw Error{FRB_E_CUDA, std::string("cudaIpcCloseMemHandle: ") + cudaGetErrorString(e)};
+    });
+}
+int frb_sum_rows(frb_renderer* r, float* d_out, const float* d_rows, uint32_t n_rows, uint64_t row_stride, uint64_t n) {
+    return guarded(r, [&] { r->impl.sum_rows(d_out, d_rows, n_rows, row_stride, n); });
+}
+
 int64_t frb_dump_schedule(frb_renderer* r, uint32_t n_slots, uint32_t* words, uint64_t cap) {
     int64_t n = 0;
     int rc = guarded(r, [&] {

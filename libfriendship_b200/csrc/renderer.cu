@@ -31,6 +31,27 @@ __global__ void pad_kernel(float* data, unsigned long long start, unsigned long 
         data[start + i] = v;
 }
 
+// K5: rank-ordered sum of the per-rank mix rows (deterministic left fold, like every other sum on the path)
+__global__ void sum_rows_kernel(float* __restrict__ out, const float* __restrict__ rows, unsigned n_rows,
+                                unsigned long long stride, unsigned long long n) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        float acc = rows[i];
+        for (unsigned r = 1; r < n_rows; r++) acc = __fadd_rn(acc, rows[r * stride + i]);
+        out[i] = acc;
+    }
+}
+
+void Renderer::sum_rows(float* d_out, const float* d_rows, uint32_t n_rows, uint64_t row_stride, uint64_t n) {
+    require_device();
+    CU(cudaSetDevice(device_));
+    if (!n || !n_rows) return;
+    unsigned blocks = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)sm_count_ * 8);
+    sum_rows_kernel<<<blocks, 256, 0, stream_>>>(d_out, d_rows, n_rows, row_stride, n);
+    CU(cudaGetLastError());
+    stats.kernel_launches++;
+}
+
 Renderer::Renderer(const frb_config& cfg) : cfg_(cfg) {
     if (cfg.device < 0) {
         // planning-only instance: graph mirror + schedule dumps; rendering is refused (there is no CPU fallback)

@@ -48,6 +48,7 @@ public:
     void fill(float* out, bool out_on_device, uint32_t n_slots, uint64_t n_times, uint64_t idx,
               const float* in_data, bool in_on_device, const uint64_t* in_row_offsets, uint32_t n_in_rows);
     void sync();
+    void sum_rows(float* d_out, const float* d_rows, uint32_t n_rows, uint64_t row_stride, uint64_t n);
 
     const Schedule& schedule(uint32_t n_slots);   // (re)builds if needed
     cudaStream_t stream() const { return stream_; }

@@ -18,12 +18,17 @@ class ShardedRenderer:
     """`renderer` defaults to a B200Renderer on `device`.  Tests inject another object with the renderer interface
     (host path: fill_buffer) to exercise the shard/reduce logic over gloo without a GPU."""
 
-    def __init__(self, rank=0, world_size=1, device=0, renderer=None, **kw):
+    def __init__(self, rank=0, world_size=1, device=0, renderer=None, exchange="nccl", **kw):
+        """exchange: "nccl" — torch.distributed reduce of the per-rank mix blocks (default);
+        "p2p" — K5: every rank's stage kernel stores its mix block straight into rank 0's slab over NVLink
+        (CUDA-IPC mapping), one barrier, rank 0 sums the rows in rank order (deterministic)."""
         self.rank, self.world_size, self.device = rank, world_size, device
         self.on_gpu = renderer is None
         self.r = B200Renderer(device=device, **kw) if renderer is None else renderer
+        self.exchange = exchange if (self.on_gpu and world_size > 1) else "nccl"
         self._out = None
         self._host = None
+        self._slabs = None          # p2p: (shape, [slab tensors on rank 0], [row pointers of this rank], step counter)
 
     def voices_of_rank(self, n_voices):
         return voices_of_rank(n_voices, self.rank, self.world_size)
@@ -47,8 +52,48 @@ class ShardedRenderer:
         """The CUDA stream the renderer launches on, as a torch stream (for CUDA-event timing)."""
         return torch.cuda.ExternalStream(self.r.stream(), device=f"cuda:{self.device}")
 
+    def _p2p_setup(self, n_slots, n_times):
+        import torch.distributed as dist
+        shape = (n_slots, n_times)
+        if self._slabs is not None and self._slabs[0] == shape:
+            return
+        n = n_slots * n_times
+        slabs, handles = [], [None, None]
+        if self.rank == 0:
+            for k in range(2):                      # double-buffered: one barrier per step is enough
+                # its own cudaMalloc: an IPC handle names a whole allocation, not a sub-block of torch's pool
+                slab = self.r.device_alloc(4 * n * self.world_size)
+                slabs.append(slab)
+                handles[k] = self.r.ipc_export(slab)
+        dist.broadcast_object_list(handles, src=0)
+        if self.rank == 0:
+            rows = list(slabs)
+        else:
+            rows = [self.r.ipc_open(h) + 4 * n * self.rank for h in handles]
+        self._slabs = [shape, slabs, rows, 0]
+
+    def _fill_p2p(self, n_slots, n_times, idx):
+        import torch.distributed as dist
+        self._p2p_setup(n_slots, n_times)
+        shape, slabs, rows, step = self._slabs
+        k = step % 2
+        self._slabs[3] = step + 1
+        # the stage kernel's output stores ARE the transfer: row `rank` of rank 0's slab, over NVLink
+        self.r.fill_buffer_device(rows[k], n_slots, n_times, idx)
+        self.r.sync()
+        dist.barrier()
+        out = self._block(n_slots, n_times)
+        if self.rank == 0:
+            n = n_slots * n_times
+            self.r.sum_rows(out.data_ptr(), slabs[k], self.world_size, n, n)
+            self.r.sync()
+        return out
+
     def fill_buffer_device(self, n_slots, n_times, idx, inputs=None):
         """Renders this rank's shard and reduces onto rank 0.  Returns the block tensor (valid on rank 0)."""
+        if self.exchange == "p2p":
+            assert not inputs
+            return self._fill_p2p(n_slots, n_times, idx)
         out = self._block(n_slots, n_times)
         if self.on_gpu:
             assert not inputs, "device path: feed external inputs through B200Renderer.fill_buffer_device directly"
@@ -59,7 +104,8 @@ class ShardedRenderer:
         return self._reduce(out)
 
     def fill_buffer(self, n_slots, n_times, idx, inputs=None):
-        """End-to-end: host ndarray on rank 0 (None elsewhere); includes the device->host copy."""
+        """End-to-end: host ndarray on rank 0 (None elsewhere); includes the device->host copy.
+        The returned array is a view of a pinned staging block that the next call overwrites."""
         out = self.fill_buffer_device(n_slots, n_times, idx, inputs)
         if not self.on_gpu:
             return out.numpy().copy() if self.rank == 0 else None
