@@ -32,14 +32,16 @@
 
 namespace frb {
 
-constexpr int OSC_K = 16;           // partials per group (independent FMA chains per thread)
+constexpr int OSC_K = 16;           // partials per group (independent FMA chains per thread) for ordinary banks
+constexpr int OSC_K_SMALL = 4;      // banks whose voices have <= 8 partials (e.g. one exciter per voice): less padding
 constexpr int OSC_THREADS = 32;     // threads (= time segments) per CTA: one warp, so the per-group barrier couples no warps
 constexpr int OSC_LMAX = 256;       // max segment length (shared memory: L * THREADS * 4 B)
 
 struct OscBankDev {
     uint32_t n_voices = 0;
     uint64_t n_partials = 0;        // as defined by the user
-    uint64_t n_records = 0;         // after per-(voice, class) padding to multiples of OSC_K
+    uint64_t n_records = 0;         // after per-(voice, class) padding to multiples of K
+    int K = OSC_K;                  // group size of this bank's record layout
     double sample_rate = 48000.0;
     float max_attack = 0.0f;
     uint32_t max_groups = 0;        // largest number of groups in one voice
@@ -137,12 +139,18 @@ std::shared_ptr<OscBankDev> osc_create(const frb_oscbank_desc* d, cudaStream_t s
     // group by (voice, class), pad every class segment to a multiple of K with silent partials
     std::vector<uint32_t> grp_begin(d->n_voices), n_grp0(d->n_voices), n_grp(d->n_voices);
     std::vector<uint64_t> order;            // source index per record, ~0 = padding
-    order.reserve(d->n_partials + (uint64_t)d->n_voices * 2 * OSC_K);
+    {
+        uint64_t mx = 0;
+        for (uint32_t v = 0; v < d->n_voices; v++) mx = std::max<uint64_t>(mx, d->voice_offsets[v + 1] - d->voice_offsets[v]);
+        b->K = (mx <= 8) ? OSC_K_SMALL : OSC_K;
+    }
+    const int K = b->K;
+    order.reserve(d->n_partials + (uint64_t)d->n_voices * 2 * K);
     float max_attack = 0.f;
     for (uint32_t v = 0; v < d->n_voices; v++) {
         uint64_t lo = d->voice_offsets[v], hi = d->voice_offsets[v + 1];
         if (hi < lo) return fail("oscbank: voice_offsets must be non-decreasing");
-        grp_begin[v] = (uint32_t)(order.size() / OSC_K);
+        grp_begin[v] = (uint32_t)(order.size() / K);
         for (int cls = 0; cls < 2; cls++) {
             for (uint64_t p = lo; p < hi; p++) {
                 double fr = d->freq_hz[p] / d->sample_rate;
@@ -150,10 +158,10 @@ std::shared_ptr<OscBankDev> osc_create(const frb_oscbank_desc* d, cudaStream_t s
                 bool c1 = fr > 0.25 && fr < 0.75;
                 if ((int)c1 == cls) order.push_back(p);
             }
-            while (order.size() % OSC_K) order.push_back(~0ull);
-            if (cls == 0) n_grp0[v] = (uint32_t)(order.size() / OSC_K) - grp_begin[v];
+            while (order.size() % K) order.push_back(~0ull);
+            if (cls == 0) n_grp0[v] = (uint32_t)(order.size() / K) - grp_begin[v];
         }
-        n_grp[v] = (uint32_t)(order.size() / OSC_K) - grp_begin[v];
+        n_grp[v] = (uint32_t)(order.size() / K) - grp_begin[v];
         b->max_groups = std::max(b->max_groups, n_grp[v]);
     }
     for (uint64_t p = 0; p < d->n_partials; p++)
@@ -459,6 +467,8 @@ static cudaError_t launch_osc_range(const OscBankDev& b, const BufferDesc* d_buf
         const int mx = OSC_LMAX * OSC_THREADS * (int)sizeof(float);
         cudaError_t e = cudaFuncSetAttribute(osc_kernel<OSC_K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(osc_kernel<OSC_K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(osc_kernel<OSC_K_SMALL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(osc_kernel<OSC_K_SMALL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -487,7 +497,8 @@ static cudaError_t launch_osc_range(const OscBankDev& b, const BufferDesc* d_buf
             st = b.side;
         }
         dim3 grid((n_att + threads - 1) / threads, b.n_voices, p.split);
-        osc_kernel<OSC_K, true><<<grid, threads, smem, st>>>(q);
+        if (b.K == OSC_K) osc_kernel<OSC_K, true><<<grid, threads, smem, st>>>(q);
+        else osc_kernel<OSC_K_SMALL, true><<<grid, threads, smem, st>>>(q);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         if (n_launches) (*n_launches)++;
@@ -498,7 +509,8 @@ static cudaError_t launch_osc_range(const OscBankDev& b, const BufferDesc* d_buf
         q.nseg = nseg_total - n_att;
         q.plane_off = (unsigned long long)n_att * L;
         dim3 grid((q.nseg + threads - 1) / threads, b.n_voices, p.split);
-        osc_kernel<OSC_K, false><<<grid, threads, smem, stream>>>(q);
+        if (b.K == OSC_K) osc_kernel<OSC_K, false><<<grid, threads, smem, stream>>>(q);
+        else osc_kernel<OSC_K_SMALL, false><<<grid, threads, smem, stream>>>(q);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         if (n_launches) (*n_launches)++;
