@@ -256,6 +256,11 @@ cudaError_t launch_fold(const BufferDesc* d_bufdesc, unsigned first, unsigned co
     return cudaGetLastError();
 }
 
+// per device, called when a renderer is created on it
+cudaError_t interp_init_device() {
+    return cudaFuncSetAttribute(interp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+}
+
 cudaError_t launch_interp(const InterpParams& p_in, unsigned n_regs, int sm_count, cudaStream_t stream) {
     if (p_in.n_groups == 0) return cudaSuccess;
     InterpParams p = p_in;
@@ -273,12 +278,6 @@ cudaError_t launch_interp(const InterpParams& p_in, unsigned n_regs, int sm_coun
     unsigned long long cap = ((unsigned long long)sm_count * per_sm + p.n_strands - 1) / p.n_strands;
     if (cap < 1) cap = 1;
     if (blocks > cap) blocks = cap;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(interp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
     interp_kernel<<<dim3((unsigned)blocks, p.n_strands), threads, smem, stream>>>(p);
     return cudaGetLastError();
 }

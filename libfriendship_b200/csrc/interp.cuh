@@ -14,6 +14,7 @@ constexpr int INTERP_VW = 2;           // float4 per thread per register: 8 cons
 
 cudaError_t launch_fold(const BufferDesc* d_bufdesc, unsigned first, unsigned count, unsigned out_buf,
                         unsigned long long lo, unsigned long long hi, int sm_count, cudaStream_t stream);
+cudaError_t interp_init_device();
 cudaError_t launch_interp(const InterpParams& p, unsigned n_regs, int sm_count, cudaStream_t stream);
 
 }  // namespace frb

@@ -414,6 +414,16 @@ __global__ void osc_reduce_kernel(OscLaunch p) {
 static cudaError_t launch_osc_range(const OscBankDev& b, const BufferDesc* d_bufdesc, uint32_t first_buf, uint64_t lo, uint64_t hi,
                                     uint32_t anchor, int sm_count, cudaStream_t stream, uint64_t* n_launches);
 
+// per device, called when a renderer is created on it: the accumulator columns need up to 32 KB of dynamic shared memory
+cudaError_t osc_init_device() {
+    const int mx = OSC_LMAX * OSC_THREADS * (int)sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(osc_kernel<OSC_K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(osc_kernel<OSC_K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(osc_kernel<OSC_K_SMALL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(osc_kernel<OSC_K_SMALL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    return e;
+}
+
 cudaError_t launch_osc(const OscBankDev& b, const BufferDesc* d_bufdesc, uint32_t first_buf, uint64_t lo, uint64_t hi,
                        uint32_t anchor, int sm_count, cudaStream_t stream, uint64_t* n_launches) {
     if (n_launches) *n_launches = 0;
@@ -462,16 +472,6 @@ static cudaError_t launch_osc_range(const OscBankDev& b, const BufferDesc* d_buf
     }
     const unsigned threads = OSC_THREADS;
     const size_t smem = (size_t)L * threads * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        const int mx = OSC_LMAX * OSC_THREADS * (int)sizeof(float);
-        cudaError_t e = cudaFuncSetAttribute(osc_kernel<OSC_K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(osc_kernel<OSC_K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(osc_kernel<OSC_K_SMALL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(osc_kernel<OSC_K_SMALL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
     // Segments that start below max_attack need the attack ramp: they get their own (slower) kernel so that each
     // kernel contains exactly one instance of the hot loop.
     unsigned n_att = 0;

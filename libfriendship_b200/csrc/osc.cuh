@@ -23,6 +23,8 @@ struct OscBankInfo {
 std::shared_ptr<OscBankDev> osc_create(const frb_oscbank_desc* d, cudaStream_t stream, std::string* err);
 OscBankInfo osc_info(const OscBankDev& b);
 
+cudaError_t osc_init_device();
+
 // Renders every voice of the bank over absolute times [lo, hi) into the voices' ring buffers
 // bufdesc[first_buf + v].  `anchor` = samples between exact re-anchors of each partial.
 cudaError_t launch_osc(const OscBankDev& b, const BufferDesc* d_bufdesc, uint32_t first_buf, uint64_t lo, uint64_t hi,

@@ -68,6 +68,8 @@ Renderer::Renderer(const frb_config& cfg) : cfg_(cfg) {
     CU(cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, device_));
     CU(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     for (auto& ev : ev_) CU(cudaEventCreate(&ev));
+    CU(interp_init_device());
+    CU(osc_init_device());
 }
 
 Renderer::~Renderer() {
@@ -178,6 +180,9 @@ void Renderer::del_node(uint32_t handle) {                                 // re
     dirty_ = true;
 }
 void Renderer::add_edge(const frb_edge& e) {                               // reference.rs:124-126
+    // the reference grows `inbound` to to_slot + 1 entries (reference.rs:150); RouteGraph validation keeps slots small
+    // before the renderer is told, a raw C caller may not
+    if (e.to_slot > (1u << 24)) throw Error{FRB_E_INVALID, "to_slot out of range"};
     if (!graph_.add_edge(e)) throw Error{FRB_E_BAD_HANDLE, "add_edge: target node does not exist (reference.rs:145)"};
     dirty_ = true;
 }
@@ -430,8 +435,53 @@ void Renderer::ingest_inputs(uint32_t n_slots, uint64_t n_times, uint64_t idx, c
 
 // ------------------------------------------------------------------------------------------------ rendering
 
+// Decides whether stage `sg` runs compiled: starts / collects the NVRTC build according to the policy flags.
+void Renderer::poll_stage_jit(size_t sg, uint64_t n_groups) {
+    const Stage& st = sched_.stages[sg];
+    StageJit& sj = stage_jit_[sg];
+    sj.uses++;
+    const bool eager = (cfg_.flags & FRB_FLAG_JIT_EAGER) || n_groups >= (1ull << 15);
+    if (sj.state == 0 && !(cfg_.flags & FRB_FLAG_NO_JIT) && st.program.size() <= 65536 &&   // bound the generated source
+        (eager || sj.uses >= 4)) {
+        if (eager) {
+            // a long block (or an explicit request) pays for the ~0.2 s of NVRTC right away
+            std::string jerr;
+            sj.k = jit_build(st, &jerr);
+            sj.state = sj.k ? 1 : 2;
+            if (!sj.k) last_jit_error = jerr;
+        } else {
+            // streaming in short blocks: compile beside the render loop, never stall a block for it
+            const std::string src = jit_generate_source(st);
+            sj.cubin = std::async(std::launch::async, [src]() {
+                std::string cubin, log;
+                return jit_compile_to_cubin(src, &cubin, &log) ? cubin : std::string();
+            });
+            sj.state = 3;
+        }
+    }
+    if (sj.state == 3 && sj.cubin.wait_for(std::chrono::seconds(0)) == std::future_status::ready) {
+        const std::string cubin = sj.cubin.get();
+        std::string jerr;
+        sj.k = cubin.empty() ? nullptr : jit_load(cubin, &jerr);
+        sj.state = sj.k ? 1 : 2;
+        if (!sj.k) last_jit_error = cubin.empty() ? "NVRTC compile failed" : jerr;
+    }
+}
+
 void Renderer::run_range(uint64_t lo, uint64_t hi, float* d_out, uint64_t t0, uint64_t t1, uint64_t out_stride) {
     if (hi <= lo) return;
+    // with profiling on, every kernel family is bracketed by CUDA events on the renderer's stream
+    auto timed = [&](float frb_timing::*field, auto&& launch) {
+        if (profiling) CU(cudaEventRecord(ev_[2], stream_));
+        launch();
+        if (profiling) {
+            CU(cudaEventRecord(ev_[3], stream_));
+            CU(cudaEventSynchronize(ev_[3]));
+            float ms = 0;
+            CU(cudaEventElapsedTime(&ms, ev_[2], ev_[3]));
+            timing.*field += ms;
+        }
+    };
     const int out_vec_ok = d_out && (t0 % 4 == 0) && (out_stride % 4 == 0) && ((uintptr_t)d_out % 16 == 0);
     uint64_t c0 = lo;
     while (c0 < hi) {
@@ -442,27 +492,19 @@ void Renderer::run_range(uint64_t lo, uint64_t hi, float* d_out, uint64_t t0, ui
                 const ExtInstance& x = sched_.ext[xi];
                 uint64_t nl = 0;
                 if (x.kind == EXT_OSCBANK) {
-                    if (profiling) CU(cudaEventRecord(ev_[2], stream_));
-                    CU(launch_osc(*osc_defs_.at(x.key), d_bufdesc_, x.first_out_buf, c0, c1, cfg_.osc_anchor, sm_count_, stream_, &nl));
-                    if (profiling) { CU(cudaEventRecord(ev_[3], stream_)); CU(cudaEventSynchronize(ev_[3])); float ms = 0; CU(cudaEventElapsedTime(&ms, ev_[2], ev_[3])); timing.osc_ms += ms; }
+                    timed(&frb_timing::osc_ms, [&] { CU(launch_osc(*osc_defs_.at(x.key), d_bufdesc_, x.first_out_buf, c0, c1, cfg_.osc_anchor, sm_count_, stream_, &nl)); });
                     stats.osc_launches += nl;
                 } else if (x.kind == EXT_DIRECTFORM) {
-                    if (profiling) CU(cudaEventRecord(ev_[2], stream_));
-                    CU(launch_directform(*df_defs_.at(x.key), d_bufdesc_, d_ext_in_bufs_[xi], x.first_out_buf, c0, c1, sm_count_, stream_, &nl));
-                    if (profiling) { CU(cudaEventRecord(ev_[3], stream_)); CU(cudaEventSynchronize(ev_[3])); float ms = 0; CU(cudaEventElapsedTime(&ms, ev_[2], ev_[3])); timing.scan_ms += ms; }
+                    timed(&frb_timing::scan_ms, [&] { CU(launch_directform(*df_defs_.at(x.key), d_bufdesc_, d_ext_in_bufs_[xi], x.first_out_buf, c0, c1, sm_count_, stream_, &nl)); });
                     stats.scan_launches += nl;
                 } else {
-                    if (profiling) CU(cudaEventRecord(ev_[2], stream_));
-                    CU(launch_fbdelay(*fb_defs_.at(x.key), d_bufdesc_, d_ext_in_bufs_[xi], x.first_out_buf, c0, c1, sm_count_, stream_, &nl));
-                    if (profiling) { CU(cudaEventRecord(ev_[3], stream_)); CU(cudaEventSynchronize(ev_[3])); float ms = 0; CU(cudaEventElapsedTime(&ms, ev_[2], ev_[3])); timing.scan_ms += ms; }
+                    timed(&frb_timing::scan_ms, [&] { CU(launch_fbdelay(*fb_defs_.at(x.key), d_bufdesc_, d_ext_in_bufs_[xi], x.first_out_buf, c0, c1, sm_count_, stream_, &nl)); });
                     stats.scan_launches += nl;
                 }
                 stats.kernel_launches += nl;
             }
             for (const FoldJob& fj : st.folds) {
-                if (profiling) CU(cudaEventRecord(ev_[2], stream_));
-                CU(launch_fold(d_bufdesc_, fj.first_buf, fj.count, fj.out_buf, c0, c1, sm_count_, stream_));
-                if (profiling) { CU(cudaEventRecord(ev_[3], stream_)); CU(cudaEventSynchronize(ev_[3])); float ms = 0; CU(cudaEventElapsedTime(&ms, ev_[2], ev_[3])); timing.interp_ms += ms; }
+                timed(&frb_timing::interp_ms, [&] { CU(launch_fold(d_bufdesc_, fj.first_buf, fj.count, fj.out_buf, c0, c1, sm_count_, stream_)); });
                 stats.kernel_launches++;
                 stats.interp_launches++;
             }
@@ -484,43 +526,15 @@ void Renderer::run_range(uint64_t lo, uint64_t hi, float* d_out, uint64_t t0, ui
             p.t1 = d_out ? t1 : t0;                  // warm-up ranges write no output
             p.out_vec_ok = out_vec_ok;
             p.sparkle_delay = (cfg_.flags & FRB_FLAG_SPARKLE_DELAY) ? 1 : 0;
-            if (profiling) CU(cudaEventRecord(ev_[2], stream_));
             // Tiered like the reference's JIT renderer (sparkle.rs:271-288 compiles lazily at the next render): a stage
             // program is interpreted until it is hot (4th launch, or a block of >= 256 Ki samples), then compiled
             // once by NVRTC into a fused kernel.  A stage that fails to compile stays on the interpreter.
-            StageJit& sj = stage_jit_[sg];
-            sj.uses++;
-            if (sj.state == 0 && !(cfg_.flags & FRB_FLAG_NO_JIT) && st.program.size() <= 65536 &&   // bound the generated source
-                ((cfg_.flags & FRB_FLAG_JIT_EAGER) || sj.uses >= 4 || p.n_groups >= (1ull << 15))) {
-                if ((cfg_.flags & FRB_FLAG_JIT_EAGER) || p.n_groups >= (1ull << 15)) {
-                    // a long block (or an explicit request) pays for the ~0.2 s of NVRTC right away
-                    std::string jerr;
-                    sj.k = jit_build(st, &jerr);
-                    sj.state = sj.k ? 1 : 2;
-                    if (!sj.k) last_jit_error = jerr;
-                } else {
-                    // streaming in short blocks: compile beside the render loop, never stall a block for it
-                    const std::string src = jit_generate_source(st);
-                    sj.cubin = std::async(std::launch::async, [src]() {
-                        std::string cubin, log;
-                        return jit_compile_to_cubin(src, &cubin, &log) ? cubin : std::string();
-                    });
-                    sj.state = 3;
-                }
-            }
-            if (sj.state == 3 && sj.cubin.wait_for(std::chrono::seconds(0)) == std::future_status::ready) {
-                const std::string cubin = sj.cubin.get();
-                std::string jerr;
-                sj.k = cubin.empty() ? nullptr : jit_load(cubin, &jerr);
-                sj.state = sj.k ? 1 : 2;
-                if (!sj.k) last_jit_error = cubin.empty() ? "NVRTC compile failed" : jerr;
-            }
-            if (sj.state == 1 && jit_launch(sj.k, p, sm_count_, stream_)) {
-                stats.jit_launches++;
-            } else {
-                CU(launch_interp(p, st.n_regs, sm_count_, stream_));
-            }
-            if (profiling) { CU(cudaEventRecord(ev_[3], stream_)); CU(cudaEventSynchronize(ev_[3])); float ms = 0; CU(cudaEventElapsedTime(&ms, ev_[2], ev_[3])); timing.interp_ms += ms; }
+            poll_stage_jit(sg, p.n_groups);
+            timed(&frb_timing::interp_ms, [&] {
+                StageJit& sj = stage_jit_[sg];
+                if (sj.state == 1 && jit_launch(sj.k, p, sm_count_, stream_)) stats.jit_launches++;
+                else CU(launch_interp(p, st.n_regs, sm_count_, stream_));
+            });
             stats.kernel_launches++;
             stats.interp_launches++;
         }

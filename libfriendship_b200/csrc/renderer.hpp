@@ -70,6 +70,7 @@ private:
     void materialise_slot(size_t r);
     void grow_slot(InputSlot& s, uint64_t need_end);
     void run_range(uint64_t lo, uint64_t hi, float* d_out, uint64_t t0, uint64_t t1, uint64_t out_stride);
+    void poll_stage_jit(size_t sg, uint64_t n_groups);
     void free_device_schedule();
 
     frb_config cfg_;
