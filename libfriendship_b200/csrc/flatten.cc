@@ -85,7 +85,7 @@ struct Flattener {
             default: return UINT32_MAX;
         }
     }
-    static bool const_delay_of(const Value& amt, uint64_t* d);   // defined below
+    bool const_delay_of(const Value& amt, uint64_t* d) const;   // defined below
     uint32_t clone_shifted(uint32_t v, uint64_t shift) {
         const Value x = s.values[v];
         switch (x.op) {
@@ -219,20 +219,24 @@ struct Flattener {
     }
 };
 
-bool const_delay(uint32_t bits, uint64_t* out);
+bool const_delay(uint32_t bits, bool sparkle, uint64_t* out);
 
-bool Flattener::const_delay_of(const Value& amt, uint64_t* d) {
+bool Flattener::const_delay_of(const Value& amt, uint64_t* d) const {
     if (amt.op == V_ZERO) { *d = 0; return true; }
-    return const_delay(amt.imm, d);
+    return const_delay(amt.imm, env.sparkle_delay, d);
 }
 
 // Delay amount of a constant `frames` signal, with the clamps of reference.rs:200-212.
 // Returns false when the Delay can never read its source (frames >= 2^64).
-bool const_delay(uint32_t bits, uint64_t* out) {
+bool const_delay(uint32_t bits, bool sparkle, uint64_t* out) {
     float d;
     std::memcpy(&d, &bits, 4);
     if (d >= 18446744073709551616.0f) return false;
-    if (!(d >= 0.0f)) { *out = 0; return true; }   // negative or NaN -> delay 0
+    if (!(d >= 0.0f)) {                             // negative or NaN
+        if (sparkle) return false;                  // sparkle.rs:525-542: the Delay outputs 0.0 and never reads its source
+        *out = 0;                                   // reference.rs:206-207: delay 0
+        return true;
+    }
     *out = (uint64_t)d;
     return true;
 }
@@ -355,7 +359,7 @@ Schedule flatten(const Graph& top, uint32_t n_slots, const FlattenEnv& env) {
                 raise(x.b, L[vi]);
                 uint64_t d = 0;
                 bool reads = true;
-                if (V[x.b].op == V_CONST) reads = const_delay(V[x.b].imm, &d);
+                if (V[x.b].op == V_CONST) reads = const_delay(V[x.b].imm, env.sparkle_delay, &d);
                 else if (V[x.b].op == V_ZERO) d = 0;
                 else d = LOOKBACK_FULL;                                  // signal-driven delay (reference.rs:200)
                 if (reads) raise(x.a, sat_add(L[vi], d));

@@ -226,6 +226,7 @@ const Schedule& Renderer::schedule(uint32_t n_slots) {
             return it == fb_defs_.end() ? 0 : fbdelay_max_delay(*it->second);
         };
         env.max_regs = 48;
+        env.sparkle_delay = (cfg_.flags & FRB_FLAG_SPARKLE_DELAY) != 0;
         Schedule s = flatten(graph_, n_slots, env);   // throws on malformed graphs; state unchanged then
         if (!host_only_) {
             CU(cudaSetDevice(device_));

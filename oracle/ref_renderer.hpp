@@ -87,6 +87,7 @@ struct NodeMap {
     std::unordered_map<uint32_t, Node> nodes;
     std::vector<std::optional<Edge>> output_edges;
     ExtMode ext_mode = ExtMode::FP64;
+    bool sparkle_delay = false;
 
     // reference.rs:141-153
     void add_edge(const Edge& e) {
@@ -138,6 +139,8 @@ struct NodeMap {
                 if (from_slot != 0) throw Panic(-4, "Delay: from_slot != 0 (reference.rs:199)");
                 float delay_frames = in(1, time);
                 if (delay_frames >= 18446744073709551616.0f) return 0.0f;      // :202-205
+                // SparkleRenderer's variant (reference sparkle.rs:525-542): `fp ULT 0` (negative OR NaN) returns 0.0
+                if (sparkle_delay && !(delay_frames >= 0.0f)) return 0.0f;
                 uint64_t delay_int;
                 if (delay_frames < 0.0f) delay_int = 0;                         // :206-207
                 else if (delay_frames != delay_frames) delay_int = 0;           // NaN: Rust saturating `as u64` gives 0
@@ -277,6 +280,10 @@ struct NodeMap {
         ext_mode = m;
         for (auto& kv : nodes) if (kv.second.user) kv.second.user->set_ext_mode(m);
     }
+    void set_sparkle_delay(bool f) {
+        sparkle_delay = f;
+        for (auto& kv : nodes) if (kv.second.user) kv.second.user->set_sparkle_delay(f);
+    }
 };
 
 // One external-input slot vector of the reference (`inputs[slot]: Vec<f32>`, reference.rs:22-25), stored as
@@ -300,6 +307,7 @@ public:
     std::vector<std::pair<uint64_t, uint64_t>> epochs;          // (slot index upper bound, base) for the tail
     uint64_t head = 0;                                          // reference.rs:26-28
     ExtMode ext_mode = ExtMode::FP64;
+    bool sparkle_delay = false;      // evaluate Delay the way SparkleRenderer does (sparkle.rs:525-542)
 
     // definitions registry (the reference passes Rc<Effect>; the C ABI passes keys)
     std::unordered_map<uint64_t, std::shared_ptr<NodeMap>> effect_defs;
@@ -384,6 +392,7 @@ public:
     void fill_buffer(float* buff, uint32_t n_slots, uint64_t n_times, uint64_t idx,
                      const std::vector<std::vector<float>>& rows) {
         nodes.set_ext_mode(ext_mode);
+        nodes.set_sparkle_delay(sparkle_delay);
         nodes.clear_memo();
         if (idx != head) {                                                      // :52-58 seek: every slot := idx zeros
             for (auto& slot : inputs) { slot.base = idx; slot.data.clear(); }

@@ -22,9 +22,11 @@ class OracleRenderer(_cabi.CRendererBase):
     _lib = _lib
     _prefix = "orc"
 
-    def __init__(self, ext_mode="fp64", **_ignored):
+    def __init__(self, ext_mode="fp64", flags=0, **_ignored):
         super().__init__(_lib.orc_create())
         _lib.orc_set_ext_mode(self._h, 0 if ext_mode == "fp64" else 1)
+        _lib.orc_set_sparkle_delay.argtypes = [C.c_void_p, C.c_int]
+        _lib.orc_set_sparkle_delay(self._h, 1 if flags & _cabi.FLAG_SPARKLE_DELAY else 0)
 
     def fill_buffer_mt(self, n_slots, n_times, idx, n_threads):
         """CPU-baseline helper: multi-threaded evaluation of the current graph (inputs already fed)."""

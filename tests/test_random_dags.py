@@ -110,3 +110,21 @@ def test_input_contract_errors():
         with pytest.raises(RendererError) as e:
             r.fill_buffer(2, 2, 4, [[1, 2, 3]])                    # row longer than n_times (reference.rs:71)
         assert e.value.code == -2
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_sparkle_delay_flag_matches_sparkle_semantics(seed):
+    """FRB_FLAG_SPARKLE_DELAY: negative / NaN delay amounts output 0.0 (reference sparkle.rs:525-542) instead of being
+    clamped to delay 0 (reference.rs:205-210).  Random graphs rich in negative / NaN / signal-driven amounts."""
+    from libfriendship_b200 import B200Renderer, FLAG_JIT_EAGER, FLAG_SPARKLE_DELAY
+    pool = [-1.0, -0.5, float("nan"), 0.0, 1.0, 2.0, 3.5, -7.0, 1.8446744e19, 5.0]
+    rec = random_graph(4000 + seed, n_inputs=2, n_nodes=14, n_outputs=2, nested_levels=1, signal_delay_prob=0.6, const_pool=pool)
+    rng = np.random.RandomState(seed)
+    rows = [(rng.randn(200) * 2).astype(np.float32) for _ in range(2)]
+    outs = []
+    for r in (B200Renderer(flags=FLAG_SPARKLE_DELAY), B200Renderer(flags=FLAG_SPARKLE_DELAY | FLAG_JIT_EAGER),
+              OracleRenderer(flags=FLAG_SPARKLE_DELAY)):
+        rec.apply(r)
+        outs.append(r.fill_buffer(2, 200, 0, rows))
+    assert_same_bits(outs[0], outs[2], f"sparkle interp seed {seed}")
+    assert_same_bits(outs[1], outs[2], f"sparkle jit seed {seed}")
