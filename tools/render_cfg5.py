@@ -1,0 +1,61 @@
+"""BASELINE.json configs[4] — offline large render: 1M partials x 256 voices, 192 kHz x 60 s, 8 x B200, output reduced
+to rank 0.  Launch:  python -m torch.distributed.run --nproc-per-node 8 tools/render_cfg5.py
+One render (no warm-up: an offline job runs once); prints one JSON line on rank 0."""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from banks import build_voice_mix_graph, detuned_bank
+from libfriendship_b200.sharded import ShardedRenderer
+
+SR, N_VOICES, N_PARTIALS, N_SAMPLES = 192000.0, 256, 1 << 20, 11_520_000
+
+
+def main():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    n_voices = int(os.environ.get("CFG5_VOICES", N_VOICES))
+    n_samples = int(os.environ.get("CFG5_SAMPLES", N_SAMPLES))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    t_setup = time.perf_counter()
+    sr = ShardedRenderer(rank=rank, world_size=world, device=local)
+    mine = sr.voices_of_rank(n_voices)
+    bank, ids = detuned_bank(n_voices, N_PARTIALS, sr=SR, seed=2, voices=mine)
+    build_voice_mix_graph(sr.r, bank, ids)
+    del bank
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_setup = time.perf_counter() - t_setup
+    t0 = time.perf_counter()
+    out = sr.fill_buffer(1, n_samples, 0)          # device render + reduce to rank 0 + D2H of the 46 MB mix
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    dt = time.perf_counter() - t0
+    if rank == 0:
+        ps = n_voices * N_PARTIALS * n_samples
+        print(json.dumps({
+            "workload": "cfg5: 2^20 partials x %d voices, 192 kHz x %.1f s (BASELINE.json configs[4])" % (n_voices, n_samples / SR),
+            "n_gpus": world, "render_s": dt, "setup_s": t_setup, "partial_samples": ps, "partial_samples_per_s": ps / dt,
+            "realtime_factor": (n_samples / SR) / dt, "out_bytes": int(out.nbytes), "finite": bool(np.isfinite(out).all()),
+            "peak_abs": float(np.abs(out).max()), "rms_last_second": float(np.sqrt(np.mean(out[0, -192000:] ** 2)))}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
