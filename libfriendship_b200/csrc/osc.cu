@@ -28,6 +28,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 namespace frb {
@@ -169,13 +170,18 @@ std::shared_ptr<OscBankDev> osc_create(const frb_oscbank_desc* d, cudaStream_t s
     b->max_attack = max_attack;
     const uint64_t n = order.size();
     b->n_records = n;
-    // Partial-range split: one CTA is one warp working through (groups / split) groups for 32 segments.  All CTAs of a
-    // launch cost the same, so the only imbalance is the partially filled last wave (148 SMs x ~12 resident CTAs):
-    // aim for voices x split >= 4096 (>= 30 waves per 64 Ki-sample block) while keeping >= 8 groups per CTA.
+    // Partial-range split: one CTA is one warp working through (groups / split) groups for 32 segments (4,096 samples).
+    // All CTAs of a launch cost the same, so the only imbalance is the partially filled last wave (148 SMs x ~12
+    // resident CTAs).  CTAs per launch = (samples / 4096) x voices x split and the split planes cost
+    // split x voices x samples x 8 B of HBM traffic, so the split is kept as SMALL as wave balance allows —
+    // voices x split >= 1024..2048 (measured sweep, tools/split_sweep.sh: 64 voices peak at 2048, 8 voices at 1024;
+    // 4096 costs 4% at 8 voices in plane traffic, 256 costs 3% in tail) — and long blocks do the rest.
     // Fixed per bank, so the order of summation (and hence the result) never depends on the block size of a render.
     {
+        uint64_t target = d->n_voices >= 32 ? 2048 : 1024;
+        if (const char* ev = getenv("FRB_OSC_SPLIT_TARGET")) target = std::max<uint64_t>(1, strtoull(ev, nullptr, 10));   // tuning aid
         uint32_t s = 1;
-        while (s < 512 && (uint64_t)d->n_voices * s < 4096 && b->max_groups / (s * 2) >= 8) s *= 2;
+        while (s < 512 && (uint64_t)d->n_voices * s < target && b->max_groups / (s * 2) >= 8) s *= 2;
         b->split = s;
     }
 

@@ -90,6 +90,22 @@ def case_cfg3(n_voices=4096, n=480000):
             "K4_frac": alg / t["scan_ms"] / 1e6 / HBM, "voice_samples_per_s": n_voices * n / (t["total_ms"] * 1e-3)}
 
 
+def case_cfg2(anchor=0):
+    """cfg2: 1,024 harmonic partials x 1 voice, 48 kHz x 10 s (one voice: parallelism only along time)."""
+    from banks import harmonic_bank
+    from libfriendship_b200 import KIND_OSCBANK
+    n = 480000
+    r = B200Renderer(osc_anchor=anchor)
+    r.define_oscbank(5, **harmonic_bank(1024))
+    r.on_add_node(1, KIND_OSCBANK, 5)
+    r.on_add_edge((1, 0, 0, 0))
+    out = torch.empty((1, n), dtype=torch.float32, device="cuda")
+    t = timed_fill(r, out, 1, n, 0, reps=5)
+    ps = 1024 * n
+    return {"case": "cfg2 1,024 partials x 1 voice x 10 s", "anchor": anchor or 128, "ms": t["total_ms"], "osc_ms": t["osc_ms"],
+            "partial_samples_per_s": ps / (t["total_ms"] * 1e-3), "realtime_factor": 10.0 / (t["total_ms"] * 1e-3)}
+
+
 def case_cfg1():
     """cfg1: 440 Hz sine through Multiply/Sum/Delay (+ Min/Mod/Div side chain), 48 kHz x 1 s, host in/out through
     frb_fill_buffer: one call, and 94 x 512-sample streaming calls.  Latency-bound: reported as us per block."""
@@ -122,7 +138,7 @@ def case_cfg1():
 if __name__ == "__main__":
     which = sys.argv[1:] or ["pure", "elementwise", "cfg3"]
     for w in which:
-        fn = {"pure": case_pure_elementwise, "elementwise": case_elementwise, "cfg3": case_cfg3, "cfg1": case_cfg1}[w]
+        fn = {"pure": case_pure_elementwise, "elementwise": case_elementwise, "cfg3": case_cfg3, "cfg1": case_cfg1, "cfg2": case_cfg2, "cfg2_64": lambda: case_cfg2(64), "cfg2_32": lambda: case_cfg2(32)}[w]
         t0 = time.time()
         try:
             res = fn()
