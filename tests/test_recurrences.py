@@ -126,3 +126,45 @@ def test_osc_excited_chain_mixed_to_one_slot():
         outs.append(r.fill_buffer(1, n, 0))
     scale = np.abs(outs[1]).max()
     assert np.abs(outs[0].astype(np.float64) - outs[1]).max() <= 1e-4 * scale
+
+
+def test_biquad_feedback_chain_all_delay_ranges():
+    """DirectForm -> FbDelay lane for lane, with and without an extra tap on the biquad output, against the fp64
+    oracle: delays shorter and longer than the 256-sample scan tile (including D = 1), ragged block boundaries.
+    (A fused single-kernel variant of this chain was measured slower than the two kernels — 7.2 ms vs 6.4 ms on
+    cfg3 — and was not kept; see DESIGN.md.)"""
+    from libfriendship_b200 import KIND_DIRECTFORM, KIND_FBDELAY
+    lanes, n = 6, 7000
+    coefs = rbj_lowpass(np.array([300.0, 800.0, 1500.0, 3000.0, 6000.0, 10000.0]), np.array([0.8, 1.5, 3.0, 0.707, 2.0, 1.0]))
+    delay = np.array([1, 3, 100, 255, 256, 1000], dtype=np.uint32)
+    gain = np.array([0.5, -0.6, 0.7, 0.8, -0.9, 0.95], dtype=np.float32)
+    x = noise(lanes, n, seed=21)
+
+    def build(r, tap):
+        r.define_directform(3, *coefs)
+        r.define_fbdelay(4, delay, gain)
+        r.on_add_node(1, KIND_DIRECTFORM, 3)
+        r.on_add_node(2, KIND_FBDELAY, 4)
+        for l in range(lanes):
+            r.on_add_edge((0, 1, l, l))
+            r.on_add_edge((1, 2, l, l))
+            r.on_add_edge((2, 0, l, l))
+        if tap:
+            r.on_add_edge((1, 0, 2, lanes))          # biquad lane 2 is also an output: no fusion
+        return lanes + (1 if tap else 0)
+
+    for tap in (False, True):
+        g, o = gpu_cls()(), OracleRenderer()
+        ns = build(g, tap)
+        build(o, tap)
+        want = o.fill_buffer(ns, n, 0, x)
+        scale = np.abs(want).max()
+        got = g.fill_buffer(ns, n, 0, x)
+        assert np.abs(got.astype(np.float64) - want).max() <= 1e-4 * scale, tap
+        g2 = gpu_cls()()
+        build(g2, tap)
+        parts, idx = [], 0
+        for m in (3, 253, 256, 1000, 2049, 3439):
+            parts.append(g2.fill_buffer(ns, m, idx, [row[idx:idx + m] for row in x]))
+            idx += m
+        assert np.abs(np.concatenate(parts, axis=1).astype(np.float64) - want).max() <= 1e-4 * scale, tap
