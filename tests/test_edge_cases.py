@@ -1,0 +1,97 @@
+"""GPU: corners of the renderer contract that the reference's own tests do not pin (parity by source reading of
+src/render/reference.rs), oracle vs CUDA, bit-exact."""
+import numpy as np
+import pytest
+
+from graphs import build_cfg1_graph, cfg1_input, f32_bits
+from oracle_binding import OracleRenderer
+from replay import assert_same_bits
+
+pytestmark = pytest.mark.gpu
+
+
+def pair():
+    from libfriendship_b200 import B200Renderer
+    return B200Renderer(), OracleRenderer()
+
+
+def test_seek_far_beyond_2_pow_32():
+    """Absolute sample indices are u64 (renderer.rs:16): a seek to 2^33 + 12345, two contiguous blocks."""
+    g, o = pair()
+    build_cfg1_graph(g, delay=100.0)
+    build_cfg1_graph(o, delay=100.0)
+    idx = (1 << 33) + 12345
+    x = cfg1_input(600)
+    for k in range(2):
+        blk = [x[300 * k:300 * (k + 1)]]
+        assert_same_bits(g.fill_buffer(2, 300, idx + 300 * k, blk), o.fill_buffer(2, 300, idx + 300 * k, blk), f"block {k}")
+
+
+def test_oscillator_phase_is_exact_beyond_2_pow_32():
+    from banks import full_scale, harmonic_bank
+    from libfriendship_b200 import KIND_OSCBANK
+    bank = harmonic_bank(64)
+    bank["tau"] = np.full(64, np.inf, dtype=np.float32)          # keep it audible at t = 2^32
+    idx = (1 << 32) + 777
+    outs = []
+    for r in pair():
+        r.define_oscbank(5, **bank)
+        r.on_add_node(1, KIND_OSCBANK, 5)
+        r.on_add_edge((1, 0, 0, 0))
+        outs.append(r.fill_buffer(1, 400, idx))
+    assert np.abs(outs[0].astype(np.float64) - outs[1]).max() <= 1e-5 * full_scale(bank)
+
+
+def test_nested_effect_is_a_private_copy_and_nodes_can_be_deleted():
+    """reference.rs:98-113: make_node deep-copies the nested graph when the node is added — redefining the effect
+    afterwards must not change existing nodes; reference.rs:121-123,127-136: del_node / del_edge."""
+    def body(factor):
+        return [(1, 3, 0), (2, 1, 0)], [(0, 1, 0, 0), (1, 0, 0, 0), (2, 1, f32_bits(factor), 1)]
+    g, o = pair()
+    x = np.arange(1, 9, dtype=np.float32)
+    for r in (g, o):
+        r.define_effect(7, *body(5.0))
+        r.on_add_node(1, 16, 7)                       # instance of "x5"
+        r.on_add_edge((0, 1, 0, 0))
+        r.on_add_edge((1, 0, 0, 0))
+        r.define_effect(7, *body(7.0))                # same key, new definition
+        r.on_add_node(2, 16, 7)                       # instance of "x7"
+        r.on_add_edge((0, 2, 0, 0))
+        r.on_add_edge((2, 0, 0, 1))
+    a, b = g.fill_buffer(2, 8, 0, [x]), o.fill_buffer(2, 8, 0, [x])
+    assert_same_bits(a, b)
+    assert (a[0] == 5 * x).all() and (a[1] == 7 * x).all()
+    for r in (g, o):
+        r.on_del_edge((2, 0, 0, 1))                   # slot 1 becomes None -> renders 0
+        r.on_del_edge((0, 2, 0, 0))
+        r.on_del_node(2)
+    a, b = g.fill_buffer(2, 8, 8, [x]), o.fill_buffer(2, 8, 8, [x])
+    assert_same_bits(a, b)
+    assert (a[1] == 0).all()
+
+
+def test_more_outputs_requested_than_connected_and_zero_length_calls():
+    g, o = pair()
+    for r in (g, o):
+        r.on_add_edge((0, 0, 0, 3))
+    x = np.arange(5, dtype=np.float32)
+    assert_same_bits(g.fill_buffer(6, 5, 0, [x]), o.fill_buffer(6, 5, 0, [x]))
+    from libfriendship_b200 import RendererError
+    for r in (g, o):
+        assert r.fill_buffer(6, 0, 5).shape == (6, 0)          # zero samples: head stays 5
+        assert r.fill_buffer(0, 4, 5).shape == (0, 4)          # zero slots: no slot is fed, head moves to 9 (reference.rs:84)
+    for r in (g, o):
+        with pytest.raises(RendererError) as e:                # slot 0 still has length 5 != 9 (reference.rs:69)
+            r.fill_buffer(6, 3, 9, [x[:3]])
+        assert e.value.code == -3
+    assert_same_bits(g.fill_buffer(6, 3, 20, [x[:3]]), o.fill_buffer(6, 3, 20, [x[:3]]))   # a seek resets the slots
+
+
+def test_edge_from_a_missing_node_is_an_error_not_a_crash():
+    from libfriendship_b200 import RendererError
+    g, o = pair()
+    for r in (g, o):
+        r.on_add_edge((5, 0, 0, 0))                   # node 5 was never added (reference.rs:186 would panic)
+        with pytest.raises(RendererError) as e:
+            r.fill_buffer(1, 4, 0)
+        assert e.value.code == -1
