@@ -1,10 +1,12 @@
 // interp.cu — K2/K3: fused elementwise + Delay pass over a block of time (sm_100a).
 //
-// One launch evaluates one stage program (schedule.hpp) for every sample of a time block.  Each thread owns
-// four consecutive samples (absolute time aligned to 4, so undelayed plane reads/writes are 128-bit and
-// coalesced); the program's registers live in shared memory as float4 columns regs[r][thread] (conflict-free),
-// so intermediates of the fused nodes never touch HBM.  Delay is an indexed read at t - floor(d) from the
-// external-input history or from a ring buffer in HBM written by an earlier stage.
+// This is the INTERPRETER tier (the immediate path after a graph edit); a hot stage is compiled by the stage JIT
+// (jit.cc) into a straight-line kernel built from the same device helpers (interp_device.inc).
+// One launch evaluates one stage program (schedule.hpp) for every sample of a time block; blockIdx.y selects one
+// of the stage's independent strands.  Each thread owns eight consecutive samples (absolute time aligned to 8, so
+// undelayed plane reads/writes are 128-bit and coalesced); the program's registers live in shared memory as
+// float4 columns (conflict-free), so intermediates of the fused nodes never touch HBM.  Delay is an indexed read
+// at t - floor(d) from the external-input history or from a ring buffer in HBM written by an earlier stage.
 //
 // Arithmetic is the reference's, bit for bit (reference src/render/reference.rs:197-262): IEEE f32 with no
 // FMA contraction (__fmul_rn/__fadd_rn/__fdiv_rn never contract), fmodf for `%`, fminf for f32::min.

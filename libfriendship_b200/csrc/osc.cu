@@ -5,25 +5,32 @@
 // Bound: the FP32 FMA pipe (128 lanes/clk/SM; measured 125 on B200 with tools/microbench/fma_peak.cu).
 // There is no dense contraction here, so tensor cores are not used.
 //
-// Design (measured choices: tools/microbench/osc_loop.cu, profiles/):
-//  * One thread owns one time SEGMENT of L consecutive samples of one voice, and walks through all partials of
-//    that voice in groups of K.  Lanes of a warp therefore differ in time, not in partial: the per-partial
-//    coefficients are warp-uniform, there is no cross-lane reduction at all (no shuffles, no barriers), and the
-//    K recurrences of a group give the scheduler K independent FMA chains per thread.
+// Design (measured choices: tools/microbench/, profiles/ncu_osc_r1*_summary.txt):
+//  * One thread owns one time SEGMENT of L = 128 consecutive samples of one voice, and walks through the partials of
+//    that voice in groups of K = 16.  Lanes of a warp therefore differ in time, not in partial: the per-partial
+//    coefficients are warp-uniform, there is no cross-lane reduction at all, and the K recurrences of a group give
+//    the scheduler K independent FMA chains per thread.  One warp per CTA.
 //  * Each partial is a damped two-state resonator in lifting form, 3 FFMA + 1 FADD per partial-sample:
-//        x <- x - a*y ;  y <- (1+cm1)*y + b*x ;  acc += y          (cos w >= 0)
-//        x <- a*y - x ;  y <- b*x - (1+cm1)*y ;  acc += y          (cos w <  0: the same resonator at pi - w, negated,
-//                                                                    which keeps a*b small and well conditioned)
-//    with a*b = (1-rho)^2 + 4 rho sin^2(w'/2), cm1 = rho^2 - 1: the eigenvalues are rho*exp(+-i w), so y is exactly
-//    amp * rho^n * sin(w n + phi) in exact arithmetic; the exponential decay costs nothing extra.
+//        x <- x - a*y ;  y <- (1+cm1)*y + b*x ;  acc += y
+//    with a*b = (1-rho)^2 + 4 rho sin^2(w'/2), cm1 = rho^2 - 1: the eigenvalues are rho*exp(+-i w'), so y is exactly
+//    amp * rho^n * sin(w' n + phi) in exact arithmetic; the exponential decay costs nothing extra.
+//    For cos w < 0 the resonator runs at w' = pi - w (keeps a*b small: Nyquist is as well conditioned as DC) on
+//    the variables (-1)^n x, (-1)^n y, which obey the very same update; the kernel flips the sign of the odd samples
+//    of the accumulator between the two classes instead of having a second loop.
+//  * The coefficients of a group are staged in shared memory and read at constant addresses, so that ptxas keeps
+//    them in UNIFORM registers: every hot FFMA then reads two vector registers, not three.  Register-file read
+//    bandwidth, not the FMA pipe, was the limit before (27% dispatch stalls).  ptxas only does this with >= 16 uses
+//    per loop iteration and ONE instance of the hot loop per kernel — hence the 16-sample unroll, the single
+//    recurrence for both classes, and the separate (slower) kernel for the few segments inside the attack ramp.
 //  * State is re-anchored exactly at the start of every segment (segments are aligned to absolute time, so the
 //    result does not depend on how a render is cut into blocks): phase = inc*n + phase0 in 64-bit fixed-point
-//    turns (exact range reduction by integer wrap-around), sin/cos by MUFU, envelope by ex2 of an fp64 product.
+//    turns (exact range reduction by integer wrap-around), sin/cos and 2^x by MUFU.
 //    With L = 128 the worst single-partial error is ~6e-6 of its amplitude (tools/osc_math_check.py).
 //  * Coefficients come from an fp64 setup kernel at definition time.
-//  * The attack ramp min(t/A,1) only matters for t < max(A): a warp-uniform branch selects a slower loop there.
 //  * Per-thread accumulators for the L samples live in shared memory as float4 columns (conflict-free),
-//    read-modify-written once per 4 samples per group: 2 LSU instructions per 16*K FMA-pipe instructions.
+//    read-modify-written once per 16 samples per group.
+//  * Voices with many partials are split into partial ranges over CTAs (fixed per bank: the summation order never
+//    depends on the block size); the range planes are summed in fixed order by osc_reduce_kernel.
 #include "osc.cuh"
 
 #include <algorithm>
