@@ -249,7 +249,6 @@ def main():
             traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
         except Exception:
             pass
-        n_blocks = -(-n_samples // 65536)
         line = {
             "metric": "rendered partial-samples/sec", "value": value, "unit": "partial-samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
@@ -263,13 +262,14 @@ def main():
                 "kernel": "osc_kernel<16,false> (K1)", "bound": "fp32_fma", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved / peak_tf, "traffic": traffic,
                 "traffic_note": "DRAM bytes of one K1 launch (ncu --set full, profiles/k1_traffic.json): parameter stream + "
-                                "partial-range planes; irrelevant to the bound (0.2% of HBM peak)",
+                                "partial-range planes, per main-kernel launch (one 131,072-sample sub-block); irrelevant to the bound (0.2% of HBM peak)",
                 "peak_source": f"derived {n_sm} SM x 128 lanes x 2 x sm_max_mhz {sm_max} (MEASURED_PEAKS.json); "
                                "tools/microbench/fma_peak.cu measured 3.60e13 FMA/s = 97% of it on this pool",
                 "algorithmic": "6 FMA-pipe slots (12 flop) per partial-sample x partial-samples per launch (BASELINE.md §3)",
                 "executed_frac": ps_per_gpu * EXECUTED_OPS_PER_PARTIAL_SAMPLE / osc_s / peak_fma,
-                "k1_family_launches_per_step": int(n_osc_launches), "main_kernel_launches_per_step": n_blocks,
-                "avg_launch_ms": float(osc_ms.item()) / n_blocks,
+                "k1_family_launches_per_step": int(n_osc_launches), "k1_ms_per_step": float(osc_ms.item()),
+                "launches_note": "K1 family = main kernel per sub-block + its plane reduce + one attack-ramp kernel; "
+                                 "achieved = algorithmic flop of the step / summed K1 time (CUDA events on the renderer's stream)",
                 "kernel_share_of_step": float(osc_ms.item()) / float(tot_ms.item()),
             },
         }
