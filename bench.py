@@ -91,7 +91,7 @@ def cpu_baseline(n_threads=None, budget_s=12.0):
     # calibrate on a short run, then size the sample for ~budget_s of CPU work
     _, sec = r.fill_buffer_mt(1, n, 0, n_threads)
     per = sec / (p * n * 2)      # the Delay re-evaluates the voice at t-d: 2 evaluations per output sample
-    n2 = int(min(48000, max(n, budget_s / max(per * p * 2, 1e-12))))
+    n2 = int(min(N_SAMPLES, max(n, budget_s / max(per * p * 2, 1e-12))))   # up to the configuration's full 10 s
     _, sec = r.fill_buffer_mt(1, n2, 4800, n_threads)     # start after the delay so both taps are live
     value = p * n2 / sec
     _, sec1 = r.fill_buffer_mt(1, max(n2 // n_threads, 64), 4800, 1)
