@@ -5,7 +5,9 @@ sharded by voice over N GPUs with one NCCL reduce of the mixed output.
 
 One "step" = one full 10 s render of the whole graph (2.013e12 partial-samples over all voices).
   value : device-resident throughput (output block stays in HBM; reduce included), CUDA-timed, max over ranks
-  e2e   : the same through the host-facing call (device->host copy of the mixed block on rank 0 inside the timed region)
+  e2e   : the same through the host-facing calls, every step: frb_define_oscbank from PINNED HOST parameter arrays (the
+          synthesis graph's only input: host->device copy + device-side regroup/setup) + frb_fill_buffer into a host
+          buffer (device->host copy of the mixed block on rank 0), all inside the timed region
   roofline : dominant kernel (K1 osc_kernel) against the FP32 FMA pipe
   cpu_baseline : the CPU oracle (restatement of the reference's per-sample renderer) on the box's host cores
 `--impl reference` times that CPU implementation alone on the same metric/config (bounded sample).
@@ -29,6 +31,7 @@ N_PARTIALS = 65536
 N_SAMPLES = 480000
 FMA_SLOTS_PER_PARTIAL_SAMPLE = 6      # rotation 4 + accumulate 1 + envelope 1 (algorithmic)
 EXECUTED_OPS_PER_PARTIAL_SAMPLE = 4   # what K1 issues: 3 FFMA + 1 FADD
+BANK_KEY = 7
 
 
 def measured_peaks():
@@ -134,8 +137,9 @@ def workload_config(n_gpus, exchange="NCCL reduce"):
             "partial_samples_per_step": N_VOICES * N_PARTIALS * N_SAMPLES,
             "sharding": f"voices round-robin over {n_gpus} GPU(s), one {exchange} exchange of the [1 x 480000] mix per step",
             "cache": "compute-bound; per-step parameter stream 201 MB/GPU-shard-of-64 > 126 MB L2, re-read every 64k-sample block",
-            "inputs": "none per step (synthesis): bank parameters are uploaded once from host arrays through "
-                      "frb_define_oscbank, outside the timed region (SURVEY.md §8d)"}
+            "inputs": "synthesis: the graph's only input is the bank's parameter arrays (24 B per partial, host). "
+                      "`value`: uploaded once, resident in HBM when the timed region starts. `e2e`: re-uploaded from pinned "
+                      "host memory through frb_define_oscbank every step, inside the timed region"}
 
 
 def main():
@@ -173,7 +177,7 @@ def main():
     sr = ShardedRenderer(rank=rank, world_size=world, device=local_rank, osc_anchor=args.osc_anchor, exchange=args.exchange)
     my_voices = sr.voices_of_rank(n_voices)
     bank, ids = detuned_bank(n_voices, n_partials, voices=my_voices)
-    build_voice_mix_graph(sr.r, bank, ids)
+    build_voice_mix_graph(sr.r, bank, ids, key=BANK_KEY)
     total_ps = n_voices * n_partials * n_samples
 
     def barrier():
@@ -204,8 +208,16 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # e2e inputs: this rank's parameter arrays in pinned host memory
+    pinned = {k: (torch.from_numpy(np.ascontiguousarray(v)).pin_memory().numpy() if isinstance(v, np.ndarray) else v)
+              for k, v in bank.items()}
+    h2d_per_step = sum(v.nbytes for v in pinned.values() if isinstance(v, np.ndarray))
+
     step_dev = lambda: sr.fill_buffer_device(1, n_samples, 0)
-    step_e2e = lambda: sr.fill_buffer(1, n_samples, 0)
+
+    def step_e2e():
+        sr.r.define_oscbank(BANK_KEY, **pinned)     # host -> device: the step's inputs
+        return sr.fill_buffer(1, n_samples, 0)      # render + reduce + device -> host
     for _ in range(args.warmup):
         step_dev()
     s0 = sr.r.stats()
@@ -216,8 +228,13 @@ def main():
     s1 = sr.r.stats()
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()
+    s2 = sr.r.stats()
     ms_e2e = timed(step_e2e, args.steps)
+    s3 = sr.r.stats()
     sampler.stop_flag = True
+    h2d = torch.tensor([h2d_per_step], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(h2d, op=dist.ReduceOp.SUM)      # all ranks' uploads
 
     # dominant kernel: K1, timed live with CUDA events on the renderer's stream (frb_set_profiling)
     sr.r.set_profiling(True)
@@ -254,8 +271,10 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(world, "NCCL reduce" if args.exchange == "nccl" else "P2P-store + rank-ordered sum (K5)"),
-            "e2e": {"value": e2e_v, "unit": "partial-samples/s", "h2d_bytes_per_step": 0,
-                    "d2h_bytes_per_step": 4 * n_samples, "ms_per_step": ms_e2e / args.steps},
+            "e2e": {"value": e2e_v, "unit": "partial-samples/s", "h2d_bytes_per_step": int(h2d.item()),
+                    "d2h_bytes_per_step": 4 * n_samples, "ms_per_step": ms_e2e / args.steps,
+                    "gpu_launches": int(s3["kernel_launches"] - s2["kernel_launches"]),
+                    "calls": "per step: frb_define_oscbank(pinned host arrays) + frb_fill_buffer(host out)"},
             "gpu_launches": int(s1["kernel_launches"] - s0["kernel_launches"]),
             "clocks": sampler.result(),
             "roofline": {

@@ -34,8 +34,11 @@
 #include "osc.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 namespace frb {
@@ -57,9 +60,13 @@ struct OscBankDev {
     float4* d_hot = nullptr;        // {a, b, cm1, k1}
     float4* d_anc = nullptr;        // {k2, amp, kappa, invA}
     uint4* d_ph = nullptr;          // {inc_lo, inc_hi, ph0_lo, ph0_hi}
+    uint64_t rec_cap = 0;           // records the three arrays above can hold
     uint32_t* d_grp_begin = nullptr;   // per voice: first group
     uint32_t* d_n_grp0 = nullptr;      // per voice: groups of class 0
     uint32_t* d_n_grp = nullptr;       // per voice: groups in total
+    uint32_t voice_cap = 0;
+    char* d_raw = nullptr;          // definition-time scratch (raw parameters, ranks); kept only by a re-defined bank
+    size_t raw_cap = 0;
     mutable float* d_planes = nullptr; // scratch for split > 1: [split][n_voices][plane_len]
     mutable uint64_t planes_cap = 0;
     mutable cudaStream_t side = nullptr;   // the (tiny, slow) attack-ramp kernel runs beside the main kernel
@@ -69,34 +76,111 @@ struct OscBankDev {
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_join) cudaEventDestroy(ev_join);
         cudaFree(d_hot); cudaFree(d_anc); cudaFree(d_ph);
-        cudaFree(d_grp_begin); cudaFree(d_n_grp0); cudaFree(d_n_grp); cudaFree(d_planes);
+        cudaFree(d_grp_begin); cudaFree(d_n_grp0); cudaFree(d_n_grp); cudaFree(d_planes); cudaFree(d_raw);
+    }
+    // a bank that replaces `src` under the same key takes over every device allocation of it (cudaMalloc / cudaFree cost
+    // milliseconds each beside a busy context; a re-definition per render must not pay them)
+    void take_buffers(OscBankDev& src) {
+        auto mv = [](auto& a, auto& b2) { a = b2; b2 = {}; };
+        mv(d_hot, src.d_hot); mv(d_anc, src.d_anc); mv(d_ph, src.d_ph); mv(rec_cap, src.rec_cap);
+        mv(d_grp_begin, src.d_grp_begin); mv(d_n_grp0, src.d_n_grp0); mv(d_n_grp, src.d_n_grp); mv(voice_cap, src.voice_cap);
+        mv(d_raw, src.d_raw); mv(raw_cap, src.raw_cap);
+        mv(d_planes, src.d_planes); mv(planes_cap, src.planes_cap);
+        mv(side, src.side); mv(ev_fork, src.ev_fork); mv(ev_join, src.ev_join);
     }
 };
 
 OscBankInfo osc_info(const OscBankDev& b) { return OscBankInfo{b.n_voices, b.n_partials}; }
+bool osc_usable(const OscBankDev& b) { return b.rec_cap >= std::max<uint64_t>(b.n_records, 1) && b.voice_cap >= std::max<uint32_t>(b.n_voices, 1); }
 
-// ------------------------------------------------------------------------------------------------------------------
-// setup: raw partial parameters (already grouped by voice and class, padded with amp = 0) -> resonator records
-__global__ void osc_setup_kernel(uint64_t n, double sample_rate, const double* __restrict__ freq,
+// Definition-time pipeline, all on the device (host work is O(n_voices)): a bank definition is the per-render "input" of a
+// synthesis graph, so its upload is on the end-to-end path (bench.py e2e re-defines the bank every step).
+//   1. osc_rank_kernel   — resonator class of every partial, its stable rank inside (voice, class), per-voice class-0 count,
+//                          longest attack ramp
+//   2. host              — group tables from the n_voices counts (prefix over voices, padding to multiples of K)
+//   3. osc_fill_kernel   — every record := the silent padding record
+//   4. osc_setup_kernel  — raw parameters -> resonator records (fp64), scattered to their (voice, class, rank) position
+
+__device__ __forceinline__ double osc_turns(double freq, double sample_rate) {
+    double fr = freq / sample_rate;
+    return fr - floor(fr);                                  // turns per sample in [0, 1)
+}
+__device__ __forceinline__ bool osc_class1(double fr) { return fr > 0.25 && fr < 0.75; }   // cos w < 0
+
+constexpr unsigned OSC_RANK_CLASS1 = 0x80000000u;
+constexpr int OSC_RANK_THREADS = 1024;
+
+// One CTA walks one voice in tiles of 1024 partials (ballot + warp totals: a block-wide stable partition).
+__global__ void __launch_bounds__(OSC_RANK_THREADS)
+osc_rank_kernel(unsigned n_voices, const unsigned long long* __restrict__ voice_offsets, double sample_rate,
+                const double* __restrict__ freq, const float* __restrict__ amp, const float* __restrict__ attack,
+                unsigned* __restrict__ rank, unsigned* __restrict__ cnt0, unsigned* __restrict__ max_attack_bits) {
+    __shared__ unsigned warp_tot[OSC_RANK_THREADS / 32];
+    const unsigned tid = threadIdx.x, w = tid >> 5, ln = tid & 31;
+    float my_att = 0.f;
+    for (unsigned v = blockIdx.x; v < n_voices; v += gridDim.x) {
+        const unsigned long long lo = voice_offsets[v], hi = voice_offsets[v + 1];
+        unsigned running0 = 0;                              // class-0 partials of this voice before the tile
+        for (unsigned long long tile = lo; tile < hi; tile += OSC_RANK_THREADS) {
+            const unsigned long long p = tile + tid;
+            const bool valid = p < hi;
+            const bool c1 = valid && osc_class1(osc_turns(freq[valid ? p : lo], sample_rate));
+            const bool c0 = valid && !c1;
+            const unsigned bal = __ballot_sync(0xffffffffu, c0);
+            if (ln == 0) warp_tot[w] = __popc(bal);
+            __syncthreads();
+            unsigned before = 0, total = 0;
+            for (unsigned k = 0; k < OSC_RANK_THREADS / 32; k++) {
+                const unsigned t = warp_tot[k];
+                before += (k < w) ? t : 0u;
+                total += t;
+            }
+            __syncthreads();
+            const unsigned n0_before = running0 + before + __popc(bal & ((1u << ln) - 1u));
+            if (valid) {
+                rank[p] = c1 ? (OSC_RANK_CLASS1 | (unsigned)((p - lo) - n0_before)) : n0_before;
+                const float at = attack[p];
+                if (at > 0.f && amp[p] != 0.f) my_att = fmaxf(my_att, at);
+            }
+            running0 += total;
+        }
+        if (tid == 0) cnt0[v] = running0;
+    }
+    for (int o = 16; o; o >>= 1) my_att = fmaxf(my_att, __shfl_xor_sync(0xffffffffu, my_att, o));
+    if (ln == 0 && my_att > 0.f) atomicMax(max_attack_bits, __float_as_uint(my_att));   // positive floats order like their bits
+}
+
+__global__ void osc_fill_kernel(uint64_t n, float4* __restrict__ hot, float4* __restrict__ anc, uint4* __restrict__ ph) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        hot[i] = make_float4(0.f, 0.f, 0.f, 0.f);           // a resonator that stays at 0
+        anc[i] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
+        ph[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
+// blockIdx.y strides the voices, blockIdx.x the partials of a voice.
+__global__ void osc_setup_kernel(unsigned n_voices, const unsigned long long* __restrict__ voice_offsets, int K,
+                                 const uint32_t* __restrict__ grp_begin, const uint32_t* __restrict__ n_grp0,
+                                 const unsigned* __restrict__ rank, double sample_rate, const double* __restrict__ freq,
                                  const float* __restrict__ amp, const float* __restrict__ phase,
                                  const float* __restrict__ attack, const float* __restrict__ tau,
                                  float4* __restrict__ hot, float4* __restrict__ anc, uint4* __restrict__ ph) {
     const double PI = 3.14159265358979323846;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const float am = amp[i];
-        if (am == 0.0f) {   // padding or silent partial: a resonator that stays at 0
-            hot[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            anc[i] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
-            ph[i] = make_uint4(0u, 0u, 0u, 0u);
-            continue;
-        }
-        double fr = freq[i] / sample_rate;
-        fr -= floor(fr);                                    // turns per sample in [0, 1)
-        const bool cls1 = fr > 0.25 && fr < 0.75;           // cos w < 0
+    for (unsigned v = blockIdx.y; v < n_voices; v += gridDim.y) {
+    const unsigned long long vlo = voice_offsets[v], vhi = voice_offsets[v + 1];
+    const uint64_t base0 = (uint64_t)grp_begin[v] * K, base1 = ((uint64_t)grp_begin[v] + n_grp0[v]) * K;
+    for (unsigned long long p = vlo + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; p < vhi;
+         p += (unsigned long long)gridDim.x * blockDim.x) {
+        const float am = amp[p];
+        if (am == 0.0f) continue;                           // silent partial: its record keeps the padding pattern
+        const unsigned rk = rank[p];
+        const uint64_t i = (rk & OSC_RANK_CLASS1) ? base1 + (rk & ~OSC_RANK_CLASS1) : base0 + rk;
+        const double fr = osc_turns(freq[p], sample_rate);
+        const bool cls1 = osc_class1(fr);
         double wp;                                          // w' in [-pi/2, pi/2]
         if (cls1) wp = PI - 2.0 * PI * fr;
         else wp = (fr <= 0.25) ? 2.0 * PI * fr : 2.0 * PI * (fr - 1.0);
-        const float tf = tau[i];
+        const float tf = tau[p];
         const bool decays = tf > 0.0f && isfinite(tf);
         const double one_m_rho = decays ? -expm1(-1.0 / (double)tf) : 0.0;
         const double rho = 1.0 - one_m_rho;
@@ -122,60 +206,117 @@ __global__ void osc_setup_kernel(uint64_t n, double sample_rate, const double* _
         const float cm1 = (float)(-(one_m_rho) * (1.0 + rho));             // rho^2 - 1
         hot[i] = make_float4(a32, b32, cm1, k1);
         const float kappa = decays ? (float)(1.4426950408889634 / (double)tf) : 0.0f;
-        const float at = attack[i];
+        const float at = attack[p];
         const float invA = (at > 0.0f) ? 1.0f / at : __int_as_float(0x7f800000);
         anc[i] = make_float4(k2, am, kappa, invA);
         const unsigned long long inc = __double2ull_rn(fr * 18446744073709551616.0);
-        double p0 = (double)phase[i] / (2.0 * PI);
+        double p0 = (double)phase[p] / (2.0 * PI);
         p0 -= floor(p0);
         const unsigned long long ph0 = __double2ull_rn(p0 * 18446744073709551616.0);
         ph[i] = make_uint4((unsigned)(inc & 0xffffffffull), (unsigned)(inc >> 32), (unsigned)(ph0 & 0xffffffffull), (unsigned)(ph0 >> 32));
     }
+    }
 }
 
-std::shared_ptr<OscBankDev> osc_create(const frb_oscbank_desc* d, cudaStream_t stream, std::string* err) {
-    auto fail = [&](const std::string& m) { if (err) *err = m; return std::shared_ptr<OscBankDev>(); };
+std::shared_ptr<OscBankDev> osc_create(const frb_oscbank_desc* d, cudaStream_t stream, std::string* err,
+                                       const std::shared_ptr<OscBankDev>& recycle) {
+    std::shared_ptr<OscBankDev> b;
+    bool stolen = false;
+    auto fail = [&](const std::string& m) {
+        if (err) *err = m;
+        if (stolen) recycle->take_buffers(*b);              // hand the allocations back (osc_usable tells if they survived)
+        return std::shared_ptr<OscBankDev>();
+    };
     if (!d->voice_offsets || (d->n_partials && (!d->freq_hz || !d->amp || !d->phase || !d->attack || !d->tau)))
         return fail("oscbank: null array");
     if (!(d->sample_rate > 0.0)) return fail("oscbank: sample_rate must be positive");
     if (d->voice_offsets[0] != 0 || d->voice_offsets[d->n_voices] != d->n_partials) return fail("oscbank: voice_offsets must span [0, n_partials]");
-    auto b = std::make_shared<OscBankDev>();
+    uint64_t mx = 0;
+    for (uint32_t v = 0; v < d->n_voices; v++) {
+        if (d->voice_offsets[v + 1] < d->voice_offsets[v]) return fail("oscbank: voice_offsets must be non-decreasing");
+        mx = std::max<uint64_t>(mx, d->voice_offsets[v + 1] - d->voice_offsets[v]);
+    }
+    if (mx >= (1ull << 31)) return fail("oscbank: more than 2^31 partials in one voice");
+    b = std::make_shared<OscBankDev>();
     b->n_voices = d->n_voices;
     b->n_partials = d->n_partials;
     b->sample_rate = d->sample_rate;
-
-    // group by (voice, class), pad every class segment to a multiple of K with silent partials
-    std::vector<uint32_t> grp_begin(d->n_voices), n_grp0(d->n_voices), n_grp(d->n_voices);
-    std::vector<uint64_t> order;            // source index per record, ~0 = padding
-    {
-        uint64_t mx = 0;
-        for (uint32_t v = 0; v < d->n_voices; v++) mx = std::max<uint64_t>(mx, d->voice_offsets[v + 1] - d->voice_offsets[v]);
-        b->K = (mx <= 8) ? OSC_K_SMALL : OSC_K;
-    }
+    b->K = (mx <= 8) ? OSC_K_SMALL : OSC_K;
     const int K = b->K;
-    order.reserve(d->n_partials + (uint64_t)d->n_voices * 2 * K);
-    float max_attack = 0.f;
-    for (uint32_t v = 0; v < d->n_voices; v++) {
-        uint64_t lo = d->voice_offsets[v], hi = d->voice_offsets[v + 1];
-        if (hi < lo) return fail("oscbank: voice_offsets must be non-decreasing");
-        grp_begin[v] = (uint32_t)(order.size() / K);
-        for (int cls = 0; cls < 2; cls++) {
-            for (uint64_t p = lo; p < hi; p++) {
-                double fr = d->freq_hz[p] / d->sample_rate;
-                fr -= std::floor(fr);
-                bool c1 = fr > 0.25 && fr < 0.75;
-                if ((int)c1 == cls) order.push_back(p);
-            }
-            while (order.size() % K) order.push_back(~0ull);
-            if (cls == 0) n_grp0[v] = (uint32_t)(order.size() / K) - grp_begin[v];
-        }
-        n_grp[v] = (uint32_t)(order.size() / K) - grp_begin[v];
+    const uint64_t np = d->n_partials;
+    const uint32_t nv = d->n_voices;
+
+#define OC(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(std::string("oscbank: ") + cudaGetErrorString(e_)); } while (0)
+    const bool trace = getenv("FRB_TRACE") != nullptr;      // tuning aid: host-clock phases of a definition on stderr
+    auto t_prev = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!trace) return;
+        cudaStreamSynchronize(stream);
+        auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[frb] define_oscbank %-18s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t_prev).count());
+        t_prev = t;
+    };
+    // raw parameters + scratch in one allocation: [freq f64][amp][phase][attack][tau][rank u32][offsets u64][cnt0 u32][max_attack u32]
+    if (recycle) {                                          // nothing of the old bank may still be in flight
+        OC(cudaStreamSynchronize(stream));
+        b->take_buffers(*recycle);
+        stolen = true;
+    }
+    const uint64_t npp = (np + 3) & ~3ull;                  // keeps every sub-array 16-byte aligned
+    const uint64_t nvp = ((uint64_t)nv + 4) & ~3ull;
+    const size_t raw_bytes = npp * (sizeof(double) + 5 * 4) + nvp * (sizeof(uint64_t) + 4) + 16;
+    if (b->raw_cap < raw_bytes) {
+        cudaFree(b->d_raw); b->d_raw = nullptr; b->raw_cap = 0;
+        OC(cudaMalloc(&b->d_raw, raw_bytes));
+        b->raw_cap = raw_bytes;
+    }
+    char* const d_raw = b->d_raw;
+    double* d_freq = reinterpret_cast<double*>(d_raw);
+    float* d_amp = reinterpret_cast<float*>(d_freq + npp);
+    float* d_phase = d_amp + npp; float* d_attack = d_phase + npp; float* d_tau = d_attack + npp;
+    unsigned* d_rank = reinterpret_cast<unsigned*>(d_tau + npp);
+    unsigned long long* d_offs = reinterpret_cast<unsigned long long*>(d_rank + npp);
+    unsigned* d_cnt0 = reinterpret_cast<unsigned*>(d_offs + nvp);
+    unsigned* d_maxatt = d_cnt0 + nvp;
+    lap("alloc raw");
+    OC(cudaMemcpyAsync(d_offs, d->voice_offsets, ((size_t)nv + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
+    OC(cudaMemsetAsync(d_maxatt, 0, 4, stream));
+    if (np) {
+        OC(cudaMemcpyAsync(d_freq, d->freq_hz, np * sizeof(double), cudaMemcpyHostToDevice, stream));
+        OC(cudaMemcpyAsync(d_amp, d->amp, np * sizeof(float), cudaMemcpyHostToDevice, stream));
+        OC(cudaMemcpyAsync(d_attack, d->attack, np * sizeof(float), cudaMemcpyHostToDevice, stream));
+    }
+    lap("h2d freq/amp/att");
+    std::vector<uint32_t> cnt0(nv, 0);
+    uint32_t max_attack_bits = 0;
+    if (nv) {
+        osc_rank_kernel<<<std::min<uint32_t>(nv, 148 * 2), OSC_RANK_THREADS, 0, stream>>>(nv, d_offs, d->sample_rate, d_freq, d_amp, d_attack, d_rank, d_cnt0, d_maxatt);
+        OC(cudaGetLastError());
+        OC(cudaMemcpyAsync(cnt0.data(), d_cnt0, (size_t)nv * 4, cudaMemcpyDeviceToHost, stream));
+    }
+    OC(cudaMemcpyAsync(&max_attack_bits, d_maxatt, 4, cudaMemcpyDeviceToHost, stream));
+    if (np) {   // the remaining parameters travel while the host waits for the counts
+        OC(cudaMemcpyAsync(d_phase, d->phase, np * sizeof(float), cudaMemcpyHostToDevice, stream));
+        OC(cudaMemcpyAsync(d_tau, d->tau, np * sizeof(float), cudaMemcpyHostToDevice, stream));
+    }
+    OC(cudaStreamSynchronize(stream));
+    lap("rank + h2d rest");
+    memcpy(&b->max_attack, &max_attack_bits, 4);
+
+    // group by (voice, class), every class segment padded to a multiple of K with silent records
+    std::vector<uint32_t> grp_begin(nv), n_grp0(nv), n_grp(nv);
+    uint64_t groups = 0;
+    for (uint32_t v = 0; v < nv; v++) {
+        const uint64_t len = d->voice_offsets[v + 1] - d->voice_offsets[v];
+        const uint64_t g0 = (cnt0[v] + K - 1) / K, g1 = (len - cnt0[v] + K - 1) / K;
+        if (groups + g0 + g1 >= (1ull << 32)) return fail("oscbank: too many partial groups");
+        grp_begin[v] = (uint32_t)groups;
+        n_grp0[v] = (uint32_t)g0;
+        n_grp[v] = (uint32_t)(g0 + g1);
+        groups += g0 + g1;
         b->max_groups = std::max(b->max_groups, n_grp[v]);
     }
-    for (uint64_t p = 0; p < d->n_partials; p++)
-        if (d->attack[p] > 0.f && d->amp[p] != 0.f) max_attack = std::max(max_attack, d->attack[p]);
-    b->max_attack = max_attack;
-    const uint64_t n = order.size();
+    const uint64_t n = groups * K;
     b->n_records = n;
     // Partial-range split: one CTA is one warp working through (groups / split) groups for 32 segments (4,096 samples).
     // All CTAs of a launch cost the same, so the only imbalance is the partially filled last wave (148 SMs x ~12
@@ -192,42 +333,43 @@ std::shared_ptr<OscBankDev> osc_create(const frb_oscbank_desc* d, cudaStream_t s
         b->split = s;
     }
 
-    std::vector<double> h_freq(n, 0.0);
-    std::vector<float> h_amp(n, 0.f), h_phase(n, 0.f), h_attack(n, 0.f), h_tau(n, 0.f);
-    for (uint64_t i = 0; i < n; i++) {
-        uint64_t p = order[i];
-        if (p == ~0ull) continue;
-        h_freq[i] = d->freq_hz[p]; h_amp[i] = d->amp[p]; h_phase[i] = d->phase[p];
-        h_attack[i] = d->attack[p]; h_tau[i] = d->tau[p];
-    }
-#define OC(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(std::string("oscbank: ") + cudaGetErrorString(e_)); } while (0)
-    double* d_freq = nullptr; float *d_amp = nullptr, *d_phase = nullptr, *d_attack = nullptr, *d_tau = nullptr;
     const uint64_t nn = std::max<uint64_t>(n, 1);
-    OC(cudaMalloc(&d_freq, nn * sizeof(double)));
-    OC(cudaMalloc(&d_amp, nn * sizeof(float))); OC(cudaMalloc(&d_phase, nn * sizeof(float)));
-    OC(cudaMalloc(&d_attack, nn * sizeof(float))); OC(cudaMalloc(&d_tau, nn * sizeof(float)));
-    OC(cudaMalloc(&b->d_hot, nn * sizeof(float4))); OC(cudaMalloc(&b->d_anc, nn * sizeof(float4))); OC(cudaMalloc(&b->d_ph, nn * sizeof(uint4)));
-    const uint32_t nv = std::max<uint32_t>(d->n_voices, 1);
-    OC(cudaMalloc(&b->d_grp_begin, nv * sizeof(uint32_t))); OC(cudaMalloc(&b->d_n_grp0, nv * sizeof(uint32_t))); OC(cudaMalloc(&b->d_n_grp, nv * sizeof(uint32_t)));
-    if (n) {
-        OC(cudaMemcpyAsync(d_freq, h_freq.data(), n * sizeof(double), cudaMemcpyHostToDevice, stream));
-        OC(cudaMemcpyAsync(d_amp, h_amp.data(), n * sizeof(float), cudaMemcpyHostToDevice, stream));
-        OC(cudaMemcpyAsync(d_phase, h_phase.data(), n * sizeof(float), cudaMemcpyHostToDevice, stream));
-        OC(cudaMemcpyAsync(d_attack, h_attack.data(), n * sizeof(float), cudaMemcpyHostToDevice, stream));
-        OC(cudaMemcpyAsync(d_tau, h_tau.data(), n * sizeof(float), cudaMemcpyHostToDevice, stream));
+    if (b->rec_cap < nn) {
+        cudaFree(b->d_hot); cudaFree(b->d_anc); cudaFree(b->d_ph);
+        b->d_hot = b->d_anc = nullptr; b->d_ph = nullptr; b->rec_cap = 0;
+        OC(cudaMalloc(&b->d_hot, nn * sizeof(float4))); OC(cudaMalloc(&b->d_anc, nn * sizeof(float4))); OC(cudaMalloc(&b->d_ph, nn * sizeof(uint4)));
+        b->rec_cap = nn;
     }
-    if (d->n_voices) {
-        OC(cudaMemcpyAsync(b->d_grp_begin, grp_begin.data(), d->n_voices * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
-        OC(cudaMemcpyAsync(b->d_n_grp0, n_grp0.data(), d->n_voices * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
-        OC(cudaMemcpyAsync(b->d_n_grp, n_grp.data(), d->n_voices * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    const uint32_t nv1 = std::max<uint32_t>(nv, 1);
+    if (b->voice_cap < nv1) {
+        cudaFree(b->d_grp_begin); cudaFree(b->d_n_grp0); cudaFree(b->d_n_grp);
+        b->d_grp_begin = b->d_n_grp0 = b->d_n_grp = nullptr; b->voice_cap = 0;
+        OC(cudaMalloc(&b->d_grp_begin, nv1 * sizeof(uint32_t))); OC(cudaMalloc(&b->d_n_grp0, nv1 * sizeof(uint32_t))); OC(cudaMalloc(&b->d_n_grp, nv1 * sizeof(uint32_t)));
+        b->voice_cap = nv1;
     }
+    if (nv) {
+        OC(cudaMemcpyAsync(b->d_grp_begin, grp_begin.data(), nv * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+        OC(cudaMemcpyAsync(b->d_n_grp0, n_grp0.data(), nv * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+        OC(cudaMemcpyAsync(b->d_n_grp, n_grp.data(), nv * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    }
+    lap("alloc records");
     if (n) {
-        unsigned blocks = (unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 8);
-        osc_setup_kernel<<<blocks, 256, 0, stream>>>(n, d->sample_rate, d_freq, d_amp, d_phase, d_attack, d_tau, b->d_hot, b->d_anc, b->d_ph);
+        const unsigned fb = (unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 8);
+        osc_fill_kernel<<<fb, 256, 0, stream>>>(n, b->d_hot, b->d_anc, b->d_ph);
+        OC(cudaGetLastError());
+        lap("fill");
+        const unsigned gy = std::min<uint32_t>(nv, 32768);
+        const unsigned gx = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((mx + 255) / 256, std::max<uint64_t>(1, 148ull * 16 / gy)));
+        osc_setup_kernel<<<dim3(gx, gy), 256, 0, stream>>>(nv, d_offs, K, b->d_grp_begin, b->d_n_grp0, d_rank, d->sample_rate, d_freq, d_amp,
+                                                           d_phase, d_attack, d_tau, b->d_hot, b->d_anc, b->d_ph);
         OC(cudaGetLastError());
     }
     OC(cudaStreamSynchronize(stream));
-    cudaFree(d_freq); cudaFree(d_amp); cudaFree(d_phase); cudaFree(d_attack); cudaFree(d_tau);
+    lap("setup");
+    if (!recycle) {   // a first definition is usually the only one: give the scratch (28 B per partial) back
+        cudaFree(b->d_raw); b->d_raw = nullptr; b->raw_cap = 0;
+        lap("free raw");
+    }
 #undef OC
     return b;
 }

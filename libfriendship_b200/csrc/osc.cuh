@@ -19,9 +19,15 @@ struct OscBankInfo {
     uint64_t n_partials;
 };
 
-// Uploads and preprocesses a bank (fp64 setup kernel).  Returns nullptr and sets *err on failure.
-std::shared_ptr<OscBankDev> osc_create(const frb_oscbank_desc* d, cudaStream_t stream, std::string* err);
+// Uploads and preprocesses a bank (class/rank, fill and fp64 setup kernels; host work is O(n_voices)).  The arrays of `d`
+// may be pageable or pinned host memory.  Returns nullptr and sets *err on failure.
+// `recycle`: the bank this one replaces under the same key, if any.  The new bank takes over all its device allocations
+// (records, scratch, partial-range planes), so that re-defining a bank before every render allocates nothing.  On success
+// `recycle` is left hollow; on failure it gets its allocations back (check osc_usable: a failed reallocation loses them).
+std::shared_ptr<OscBankDev> osc_create(const frb_oscbank_desc* d, cudaStream_t stream, std::string* err,
+                                       const std::shared_ptr<OscBankDev>& recycle = nullptr);
 OscBankInfo osc_info(const OscBankDev& b);
+bool osc_usable(const OscBankDev& b);   // false for a bank whose allocations were lost to a failed re-definition
 
 cudaError_t osc_init_device();
 

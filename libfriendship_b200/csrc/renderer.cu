@@ -136,9 +136,21 @@ void Renderer::define_oscbank(uint64_t key, const frb_oscbank_desc* d) {
     require_device();
     CU(cudaSetDevice(device_));
     std::string err;
-    auto b = osc_create(d, stream_, &err);
-    if (!b) throw Error{FRB_E_INVALID, err};
-    stats.h2d_bytes += d->n_partials * (sizeof(double) + 4 * sizeof(float));
+    std::shared_ptr<OscBankDev> old;
+    if (auto it = osc_defs_.find(key); it != osc_defs_.end()) old = it->second;
+    const uint32_t old_voices = old ? osc_info(*old).n_voices : d->n_voices;
+    auto b = osc_create(d, stream_, &err, old);
+    if (!b) {
+        if (old && !osc_usable(*old)) { osc_defs_.erase(key); dirty_ = true; }   // its allocations went into the failed attempt
+        throw Error{FRB_E_INVALID, err};
+    }
+    stats.h2d_bytes += d->n_partials * (sizeof(double) + 4 * sizeof(float)) + ((uint64_t)d->n_voices + 1) * sizeof(uint64_t);
+    stats.kernel_launches += 3;   // rank, fill, setup
+    if (old) {
+        // re-definition = new parameters for the same node (the per-render input of a synthesis graph)
+        if (old_voices != d->n_voices) dirty_ = true;       // the lane count is part of the schedule
+        cache_valid_ = false;                               // rings hold the old bank's samples
+    }
     osc_defs_[key] = b;
 }
 void Renderer::define_directform(uint64_t key, const frb_directform_desc* d) {

@@ -120,3 +120,50 @@ def test_many_groups_split_planes_path():
     gpu = render_bank(B200Renderer, bank, n, 20000, n_voices=2)
     ref = render_bank(OracleRenderer, bank, n, 20000, n_voices=2)
     assert np.abs(gpu.astype(np.float64) - ref).max() <= TOL * full_scale(bank)
+
+
+def test_device_regroup_ragged_voices_mixed_classes():
+    """The definition pipeline groups partials by (voice, resonator class) on the device: ragged voices (empty, 1, a
+    few, several 1,024-partial tiles), classes interleaved partial by partial, silent partials in between."""
+    from libfriendship_b200 import B200Renderer
+    rng = np.random.RandomState(11)
+    lens = [0, 1, 7, 3000, 0, 1025, 33]
+    vo = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    P = int(vo[-1])
+    freq = rng.uniform(10, 23900, P)
+    freq[::2] = rng.uniform(10, 11900, len(freq[::2]))        # class 0 / class 1 alternate
+    freq[1::2] = rng.uniform(12100, 23900, len(freq[1::2]))
+    amp = (rng.uniform(0.1, 1, P) / 64).astype(np.float32)
+    amp[rng.randint(0, P, 40)] = 0.0
+    bank = dict(sample_rate=48000.0, voice_offsets=vo, freq_hz=freq, amp=amp,
+                phase=rng.uniform(-3, 3, P).astype(np.float32), attack=rng.uniform(0, 300, P).astype(np.float32),
+                tau=rng.uniform(2000, 90000, P).astype(np.float32))
+    nv = len(lens)
+    for idx in (0, 77777):
+        gpu = render_bank(B200Renderer, bank, 700, idx, n_voices=nv)
+        ref = render_bank(OracleRenderer, bank, 700, idx, n_voices=nv)
+        assert np.abs(gpu.astype(np.float64) - ref).max() <= TOL * full_scale(bank)
+        assert (gpu[0] == 0).all() and (gpu[4] == 0).all()
+
+
+def test_redefine_bank_replaces_parameters():
+    """frb_define_oscbank on an existing key replaces the node's parameters (the per-render input of a synthesis
+    graph): the next render uses the new bank, also retroactively through a Delay (pure function of absolute time)."""
+    from libfriendship_b200 import B200Renderer
+    bank_a, ids = detuned_bank(3, 300, seed=5)
+    bank_b, _ = detuned_bank(3, 300, seed=6)
+    bank_b["amp"] = (bank_b["amp"] * 0.5).astype(np.float32)
+    g = B200Renderer()
+    build_voice_mix_graph(g, bank_a, ids, delay0=100.0)
+    first = g.fill_buffer(1, 2000, 0)
+    g.define_oscbank(7, **bank_b)
+    second = g.fill_buffer(1, 2000, 2000)                     # continues at the head: the delay taps reach back before 2000
+    for bank, got, idx in ((bank_a, first, 0), (bank_b, second, 2000)):
+        o = OracleRenderer()
+        build_voice_mix_graph(o, bank, ids, delay0=100.0)
+        ref = o.fill_buffer(1, 2000, idx)
+        assert np.abs(got.astype(np.float64) - ref).max() <= TOL * full_scale(bank) * 3 * 1.3
+    # same parameters again: identical bits to a fresh renderer (nothing of the old definition survives)
+    g.define_oscbank(7, **bank_a)
+    again = g.fill_buffer(1, 2000, 0)
+    assert_same_bits(again, first, "redefine")
