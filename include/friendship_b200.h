@@ -147,6 +147,22 @@ int frb_fill_buffer_device(frb_renderer* r, float* d_out, uint32_t n_slots, uint
 int frb_sync(frb_renderer* r);
 void* frb_stream(frb_renderer* r);   /* the cudaStream_t the renderer launches on */
 
+/* ---- N4: streaming render — the step after the path ----
+ * The reference hands every rendered buffer to Client::audio_rendered (src/dispatch.rs:151, src/client/client.rs:8-15);
+ * a long offline render (BASELINE.json configs[4]: 11.52 M samples) must move its output off the device without
+ * stalling the render.  frb_render_stream renders [idx, idx + n_total) as consecutive fill_buffer calls of `block`
+ * samples (the last one shorter) — same results, bit for bit, as those calls — pipelined: while block k renders, block
+ * k-1 travels device->host into one of two pinned staging buffers on a copy stream and the host thread runs `sink` on
+ * it; the external inputs of block k+1 are fetched through `source` into pinned memory meanwhile.
+ *   source(user, rows, n_in_rows, n_times, idx): fill rows[r * n_times + i] = external input slot r at time idx + i;
+ *           may be NULL when n_in_rows == 0.  Non-zero return aborts the render (FRB_E_INVALID).
+ *   sink(user, block, n_slots, n_times, idx): block is row-major [n_slots x n_times], valid during the call
+ *           (= audio_rendered(buffer, idx)).  Non-zero return aborts the render. */
+typedef int (*frb_source_fn)(void* user, float* rows, uint32_t n_in_rows, uint64_t n_times, uint64_t idx);
+typedef int (*frb_sink_fn)(void* user, const float* block, uint32_t n_slots, uint64_t n_times, uint64_t idx);
+int frb_render_stream(frb_renderer* r, uint32_t n_slots, uint64_t idx, uint64_t n_total, uint64_t block,
+                      uint32_t n_in_rows, frb_source_fn source, frb_sink_fn sink, void* user);
+
 /* ---- K5: cross-GPU mix without a separate collective ----
  * One process per GPU.  Rank 0 owns a slab [world x n_slots x n_times] in its HBM; every rank renders its shard of
  * the voices with frb_fill_buffer_device pointing at ITS row of that slab (the stage kernel's output stores go

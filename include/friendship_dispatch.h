@@ -53,8 +53,23 @@ int frd_query_id(frd_dispatch* d, uint32_t handle);
 /* OscRenderer::RenderRange(range, num_slots, inputs) (dispatch.rs:66-76, :147-153) */
 int frd_render_range(frd_dispatch* d, uint64_t start, uint64_t end, uint32_t n_slots,
                      const float* in_data, const uint64_t* in_row_offsets, uint32_t n_in_rows);
+/* N4: RenderRange over [start, end) delivered as consecutive audio_rendered(buffer, idx) calls of
+ * `block` samples (no inputs) — what a client sending back-to-back RenderRange messages gets, bit for bit, but
+ * pipelined through frb_render_stream: block k renders while block k-1 is copied to pinned host memory and handed to
+ * the client.  This is how an offline render (BASELINE.json configs[4]) leaves the device. */
+int frd_render_stream(frd_dispatch* d, uint64_t start, uint64_t end, uint32_t n_slots, uint64_t block);
 /* OscResMan::AddDir (dispatch.rs:80-86, :155-159) */
 int frd_add_dir(frd_dispatch* d, const char* path);
+
+/* N4 output sink: a RIFF/WAVE writer (IEEE float32, slot s = channel s) usable as a Client.  The reference leaves
+ * file output to the client (README.md:22-26); this is that client.  frd_wav_audio_rendered has the signature of
+ * frd_client.audio_rendered with `user` = the frd_wav*; blocks must arrive in order (idx is not used to seek). */
+typedef struct frd_wav frd_wav;
+frd_wav* frd_wav_open(const char* path, uint32_t n_channels, uint32_t sample_rate);   /* NULL on failure */
+int      frd_wav_write(frd_wav* w, const float* buffer, uint32_t n_slots, uint64_t n_times);
+void     frd_wav_audio_rendered(void* user, const float* buffer, uint32_t n_slots, uint64_t n_times, uint64_t idx);
+int      frd_wav_close(frd_wav* w);          /* patches the header, frees w; FRB_OK iff every write succeeded */
+const char* frd_wav_error(const frd_wav* w);
 
 /* helpers: SHA-256 of a file (what tests/load_effect.rs:84-88 computes) and the graph as an AdjList JSON */
 int frd_sha256_file(const char* path, uint8_t out[32]);

@@ -29,6 +29,10 @@ _lib.frb_device_free.argtypes = [_C.c_void_p, _C.c_void_p]
 _lib.frb_ipc_export.argtypes = [_C.c_void_p, _C.c_void_p, _C.POINTER(_C.c_ubyte)]
 _lib.frb_ipc_open.argtypes = [_C.c_void_p, _C.POINTER(_C.c_ubyte), _C.POINTER(_C.c_void_p)]
 _lib.frb_ipc_close.argtypes = [_C.c_void_p, _C.c_void_p]
+SOURCE_FN = _C.CFUNCTYPE(_C.c_int, _C.c_void_p, _C.POINTER(_C.c_float), _C.c_uint32, _C.c_uint64, _C.c_uint64)
+SINK_FN = _C.CFUNCTYPE(_C.c_int, _C.c_void_p, _C.POINTER(_C.c_float), _C.c_uint32, _C.c_uint64, _C.c_uint64)
+_lib.frb_render_stream.argtypes = [_C.c_void_p, _C.c_uint32, _C.c_uint64, _C.c_uint64, _C.c_uint64, _C.c_uint32,
+                                   SOURCE_FN, SINK_FN, _C.c_void_p]
 _lib.frb_sum_rows.argtypes = [_C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_uint32, _C.c_uint64, _C.c_uint64]
 
 
@@ -59,6 +63,41 @@ class B200Renderer(_cabi.CRendererBase):
         n_rows = len(offs) - 1
         self._check(_lib.frb_fill_buffer_device(self._h, d_out_ptr, n_slots, n_times, idx, d_in_ptr,
                                                 offs.ctypes.data_as(_C.POINTER(_C.c_uint64)), n_rows))
+
+    # ---- N4: pipelined block render (pinned double-buffered staging both ways) ----
+    def render_stream(self, n_slots, idx, n_total, block, sink, n_in_rows=0, source=None):
+        """Renders [idx, idx + n_total) as consecutive fill_buffer calls of `block` samples.
+        sink(block_array [n_slots x n], idx): the array is a view of pinned staging memory, valid during the call.
+        source(idx, n) -> array-like [n_in_rows x n]: external-input rows of the block starting at idx."""
+        import numpy as np
+        errors = []
+
+        def c_sink(user, ptr, ns, nt, t):
+            try:
+                n = ns * nt
+                arr = np.ctypeslib.as_array(ptr, shape=(n,)).reshape(ns, nt) if n else np.zeros((ns, nt), np.float32)
+                sink(arr, t)
+                return 0
+            except BaseException as e:      # never unwind through the C frames
+                errors.append(e)
+                return 1
+
+        def c_source(user, ptr, nr, nt, t):
+            try:
+                rows = np.asarray(source(t, nt), dtype=np.float32).reshape(nr, nt)
+                if nr * nt:
+                    np.ctypeslib.as_array(ptr, shape=(nr * nt,))[:] = rows.ravel()
+                return 0
+            except BaseException as e:
+                errors.append(e)
+                return 1
+
+        cb_sink = SINK_FN(c_sink)
+        cb_source = SOURCE_FN(c_source) if n_in_rows else SOURCE_FN()
+        rc = _lib.frb_render_stream(self._h, n_slots, idx, n_total, block, n_in_rows, cb_source, cb_sink, None)
+        if errors:
+            raise errors[0]
+        self._check(rc)
 
     def sync(self):
         self._check(_lib.frb_sync(self._h))

@@ -83,6 +83,7 @@ EXPORTS = [
     "frb_define_directform", "frb_define_fbdelay", "frb_add_node", "frb_del_node", "frb_add_edge", "frb_del_edge",
     "frb_fill_buffer", "frb_fill_buffer_device", "frb_sync", "frb_stream", "frb_dump_schedule", "frb_get_stats",
     "frb_set_profiling", "frb_get_timing", "frb_version", "frb_jit_source", "frb_jit_cubin_size", "frb_device_alloc", "frb_device_free", "frb_ipc_export", "frb_ipc_open", "frb_ipc_close", "frb_sum_rows",
+    "frb_render_stream",
 ]
 
 

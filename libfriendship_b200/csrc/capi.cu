@@ -91,6 +91,10 @@ int frb_fill_buffer_device(frb_renderer* r, float* d_out, uint32_t n_slots, uint
         r->impl.fill(d_out, true, n_slots, n_times, idx, d_in_data, true, in_row_offsets, n_in_rows);
     });
 }
+int frb_render_stream(frb_renderer* r, uint32_t n_slots, uint64_t idx, uint64_t n_total, uint64_t block,
+                      uint32_t n_in_rows, frb_source_fn source, frb_sink_fn sink, void* user) {
+    return guarded(r, [&] { r->impl.render_stream(n_slots, idx, n_total, block, n_in_rows, source, sink, user); });
+}
 int frb_sync(frb_renderer* r) { return guarded(r, [&] { r->impl.sync(); }); }
 void* frb_stream(frb_renderer* r) { return r ? (void*)r->impl.stream() : nullptr; }
 

@@ -5,6 +5,7 @@
 
 #include "../../../include/friendship_dispatch.h"
 #include "routing.hpp"
+#include "wav.hpp"
 
 using namespace frb::host;
 
@@ -155,11 +156,52 @@ int frd_render_range(frd_dispatch* d, uint64_t start, uint64_t end, uint32_t n_s
     if (d->client.audio_rendered) d->client.audio_rendered(d->client.user, buff.data(), n_slots, n_times, start);
     return FRB_OK;
 }
+static int stream_sink(void* user, const float* block, uint32_t n_slots, uint64_t n_times, uint64_t idx) {
+    auto* d = static_cast<frd_dispatch*>(user);
+    if (d->client.audio_rendered) d->client.audio_rendered(d->client.user, block, n_slots, n_times, idx);   // dispatch.rs:151
+    return 0;
+}
+int frd_render_stream(frd_dispatch* d, uint64_t start, uint64_t end, uint32_t n_slots, uint64_t block) {
+    if (!d || end < start || block == 0) return FRD_E_BAD_MESSAGE;
+    return renderer_rc(d, frb_render_stream(d->renderer, n_slots, start, end - start, block, 0, nullptr, stream_sink, d));
+}
 int frd_add_dir(frd_dispatch* d, const char* path) {                                      // dispatch.rs:155-159
     if (!d || !path) return FRD_E_BAD_MESSAGE;
     d->resman.add_dir(path);
     return FRB_OK;
 }
+}  // extern "C"
+
+struct frd_wav {
+    WavWriter w;
+    std::string err;
+    bool failed = false;
+};
+
+extern "C" {
+
+frd_wav* frd_wav_open(const char* path, uint32_t n_channels, uint32_t sample_rate) {
+    if (!path) return nullptr;
+    auto* w = new frd_wav();
+    if (!w->w.open(path, n_channels, sample_rate, &w->err)) { delete w; return nullptr; }
+    return w;
+}
+int frd_wav_write(frd_wav* w, const float* buffer, uint32_t n_slots, uint64_t n_times) {
+    if (!w || (!buffer && n_times)) return FRD_E_BAD_MESSAGE;
+    if (!w->w.write(buffer, n_slots, n_times, &w->err)) { w->failed = true; return FRD_E_BAD_MESSAGE; }
+    return FRB_OK;
+}
+void frd_wav_audio_rendered(void* user, const float* buffer, uint32_t n_slots, uint64_t n_times, uint64_t) {
+    frd_wav_write(static_cast<frd_wav*>(user), buffer, n_slots, n_times);
+}
+int frd_wav_close(frd_wav* w) {
+    if (!w) return FRD_E_BAD_MESSAGE;
+    const bool ok = w->w.close() && !w->failed;
+    delete w;
+    return ok ? FRB_OK : FRD_E_BAD_MESSAGE;
+}
+const char* frd_wav_error(const frd_wav* w) { return w ? w->err.c_str() : "wav: cannot open"; }
+
 int frd_sha256_file(const char* path, uint8_t out[32]) {
     std::string bytes;
     if (!path || !ResMan::read_file(path, &bytes)) return FRD_E_BAD_MESSAGE;

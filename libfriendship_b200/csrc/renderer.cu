@@ -82,6 +82,14 @@ Renderer::~Renderer() {
     if (d_in_stage_) cudaFree(d_in_stage_);
     if (d_out_) cudaFree(d_out_);
     if (d_bufdesc_) cudaFree(d_bufdesc_);
+    for (auto& st : sstage_) {
+        if (st.d_out) cudaFree(st.d_out);
+        if (st.h_out) cudaFreeHost(st.h_out);
+        if (st.h_in) cudaFreeHost(st.h_in);
+        if (st.rendered) cudaEventDestroy(st.rendered);
+        if (st.copied) cudaEventDestroy(st.copied);
+    }
+    if (copy_stream_) cudaStreamDestroy(copy_stream_);
     for (auto& ev : ev_) if (ev) cudaEventDestroy(ev);
     if (stream_) cudaStreamDestroy(stream_);
 }
@@ -579,9 +587,16 @@ void Renderer::fill(float* out, bool out_on_device, uint32_t n_slots, uint64_t n
                 if (d_indesc_) { CU(cudaStreamSynchronize(stream_)); CU(cudaFree(d_indesc_)); }
                 d_indesc_cap_ = std::max<size_t>(nin * 2, 16);
                 CU(cudaMalloc(&d_indesc_, d_indesc_cap_ * sizeof(InputDesc)));
+                h_indesc_.clear();
             }
-            CU(cudaMemcpyAsync(d_indesc_, h.data(), nin * sizeof(InputDesc), cudaMemcpyHostToDevice, stream_));
-            CU(cudaStreamSynchronize(stream_));
+            // the table travels by value from a host vector that must outlive the copy: h_indesc_ is only rewritten
+            // after the previous copy was waited for
+            if (h_indesc_.size() != nin || memcmp(h_indesc_.data(), h.data(), nin * sizeof(InputDesc)) != 0) {
+                CU(cudaStreamSynchronize(stream_));
+                h_indesc_ = h;
+                CU(cudaMemcpyAsync(d_indesc_, h_indesc_.data(), nin * sizeof(InputDesc), cudaMemcpyHostToDevice, stream_));
+                CU(cudaStreamSynchronize(stream_));
+            }
         }
         ensure_rings(t1);
 
@@ -616,6 +631,78 @@ void Renderer::fill(float* out, bool out_on_device, uint32_t n_slots, uint64_t n
         CU(cudaEventElapsedTime(&timing.total_ms, ev_[0], ev_[1]));
     }
     if (!out_on_device) CU(cudaStreamSynchronize(stream_));
+}
+
+// N4 (include/friendship_b200.h): consecutive fill_buffer calls of `block` samples, two blocks in flight.
+void Renderer::render_stream(uint32_t n_slots, uint64_t idx, uint64_t n_total, uint64_t block, uint32_t n_in_rows,
+                             frb_source_fn source, frb_sink_fn sink, void* user) {
+    require_device();
+    CU(cudaSetDevice(device_));
+    if (!sink) throw Error{FRB_E_INVALID, "render_stream: sink is NULL"};
+    if (n_in_rows && !source) throw Error{FRB_E_INVALID, "render_stream: inputs without a source"};
+    if (block == 0) throw Error{FRB_E_INVALID, "render_stream: block must be positive"};
+    if (idx + n_total < idx) throw Error{FRB_E_INVALID, "idx + n_total overflows"};
+    block = std::min(block, std::max<uint64_t>(n_total, 1));
+    if (!copy_stream_) CU(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+    const size_t out_n = (size_t)n_slots * block, in_n = (size_t)n_in_rows * block;
+    for (auto& st : sstage_) {
+        if (!st.rendered) { CU(cudaEventCreateWithFlags(&st.rendered, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&st.copied, cudaEventDisableTiming)); }
+        if (st.out_cap < out_n) {
+            CU(cudaStreamSynchronize(stream_)); CU(cudaStreamSynchronize(copy_stream_));
+            if (st.d_out) CU(cudaFree(st.d_out));
+            if (st.h_out) CU(cudaFreeHost(st.h_out));
+            st.d_out = st.h_out = nullptr; st.out_cap = 0;
+            CU(cudaMalloc(&st.d_out, std::max<size_t>(out_n, 1) * sizeof(float)));
+            CU(cudaMallocHost(&st.h_out, std::max<size_t>(out_n, 1) * sizeof(float)));
+            st.out_cap = out_n;
+        }
+        if (st.in_cap < in_n) {
+            CU(cudaStreamSynchronize(stream_));
+            if (st.h_in) CU(cudaFreeHost(st.h_in));
+            st.h_in = nullptr; st.in_cap = 0;
+            CU(cudaMallocHost(&st.h_in, in_n * sizeof(float)));
+            st.in_cap = in_n;
+        }
+    }
+    std::vector<uint64_t> offs(n_in_rows + 1);
+    struct Pending { bool live = false; uint64_t t = 0, n = 0; } pend[2];
+    auto deliver = [&](int b) {                               // wait for block b's copy, hand it to the sink
+        if (!pend[b].live) return;
+        pend[b].live = false;
+        CU(cudaEventSynchronize(sstage_[b].copied));
+        if (sink(user, sstage_[b].h_out, n_slots, pend[b].n, pend[b].t) != 0) throw Error{FRB_E_INVALID, "render_stream: sink failed"};
+    };
+    try {
+        // a zero-length render is one zero-length fill_buffer (bookkeeping only) and one empty buffer for the sink
+        const uint64_t n_blocks = n_total ? (n_total + block - 1) / block : 1;
+        uint64_t t = idx;
+        for (uint64_t k = 0; k < n_blocks; k++) {
+            const int b = (int)(k & 1);
+            StreamStage& st = sstage_[b];
+            const uint64_t n = std::min(block, idx + n_total - t);
+            if (n_in_rows) {
+                // st.h_in was last read by the host->device copy of block k-2, which finished before that block was delivered
+                if (source(user, st.h_in, n_in_rows, n, t) != 0) throw Error{FRB_E_INVALID, "render_stream: source failed"};
+                for (uint32_t r = 0; r <= n_in_rows; r++) offs[r] = (uint64_t)r * n;
+            }
+            // st.d_out was last read by the device->host copy of block k-2 (delivered already: the event has fired)
+            fill(st.d_out, true, n_slots, n, t, n_in_rows ? st.h_in : nullptr, false, offs.data(), n_in_rows);
+            CU(cudaEventRecord(st.rendered, stream_));
+            CU(cudaStreamWaitEvent(copy_stream_, st.rendered, 0));
+            if ((size_t)n_slots * n)
+                CU(cudaMemcpyAsync(st.h_out, st.d_out, (size_t)n_slots * n * sizeof(float), cudaMemcpyDeviceToHost, copy_stream_));
+            stats.d2h_bytes += (size_t)n_slots * n * sizeof(float);
+            CU(cudaEventRecord(st.copied, copy_stream_));
+            pend[b] = Pending{true, t, n};
+            deliver(b ^ 1);                                   // block k-1: the GPU is busy with block k meanwhile
+            t += n;
+        }
+        deliver((int)((n_blocks - 1) & 1));                   // only the last block is still pending
+    } catch (...) {
+        cudaStreamSynchronize(stream_);                       // nothing of an aborted render stays in flight
+        cudaStreamSynchronize(copy_stream_);
+        throw;
+    }
 }
 
 void Renderer::sync() {

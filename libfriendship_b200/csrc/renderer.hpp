@@ -47,6 +47,9 @@ public:
     // Renderer::fill_buffer
     void fill(float* out, bool out_on_device, uint32_t n_slots, uint64_t n_times, uint64_t idx,
               const float* in_data, bool in_on_device, const uint64_t* in_row_offsets, uint32_t n_in_rows);
+    // N4: pipelined block render with pinned double-buffered staging both ways (include/friendship_b200.h)
+    void render_stream(uint32_t n_slots, uint64_t idx, uint64_t n_total, uint64_t block, uint32_t n_in_rows,
+                       frb_source_fn source, frb_sink_fn sink, void* user);
     void sync();
     void sum_rows(float* d_out, const float* d_rows, uint32_t n_rows, uint64_t row_stride, uint64_t n);
 
@@ -119,6 +122,13 @@ private:
     // output staging
     float* d_out_ = nullptr;
     size_t d_out_cap_ = 0;
+    std::vector<InputDesc> h_indesc_;                              // what d_indesc_ currently holds
+
+    // streaming render (N4): two blocks in flight
+    struct StreamStage { float* d_out = nullptr; float* h_out = nullptr; float* h_in = nullptr;
+                         size_t out_cap = 0, in_cap = 0; cudaEvent_t rendered = nullptr, copied = nullptr; };
+    StreamStage sstage_[2];
+    cudaStream_t copy_stream_ = nullptr;
 
     // cached rings are valid for a fill that starts exactly at cache_head_
     bool cache_valid_ = false;

@@ -62,6 +62,13 @@ _lib.frd_del_edge.argtypes = [C.c_void_p, _cabi.frb_edge]
 _lib.frd_query_meta.argtypes = [C.c_void_p, C.c_uint32]
 _lib.frd_query_id.argtypes = [C.c_void_p, C.c_uint32]
 _lib.frd_render_range.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint64), C.c_uint32]
+_lib.frd_render_stream.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64]
+_lib.frd_wav_open.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32]
+_lib.frd_wav_open.restype = C.c_void_p
+_lib.frd_wav_write.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64]
+_lib.frd_wav_close.argtypes = [C.c_void_p]
+_lib.frd_wav_error.argtypes = [C.c_void_p]
+_lib.frd_wav_error.restype = C.c_char_p
 _lib.frd_add_dir.argtypes = [C.c_void_p, C.c_char_p]
 _lib.frd_sha256_file.argtypes = [C.c_char_p, C.c_char_p]
 _lib.frd_adjlist_json.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64]
@@ -86,6 +93,29 @@ class Client:
 
     def node_id(self, handle, id):
         pass
+
+
+class WavClient(Client):
+    """N4 output sink: a Client whose audio_rendered appends every buffer to a float32 WAV file (slot s = channel s;
+    the C writer of include/friendship_dispatch.h).  The reference leaves file output to the client (README.md:22-26)."""
+
+    def __init__(self, path, n_channels, sample_rate):
+        self._w = _lib.frd_wav_open(str(path).encode(), n_channels, int(sample_rate))
+        if not self._w:
+            raise OSError(f"cannot create {path}")
+        self.frames = 0
+
+    def audio_rendered(self, buffer, idx):
+        buffer = np.ascontiguousarray(buffer, dtype=np.float32)
+        if _lib.frd_wav_write(self._w, buffer.ctypes.data, buffer.shape[0], buffer.shape[1]) != 0:
+            raise OSError(_lib.frd_wav_error(self._w).decode())
+        self.frames += buffer.shape[1]
+
+    def close(self):
+        if self._w:
+            w, self._w = self._w, None
+            if _lib.frd_wav_close(w) != 0:
+                raise OSError("wav: close failed")
 
 
 class Dispatch:
@@ -146,6 +176,11 @@ class Dispatch:
         data, offs, n_rows = _cabi.CRendererBase._jagged(inputs)
         self._check(_lib.frd_render_range(self._h, start, end, n_slots, data.ctypes.data,
                                           offs.ctypes.data_as(C.POINTER(C.c_uint64)), n_rows))
+
+    def render_stream(self, start, end, n_slots, block):
+        """N4: [start, end) as consecutive audio_rendered callbacks of `block` samples, render / copy / client
+        overlapped (include/friendship_dispatch.h)."""
+        self._check(_lib.frd_render_stream(self._h, start, end, n_slots, block))
 
     # ---- OscResMan ----
     def add_dir(self, path):

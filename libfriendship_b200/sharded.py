@@ -117,3 +117,53 @@ class ShardedRenderer:
         self._host.copy_(out, non_blocking=True)
         torch.cuda.synchronize(self.device)
         return self._host.numpy()
+
+    def render_stream(self, n_slots, idx, n_total, block, sink):
+        """N4 at N GPUs: [idx, idx + n_total) in blocks of `block` samples; every block is rendered by all ranks, reduced
+        onto rank 0 and handed to `sink(block_array, idx)` there (a view of pinned staging memory, valid during the
+        call).  Two blocks in flight: while block k renders and reduces, block k-1 travels device->host on a copy
+        stream and runs through the sink.  Same bits as the fill_buffer calls it stands for."""
+        assert block > 0
+        n_blocks = max(1, -(-n_total // block))
+        if not self.on_gpu:
+            t = idx
+            for _ in range(n_blocks):
+                n = min(block, idx + n_total - t)
+                out = self.fill_buffer(n_slots, n, t)
+                if self.rank == 0:
+                    sink(out, t)
+                t += n
+            return
+        dev = f"cuda:{self.device}"
+        cap = n_slots * min(block, max(n_total, 1))
+        copy_stream = torch.cuda.Stream(device=dev)
+        dflat = [torch.empty(cap, dtype=torch.float32, device=dev) for _ in range(2)]
+        hflat = [torch.empty(cap, dtype=torch.float32, pin_memory=True) for _ in range(2)] if self.rank == 0 else None
+        copied = [torch.cuda.Event(), torch.cuda.Event()]
+        pending = [None, None]
+
+        def deliver(b):                                  # wait for block b's copy, hand it to the sink
+            if pending[b] is None:
+                return
+            t, n = pending[b]
+            pending[b] = None
+            copied[b].synchronize()
+            if self.rank == 0:
+                sink(hflat[b][:n_slots * n].view(n_slots, n).numpy(), t)
+
+        t = idx
+        for k in range(n_blocks):
+            b = k & 1
+            n = min(block, idx + n_total - t)
+            # dflat[b] was last read by the copy of block k-2, delivered (hence complete) during iteration k-1
+            self._out = dflat[b][:n_slots * n].view(n_slots, n)
+            out = self.fill_buffer_device(n_slots, n, t)        # render + exchange; complete on return
+            if self.rank == 0:
+                with torch.cuda.stream(copy_stream):
+                    hflat[b][:n_slots * n].view(n_slots, n).copy_(out, non_blocking=True)
+            copied[b].record(copy_stream)
+            pending[b] = (t, n)
+            deliver(b ^ 1)                                       # block k-1 runs through the sink while k+1 renders
+            t += n
+        deliver((n_blocks - 1) & 1)
+        self._out = None

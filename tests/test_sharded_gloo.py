@@ -30,10 +30,14 @@ def _worker(rank, world, port, q):
     build_voice_mix_graph(sr.r, bank, ids, delay0=100.0)
     out = sr.fill_buffer(1, N, 0)
     out2 = sr.fill_buffer(1, 300, N)            # a second, contiguous block
+    blocks = []
+    sr.render_stream(1, 0, N, 256, lambda blk, t: blocks.append((t, blk.copy())))   # N4: streamed in ragged blocks
     if rank == 0:
+        assert [t for t, _ in blocks] == [0, 256, 512]
+        assert np.array_equal(np.concatenate([b for _, b in blocks], axis=1), out)
         q.put((out, out2))
     else:
-        assert out is None
+        assert out is None and not blocks
     dist.barrier()
     dist.destroy_process_group()
 

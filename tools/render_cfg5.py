@@ -1,6 +1,9 @@
 """BASELINE.json configs[4] — offline large render: 1M partials x 256 voices, 192 kHz x 60 s, 8 x B200, output reduced
 to rank 0.  Launch:  python -m torch.distributed.run --nproc-per-node 8 tools/render_cfg5.py
-One render (no warm-up: an offline job runs once); prints one JSON line on rank 0."""
+One render (no warm-up: an offline job runs once); prints one JSON line on rank 0.
+The output leaves the device through the N4 streaming path (ShardedRenderer.render_stream): blocks of CFG5_BLOCK samples
+(default 2^20) are reduced onto rank 0, copied to pinned host memory and appended to a float32 WAV file (CFG5_WAV, default
+gpurun_out/cfg5.wav; empty = keep the blocks in memory only) while the next block renders."""
 import json
 import os
 import sys
@@ -39,8 +42,24 @@ def main():
     if world > 1:
         dist.barrier()
     t_setup = time.perf_counter() - t_setup
+    block = int(os.environ.get("CFG5_BLOCK", 1 << 20))
+    wav_path = os.environ.get("CFG5_WAV", os.path.join(ROOT, "gpurun_out", "cfg5.wav"))
+    wav = None
+    if rank == 0 and wav_path:
+        from libfriendship_b200.dispatch import WavClient
+        os.makedirs(os.path.dirname(wav_path), exist_ok=True)
+        wav = WavClient(wav_path, 1, int(SR))
+    out = np.zeros((1, n_samples), dtype=np.float32) if rank == 0 else None
+
+    def sink(blk, t):                              # rank 0, while the next block renders
+        out[:, t:t + blk.shape[1]] = blk
+        if wav:
+            wav.audio_rendered(blk, t)
+
     t0 = time.perf_counter()
-    out = sr.fill_buffer(1, n_samples, 0)          # device render + reduce to rank 0 + D2H of the 46 MB mix
+    sr.render_stream(1, 0, n_samples, block, sink)   # render + reduce to rank 0 + pipelined D2H + file
+    if wav:
+        wav.close()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -50,7 +69,8 @@ def main():
         print(json.dumps({
             "workload": "cfg5: 2^20 partials x %d voices, 192 kHz x %.1f s (BASELINE.json configs[4])" % (n_voices, n_samples / SR),
             "n_gpus": world, "render_s": dt, "setup_s": t_setup, "partial_samples": ps, "partial_samples_per_s": ps / dt,
-            "realtime_factor": (n_samples / SR) / dt, "out_bytes": int(out.nbytes), "finite": bool(np.isfinite(out).all()),
+            "realtime_factor": (n_samples / SR) / dt, "out_bytes": int(out.nbytes), "block": block,
+            "wav": (os.path.relpath(wav_path, ROOT) if wav_path else None), "finite": bool(np.isfinite(out).all()),
             "peak_abs": float(np.abs(out).max()), "rms_last_second": float(np.sqrt(np.mean(out[0, -192000:] ** 2)))}))
     if world > 1:
         dist.barrier()
