@@ -3,7 +3,7 @@ to rank 0.  Launch:  python -m torch.distributed.run --nproc-per-node 8 tools/re
 One render (no warm-up: an offline job runs once); prints one JSON line on rank 0.
 The output leaves the device through the N4 streaming path (ShardedRenderer.render_stream): blocks of CFG5_BLOCK samples
 (default 2^20) are reduced onto rank 0, copied to pinned host memory and appended to a float32 WAV file (CFG5_WAV, default
-gpurun_out/cfg5.wav; empty = keep the blocks in memory only) while the next block renders."""
+/tmp/cfg5.wav; empty = keep the blocks in memory only) while the next block renders."""
 import json
 import os
 import sys
@@ -43,7 +43,7 @@ def main():
         dist.barrier()
     t_setup = time.perf_counter() - t_setup
     block = int(os.environ.get("CFG5_BLOCK", 1 << 20))
-    wav_path = os.environ.get("CFG5_WAV", os.path.join(ROOT, "gpurun_out", "cfg5.wav"))
+    wav_path = os.environ.get("CFG5_WAV", "/tmp/cfg5.wav")
     wav = None
     if rank == 0 and wav_path:
         from libfriendship_b200.dispatch import WavClient
