@@ -75,6 +75,8 @@ typedef struct frb_config {
                                       instead of clamping to delay 0 (reference.rs:205-210, the default) */
 #define FRB_FLAG_NO_JIT        2u  /* always interpret stage programs; never compile them (see frb_jit_cubin_size) */
 #define FRB_FLAG_JIT_EAGER     4u  /* compile a stage program the first time it runs (default: once it is hot) */
+#define FRB_FLAG_NO_CHAIN_FUSION 8u /* run DirectForm -> FbDelay chains as two kernels (16 B per lane-sample) even where the
+                                      fused kernel (8 B) applies; same bits either way (tests compare the two) */
 
 /* Oscillator bank definition (extension).  Voice v owns partials [voice_offsets[v], voice_offsets[v+1]).
  *   out_v(t) = sum_p amp_p * min(t/attack_p, 1) * exp(-t/tau_p) * sin(2*pi*freq_p*t/sample_rate + phase_p)
@@ -202,6 +204,7 @@ typedef struct frb_stats {
     uint64_t interp_launches;
     uint64_t scan_launches;
     uint64_t jit_launches;      /* stage launches that ran a JIT-compiled kernel instead of the interpreter */
+    uint64_t chain_launches;    /* fused DirectForm -> FbDelay launches (counted in scan_launches too) */
 } frb_stats;
 int frb_get_stats(const frb_renderer* r, frb_stats* out);
 

@@ -35,6 +35,7 @@ KIND_FBDELAY = 34
 FLAG_SPARKLE_DELAY = 1
 FLAG_NO_JIT = 2
 FLAG_JIT_EAGER = 4
+FLAG_NO_CHAIN_FUSION = 8
 
 
 class frb_edge(C.Structure):
@@ -70,7 +71,8 @@ class frb_fbdelay_desc(C.Structure):
 
 class frb_stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("kernel_launches", "h2d_bytes", "d2h_bytes", "schedule_builds",
-                                           "osc_launches", "interp_launches", "scan_launches", "jit_launches")]
+                                           "osc_launches", "interp_launches", "scan_launches", "jit_launches",
+                                           "chain_launches")]
 
 
 class frb_timing(C.Structure):

@@ -168,6 +168,7 @@ void Renderer::define_directform(uint64_t key, const frb_directform_desc* d) {
     std::string err;
     auto b = directform_create(d, stream_, &err);
     if (!b) throw Error{FRB_E_INVALID, err};
+    if (df_defs_.count(key)) { CU(cudaStreamSynchronize(stream_)); dirty_ = true; }   // lane count / fusability may change
     df_defs_[key] = b;
 }
 void Renderer::define_fbdelay(uint64_t key, const frb_fbdelay_desc* d) {
@@ -185,6 +186,7 @@ void Renderer::define_fbdelay(uint64_t key, const frb_fbdelay_desc* d) {
     std::string err;
     auto b = fbdelay_create(d, stream_, &err);
     if (!b) throw Error{FRB_E_INVALID, err};
+    if (fb_defs_.count(key)) { CU(cudaStreamSynchronize(stream_)); dirty_ = true; }   // lookbacks / fusability may change
     fb_defs_[key] = b;
 }
 
@@ -297,6 +299,42 @@ void Renderer::upload_schedule() {
         CU(cudaMemcpyAsync(d_ext_in_bufs_[i], x.in_bufs.data(), x.in_bufs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream_));
     }
     CU(cudaStreamSynchronize(stream_));   // host vectors above may go away
+
+    // Chain fusion: a FbDelay instance whose lane l reads lane l of a DirectForm instance of the same stage, when nothing
+    // else reads that biquad (no other node, no output slot, no other lane), runs with it in one kernel and the
+    // biquad's output rings are never allocated.
+    chain_of_.assign(sched_.ext.size(), -1);
+    chained_.assign(sched_.ext.size(), 0);
+    chain_state_.assign(sched_.ext.size(), nullptr);
+    if (!(cfg_.flags & FRB_FLAG_NO_CHAIN_FUSION)) {
+        const auto& V = sched_.values;
+        std::vector<uint32_t> uses(V.size(), 0);
+        for (const Value& x : V) {
+            if (x.op == V_DELAY || (x.op >= V_SUM2 && x.op <= V_MIN)) { uses[x.a]++; uses[x.b]++; }
+            if (x.op == V_TAP || x.op == V_GATE) uses[x.a]++;
+        }
+        for (uint32_t o : sched_.outputs) uses[o]++;
+        for (const auto& inst : sched_.ext) for (uint32_t in : inst.inputs) uses[in]++;
+        for (size_t j = 0; j < sched_.ext.size(); j++) {
+            const ExtInstance& fb = sched_.ext[j];
+            if (fb.kind != EXT_FBDELAY || fb.n_lanes == 0) continue;
+            const Value& v0 = V[fb.inputs[0]];
+            if (v0.op != V_EXT) continue;
+            const uint32_t i = v0.a;
+            const ExtInstance& df = sched_.ext[i];
+            if (df.kind != EXT_DIRECTFORM || df.n_lanes != fb.n_lanes || df.stage != fb.stage || chained_[i]) continue;
+            bool ok = true;
+            for (uint32_t l = 0; l < fb.n_lanes && ok; l++) {
+                const Value& v = V[fb.inputs[l]];
+                ok = v.op == V_EXT && v.a == i && v.imm == l && uses[fb.inputs[l]] == 1;
+            }
+            if (!ok || !chain_fusable(*df_defs_.at(df.key), *fb_defs_.at(fb.key))) continue;
+            chain_state_[j] = chain_state_create(fb.n_lanes);
+            if (!chain_state_[j]) throw Error{FRB_E_CUDA, "out of device memory (chain state)"};
+            chain_of_[j] = (int32_t)i;
+            chained_[i] = 1;
+        }
+    }
 }
 
 // Ring buffers: capacity = pow2 >= lookback + block (+ slack); LOOKBACK_FULL rings hold [0, t_end).
@@ -314,6 +352,7 @@ void Renderer::ensure_rings(uint64_t t_end) {
     }
     for (auto& g : ring_groups_) {
         const BufferInfo& b = sched_.buffers[g.first];
+        if (b.ext != ~0u && chained_[b.ext]) continue;   // the biquad of a fused chain: its output stays in registers
         const bool full = b.lookback == LOOKBACK_FULL;
         uint64_t need = full ? pow2_ceil(t_end + 8) : pow2_ceil(b.lookback + chunk_ + 8);
         if (need <= g.cap) continue;
@@ -515,6 +554,14 @@ void Renderer::run_range(uint64_t lo, uint64_t hi, float* d_out, uint64_t t0, ui
                 if (x.kind == EXT_OSCBANK) {
                     timed(&frb_timing::osc_ms, [&] { CU(launch_osc(*osc_defs_.at(x.key), d_bufdesc_, x.first_out_buf, c0, c1, cfg_.osc_anchor, sm_count_, stream_, &nl)); });
                     stats.osc_launches += nl;
+                } else if (x.kind == EXT_DIRECTFORM && chained_[xi]) {
+                    continue;                                   // runs inside its comb's launch
+                } else if (x.kind == EXT_FBDELAY && chain_of_[xi] >= 0) {
+                    const uint32_t di = (uint32_t)chain_of_[xi];
+                    const ExtInstance& df = sched_.ext[di];
+                    timed(&frb_timing::scan_ms, [&] { CU(launch_dfcomb(*df_defs_.at(df.key), *fb_defs_.at(x.key), *chain_state_[xi], d_bufdesc_, d_ext_in_bufs_[di], x.first_out_buf, c0, c1, stream_, &nl)); });
+                    stats.scan_launches += nl;
+                    stats.chain_launches += nl;
                 } else if (x.kind == EXT_DIRECTFORM) {
                     timed(&frb_timing::scan_ms, [&] { CU(launch_directform(*df_defs_.at(x.key), d_bufdesc_, d_ext_in_bufs_[xi], x.first_out_buf, c0, c1, sm_count_, stream_, &nl)); });
                     stats.scan_launches += nl;

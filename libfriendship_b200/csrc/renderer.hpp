@@ -101,6 +101,11 @@ private:
     struct StageJit { JitKernel* k = nullptr; int state = 0; uint64_t uses = 0; std::future<std::string> cubin; };
     std::vector<StageJit> stage_jit_;
     std::vector<uint32_t*> d_ext_in_bufs_;      // per extension instance: input ring ids per lane
+    // Fused DirectForm -> FbDelay chains (scan.cu dfcomb_kernel): chain_of_[fb instance] = df instance whose lanes feed it
+    // one to one and nothing else; chained_[df instance] = 1 (not launched, its output rings are not allocated)
+    std::vector<int32_t> chain_of_;
+    std::vector<uint8_t> chained_;
+    std::vector<std::shared_ptr<ChainStateDev>> chain_state_;   // per fb instance
     std::vector<BufferDesc> h_bufdesc_;
     struct RingGroup { uint32_t first, count; float* data; uint64_t cap; };   // consecutive buffers in one allocation
     std::vector<RingGroup> ring_groups_;

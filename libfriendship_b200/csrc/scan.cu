@@ -20,6 +20,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <type_traits>
 #include <vector>
 
 namespace frb {
@@ -38,14 +39,23 @@ struct DirectFormDev {
 struct FbDelayDev {
     uint32_t n_lanes = 0;
     uint64_t max_delay = 0;
+    uint64_t min_delay = ~0ull;
     uint32_t* d_delay = nullptr;
     float* d_gain = nullptr;
     ~FbDelayDev() { cudaFree(d_delay); cudaFree(d_gain); }
 };
 
+struct ChainStateDev {            // biquad carry of a fused DirectForm -> FbDelay chain: {x[n-1], x[n-2], y[n-1], y[n-2]} at `time`
+    float4* d_state = nullptr;
+    uint32_t n_lanes = 0;
+    uint64_t time = 0;
+    ~ChainStateDev() { cudaFree(d_state); }
+};
+
 uint32_t directform_lanes(const DirectFormDev& f) { return f.n_lanes; }
 uint32_t fbdelay_lanes(const FbDelayDev& f) { return f.n_lanes; }
 uint64_t fbdelay_max_delay(const FbDelayDev& f) { return f.max_delay; }
+uint64_t fbdelay_min_delay(const FbDelayDev& f) { return f.min_delay; }
 
 std::shared_ptr<DirectFormDev> directform_create(const frb_directform_desc* d, cudaStream_t stream, std::string* err) {
     auto fail = [&](const std::string& m) { if (err) *err = m; return std::shared_ptr<DirectFormDev>(); };
@@ -86,6 +96,7 @@ std::shared_ptr<FbDelayDev> fbdelay_create(const frb_fbdelay_desc* d, cudaStream
     for (uint32_t i = 0; i < d->n_lanes; i++) {
         if (d->delay[i] < 1) return fail("fbdelay: delay must be >= 1");
         f->max_delay = std::max<uint64_t>(f->max_delay, d->delay[i]);
+        f->min_delay = std::min<uint64_t>(f->min_delay, d->delay[i]);
     }
     const size_t n = std::max<uint32_t>(d->n_lanes, 1);
     if (cudaMalloc(&f->d_delay, n * sizeof(uint32_t)) != cudaSuccess || cudaMalloc(&f->d_gain, n * sizeof(float)) != cudaSuccess)
@@ -103,6 +114,46 @@ __device__ __forceinline__ float ring_at(const BufferDesc& b, long long t) {
     return t >= 0 ? b.data[(unsigned long long)t & b.mask] : 0.0f;    // every signal is 0 before t = 0
 }
 
+// The biquad over one tile of 32 threads x 8 samples, shared by directform_kernel and dfcomb_kernel (same bits).
+//   x[0..9]: this thread's samples x[2..9] preceded by the two before them (x[0] = x[t0-2], x[1] = x[t0-1]);
+//   (cy1, cy2) = (y[tb-1], y[tb-2]), the carry into the tile (read by lane 0 only);  P(k) = A^(8*2^k), row-major 2x2.
+// Every thread runs its 8 samples from a zero state — lane 0 from the carry — the end states are combined by a
+// Kogge-Stone scan with the operator "v_i <- v_i + A^(8*2^k) v_(i-2^k)", which leaves in lane i the true state at the end
+// of its run; its left neighbour's is the state it re-runs from.  Out: yv[0..7], (y1, y2) = (y[t0+7], y[t0+6]).
+template <class PF>
+__device__ __forceinline__ void biquad_tile(const float (&x)[DF_PER_THREAD + 2], float cy1, float cy2, PF P, float b0, float b1,
+                                            float b2, float a1, float a2, unsigned wl, float (&yv)[DF_PER_THREAD],
+                                            float& y1, float& y2) {
+    float u[DF_PER_THREAD];
+#pragma unroll
+    for (int j = 0; j < DF_PER_THREAD; j++) u[j] = fmaf(b2, x[j], fmaf(b1, x[j + 1], b0 * x[j + 2]));
+    const float s1 = wl ? 0.f : cy1, s2 = wl ? 0.f : cy2;
+    float e1 = s1, e2 = s2;
+#pragma unroll
+    for (int j = 0; j < DF_PER_THREAD; j++) {
+        const float y = fmaf(-a2, e2, fmaf(-a1, e1, u[j]));
+        e2 = e1; e1 = y;
+    }
+    float v1 = e1, v2 = e2;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        const float4 Pk = P(k);
+        const float o1 = __shfl_up_sync(0xffffffffu, v1, 1u << k), o2 = __shfl_up_sync(0xffffffffu, v2, 1u << k);
+        if (wl >= (1u << k)) {
+            v1 += Pk.x * o1 + Pk.y * o2;
+            v2 += Pk.z * o1 + Pk.w * o2;
+        }
+    }
+    const float p1 = __shfl_up_sync(0xffffffffu, v1, 1), p2 = __shfl_up_sync(0xffffffffu, v2, 1);
+    y1 = wl ? p1 : s1;                                              // (y[t0-1], y[t0-2])
+    y2 = wl ? p2 : s2;
+#pragma unroll
+    for (int j = 0; j < DF_PER_THREAD; j++) {
+        const float y = fmaf(-a2, y2, fmaf(-a1, y1, u[j]));
+        yv[j] = y; y2 = y1; y1 = y;
+    }
+}
+
 // One WARP per lane (4 lanes per CTA): tiles of 32 threads x 8 samples, warp-level scan only, no block barriers.
 __global__ void __launch_bounds__(DF_CTA_THREADS)
 directform_kernel(const float* __restrict__ coef, const float* __restrict__ pw, const BufferDesc* __restrict__ bufdesc,
@@ -115,10 +166,10 @@ directform_kernel(const float* __restrict__ coef, const float* __restrict__ pw, 
     const BufferDesc yout = bufdesc[first_out_buf + lane];
     const float b0 = coef[lane * 5 + 0], b1 = coef[lane * 5 + 1], b2 = coef[lane * 5 + 2];
     const float a1 = coef[lane * 5 + 3], a2 = coef[lane * 5 + 4];
-    // A^(8*2^k), k = 0..5, in registers (warp-uniform)
-    float P[6][4];
+    // A^(8*2^k), k < 5, in registers (warp-uniform)
+    float P[5][4];
 #pragma unroll
-    for (int k = 0; k < 6; k++)
+    for (int k = 0; k < 5; k++)
 #pragma unroll
         for (int j = 0; j < 4; j++) P[k][j] = pw[((size_t)lane * DF_LEVELS + k) * 4 + j];
 
@@ -142,45 +193,8 @@ directform_kernel(const float* __restrict__ coef, const float* __restrict__ pw, 
         const float px1 = __shfl_up_sync(0xffffffffu, x[9], 1), px2 = __shfl_up_sync(0xffffffffu, x[8], 1);
         x[1] = wl ? px1 : x1c;
         x[0] = wl ? px2 : x2c;
-        float u[DF_PER_THREAD];
-#pragma unroll
-        for (int j = 0; j < DF_PER_THREAD; j++) u[j] = fmaf(b2, x[j], fmaf(b1, x[j + 1], b0 * x[j + 2]));
-        // zero-state run: end state e = (y[7], y[6])
-        float e1 = 0.f, e2 = 0.f;
-#pragma unroll
-        for (int j = 0; j < DF_PER_THREAD; j++) {
-            const float y = fmaf(-a2, e2, fmaf(-a1, e1, u[j]));
-            e2 = e1; e1 = y;
-        }
-        // inclusive scan over the warp: v_i <- v_i + A^(8*2^k) v_(i-2^k)
-        float v1 = e1, v2 = e2;
-#pragma unroll
-        for (int k = 0; k < 5; k++) {
-            const float o1 = __shfl_up_sync(0xffffffffu, v1, 1u << k), o2 = __shfl_up_sync(0xffffffffu, v2, 1u << k);
-            if (wl >= (1u << k)) {
-                v1 += P[k][0] * o1 + P[k][1] * o2;
-                v2 += P[k][2] * o1 + P[k][3] * o2;
-            }
-        }
-        // state entering this thread = A^(8*wl) carry + exclusive prefix
-        float p1 = __shfl_up_sync(0xffffffffu, v1, 1), p2 = __shfl_up_sync(0xffffffffu, v2, 1);
-        if (wl == 0) { p1 = 0.f; p2 = 0.f; }
-        float h1 = y1c, h2 = y2c;
-#pragma unroll
-        for (int k = 0; k < 5; k++) {
-            if (wl & (1u << k)) {
-                const float n1 = P[k][0] * h1 + P[k][1] * h2;
-                const float n2 = P[k][2] * h1 + P[k][3] * h2;
-                h1 = n1; h2 = n2;
-            }
-        }
-        float y1 = h1 + p1, y2 = h2 + p2;                           // (y[t0-1], y[t0-2])
-        float yv[DF_PER_THREAD];
-#pragma unroll
-        for (int j = 0; j < DF_PER_THREAD; j++) {
-            const float y = fmaf(-a2, y2, fmaf(-a1, y1, u[j]));
-            yv[j] = y; y2 = y1; y1 = y;
-        }
+        float yv[DF_PER_THREAD], y1, y2;
+        biquad_tile(x, y1c, y2c, [&](int k) { return make_float4(P[k][0], P[k][1], P[k][2], P[k][3]); }, b0, b1, b2, a1, a2, wl, yv, y1, y2);
         if (vec && t0 + DF_PER_THREAD <= hi) {
             *reinterpret_cast<float4*>(yout.data + (t0 & yout.mask)) = make_float4(yv[0], yv[1], yv[2], yv[3]);
             *reinterpret_cast<float4*>(yout.data + ((t0 + 4) & yout.mask)) = make_float4(yv[4], yv[5], yv[6], yv[7]);
@@ -228,6 +242,244 @@ fbdelay_kernel(const uint32_t* __restrict__ delay, const float* __restrict__ gai
             yout.data[t & yout.mask] = yp;
         }
     }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// Fused chain: DirectForm lane l -> FbDelay lane l, when nothing else reads the biquad's output.  8 B per lane-sample of
+// HBM traffic (read x once, write z once) instead of 16 B for the two separate kernels: the biquad's y never leaves the
+// registers.  One warp per lane, tiles of 32 threads x 8 samples:
+//   * the x tile of the NEXT iteration is loaded before this one is computed (the per-tile dependency chain — FIR,
+//     zero-state run, warp scan, re-run, comb — is ~400 cycles and there are only ~28 lanes per SM to hide DRAM behind);
+//   * the biquad is biquad_tile, shared with directform_kernel (same bits);
+//   * the comb z[n] = y[n] + g z[n - D] takes z[n - D] from the output ring for every sample whose tap lies before the
+//     tile (all of them when D >= 256: three aligned 128-bit loads per thread, L2 hits, issued before the biquad), and
+//     for D < 256 resolves the taps inside the tile in ceil(256 / D) phases through a padded per-warp shared-memory
+//     tile.  Same two roundings per sample as fbdelay_kernel: given the same y the bits are identical.
+//   * the biquad carry {x[n-1], x[n-2], y[n-1], y[n-2]} at the end of the block is kept in a per-lane state array (the
+//     y ring that directform_kernel re-reads it from does not exist here).
+constexpr int CH_TILE = 32 * DF_PER_THREAD;
+constexpr int CH_ZPAD = CH_TILE + CH_TILE / 8;     // index n -> n + (n >> 3): 8 consecutive samples per lane, no bank conflicts
+constexpr int CH_QUADS = 64 + 8;                   // 64 quads per tile, skewed: position q + (q >> 3)
+constexpr int CH_MIN_DELAY = 32;                   // at most 8 phases per tile; shorter combs use the separate kernels
+
+__device__ __forceinline__ int ch_pad(int n) { return n + (n >> 3); }
+__device__ __forceinline__ unsigned ch_qpos(unsigned q) { return q + (q >> 3); }
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {   // L2 only (.cg): coherent with this
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n"                         // warp's earlier global stores
+                 :: "r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(DF_CTA_THREADS, 7)
+dfcomb_kernel(const float* __restrict__ coef, const float* __restrict__ pw, const uint32_t* __restrict__ delay,
+              const float* __restrict__ gain, const BufferDesc* __restrict__ bufdesc, const uint32_t* __restrict__ in_bufs,
+              uint32_t first_out_buf, float4* __restrict__ state, unsigned n_lanes, unsigned long long lo, unsigned long long hi) {
+    constexpr int NW = DF_CTA_THREADS / 32;
+    __shared__ float s_z[NW][CH_ZPAD];                 // z of the current tile (combs shorter than a tile)
+    __shared__ float4 s_pw[NW][5];                     // A^(8*2^k), k < 5
+    __shared__ float4 s_c[NW];                         // carry between fast tiles
+    // Tiles staged in shared memory as quads (4 samples), quad q at position q + (q >> 3): the copies to and from global
+    // memory are coalesced (lane i moves quads i and 32 + i: 512 contiguous bytes per instruction), a thread's own 8
+    // samples are quads 2 wl, 2 wl + 1, and both patterns are free of bank conflicts with this skew.
+    __shared__ float4 s_x[NW][2][CH_QUADS];            // x tiles in flight (double buffered)
+    __shared__ float4 s_q[NW][CH_QUADS + 4];           // taps of the current tile: 67 quads from (tb - D - sh)
+    __shared__ float4 s_o[NW][CH_QUADS];               // z of the current tile on its way out
+    const unsigned wl = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    const unsigned lane = blockIdx.x * NW + wi;
+    if (lane >= n_lanes) return;                                   // whole warp exits together
+    const BufferDesc xin = bufdesc[in_bufs[lane]];
+    const BufferDesc zout = bufdesc[first_out_buf + lane];
+    const float b0 = coef[lane * 5 + 0], b1 = coef[lane * 5 + 1], b2 = coef[lane * 5 + 2];
+    const float a1 = coef[lane * 5 + 3], a2 = coef[lane * 5 + 4];
+    const unsigned Du = delay[lane];
+    const float g = gain[lane];
+    if (wl < 5) s_pw[wi][wl] = reinterpret_cast<const float4*>(pw + (size_t)lane * DF_LEVELS * 4)[wl];
+    __syncwarp();
+    const float4* P = s_pw[wi];                                     // warp-uniform: read by broadcast
+    float* zt = s_z[wi];
+
+    float x1c = 0.f, x2c = 0.f, y1c = 0.f, y2c = 0.f;               // every signal is 0 before t = 0
+    if (lo > 0) { const float4 st = state[lane]; x1c = st.x; x2c = st.y; y1c = st.z; y2c = st.w; }
+
+    auto Pk = [&](int k) { return P[k]; };
+    // comb: z[n] = y[n] + g z[n - D], two roundings like fbdelay_kernel.  zq[sh + j] = z[t0 + j - D] for the taps that lie
+    // before the tile; the taps inside the tile (D < 256) are resolved in ceil(256 / D) phases through shared memory.
+    auto comb = [&](const float (&yv)[DF_PER_THREAD], const float (&zq)[12], int sh, float (&z)[DF_PER_THREAD]) {
+        switch (sh) {   // warp-uniform
+            case 0:
+#pragma unroll
+                for (int j = 0; j < DF_PER_THREAD; j++) z[j] = __fadd_rn(yv[j], __fmul_rn(g, zq[j]));
+                break;
+            case 1:
+#pragma unroll
+                for (int j = 0; j < DF_PER_THREAD; j++) z[j] = __fadd_rn(yv[j], __fmul_rn(g, zq[j + 1]));
+                break;
+            case 2:
+#pragma unroll
+                for (int j = 0; j < DF_PER_THREAD; j++) z[j] = __fadd_rn(yv[j], __fmul_rn(g, zq[j + 2]));
+                break;
+            default:
+#pragma unroll
+                for (int j = 0; j < DF_PER_THREAD; j++) z[j] = __fadd_rn(yv[j], __fmul_rn(g, zq[j + 3]));
+                break;
+        }
+        if (Du < (unsigned)CH_TILE) {                               // z above is final only for samples n < D of the tile
+            const int Di = (int)Du, nb = (int)wl * DF_PER_THREAD;
+#pragma unroll
+            for (int j = 0; j < DF_PER_THREAD; j++) zt[ch_pad(nb + j)] = z[j];
+            __syncwarp();
+            for (int ph = Di; ph < CH_TILE; ph += Di) {             // samples [ph, ph + D) read z of [ph - D, ph)
+                if (nb + DF_PER_THREAD > ph && nb < ph + Di) {
+#pragma unroll
+                    for (int j = 0; j < DF_PER_THREAD; j++) {
+                        const int n = nb + j;
+                        if (n >= ph && n < ph + Di) {
+                            z[j] = __fadd_rn(yv[j], __fmul_rn(g, zt[ch_pad(n - Di)]));
+                            zt[ch_pad(n)] = z[j];
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    };
+    float4* carry = &s_c[wi];                                       // {x[tb-1], x[tb-2], y[tb-1], y[tb-2]} for the fast tiles
+    const int sh = (int)(((long long)lo - (long long)Du) & 3);     // (t0 - D) & 3 of every thread of every tile: tb = lo (mod 4)
+    // Any tile: ragged ends, an unaligned block start, the first D + 4 samples after t = 0, rings beyond 2^32 floats.
+    auto slow_tile = [&](unsigned long long tb) {
+        const unsigned long long t0 = tb + (unsigned long long)wl * DF_PER_THREAD;
+        float x[DF_PER_THREAD + 2], yv[DF_PER_THREAD], zq[12], z[DF_PER_THREAD], y1, y2;
+        const long long Bq = (long long)t0 - (long long)Du - sh;
+#pragma unroll
+        for (int k = 0; k < 12; k++) {
+            const long long q = Bq + k;
+            zq[k] = (q >= 0 && q < (long long)tb) ? __ldcg(zout.data + ((unsigned long long)q & zout.mask)) : 0.0f;
+        }
+#pragma unroll
+        for (int j = 0; j < DF_PER_THREAD; j++) x[2 + j] = (t0 + j < hi) ? xin.data[(t0 + j) & xin.mask] : 0.0f;
+        const float px1 = __shfl_up_sync(0xffffffffu, x[9], 1), px2 = __shfl_up_sync(0xffffffffu, x[8], 1);
+        x[1] = wl ? px1 : x1c;
+        x[0] = wl ? px2 : x2c;
+        biquad_tile(x, y1c, y2c, Pk, b0, b1, b2, a1, a2, wl, yv, y1, y2);
+        if (tb + CH_TILE >= hi) {                                   // the block's last two samples: carry of the next launch
+#pragma unroll
+            for (int j = 0; j < DF_PER_THREAD; j++) {
+                if (t0 + j + 1 == hi) { state[lane].x = x[2 + j]; state[lane].z = yv[j]; }
+                if (t0 + j + 2 == hi) { state[lane].y = x[2 + j]; state[lane].w = yv[j]; }
+            }
+            if (wl == 0 && tb + 1 == hi) { state[lane].y = x1c; state[lane].w = y1c; }   // hi - 2 lies before the tile
+        }
+        comb(yv, zq, sh, z);
+#pragma unroll
+        for (int j = 0; j < DF_PER_THREAD; j++)
+            if (t0 + j < hi) zout.data[(t0 + j) & zout.mask] = z[j];
+        __syncwarp();                                               // the next tile's taps read this tile's stores
+        y1c = __shfl_sync(0xffffffffu, y1, 31); y2c = __shfl_sync(0xffffffffu, y2, 31);
+        x1c = __shfl_sync(0xffffffffu, x[9], 31); x2c = __shfl_sync(0xffffffffu, x[8], 31);
+    };
+
+    const bool can_fast = (((xin.mask | zout.mask) >> 32) == 0) && (lo % 4 == 0);
+    unsigned long long tb = lo;
+    while (tb < hi && !(can_fast && tb >= (unsigned long long)Du + 4 && tb + CH_TILE <= hi)) { slow_tile(tb); tb += CH_TILE; }
+    if (tb < hi) {
+        // Fast tiles: full, 16-byte aligned, every tap at a time >= 0, 32-bit ring indices.  Global -> shared copies
+        // (cp.async, no registers held): the x tile of the NEXT iteration and this tile's taps are in flight during the
+        // biquad; every thread reads back only what it copied itself, so no barrier is needed for them.
+        const unsigned long long n_fast = (hi - tb) / CH_TILE;
+        const unsigned xm = (unsigned)xin.mask, zm = (unsigned)zout.mask;
+        unsigned xb = (unsigned)(tb & xin.mask);                                // ring index of the tile's first sample
+        unsigned zb = (unsigned)(tb & zout.mask);
+        unsigned qb = (unsigned)((tb - Du - (unsigned)sh) & zout.mask);         // ... of the first tap quad (16-byte aligned)
+        float4 (*sx)[CH_QUADS] = s_x[wi];
+        float4* sq = s_q[wi];
+        float4* so = s_o[wi];
+        const unsigned pa = ch_qpos(wl), pb = ch_qpos(32u + wl);               // this lane's two quads of a coalesced copy
+        const unsigned p0 = ch_qpos(2u * wl), p1 = ch_qpos(2u * wl + 1u), p2 = ch_qpos(2u * wl + 2u);   // its own samples
+        // history (x[t0-2], x[t0-1]) = the quad before this thread's own; lane 0 reads the carry slot instead
+        const unsigned ph = ch_qpos(wl ? 2u * wl - 1u : 0u);
+        if (wl == 0) *carry = make_float4(x1c, x2c, y1c, y2c);
+        cp_async16(&sx[0][pa], xin.data + ((xb + 4u * wl) & xm));
+        cp_async16(&sx[0][pb], xin.data + ((xb + 128u + 4u * wl) & xm));
+        cp_async_commit();
+        for (unsigned long long k = 0; k < n_fast; k++) {
+            const unsigned cur = (unsigned)k & 1u;
+            cp_async16(&sq[pa], zout.data + ((qb + 4u * wl) & zm));
+            cp_async16(&sq[pb], zout.data + ((qb + 128u + 4u * wl) & zm));
+            if (wl < 3) cp_async16(&sq[ch_qpos(64u + wl)], zout.data + ((qb + 256u + 4u * wl) & zm));
+            cp_async_commit();                                      // group "taps of tile k"
+            xb = (xb + CH_TILE) & xm;
+            if (k + 1 < n_fast) {
+                cp_async16(&sx[cur ^ 1][pa], xin.data + ((xb + 4u * wl) & xm));
+                cp_async16(&sx[cur ^ 1][pb], xin.data + ((xb + 128u + 4u * wl) & xm));
+            }
+            cp_async_commit();                                      // group "x of tile k + 1" (possibly empty)
+            cp_async_wait<2>();                                     // x of tile k has landed (every lane's share of it)
+            __syncwarp();
+            float x[DF_PER_THREAD + 2], yv[DF_PER_THREAD], y1, y2;
+            const float4 cr = *carry;                               // broadcast read
+            {
+                const float4 v0 = sx[cur][p0], v1 = sx[cur][p1], vh = sx[cur][ph];
+                x[2] = v0.x; x[3] = v0.y; x[4] = v0.z; x[5] = v0.w; x[6] = v1.x; x[7] = v1.y; x[8] = v1.z; x[9] = v1.w;
+                x[0] = wl ? vh.z : cr.y;
+                x[1] = wl ? vh.w : cr.x;
+            }
+            biquad_tile(x, cr.z, cr.w, Pk, b0, b1, b2, a1, a2, wl, yv, y1, y2);
+            if (wl == 31) {
+                const float4 c = make_float4(x[9], x[8], y1, y2);
+                *carry = c;                                         // read by everyone after the barriers below
+                if (k + 1 == n_fast && tb + CH_TILE == hi) state[lane] = c;
+            }
+            cp_async_wait<1>();                                     // the taps have landed
+            __syncwarp();
+            float zq[12], z[DF_PER_THREAD];
+            {
+                const float4 v0 = sq[p0], v1 = sq[p1], v2 = sq[p2];
+                zq[0] = v0.x; zq[1] = v0.y; zq[2] = v0.z; zq[3] = v0.w; zq[4] = v1.x; zq[5] = v1.y; zq[6] = v1.z; zq[7] = v1.w;
+                zq[8] = v2.x; zq[9] = v2.y; zq[10] = v2.z; zq[11] = v2.w;
+            }
+            comb(yv, zq, sh, z);
+            so[p0] = make_float4(z[0], z[1], z[2], z[3]);
+            so[p1] = make_float4(z[4], z[5], z[6], z[7]);
+            __syncwarp();
+            *reinterpret_cast<float4*>(zout.data + ((zb + 4u * wl) & zm)) = so[pa];
+            *reinterpret_cast<float4*>(zout.data + ((zb + 128u + 4u * wl) & zm)) = so[pb];
+            __syncwarp();                                           // the next tile's taps read these stores
+            qb += CH_TILE; zb += CH_TILE;
+            tb += CH_TILE;
+        }
+        { const float4 c = *carry; x1c = c.x; x2c = c.y; y1c = c.z; y2c = c.w; }   // for the ragged tail, if any
+        cp_async_wait<0>();
+        while (tb < hi) { slow_tile(tb); tb += CH_TILE; }
+    }
+}
+
+bool chain_fusable(const DirectFormDev& df, const FbDelayDev& fb) {
+    return df.n_lanes == fb.n_lanes && df.n_lanes > 0 && fb.min_delay >= (uint64_t)CH_MIN_DELAY;
+}
+
+std::shared_ptr<ChainStateDev> chain_state_create(uint32_t n_lanes) {
+    auto s = std::make_shared<ChainStateDev>();
+    s->n_lanes = n_lanes;
+    if (cudaMalloc(&s->d_state, std::max<uint32_t>(n_lanes, 1) * sizeof(float4)) != cudaSuccess) return nullptr;
+    return s;
+}
+
+cudaError_t launch_dfcomb(const DirectFormDev& df, const FbDelayDev& fb, ChainStateDev& st, const BufferDesc* d_bufdesc,
+                          const uint32_t* d_in_bufs, uint32_t first_out_buf, uint64_t lo, uint64_t hi, cudaStream_t stream,
+                          uint64_t* n_launches) {
+    if (n_launches) *n_launches = 0;
+    if (hi <= lo || df.n_lanes == 0) return cudaSuccess;
+    if (lo != 0 && lo != st.time) return cudaErrorInvalidValue;    // the renderer restarts recurrences at t = 0 or continues
+    const unsigned per_cta = DF_CTA_THREADS / 32;
+    dfcomb_kernel<<<(df.n_lanes + per_cta - 1) / per_cta, DF_CTA_THREADS, 0, stream>>>(
+        df.d_coef, df.d_pow, fb.d_delay, fb.d_gain, d_bufdesc, d_in_bufs, first_out_buf, st.d_state, df.n_lanes, lo, hi);
+    st.time = hi;
+    if (n_launches) *n_launches = 1;
+    return cudaGetLastError();
 }
 
 cudaError_t launch_directform(const DirectFormDev& f, const BufferDesc* d_bufdesc, const uint32_t* d_in_bufs,

@@ -168,3 +168,90 @@ def test_biquad_feedback_chain_all_delay_ranges():
             parts.append(g2.fill_buffer(ns, m, idx, [row[idx:idx + m] for row in x]))
             idx += m
         assert np.abs(np.concatenate(parts, axis=1).astype(np.float64) - want).max() <= 1e-4 * scale, tap
+
+
+# ---- fused DirectForm -> FbDelay chain (dfcomb_kernel): same bits as the two separate kernels ----
+
+def _chain_graph(r, coefs, delay, gain, tap_biquad=False):
+    from libfriendship_b200 import KIND_DIRECTFORM, KIND_FBDELAY
+    lanes = len(delay)
+    r.define_directform(3, *coefs)
+    r.define_fbdelay(4, delay, gain)
+    r.on_add_node(1, KIND_DIRECTFORM, 3)
+    r.on_add_node(2, KIND_FBDELAY, 4)
+    for l in range(lanes):
+        r.on_add_edge((0, 1, l, l))
+        r.on_add_edge((1, 2, l, l))
+        r.on_add_edge((2, 0, l, l))
+    if tap_biquad:
+        r.on_add_edge((1, 0, 0, lanes))     # the biquad's lane 0 is also an output: the chain may not be fused
+    return lanes + (1 if tap_biquad else 0)
+
+
+CHAIN_DELAYS = np.array([32, 33, 100, 255, 256, 257, 300, 511, 512, 999, 1000, 5000, 20000], dtype=np.uint32)
+
+
+@pytest.mark.parametrize("blocks", [[30000], [1, 254, 257, 4096, 3, 25389], [777] * 30])
+def test_fused_chain_equals_separate_kernels_bit_exact(blocks):
+    from libfriendship_b200 import FLAG_NO_CHAIN_FUSION
+    lanes = len(CHAIN_DELAYS)
+    fc = np.geomspace(60.0, 15000.0, lanes)
+    q = np.linspace(0.707, 4.0, lanes)
+    coefs = rbj_lowpass(fc, q)
+    gain = np.linspace(-0.95, 0.95, lanes).astype(np.float32)
+    n = sum(blocks)
+    x = noise(lanes, n, seed=9)
+    outs, launches = [], []
+    for flags in (0, FLAG_NO_CHAIN_FUSION):
+        r = gpu_cls()(flags=flags)
+        _chain_graph(r, coefs, CHAIN_DELAYS, gain)
+        parts, idx = [], 0
+        for m in blocks:
+            parts.append(r.fill_buffer(lanes, m, idx, [row[idx:idx + m] for row in x]))
+            idx += m
+        outs.append(np.concatenate(parts, axis=1))
+        launches.append(r.stats()["chain_launches"])
+    assert launches[0] > 0 and launches[1] == 0
+    assert_same_bits(outs[0], outs[1], "fused chain vs separate kernels")
+    # and both are the recurrence: fp64 oracle within the north star's 1e-4 of full scale
+    o = OracleRenderer()
+    _chain_graph(o, coefs, CHAIN_DELAYS, gain)
+    ref = o.fill_buffer(lanes, n, 0, x)
+    scale = np.abs(ref).max()
+    assert np.abs(outs[0].astype(np.float64) - ref).max() <= 1e-4 * scale
+
+
+def test_chain_not_fused_when_biquad_is_tapped_or_comb_is_short():
+    lanes = 3
+    coefs = rbj_lowpass(np.array([300.0, 1000.0, 5000.0]), np.array([1.0, 2.0, 0.8]))
+    gain = np.array([0.5, 0.6, 0.7], dtype=np.float32)
+    x = noise(lanes, 5000, seed=2)
+    for delay, tap in ((np.array([100, 200, 300], dtype=np.uint32), True), (np.array([100, 31, 300], dtype=np.uint32), False)):
+        r, o = gpu_cls()(), OracleRenderer()
+        n_out = _chain_graph(r, coefs, delay, gain, tap_biquad=tap)
+        _chain_graph(o, coefs, delay, gain, tap_biquad=tap)
+        a = r.fill_buffer(n_out, 5000, 0, x)
+        b = o.fill_buffer(n_out, 5000, 0, x)
+        assert r.stats()["chain_launches"] == 0
+        assert np.abs(a.astype(np.float64) - b).max() <= 1e-4 * np.abs(b).max()
+
+
+def test_fused_chain_seek_and_redefinition():
+    """A seek restarts the recurrence from t = 0 (pure function of absolute time); re-defining the comb re-plans."""
+    lanes = 4
+    coefs = rbj_lowpass(np.array([200.0, 800.0, 3000.0, 9000.0]), np.array([0.8, 1.5, 3.0, 1.0]))
+    delay = np.array([64, 300, 700, 1500], dtype=np.uint32)
+    gain = np.full(lanes, 0.8, dtype=np.float32)
+    x = noise(lanes, 6000, seed=3)
+    r, o = gpu_cls()(), OracleRenderer()
+    _chain_graph(r, coefs, delay, gain)
+    _chain_graph(o, coefs, delay, gain)
+    for idx, n in ((0, 3000), (3000, 3000)):
+        a = r.fill_buffer(lanes, n, idx, [row[idx:idx + n] for row in x])
+        b = o.fill_buffer(lanes, n, idx, [row[idx:idx + n] for row in x])
+        assert np.abs(a.astype(np.float64) - b).max() <= 1e-4 * max(np.abs(b).max(), 1e-3)
+    # seek back: the external inputs are forgotten (zeros), the filters restart from t = 0
+    a = r.fill_buffer(lanes, 500, 1000, [row[:500] for row in x])
+    b = o.fill_buffer(lanes, 500, 1000, [row[:500] for row in x])
+    assert np.abs(a.astype(np.float64) - b).max() <= 1e-4 * max(np.abs(b).max(), 1e-3)
+    assert r.stats()["chain_launches"] > 0
