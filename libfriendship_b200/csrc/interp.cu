@@ -180,52 +180,52 @@ interp_kernel(InterpParams p) {
     }
 }
 
-// Left fold of `count` consecutive planes (lanes of one extension instance: plane i = base + i * stride) into one
-// ring, adds in the chain's own order.  The block is short (the ring budget caps it at 64 Ki samples for 4,096
-// lanes), so the parallelism has to come from loads in flight per thread: 4 samples per thread (128-bit loads) and
-// 16 independent plane loads issued before the 16 ordered adds.
-// volatile: keeps the 16 loads of a batch ahead of the adds (the compiler otherwise sinks each load next to its use
-// to save registers, which leaves only a few loads in flight per thread)
-__device__ __forceinline__ float4 ld_stream_f4(const float* p) {
-    float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+// fold: ((x0 + x1) + x2) + ... over consecutive planes of one extension instance (the "voices summed to one slot" mix),
+// in the chain's own order.  HBM-bound: reads count x 4 B per sample.
+// volatile asm: keeps the loads of a batch ahead of the adds (the compiler otherwise sinks each load next to its use to
+// save registers, which leaves only a few loads in flight per thread)
+__device__ __forceinline__ float ld_stream_f1(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
     return v;
 }
 
-__global__ void __launch_bounds__(64)
+// One thread = ONE sample, walking the planes in order.  The sum is a left fold (bit-exact with the Sum2 chain it stands
+// for), so the only parallelism is across samples, and a block is at most 64 Ki - 1 Mi samples: ~440 - 7,000 samples per SM.
+// What hides DRAM latency is therefore the depth of the per-thread load pipeline, and scalar lanes afford the deepest one
+// for the registers: FB loads of batch k+1 are issued before the FB ordered adds of batch k (2 x FB x 4 B in flight per
+// thread; a float4-per-thread version at FB = 16 has the same bytes in flight per thread but a quarter of the threads).
+constexpr int FOLD_THREADS = 256;
+constexpr int FOLD_FB = 32;
+
+__global__ void __launch_bounds__(FOLD_THREADS)
 fold_kernel(const BufferDesc* __restrict__ bufs, unsigned first, unsigned count, unsigned out_buf,
             unsigned long long lo, unsigned long long hi) {
     const BufferDesc b0 = bufs[first];
     const BufferDesc ob = bufs[out_buf];
     const unsigned long long stride = (unsigned long long)(bufs[first + 1].data - b0.data);
-    const unsigned long long lo4 = lo & ~3ull;
-    const unsigned long long n4 = (hi - lo4 + 3) / 4;
-    for (unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; g < n4;
+    const unsigned long long n = hi - lo;
+    for (unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; g < n;
          g += (unsigned long long)gridDim.x * blockDim.x) {
-        const unsigned long long t = lo4 + 4 * g;
+        const unsigned long long t = lo + g;
         const float* base = b0.data + (t & b0.mask);
-        float4 acc = __ldg(reinterpret_cast<const float4*>(base));
+        float acc = ld_stream_f1(base);
         unsigned i = 1;
-        // software pipeline: the 16 loads of batch k+1 are issued before the 16 ordered adds of batch k, so the adds
-        // never wait on a load that was just issued
-        constexpr int FB = 16;
-        float4 cur[FB];
+        constexpr int FB = FOLD_FB;
+        float cur[FB];
         const unsigned n_batches = (count - 1) / FB;
         if (n_batches) {
 #pragma unroll
-            for (int q = 0; q < FB; q++) cur[q] = ld_stream_f4(base + (unsigned long long)(i + q) * stride);
+            for (int q = 0; q < FB; q++) cur[q] = ld_stream_f1(base + (unsigned long long)(i + q) * stride);
             for (unsigned bi = 0; bi < n_batches; bi++) {
-                float4 nxt[FB];
+                float nxt[FB];
                 const unsigned j = i + FB;
                 if (bi + 1 < n_batches) {
 #pragma unroll
-                    for (int q = 0; q < FB; q++) nxt[q] = ld_stream_f4(base + (unsigned long long)(j + q) * stride);
+                    for (int q = 0; q < FB; q++) nxt[q] = ld_stream_f1(base + (unsigned long long)(j + q) * stride);
                 }
 #pragma unroll
-                for (int q = 0; q < FB; q++) {
-                    acc.x = __fadd_rn(acc.x, cur[q].x); acc.y = __fadd_rn(acc.y, cur[q].y);
-                    acc.z = __fadd_rn(acc.z, cur[q].z); acc.w = __fadd_rn(acc.w, cur[q].w);
-                }
+                for (int q = 0; q < FB; q++) acc = __fadd_rn(acc, cur[q]);
                 if (bi + 1 < n_batches) {
 #pragma unroll
                     for (int q = 0; q < FB; q++) cur[q] = nxt[q];
@@ -233,28 +233,17 @@ fold_kernel(const BufferDesc* __restrict__ bufs, unsigned first, unsigned count,
                 i = j;
             }
         }
-        for (; i < count; i++) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(base + (unsigned long long)i * stride));
-            acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y);
-            acc.z = __fadd_rn(acc.z, v.z); acc.w = __fadd_rn(acc.w, v.w);
-        }
-        // samples outside [lo, hi) were only read (their planes hold older or not-yet-final data): never written
-        const float r[4] = {acc.x, acc.y, acc.z, acc.w};
-        if (t >= lo && t + 4 <= hi) *reinterpret_cast<float4*>(ob.data + (t & ob.mask)) = acc;
-        else
-#pragma unroll
-            for (int u = 0; u < 4; u++)
-                if (t + u >= lo && t + u < hi) ob.data[(t + u) & ob.mask] = r[u];
+        for (; i < count; i++) acc = __fadd_rn(acc, ld_stream_f1(base + (unsigned long long)i * stride));
+        ob.data[t & ob.mask] = acc;
     }
 }
 
 cudaError_t launch_fold(const BufferDesc* d_bufdesc, unsigned first, unsigned count, unsigned out_buf,
                         unsigned long long lo, unsigned long long hi, int sm_count, cudaStream_t stream) {
     if (hi <= lo) return cudaSuccess;
-    const unsigned long long n4 = (hi - (lo & ~3ull) + 3) / 4;
-    unsigned long long blocks = (n4 + 63) / 64;
-    if (blocks > (unsigned long long)sm_count * 16) blocks = (unsigned long long)sm_count * 16;
-    fold_kernel<<<(unsigned)blocks, 64, 0, stream>>>(d_bufdesc, first, count, out_buf, lo, hi);
+    unsigned long long blocks = (hi - lo + FOLD_THREADS - 1) / FOLD_THREADS;
+    if (blocks > (unsigned long long)sm_count * 8) blocks = (unsigned long long)sm_count * 8;
+    fold_kernel<<<(unsigned)blocks, FOLD_THREADS, 0, stream>>>(d_bufdesc, first, count, out_buf, lo, hi);
     return cudaGetLastError();
 }
 

@@ -44,7 +44,8 @@
 namespace frb {
 
 constexpr int OSC_K = 16;           // partials per group (independent FMA chains per thread) for ordinary banks
-constexpr int OSC_K_SMALL = 4;      // banks whose voices have <= 8 partials (e.g. one exciter per voice): less padding
+constexpr int OSC_K_SMALL = 4;      // banks whose voices have <= 8 partials: less padding
+constexpr int OSC_K_ONE = 1;        // banks of one-partial voices (one exciter per voice, BASELINE configs[2]): no padding
 constexpr int OSC_THREADS = 32;     // threads (= time segments) per CTA: one warp, so the per-group barrier couples no warps
 constexpr int OSC_LMAX = 256;       // max segment length (shared memory: L * THREADS * 4 B)
 
@@ -241,7 +242,7 @@ std::shared_ptr<OscBankDev> osc_create(const frb_oscbank_desc* d, cudaStream_t s
     b->n_voices = d->n_voices;
     b->n_partials = d->n_partials;
     b->sample_rate = d->sample_rate;
-    b->K = (mx <= 8) ? OSC_K_SMALL : OSC_K;
+    b->K = (mx <= 1) ? OSC_K_ONE : (mx <= 8) ? OSC_K_SMALL : OSC_K;
     const int K = b->K;
     const uint64_t np = d->n_partials;
     const uint32_t nv = d->n_voices;
@@ -589,6 +590,8 @@ cudaError_t osc_init_device() {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(osc_kernel<OSC_K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(osc_kernel<OSC_K_SMALL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(osc_kernel<OSC_K_SMALL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(osc_kernel<OSC_K_ONE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(osc_kernel<OSC_K_ONE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     return e;
 }
 
@@ -666,7 +669,8 @@ static cudaError_t launch_osc_range(const OscBankDev& b, const BufferDesc* d_buf
         }
         dim3 grid((n_att + threads - 1) / threads, b.n_voices, p.split);
         if (b.K == OSC_K) osc_kernel<OSC_K, true><<<grid, threads, smem, st>>>(q);
-        else osc_kernel<OSC_K_SMALL, true><<<grid, threads, smem, st>>>(q);
+        else if (b.K == OSC_K_SMALL) osc_kernel<OSC_K_SMALL, true><<<grid, threads, smem, st>>>(q);
+        else osc_kernel<OSC_K_ONE, true><<<grid, threads, smem, st>>>(q);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         if (n_launches) (*n_launches)++;
@@ -678,7 +682,8 @@ static cudaError_t launch_osc_range(const OscBankDev& b, const BufferDesc* d_buf
         q.plane_off = (unsigned long long)n_att * L;
         dim3 grid((q.nseg + threads - 1) / threads, b.n_voices, p.split);
         if (b.K == OSC_K) osc_kernel<OSC_K, false><<<grid, threads, smem, stream>>>(q);
-        else osc_kernel<OSC_K_SMALL, false><<<grid, threads, smem, stream>>>(q);
+        else if (b.K == OSC_K_SMALL) osc_kernel<OSC_K_SMALL, false><<<grid, threads, smem, stream>>>(q);
+        else osc_kernel<OSC_K_ONE, false><<<grid, threads, smem, stream>>>(q);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         if (n_launches) (*n_launches)++;

@@ -281,14 +281,6 @@ void Renderer::upload_schedule() {
         CU(cudaMemcpy(d_programs_[i], words.data(), bytes, cudaMemcpyHostToDevice));
         stats.h2d_bytes += bytes;
     }
-    // Block length: as long as the rings allow (more samples per launch = more parallelism for the stage kernels),
-    // with the ring memory (<= 2 x block x 4 B per ring) kept under ~8 GB.
-    {
-        const uint64_t nb = std::max<uint64_t>(sched_.buffers.size(), 1);
-        uint64_t c = 1ull << 20;
-        while (c > (1ull << 14) && 2 * c * nb > (1ull << 31)) c >>= 1;
-        chunk_ = c;
-    }
     h_bufdesc_.assign(sched_.buffers.size(), BufferDesc{nullptr, 0});
     bufdesc_dirty_ = true;
     d_ext_in_bufs_.assign(sched_.ext.size(), nullptr);
@@ -334,6 +326,16 @@ void Renderer::upload_schedule() {
             chain_of_[j] = (int32_t)i;
             chained_[i] = 1;
         }
+    }
+    // Block length: as long as the rings allow (more samples per launch = more parallelism for the stage kernels),
+    // with the ring memory (<= 2 x block x 4 B per allocated ring) kept under ~8 GB.
+    {
+        uint64_t nb = 0;
+        for (const BufferInfo& bi : sched_.buffers) nb += !(bi.ext != ~0u && chained_[bi.ext]);
+        nb = std::max<uint64_t>(nb, 1);
+        uint64_t c = 1ull << 20;
+        while (c > (1ull << 14) && 2 * c * nb > (1ull << 31)) c >>= 1;
+        chunk_ = c;
     }
 }
 

@@ -74,20 +74,25 @@ def case_pure_elementwise(n_slots=64, n=1 << 22):
             "algorithmic_GBs": alg / t["interp_ms"] / 1e6, "peak_GBs": HBM, "frac": alg / t["interp_ms"] / 1e6 / HBM}
 
 
-def case_cfg3(n_voices=4096, n=480000):
-    """cfg3: per voice 1-partial oscillator -> biquad -> feedback delay, mixed to one slot.  K4 algorithmic traffic:
-    8 B per voice-sample per node (2 nodes)."""
+def case_cfg3(n_voices=4096, n=480000, flags=0):
+    """cfg3: per voice 1-partial oscillator -> biquad -> feedback delay, mixed to one slot.  K4 algorithmic traffic
+    (SURVEY.md §8d): 8 B per voice-sample for the fused biquad -> comb chain (read x, write y); the two separate kernels
+    (FLAG_NO_CHAIN_FUSION) move 16 B."""
     from banks import detuned_bank
     from filters import build_cfg3_graph
-    r = B200Renderer()
+    r = B200Renderer(flags=flags)
     bank, _ = detuned_bank(n_voices, 1, seed=5)
     build_cfg3_graph(r, n_voices, excitation="osc", bank=bank, mix_to_one=True)
     out = torch.empty((1, n), dtype=torch.float32, device="cuda")
     t = timed_fill(r, out, 1, n, 0, reps=3)
-    alg = 16.0 * n_voices * n
-    return {"case": "cfg3 osc->DirectForm->FbDelay->mix", "voices": n_voices, "samples": n, "ms": t["total_ms"], "scan_ms": t["scan_ms"],
-            "osc_ms": t["osc_ms"], "interp_ms": t["interp_ms"], "K4_algorithmic_GBs": alg / t["scan_ms"] / 1e6, "peak_GBs": HBM,
-            "K4_frac": alg / t["scan_ms"] / 1e6 / HBM, "voice_samples_per_s": n_voices * n / (t["total_ms"] * 1e-3)}
+    alg = 8.0 * n_voices * n
+    fused = r.stats()["chain_launches"] > 0
+    moved = alg if fused else 2 * alg
+    return {"case": "cfg3 osc->DirectForm->FbDelay->mix" + ("" if fused else " (chain fusion off)"), "voices": n_voices, "samples": n,
+            "ms": t["total_ms"], "scan_ms": t["scan_ms"], "osc_ms": t["osc_ms"], "fold_ms": t["interp_ms"],
+            "K4_algorithmic_GBs": alg / t["scan_ms"] / 1e6, "peak_GBs": HBM, "K4_frac": alg / t["scan_ms"] / 1e6 / HBM,
+            "K4_kernel_bytes_GBs": moved / t["scan_ms"] / 1e6, "osc_write_GBs": 4.0 * n_voices * n / t["osc_ms"] / 1e6,
+            "fold_read_GBs": 4.0 * n_voices * n / t["interp_ms"] / 1e6, "voice_samples_per_s": n_voices * n / (t["total_ms"] * 1e-3)}
 
 
 def case_cfg2(anchor=0):
@@ -138,7 +143,7 @@ def case_cfg1():
 if __name__ == "__main__":
     which = sys.argv[1:] or ["pure", "elementwise", "cfg3"]
     for w in which:
-        fn = {"pure": case_pure_elementwise, "elementwise": case_elementwise, "cfg3": case_cfg3, "cfg1": case_cfg1, "cfg2": case_cfg2, "cfg2_64": lambda: case_cfg2(64), "cfg2_32": lambda: case_cfg2(32)}[w]
+        fn = {"pure": case_pure_elementwise, "elementwise": case_elementwise, "cfg3": case_cfg3, "cfg3_unfused": lambda: case_cfg3(flags=8), "cfg1": case_cfg1, "cfg2": case_cfg2, "cfg2_64": lambda: case_cfg2(64), "cfg2_32": lambda: case_cfg2(32)}[w]
         t0 = time.time()
         try:
             res = fn()
