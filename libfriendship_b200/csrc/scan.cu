@@ -2,16 +2,17 @@
 // not in the reference: SURVEY.md F2 — the reference rejects cycles, so feedback only exists as these nodes).
 //
 // Bound: HBM.  Algorithmic traffic = 8 B per lane-sample for each node (read x, write y): each kernel reads its
-// input ring once and writes its output ring once; no intermediate touches HBM.
+// input ring once and writes its output ring once; no intermediate touches HBM.  A biquad that feeds a comb lane for
+// lane (and nothing else) runs fused with it: 8 B per lane-sample for the pair (dfcomb_kernel below).
 //
 // DirectForm (biquad, Direct Form I), per lane:  y[n] = b0 x[n] + b1 x[n-1] + b2 x[n-2] - a1 y[n-1] - a2 y[n-2].
-//   One CTA owns one lane and walks the block in tiles of 256 threads x 8 samples.  Inside a tile the recurrence is
-//   evaluated as a parallel prefix scan over the recurrence's transfer matrices: every thread runs its 8 samples
-//   from a zero state, the 2-vectors of end states are combined with a Kogge-Stone scan whose operator is
-//   "multiply by A^(8*2^k) and add" (A = [[-a1, -a2], [1, 0]]; the powers come from an fp64 setup at definition
-//   time), then every thread re-runs its 8 samples from its true initial state.  The carry between tiles and
-//   between launches is just the last two samples of x and y, re-read from the rings, so consecutive blocks
-//   continue exactly.
+//   One WARP owns one lane and walks the block in tiles of 32 threads x 8 samples.  Inside a tile the recurrence is
+//   evaluated as a parallel prefix scan over the recurrence's transfer matrices (biquad_tile): every thread runs its
+//   8 samples from a zero state (lane 0 from the carry), the 2-vectors of end states are combined with a Kogge-Stone
+//   scan whose operator is "multiply by A^(8*2^k) and add" (A = [[-a1, -a2], [1, 0]]; the powers come from an fp64
+//   setup at definition time), then every thread re-runs its 8 samples from its true initial state.  The carry
+//   between tiles and between launches is just the last two samples of x and y, re-read from the rings, so
+//   consecutive blocks continue exactly.
 //
 // FbDelay, per lane:  y[n] = x[n] + g y[n-D].  D independent first-order recurrences with stride D: one CTA per
 //   lane steps through time D samples at a time, all D phases in parallel; every output is computed in the same
