@@ -186,7 +186,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    rstream = sr.render_stream()
+    rstream = sr.cuda_stream()
 
     def timed(fn, steps):
         # CUDA events on the stream the kernels are launched on (the renderer's own stream); every step ends with a

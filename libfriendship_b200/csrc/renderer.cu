@@ -638,10 +638,8 @@ void Renderer::fill(float* out, bool out_on_device, uint32_t n_slots, uint64_t n
                 CU(cudaMalloc(&d_indesc_, d_indesc_cap_ * sizeof(InputDesc)));
                 h_indesc_.clear();
             }
-            // the table travels by value from a host vector that must outlive the copy: h_indesc_ is only rewritten
-            // after the previous copy was waited for
+            // the table is re-uploaded only when it changed (the copy below is waited for, so h_indesc_ is free to rewrite)
             if (h_indesc_.size() != nin || memcmp(h_indesc_.data(), h.data(), nin * sizeof(InputDesc)) != 0) {
-                CU(cudaStreamSynchronize(stream_));
                 h_indesc_ = h;
                 CU(cudaMemcpyAsync(d_indesc_, h_indesc_.data(), nin * sizeof(InputDesc), cudaMemcpyHostToDevice, stream_));
                 CU(cudaStreamSynchronize(stream_));

@@ -48,7 +48,7 @@ class ShardedRenderer:
                 torch.cuda.current_stream(self.device).synchronize()
         return out
 
-    def render_stream(self):
+    def cuda_stream(self):
         """The CUDA stream the renderer launches on, as a torch stream (for CUDA-event timing)."""
         return torch.cuda.ExternalStream(self.r.stream(), device=f"cuda:{self.device}")
 

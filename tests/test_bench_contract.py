@@ -1,0 +1,53 @@
+"""CPU: bench.py / tools call into the package with signatures that exist (no GPU needed to catch a renamed or
+shadowed method), and the bench line's static parts follow the driver's contract."""
+import ast
+import inspect
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _calls_on(tree, base):
+    """(method, n_positional, keywords) for every call of the form <base>.<method>(...), base like 'sr' or 'sr.r'."""
+    out = []
+    for node in ast.walk(tree):
+        if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and ast.unparse(node.func.value) == base:
+            if any(isinstance(a, ast.Starred) for a in node.args):
+                continue
+            kws = [k.arg for k in node.keywords if k.arg is not None]
+            has_splat = any(k.arg is None for k in node.keywords)
+            out.append((node.func.attr, len(node.args), kws, has_splat))
+    return out
+
+
+def _check(cls, calls, where):
+    for name, n_pos, kws, has_splat in calls:
+        fn = getattr(cls, name, None)
+        assert fn is not None, f"{where}: {cls.__name__}.{name} does not exist"
+        sig = inspect.signature(fn)
+        if has_splat:
+            continue
+        try:
+            sig.bind(None, *([0] * n_pos), **{k: 0 for k in kws})
+        except TypeError as e:
+            raise AssertionError(f"{where}: {cls.__name__}.{name}{sig} called with {n_pos} positional + {kws}: {e}")
+
+
+def test_bench_and_tools_call_existing_methods():
+    from libfriendship_b200 import B200Renderer
+    from libfriendship_b200.sharded import ShardedRenderer
+    for rel in ("bench.py", "tools/render_cfg5.py"):
+        tree = ast.parse(open(os.path.join(ROOT, rel)).read())
+        sr_calls = _calls_on(tree, "sr")
+        assert sr_calls, rel
+        _check(ShardedRenderer, sr_calls, rel)
+        _check(B200Renderer, _calls_on(tree, "sr.r"), rel)
+
+
+def test_bench_line_static_contract():
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    for key in ('"metric"', '"value"', '"unit"', '"n_gpus"', '"steps"', '"warmup"', '"ms_per_step"', '"higher_is_better"',
+                '"scaling"', '"vs_baseline"', '"dtype"', '"data"', '"config"', '"e2e"', '"h2d_bytes_per_step"',
+                '"d2h_bytes_per_step"', '"gpu_launches"', '"clocks"', '"roofline"', '"cpu_baseline"', '"impl"'):
+        assert key in src, key
+    assert "/root/reference" not in src
