@@ -487,13 +487,20 @@ __global__ void __launch_bounds__(OSC_THREADS) osc_kernel(OscLaunch p) {
     extern __shared__ float4 s_acc_all[];
     __shared__ OscStage<K> stage;                            // static: constant addresses -> uniform-register loads
     const unsigned nthr = blockDim.x;
-    const unsigned cstride = nthr + 1;                       // column stride in float4: odd, see the write-out
+    // Banks of small voices (K < 16) are bound by their ring writes, not by the FMA pipe: they use an odd column stride
+    // and a cooperative, coalesced write-out.  The big-bank kernel keeps stride nthr and per-thread columns: its output
+    // is 0.2% of its traffic, and the other layout costs it 1.8% (ptxas allocates 70 registers instead of 78 and the
+    // hot loop picks up register-bank dispatch stalls: ncu r1i vs r1f).  The register allocation of that kernel is
+    // fragile — even replacing `live` below by an equivalent test at the end renumbers the hot loop's registers and
+    // costs 1% — so the K = 16 path is kept instruction-for-instruction as measured in r1f (checked by a SASS diff).
+    constexpr bool COOP = K < OSC_K;
+    const unsigned cstride = COOP ? nthr + 1 : nthr;         // column stride in float4
     const int L = p.L;
     float4* s_acc = s_acc_all + threadIdx.x;                 // column of this thread: s_acc[j4 * cstride]
     const unsigned seg = blockIdx.x * nthr + threadIdx.x;
     const unsigned v = blockIdx.y;
     const unsigned sp = blockIdx.z;
-    // threads whose segment lies beyond the window compute too (their columns are dropped at the write-out)
+    const bool live = seg < p.nseg;                          // dead threads compute too (dropped at the end)
     const unsigned long long n0 = (p.seg0 + seg) * (unsigned long long)L;
     for (int j4 = 0; j4 < L / 4; j4++) s_acc[j4 * cstride] = make_float4(0.f, 0.f, 0.f, 0.f);
 
@@ -522,6 +529,28 @@ __global__ void __launch_bounds__(OSC_THREADS) osc_kernel(OscLaunch p) {
         osc_group<K, ATTACK>(stage.hot, stage.anc, stage.ph, n0, L, s_acc, cstride);
     }
     if (g_mid < g_hi) flip_odd();                            // back: out[j] = acc0[j] + (-1)^j acc1[j]
+    if constexpr (!COOP) {
+        if (!live) return;
+        if (p.split == 1) {
+            const BufferDesc bd = p.bufdesc[p.first_buf + v];
+            for (int j4 = 0; j4 < L / 4; j4++) {
+                const unsigned long long t = n0 + 4ull * j4;
+                const float4 acc = s_acc[j4 * nthr];
+                if (t >= p.lo && t + 4 <= p.hi) {
+                    *reinterpret_cast<float4*>(bd.data + (t & bd.mask)) = acc;
+                } else {
+                    const float r[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (t + u >= p.lo && t + u < p.hi) bd.data[(t + u) & bd.mask] = r[u];
+                }
+            }
+        } else {
+            float* plane = p.planes + ((size_t)sp * p.n_voices + v) * p.plane_len + p.plane_off + (size_t)seg * L;
+            for (int j4 = 0; j4 < L / 4; j4++) *reinterpret_cast<float4*>(plane + 4 * j4) = s_acc[j4 * nthr];
+        }
+        return;
+    }
     // Write-out, cooperative: the CTA's 32 segments are contiguous in time, so quad q of the CTA (4 samples) lives in
     // column q / (L/4), row q % (L/4); consecutive lanes take consecutive quads and every store instruction covers 512
     // contiguous bytes.  (One thread writing its own column = 32 lanes 4*L bytes apart: 5.4 ms instead of 1.9 ms for
@@ -642,7 +671,8 @@ static cudaError_t launch_osc_range(const OscBankDev& b, const BufferDesc* d_buf
         p.planes = b.d_planes;
     }
     const unsigned threads = OSC_THREADS;
-    const size_t smem = (size_t)L * (threads + 1) * sizeof(float);   // L/4 rows of (threads + 1) float4 columns
+    // L/4 rows of float4 columns: threads + 1 of them for the small-voice kernels (odd stride), threads for K = 16
+    const size_t smem = (size_t)L * (threads + (b.K < OSC_K ? 1 : 0)) * sizeof(float);
     // Segments that start below max_attack need the attack ramp: they get their own (slower) kernel so that each
     // kernel contains exactly one instance of the hot loop.
     unsigned n_att = 0;
