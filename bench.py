@@ -279,7 +279,11 @@ def main():
             "clocks": sampler.result(),
             "roofline": {
                 "kernel": "osc_kernel<16,false> (K1)", "bound": "fp32_fma", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved / peak_tf, "traffic": traffic,
+                "frac": achieved / peak_tf,
+                "frac_note": "above 1 because SURVEY.md §8d counts 6 FMA-pipe slots per partial-sample and K1 needs 4 "
+                             "(the decay is folded into the rotation's eigenvalues, amplitude into the anchor): "
+                             "executed_frac is the pipe utilisation in issued ops",
+                "traffic": traffic,
                 "traffic_note": "DRAM bytes of one K1 launch (ncu --set full, profiles/k1_traffic.json): parameter stream + "
                                 "partial-range planes, per main-kernel launch (one 131,072-sample sub-block); irrelevant to the bound (0.2% of HBM peak)",
                 "peak_source": f"derived {n_sm} SM x 128 lanes x 2 x sm_max_mhz {sm_max} (MEASURED_PEAKS.json); "
