@@ -105,7 +105,7 @@ def cpu_baseline(n_threads=None, budget_s=12.0):
             "value_1thread": value1}
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, out):
     if rank != 0:
         return
     vals = []
@@ -127,7 +127,7 @@ def run_reference(args, rank, world):
         "note": "the reference (Rust 2017-nightly + LLVM 3.8) cannot be built here; this is the C++ restatement of its "
                 "per-sample renderer (oracle/), all host threads, bounded sample extrapolated linearly",
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=out, flush=True)
 
 
 def workload_config(n_gpus, exchange="NCCL reduce"):
@@ -142,7 +142,18 @@ def workload_config(n_gpus, exchange="NCCL reduce"):
                       "host memory through frb_define_oscbank every step, inside the timed region"}
 
 
+def _claim_stdout():
+    """The driver reads ONE JSON line from stdout.  Libraries write there too (NCCL prints its version line to stdout
+    when NCCL_DEBUG is set in the environment), so file descriptor 1 is pointed at stderr for the whole run and the
+    JSON line goes to a private duplicate of the original stdout."""
+    sys.stdout.flush()
+    out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return out
+
+
 def main():
+    out = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -162,7 +173,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, out)
         return
 
     import torch
@@ -300,7 +311,7 @@ def main():
             line["config"]["workload"] = f"DEBUG reduced workload {n_voices}x{n_partials}x{n_samples}: not a valid bench number"
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
-        print(json.dumps(line))
+        print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

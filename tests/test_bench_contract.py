@@ -51,3 +51,22 @@ def test_bench_line_static_contract():
                 '"d2h_bytes_per_step"', '"gpu_launches"', '"clocks"', '"roofline"', '"cpu_baseline"', '"impl"'):
         assert key in src, key
     assert "/root/reference" not in src
+
+
+def test_reference_arm_prints_exactly_one_json_line():
+    """`bench.py --impl reference` runs on host cores only (no GPU): stdout must be ONE JSON line with the contract's
+    keys, whatever libraries print (stdout is reserved for it)."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, NCCL_DEBUG="VERSION")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "partial-samples/s" and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["value"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "cfg4" in d["config"]["workload"]

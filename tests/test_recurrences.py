@@ -255,3 +255,68 @@ def test_fused_chain_seek_and_redefinition():
     b = o.fill_buffer(lanes, 500, 1000, [row[:500] for row in x])
     assert np.abs(a.astype(np.float64) - b).max() <= 1e-4 * max(np.abs(b).max(), 1e-3)
     assert r.stats()["chain_launches"] > 0
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_graphs_around_chains(seed):
+    """Extension chains inside random primitive graphs: biquad inputs computed by primitives, comb outputs delayed /
+    mixed / routed to several slots, lanes aligned (fusable), permuted or tapped (not fusable).  Whatever the planner
+    decides, the fused build must equal the unfused build bit for bit, and both the fp64 oracle within 1e-4."""
+    from libfriendship_b200 import (FLAG_NO_CHAIN_FUSION, KIND_DELAY, KIND_DIRECTFORM, KIND_FBDELAY, KIND_MINIMUM,
+                                    KIND_MULTIPLY, KIND_SUM2)
+    from graphs import GraphBuilder
+    rng = np.random.RandomState(900 + seed)
+    lanes = int(rng.randint(1, 6))
+    fc = rng.uniform(100.0, 12000.0, lanes)
+    q = rng.uniform(0.6, 3.0, lanes)
+    coefs = rbj_lowpass(fc, q)
+    delay = rng.choice([32, 40, 100, 255, 256, 300, 700, 2000], lanes).astype(np.uint32)
+    if seed % 4 == 3:
+        delay[rng.randint(lanes)] = rng.choice([1, 5, 31])          # a short comb: the planner must not fuse
+    gain = rng.uniform(-0.9, 0.9, lanes).astype(np.float32)
+    perm = rng.permutation(lanes) if seed % 3 == 1 else np.arange(lanes)
+    tap = seed % 3 == 2
+    n_out = 3
+    blocks = [int(b) for b in rng.choice([1, 100, 255, 256, 1000, 3000], 4)]
+    x = noise(2, sum(blocks), seed=seed)
+
+    def build(r):
+        r.define_directform(3, *coefs)
+        r.define_fbdelay(4, delay, gain)
+        g = GraphBuilder(r)
+        DF, FB = 500, 501
+        r.on_add_node(DF, KIND_DIRECTFORM, 3)
+        r.on_add_node(FB, KIND_FBDELAY, 4)
+        pre = [g.input(0), g.input(1), g.node(KIND_MULTIPLY, g.input(0), g.const(0.5)),
+               g.node(KIND_SUM2, g.input(0), g.node(KIND_DELAY, g.input(1), g.const(7.0)))]
+        for l in range(lanes):
+            src = pre[(seed + l) % len(pre)]
+            r.on_add_edge((src[0], DF, src[1], l))
+            r.on_add_edge((DF, FB, int(perm[l]), l))
+        outs = [(FB, l) for l in range(lanes)]
+        mix = outs[0]
+        for o in outs[1:]:
+            mix = g.node(KIND_SUM2, mix, o)
+        g.output(0, mix)
+        g.output(1, g.node(KIND_SUM2, g.node(KIND_DELAY, outs[-1], g.const(33.0)), g.node(KIND_MINIMUM, outs[0], g.const(0.25))))
+        g.output(2, (DF, 0) if tap else outs[lanes // 2])
+
+    outs_all = []
+    for flags in (0, FLAG_NO_CHAIN_FUSION):
+        r = gpu_cls()(flags=flags)
+        build(r)
+        parts, idx = [], 0
+        for m in blocks:
+            parts.append(r.fill_buffer(n_out, m, idx, [row[idx:idx + m] for row in x]))
+            idx += m
+        outs_all.append(np.concatenate(parts, axis=1))
+        fused = r.stats()["chain_launches"] > 0
+        if flags == 0:
+            expect = (not tap) and (seed % 3 != 1 or lanes == 1 or (perm == np.arange(lanes)).all()) and delay.min() >= 32
+            assert fused == expect, (seed, fused, expect)
+    assert_same_bits(outs_all[0], outs_all[1], f"chain seed {seed}")
+    o = OracleRenderer()
+    build(o)
+    ref = o.fill_buffer(n_out, sum(blocks), 0, x)
+    scale = max(np.abs(ref).max(), 1e-3)
+    assert np.abs(outs_all[0].astype(np.float64) - ref).max() <= 1e-4 * scale

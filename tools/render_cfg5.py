@@ -70,7 +70,7 @@ def main():
             "workload": "cfg5: 2^20 partials x %d voices, 192 kHz x %.1f s (BASELINE.json configs[4])" % (n_voices, n_samples / SR),
             "n_gpus": world, "render_s": dt, "setup_s": t_setup, "partial_samples": ps, "partial_samples_per_s": ps / dt,
             "realtime_factor": (n_samples / SR) / dt, "out_bytes": int(out.nbytes), "block": block,
-            "wav": (os.path.relpath(wav_path, ROOT) if wav_path else None), "finite": bool(np.isfinite(out).all()),
+            "wav": (wav_path or None), "finite": bool(np.isfinite(out).all()),
             "peak_abs": float(np.abs(out).max()), "rms_last_second": float(np.sqrt(np.mean(out[0, -192000:] ** 2)))}))
     if world > 1:
         dist.barrier()
