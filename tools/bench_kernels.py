@@ -74,13 +74,13 @@ def case_pure_elementwise(n_slots=64, n=1 << 22):
             "algorithmic_GBs": alg / t["interp_ms"] / 1e6, "peak_GBs": HBM, "frac": alg / t["interp_ms"] / 1e6 / HBM}
 
 
-def case_cfg3(n_voices=4096, n=480000, flags=0):
+def case_cfg3(n_voices=4096, n=480000, flags=0, osc_anchor=0):
     """cfg3: per voice 1-partial oscillator -> biquad -> feedback delay, mixed to one slot.  K4 algorithmic traffic
     (SURVEY.md §8d): 8 B per voice-sample for the fused biquad -> comb chain (read x, write y); the two separate kernels
     (FLAG_NO_CHAIN_FUSION) move 16 B."""
     from banks import detuned_bank
     from filters import build_cfg3_graph
-    r = B200Renderer(flags=flags)
+    r = B200Renderer(flags=flags, osc_anchor=osc_anchor)
     bank, _ = detuned_bank(n_voices, 1, seed=5)
     build_cfg3_graph(r, n_voices, excitation="osc", bank=bank, mix_to_one=True)
     out = torch.empty((1, n), dtype=torch.float32, device="cuda")
@@ -143,7 +143,8 @@ def case_cfg1():
 if __name__ == "__main__":
     which = sys.argv[1:] or ["pure", "elementwise", "cfg3"]
     for w in which:
-        fn = {"pure": case_pure_elementwise, "elementwise": case_elementwise, "cfg3": case_cfg3, "cfg3_unfused": lambda: case_cfg3(flags=8), "cfg1": case_cfg1, "cfg2": case_cfg2, "cfg2_64": lambda: case_cfg2(64), "cfg2_32": lambda: case_cfg2(32)}[w]
+        fn = {"pure": case_pure_elementwise, "elementwise": case_elementwise, "cfg3": case_cfg3, "cfg3_unfused": lambda: case_cfg3(flags=8), "cfg3_L64": lambda: case_cfg3(osc_anchor=64), "cfg3_L32": lambda: case_cfg3(osc_anchor=32),
+          "cfg3_L128": lambda: case_cfg3(osc_anchor=128), "cfg3_L256": lambda: case_cfg3(osc_anchor=256), "cfg1": case_cfg1, "cfg2": case_cfg2, "cfg2_64": lambda: case_cfg2(64), "cfg2_32": lambda: case_cfg2(32)}[w]
         t0 = time.time()
         try:
             res = fn()
