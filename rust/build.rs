@@ -7,8 +7,10 @@ use std::process::Command;
 fn main() {
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let csrc = PathBuf::from("friendship-b200/libfriendship_b200/csrc");
+    // the same translation units as __graft_entry__.py (the C++ Dispatch restatement host/dispatch.cc is not needed:
+    // Dispatch stays in Rust).  interp_device_src.cc is generated from interp_device.inc by __graft_entry__.py.
     let units = [("capi.cu", false), ("renderer.cu", false), ("interp.cu", false), ("flatten.cc", false),
-                 ("osc.cu", true), ("scan.cu", true)];
+                 ("jit.cc", false), ("interp_device_src.cc", false), ("osc.cu", true), ("scan.cu", true)];
     let mut objs = vec![];
     for (src, fmad) in units.iter() {
         let obj = out.join(format!("{}.o", src));
@@ -29,5 +31,6 @@ fn main() {
     println!("cargo:rustc-link-search=native=/usr/local/cuda/lib64");
     println!("cargo:rustc-link-lib=cudart");
     println!("cargo:rustc-link-lib=stdc++");
+    println!("cargo:rustc-link-lib=dl");          // the stage JIT dlopens NVRTC and the driver API
     println!("cargo:rerun-if-changed=friendship-b200/libfriendship_b200/csrc");
 }
