@@ -183,22 +183,25 @@ directform_kernel(const float* __restrict__ coef, const float* __restrict__ pw, 
         const unsigned long long t0 = tb + (unsigned long long)wl * DF_PER_THREAD;
         float x[DF_PER_THREAD + 2];
         if (vec && t0 + DF_PER_THREAD <= hi) {
-            const float4 v0 = *reinterpret_cast<const float4*>(xin.data + (t0 & xin.mask));
-            const float4 v1 = *reinterpret_cast<const float4*>(xin.data + ((t0 + 4) & xin.mask));
-            x[2] = v0.x; x[3] = v0.y; x[4] = v0.z; x[5] = v0.w; x[6] = v1.x; x[7] = v1.y; x[8] = v1.z; x[9] = v1.w;
+#pragma unroll
+            for (int jq = 0; jq < DF_PER_THREAD / 4; jq++) {
+                const float4 v = *reinterpret_cast<const float4*>(xin.data + ((t0 + 4 * jq) & xin.mask));
+                x[2 + 4 * jq] = v.x; x[3 + 4 * jq] = v.y; x[4 + 4 * jq] = v.z; x[5 + 4 * jq] = v.w;
+            }
         } else {
 #pragma unroll
             for (int j = 0; j < DF_PER_THREAD; j++) x[2 + j] = (t0 + j < hi) ? xin.data[(t0 + j) & xin.mask] : 0.0f;
         }
         // two samples of history from the previous thread (lane 0: from the carry)
-        const float px1 = __shfl_up_sync(0xffffffffu, x[9], 1), px2 = __shfl_up_sync(0xffffffffu, x[8], 1);
+        const float px1 = __shfl_up_sync(0xffffffffu, x[DF_PER_THREAD + 1], 1), px2 = __shfl_up_sync(0xffffffffu, x[DF_PER_THREAD], 1);
         x[1] = wl ? px1 : x1c;
         x[0] = wl ? px2 : x2c;
         float yv[DF_PER_THREAD], y1, y2;
         biquad_tile(x, y1c, y2c, [&](int k) { return make_float4(P[k][0], P[k][1], P[k][2], P[k][3]); }, b0, b1, b2, a1, a2, wl, yv, y1, y2);
         if (vec && t0 + DF_PER_THREAD <= hi) {
-            *reinterpret_cast<float4*>(yout.data + (t0 & yout.mask)) = make_float4(yv[0], yv[1], yv[2], yv[3]);
-            *reinterpret_cast<float4*>(yout.data + ((t0 + 4) & yout.mask)) = make_float4(yv[4], yv[5], yv[6], yv[7]);
+#pragma unroll
+            for (int jq = 0; jq < DF_PER_THREAD / 4; jq++)
+                *reinterpret_cast<float4*>(yout.data + ((t0 + 4 * jq) & yout.mask)) = make_float4(yv[4 * jq], yv[4 * jq + 1], yv[4 * jq + 2], yv[4 * jq + 3]);
         } else {
 #pragma unroll
             for (int j = 0; j < DF_PER_THREAD; j++)
@@ -206,7 +209,7 @@ directform_kernel(const float* __restrict__ coef, const float* __restrict__ pw, 
         }
         // carries for the next tile come from the last thread
         y1c = __shfl_sync(0xffffffffu, y1, 31); y2c = __shfl_sync(0xffffffffu, y2, 31);
-        x1c = __shfl_sync(0xffffffffu, x[9], 31); x2c = __shfl_sync(0xffffffffu, x[8], 31);
+        x1c = __shfl_sync(0xffffffffu, x[DF_PER_THREAD + 1], 31); x2c = __shfl_sync(0xffffffffu, x[DF_PER_THREAD], 31);
     }
 }
 
@@ -249,23 +252,32 @@ fbdelay_kernel(const uint32_t* __restrict__ delay, const float* __restrict__ gai
 // ------------------------------------------------------------------------------------------------------------------
 // Fused chain: DirectForm lane l -> FbDelay lane l, when nothing else reads the biquad's output.  8 B per lane-sample of
 // HBM traffic (read x once, write z once) instead of 16 B for the two separate kernels: the biquad's y never leaves the
-// registers.  One warp per lane, tiles of 32 threads x 8 samples:
-//   * the x tile of the NEXT iteration is loaded before this one is computed (the per-tile dependency chain — FIR,
-//     zero-state run, warp scan, re-run, comb — is ~400 cycles and there are only ~28 lanes per SM to hide DRAM behind);
-//   * the biquad is biquad_tile, shared with directform_kernel (same bits);
-//   * the comb z[n] = y[n] + g z[n - D] takes z[n - D] from the output ring for every sample whose tap lies before the
-//     tile (all of them when D >= 256: three aligned 128-bit loads per thread, L2 hits, issued before the biquad), and
-//     for D < 256 resolves the taps inside the tile in ceil(256 / D) phases through a padded per-warp shared-memory
-//     tile.  Same two roundings per sample as fbdelay_kernel: given the same y the bits are identical.
+// SM.  One warp per lane, tiles of 32 threads x DF_PER_THREAD samples:
+//   * tiles travel between HBM and shared memory as quads (4 samples) in coalesced rows — lane i moves quads i, 32 + i,
+//     ... : 512 contiguous bytes per instruction — with cp.async (no registers held): the x tile of the NEXT iteration
+//     and this tile's comb taps are in flight during the biquad;
+//   * the biquad is biquad_tile, shared with directform_kernel (same bits); a thread's own samples are consecutive quads
+//     of the tile, which sits in shared memory skewed (quad q at q + (q >> 3)) so that both this pattern and the
+//     coalesced one are free of bank conflicts; y goes back into the same tile;
+//   * the comb z[n] = y[n] + g z[n - D] runs as a second pass over the tile in the COALESCED mapping, in chunks of 32 E
+//     samples (E = 4, 2 or 1 samples per thread; chunk <= D, so a chunk never reads its own outputs).  All taps come from
+//     one window W[r] = z[tb - D - sh + r], r < tile + 4 (sh = (tb - D) & 3 makes the window 16-byte aligned): the part
+//     before the tile (r < D + sh) is copied from the output ring (L2 hits), and every chunk stores its z into the
+//     window at r + D + sh as well (an aligned quad, since D + sh = tb = 0 mod 4), where later chunks of the same tile
+//     find it.  Short delays therefore cost one barrier per chunk, not a pass per D samples.  With E = 4 the chunk's z
+//     goes straight from registers to the ring (512 contiguous bytes).  Same two roundings per sample as
+//     fbdelay_kernel: given the same y the bits are identical;
 //   * the biquad carry {x[n-1], x[n-2], y[n-1], y[n-2]} at the end of the block is kept in a per-lane state array (the
 //     y ring that directform_kernel re-reads it from does not exist here).
-constexpr int CH_TILE = 32 * DF_PER_THREAD;
-constexpr int CH_ZPAD = CH_TILE + CH_TILE / 8;     // index n -> n + (n >> 3): 8 consecutive samples per lane, no bank conflicts
-constexpr int CH_QUADS = 64 + 8;                   // 64 quads per tile, skewed: position q + (q >> 3)
-constexpr int CH_MIN_DELAY = 32;                   // at most 8 phases per tile; shorter combs use the separate kernels
+constexpr int CH_TILE = 32 * DF_PER_THREAD;        // samples per tile
+constexpr int CH_TQ = CH_TILE / 4;                 // quads per tile
+constexpr int CH_QUADS = CH_TQ + CH_TQ / 8;        // ... skewed: quad q at position q + (q >> 3)
+constexpr int CH_WQ = CH_TQ + 2;                   // tap window: r < tile + 4 used, one more quad is read (and ignored)
+constexpr int CH_TPQ = DF_PER_THREAD / 4;          // quads per thread
+constexpr int CH_MIN_DELAY = 32;                   // shorter combs use the separate kernels
 
-__device__ __forceinline__ int ch_pad(int n) { return n + (n >> 3); }
 __device__ __forceinline__ unsigned ch_qpos(unsigned q) { return q + (q >> 3); }
+__device__ __forceinline__ unsigned ch_fpos(unsigned m) { return (ch_qpos(m >> 2) << 2) | (m & 3u); }   // sample m of a tile
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {   // L2 only (.cg): coherent with this
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n"                         // warp's earlier global stores
@@ -275,185 +287,198 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory"); }
 
+struct __align__(16) ChainWarpSmem {               // what one warp (= one lane of the chain) keeps in shared memory
+    float4 x[2][CH_QUADS];                         // x tiles in flight (double buffered); the current one becomes y, then z
+    float4 w[CH_WQ];                               // tap window of the current tile
+    float4 pw[5];                                  // A^(S * 2^k), k < 5 (read by broadcast)
+    float4 c;                                      // carry between fast tiles {x[tb-1], x[tb-2], y[tb-1], y[tb-2]}
+};
+
+// z of 4 samples: a[0..7] are two consecutive quads of the tap window, the taps are a[SH .. SH + 3]
+template <int SH>
+__device__ __forceinline__ float4 comb_quad(const float4 y, const float4 a0, const float4 a1, float g) {
+    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    return make_float4(__fadd_rn(y.x, __fmul_rn(g, a[SH])), __fadd_rn(y.y, __fmul_rn(g, a[SH + 1])),
+                       __fadd_rn(y.z, __fmul_rn(g, a[SH + 2])), __fadd_rn(y.w, __fmul_rn(g, a[SH + 3])));
+}
+
 __global__ void __launch_bounds__(DF_CTA_THREADS, 7)
 dfcomb_kernel(const float* __restrict__ coef, const float* __restrict__ pw, const uint32_t* __restrict__ delay,
               const float* __restrict__ gain, const BufferDesc* __restrict__ bufdesc, const uint32_t* __restrict__ in_bufs,
               uint32_t first_out_buf, float4* __restrict__ state, unsigned n_lanes, unsigned long long lo, unsigned long long hi) {
     constexpr int NW = DF_CTA_THREADS / 32;
-    __shared__ float s_z[NW][CH_ZPAD];                 // z of the current tile (combs shorter than a tile)
-    __shared__ float4 s_pw[NW][5];                     // A^(8*2^k), k < 5
-    __shared__ float4 s_c[NW];                         // carry between fast tiles
-    // Tiles staged in shared memory as quads (4 samples), quad q at position q + (q >> 3): the copies to and from global
-    // memory are coalesced (lane i moves quads i and 32 + i: 512 contiguous bytes per instruction), a thread's own 8
-    // samples are quads 2 wl, 2 wl + 1, and both patterns are free of bank conflicts with this skew.
-    __shared__ float4 s_x[NW][2][CH_QUADS];            // x tiles in flight (double buffered)
-    __shared__ float4 s_q[NW][CH_QUADS + 4];           // taps of the current tile: 67 quads from (tb - D - sh)
-    __shared__ float4 s_o[NW][CH_QUADS];               // z of the current tile on its way out
+    __shared__ ChainWarpSmem s_all[NW];
     const unsigned wl = threadIdx.x & 31, wi = threadIdx.x >> 5;
     const unsigned lane = blockIdx.x * NW + wi;
     if (lane >= n_lanes) return;                                   // whole warp exits together
+    ChainWarpSmem& S = s_all[wi];
     const BufferDesc xin = bufdesc[in_bufs[lane]];
     const BufferDesc zout = bufdesc[first_out_buf + lane];
     const float b0 = coef[lane * 5 + 0], b1 = coef[lane * 5 + 1], b2 = coef[lane * 5 + 2];
     const float a1 = coef[lane * 5 + 3], a2 = coef[lane * 5 + 4];
     const unsigned Du = delay[lane];
     const float g = gain[lane];
-    if (wl < 5) s_pw[wi][wl] = reinterpret_cast<const float4*>(pw + (size_t)lane * DF_LEVELS * 4)[wl];
+    if (wl < 5) S.pw[wl] = reinterpret_cast<const float4*>(pw + (size_t)lane * DF_LEVELS * 4)[wl];
     __syncwarp();
-    const float4* P = s_pw[wi];                                     // warp-uniform: read by broadcast
-    float* zt = s_z[wi];
+    const float4* P = S.pw;                                         // warp-uniform: read by broadcast
+    auto Pk = [&](int k) { return P[k]; };
 
     float x1c = 0.f, x2c = 0.f, y1c = 0.f, y2c = 0.f;               // every signal is 0 before t = 0
     if (lo > 0) { const float4 st = state[lane]; x1c = st.x; x2c = st.y; y1c = st.z; y2c = st.w; }
 
-    auto Pk = [&](int k) { return P[k]; };
-    // comb: z[n] = y[n] + g z[n - D], two roundings like fbdelay_kernel.  zq[sh + j] = z[t0 + j - D] for the taps that lie
-    // before the tile; the taps inside the tile (D < 256) are resolved in ceil(256 / D) phases through shared memory.
-    auto comb = [&](const float (&yv)[DF_PER_THREAD], const float (&zq)[12], int sh, float (&z)[DF_PER_THREAD]) {
-        switch (sh) {   // warp-uniform
-            case 0:
-#pragma unroll
-                for (int j = 0; j < DF_PER_THREAD; j++) z[j] = __fadd_rn(yv[j], __fmul_rn(g, zq[j]));
-                break;
-            case 1:
-#pragma unroll
-                for (int j = 0; j < DF_PER_THREAD; j++) z[j] = __fadd_rn(yv[j], __fmul_rn(g, zq[j + 1]));
-                break;
-            case 2:
-#pragma unroll
-                for (int j = 0; j < DF_PER_THREAD; j++) z[j] = __fadd_rn(yv[j], __fmul_rn(g, zq[j + 2]));
-                break;
-            default:
-#pragma unroll
-                for (int j = 0; j < DF_PER_THREAD; j++) z[j] = __fadd_rn(yv[j], __fmul_rn(g, zq[j + 3]));
-                break;
-        }
-        if (Du < (unsigned)CH_TILE) {                               // z above is final only for samples n < D of the tile
-            const int Di = (int)Du, nb = (int)wl * DF_PER_THREAD;
-#pragma unroll
-            for (int j = 0; j < DF_PER_THREAD; j++) zt[ch_pad(nb + j)] = z[j];
-            __syncwarp();
-            for (int ph = Di; ph < CH_TILE; ph += Di) {             // samples [ph, ph + D) read z of [ph - D, ph)
-                if (nb + DF_PER_THREAD > ph && nb < ph + Di) {
-#pragma unroll
-                    for (int j = 0; j < DF_PER_THREAD; j++) {
-                        const int n = nb + j;
-                        if (n >= ph && n < ph + Di) {
-                            z[j] = __fadd_rn(yv[j], __fmul_rn(g, zt[ch_pad(n - Di)]));
-                            zt[ch_pad(n)] = z[j];
-                        }
-                    }
-                }
-                __syncwarp();
-            }
-        }
-    };
-    float4* carry = &s_c[wi];                                       // {x[tb-1], x[tb-2], y[tb-1], y[tb-2]} for the fast tiles
-    const int sh = (int)(((long long)lo - (long long)Du) & 3);     // (t0 - D) & 3 of every thread of every tile: tb = lo (mod 4)
+    const unsigned sh = (unsigned)(((long long)lo - (long long)Du) & 3);   // (tb - D) & 3 of every tile: tb = lo (mod 4)
     // Any tile: ragged ends, an unaligned block start, the first D + 4 samples after t = 0, rings beyond 2^32 floats.
+    // Same biquad_tile; the comb walks the tile in chunks of 32 samples (<= D) with its taps straight from the ring.
     auto slow_tile = [&](unsigned long long tb) {
         const unsigned long long t0 = tb + (unsigned long long)wl * DF_PER_THREAD;
-        float x[DF_PER_THREAD + 2], yv[DF_PER_THREAD], zq[12], z[DF_PER_THREAD], y1, y2;
-        const long long Bq = (long long)t0 - (long long)Du - sh;
+        float* tf = reinterpret_cast<float*>(S.x[0]);
+        {
+            float x[DF_PER_THREAD + 2], yv[DF_PER_THREAD], y1, y2;
 #pragma unroll
-        for (int k = 0; k < 12; k++) {
-            const long long q = Bq + k;
-            zq[k] = (q >= 0 && q < (long long)tb) ? __ldcg(zout.data + ((unsigned long long)q & zout.mask)) : 0.0f;
-        }
+            for (int j = 0; j < DF_PER_THREAD; j++) x[2 + j] = (t0 + j < hi) ? xin.data[(t0 + j) & xin.mask] : 0.0f;
+            const float px1 = __shfl_up_sync(0xffffffffu, x[DF_PER_THREAD + 1], 1), px2 = __shfl_up_sync(0xffffffffu, x[DF_PER_THREAD], 1);
+            x[1] = wl ? px1 : x1c;
+            x[0] = wl ? px2 : x2c;
+            biquad_tile(x, y1c, y2c, Pk, b0, b1, b2, a1, a2, wl, yv, y1, y2);
+            if (tb + CH_TILE >= hi) {                               // the block's last two samples: carry of the next launch
 #pragma unroll
-        for (int j = 0; j < DF_PER_THREAD; j++) x[2 + j] = (t0 + j < hi) ? xin.data[(t0 + j) & xin.mask] : 0.0f;
-        const float px1 = __shfl_up_sync(0xffffffffu, x[9], 1), px2 = __shfl_up_sync(0xffffffffu, x[8], 1);
-        x[1] = wl ? px1 : x1c;
-        x[0] = wl ? px2 : x2c;
-        biquad_tile(x, y1c, y2c, Pk, b0, b1, b2, a1, a2, wl, yv, y1, y2);
-        if (tb + CH_TILE >= hi) {                                   // the block's last two samples: carry of the next launch
-#pragma unroll
-            for (int j = 0; j < DF_PER_THREAD; j++) {
-                if (t0 + j + 1 == hi) { state[lane].x = x[2 + j]; state[lane].z = yv[j]; }
-                if (t0 + j + 2 == hi) { state[lane].y = x[2 + j]; state[lane].w = yv[j]; }
+                for (int j = 0; j < DF_PER_THREAD; j++) {
+                    if (t0 + j + 1 == hi) { state[lane].x = x[2 + j]; state[lane].z = yv[j]; }
+                    if (t0 + j + 2 == hi) { state[lane].y = x[2 + j]; state[lane].w = yv[j]; }
+                }
+                if (wl == 0 && tb + 1 == hi) { state[lane].y = x1c; state[lane].w = y1c; }   // hi - 2 lies before the tile
             }
-            if (wl == 0 && tb + 1 == hi) { state[lane].y = x1c; state[lane].w = y1c; }   // hi - 2 lies before the tile
-        }
-        comb(yv, zq, sh, z);
 #pragma unroll
-        for (int j = 0; j < DF_PER_THREAD; j++)
-            if (t0 + j < hi) zout.data[(t0 + j) & zout.mask] = z[j];
-        __syncwarp();                                               // the next tile's taps read this tile's stores
-        y1c = __shfl_sync(0xffffffffu, y1, 31); y2c = __shfl_sync(0xffffffffu, y2, 31);
-        x1c = __shfl_sync(0xffffffffu, x[9], 31); x2c = __shfl_sync(0xffffffffu, x[8], 31);
+            for (int j = 0; j < DF_PER_THREAD; j++) tf[ch_fpos(wl * DF_PER_THREAD + j)] = yv[j];
+            y1c = __shfl_sync(0xffffffffu, y1, 31); y2c = __shfl_sync(0xffffffffu, y2, 31);
+            x1c = __shfl_sync(0xffffffffu, x[DF_PER_THREAD + 1], 31); x2c = __shfl_sync(0xffffffffu, x[DF_PER_THREAD], 31);
+        }
+        __syncwarp();
+        for (unsigned m = wl; m < (unsigned)CH_TILE; m += 32) {
+            const unsigned long long t = tb + m;
+            if (t < hi) {
+                float tap = 0.0f;
+                if (m >= Du) tap = tf[ch_fpos(m - Du)];
+                else if (t >= Du) tap = __ldcg(zout.data + ((t - Du) & zout.mask));
+                const float z = __fadd_rn(tf[ch_fpos(m)], __fmul_rn(g, tap));
+                tf[ch_fpos(m)] = z;
+                zout.data[t & zout.mask] = z;
+            }
+            __syncwarp();                                           // the next chunk (and the next tile's taps) read these
+        }
     };
 
     const bool can_fast = (((xin.mask | zout.mask) >> 32) == 0) && (lo % 4 == 0);
     unsigned long long tb = lo;
     while (tb < hi && !(can_fast && tb >= (unsigned long long)Du + 4 && tb + CH_TILE <= hi)) { slow_tile(tb); tb += CH_TILE; }
     if (tb < hi) {
-        // Fast tiles: full, 16-byte aligned, every tap at a time >= 0, 32-bit ring indices.  Global -> shared copies
-        // (cp.async, no registers held): the x tile of the NEXT iteration and this tile's taps are in flight during the
-        // biquad; every thread reads back only what it copied itself, so no barrier is needed for them.
+        // Fast tiles: full, 16-byte aligned, every tap at a time >= 0, 32-bit ring indices.
         const unsigned long long n_fast = (hi - tb) / CH_TILE;
         const unsigned xm = (unsigned)xin.mask, zm = (unsigned)zout.mask;
         unsigned xb = (unsigned)(tb & xin.mask);                                // ring index of the tile's first sample
         unsigned zb = (unsigned)(tb & zout.mask);
-        unsigned qb = (unsigned)((tb - Du - (unsigned)sh) & zout.mask);         // ... of the first tap quad (16-byte aligned)
-        float4 (*sx)[CH_QUADS] = s_x[wi];
-        float4* sq = s_q[wi];
-        float4* so = s_o[wi];
-        const unsigned pa = ch_qpos(wl), pb = ch_qpos(32u + wl);               // this lane's two quads of a coalesced copy
-        const unsigned p0 = ch_qpos(2u * wl), p1 = ch_qpos(2u * wl + 1u), p2 = ch_qpos(2u * wl + 2u);   // its own samples
-        // history (x[t0-2], x[t0-1]) = the quad before this thread's own; lane 0 reads the carry slot instead
-        const unsigned ph = ch_qpos(wl ? 2u * wl - 1u : 0u);
-        if (wl == 0) *carry = make_float4(x1c, x2c, y1c, y2c);
-        cp_async16(&sx[0][pa], xin.data + ((xb + 4u * wl) & xm));
-        cp_async16(&sx[0][pb], xin.data + ((xb + 128u + 4u * wl) & xm));
+        unsigned qb = (unsigned)((tb - Du - sh) & zout.mask);                   // ... of the window's first quad
+        const unsigned dq = (Du + sh) >> 2;                                     // window quad of the tile's first sample
+        float* wf = reinterpret_cast<float*>(S.w);
+        if (wl == 0) S.c = make_float4(x1c, x2c, y1c, y2c);
+#pragma unroll
+        for (int c = 0; c < CH_TQ / 32; c++)
+            cp_async16(&S.x[0][ch_qpos(32u * c + wl)], xin.data + ((xb + 128u * c + 4u * wl) & xm));
         cp_async_commit();
         for (unsigned long long k = 0; k < n_fast; k++) {
             const unsigned cur = (unsigned)k & 1u;
-            cp_async16(&sq[pa], zout.data + ((qb + 4u * wl) & zm));
-            cp_async16(&sq[pb], zout.data + ((qb + 128u + 4u * wl) & zm));
-            if (wl < 3) cp_async16(&sq[ch_qpos(64u + wl)], zout.data + ((qb + 256u + 4u * wl) & zm));
+            float4* xs = S.x[cur];
+#pragma unroll
+            for (int c = 0; c < CH_TQ / 32; c++)
+                cp_async16(&S.w[32u * c + wl], zout.data + ((qb + 128u * c + 4u * wl) & zm));
+            if (wl == 0) cp_async16(&S.w[CH_TQ], zout.data + ((qb + (unsigned)CH_TILE) & zm));
             cp_async_commit();                                      // group "taps of tile k"
             xb = (xb + CH_TILE) & xm;
             if (k + 1 < n_fast) {
-                cp_async16(&sx[cur ^ 1][pa], xin.data + ((xb + 4u * wl) & xm));
-                cp_async16(&sx[cur ^ 1][pb], xin.data + ((xb + 128u + 4u * wl) & xm));
+#pragma unroll
+                for (int c = 0; c < CH_TQ / 32; c++)
+                    cp_async16(&S.x[cur ^ 1][ch_qpos(32u * c + wl)], xin.data + ((xb + 128u * c + 4u * wl) & xm));
             }
             cp_async_commit();                                      // group "x of tile k + 1" (possibly empty)
             cp_async_wait<2>();                                     // x of tile k has landed (every lane's share of it)
             __syncwarp();
-            float x[DF_PER_THREAD + 2], yv[DF_PER_THREAD], y1, y2;
-            const float4 cr = *carry;                               // broadcast read
             {
-                const float4 v0 = sx[cur][p0], v1 = sx[cur][p1], vh = sx[cur][ph];
-                x[2] = v0.x; x[3] = v0.y; x[4] = v0.z; x[5] = v0.w; x[6] = v1.x; x[7] = v1.y; x[8] = v1.z; x[9] = v1.w;
+                float x[DF_PER_THREAD + 2], yv[DF_PER_THREAD], y1, y2;
+                const float4 cr = S.c;                              // broadcast read
+#pragma unroll
+                for (int jq = 0; jq < CH_TPQ; jq++) {
+                    const float4 v = xs[ch_qpos(CH_TPQ * wl + jq)];
+                    x[2 + 4 * jq] = v.x; x[3 + 4 * jq] = v.y; x[4 + 4 * jq] = v.z; x[5 + 4 * jq] = v.w;
+                }
+                // history (x[t0-2], x[t0-1]) = the quad before this thread's own; lane 0 reads the carry instead
+                const float4 vh = xs[ch_qpos(wl ? CH_TPQ * wl - 1u : 0u)];
                 x[0] = wl ? vh.z : cr.y;
                 x[1] = wl ? vh.w : cr.x;
-            }
-            biquad_tile(x, cr.z, cr.w, Pk, b0, b1, b2, a1, a2, wl, yv, y1, y2);
-            if (wl == 31) {
-                const float4 c = make_float4(x[9], x[8], y1, y2);
-                *carry = c;                                         // read by everyone after the barriers below
-                if (k + 1 == n_fast && tb + CH_TILE == hi) state[lane] = c;
+                biquad_tile(x, cr.z, cr.w, Pk, b0, b1, b2, a1, a2, wl, yv, y1, y2);
+                __syncwarp();                                       // everyone has read its x (and the carry): y may overwrite them
+                if (wl == 31) {
+                    const float4 c = make_float4(x[DF_PER_THREAD + 1], x[DF_PER_THREAD], y1, y2);
+                    S.c = c;
+                    if (k + 1 == n_fast && tb + CH_TILE == hi) state[lane] = c;
+                }
+#pragma unroll
+                for (int jq = 0; jq < CH_TPQ; jq++)
+                    xs[ch_qpos(CH_TPQ * wl + jq)] = make_float4(yv[4 * jq], yv[4 * jq + 1], yv[4 * jq + 2], yv[4 * jq + 3]);
             }
             cp_async_wait<1>();                                     // the taps have landed
-            __syncwarp();
-            float zq[12], z[DF_PER_THREAD];
-            {
-                const float4 v0 = sq[p0], v1 = sq[p1], v2 = sq[p2];
-                zq[0] = v0.x; zq[1] = v0.y; zq[2] = v0.z; zq[3] = v0.w; zq[4] = v1.x; zq[5] = v1.y; zq[6] = v1.z; zq[7] = v1.w;
-                zq[8] = v2.x; zq[9] = v2.y; zq[10] = v2.z; zq[11] = v2.w;
+            __syncwarp();                                           // ... and y is where the coalesced mapping finds it
+            if (Du >= 128u) {                                       // warp-uniform
+                const bool inside = Du < (unsigned)CH_TILE;         // some taps are outputs of this very tile
+#pragma unroll
+                for (int c = 0; c < CH_TQ / 32; c++) {
+                    const unsigned q = 32u * c + wl;
+                    const float4 t0 = S.w[q], t1 = S.w[q + 1], y = xs[ch_qpos(q)];
+                    float4 z;
+                    switch (sh) {                                   // warp-uniform
+                        case 0: z = comb_quad<0>(y, t0, t1, g); break;
+                        case 1: z = comb_quad<1>(y, t0, t1, g); break;
+                        case 2: z = comb_quad<2>(y, t0, t1, g); break;
+                        default: z = comb_quad<3>(y, t0, t1, g); break;
+                    }
+                    *reinterpret_cast<float4*>(zout.data + ((zb + 4u * q) & zm)) = z;
+                    if (inside && c + 1 < CH_TQ / 32) {
+                        if (q + dq <= (unsigned)CH_TQ) S.w[q + dq] = z;
+                        __syncwarp();
+                    }
+                }
+            } else {
+                float* tf = reinterpret_cast<float*>(xs);
+                if (Du >= 64u) {                                    // chunks of 64 samples, two per thread
+                    for (unsigned m = 2u * wl; m < (unsigned)CH_TILE; m += 64u) {
+                        const float2 y = *reinterpret_cast<const float2*>(tf + ch_fpos(m));
+                        const float z0 = __fadd_rn(y.x, __fmul_rn(g, wf[m + sh])), z1 = __fadd_rn(y.y, __fmul_rn(g, wf[m + sh + 1u]));
+                        *reinterpret_cast<float2*>(tf + ch_fpos(m)) = make_float2(z0, z1);
+                        const unsigned r = m + Du + sh;
+                        if (r < (unsigned)CH_TILE + 4u) *reinterpret_cast<float2*>(wf + r) = make_float2(z0, z1);
+                        __syncwarp();
+                    }
+                } else {                                            // chunks of 32 samples (D >= 32)
+                    for (unsigned m = wl; m < (unsigned)CH_TILE; m += 32u) {
+                        const float z = __fadd_rn(tf[ch_fpos(m)], __fmul_rn(g, wf[m + sh]));
+                        tf[ch_fpos(m)] = z;
+                        const unsigned r = m + Du + sh;
+                        if (r < (unsigned)CH_TILE + 4u) wf[r] = z;
+                        __syncwarp();
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < CH_TQ / 32; c++) {
+                    const unsigned q = 32u * c + wl;
+                    *reinterpret_cast<float4*>(zout.data + ((zb + 4u * q) & zm)) = xs[ch_qpos(q)];
+                }
             }
-            comb(yv, zq, sh, z);
-            so[p0] = make_float4(z[0], z[1], z[2], z[3]);
-            so[p1] = make_float4(z[4], z[5], z[6], z[7]);
-            __syncwarp();
-            *reinterpret_cast<float4*>(zout.data + ((zb + 4u * wl) & zm)) = so[pa];
-            *reinterpret_cast<float4*>(zout.data + ((zb + 128u + 4u * wl) & zm)) = so[pb];
             __syncwarp();                                           // the next tile's taps read these stores
             qb += CH_TILE; zb += CH_TILE;
             tb += CH_TILE;
         }
-        { const float4 c = *carry; x1c = c.x; x2c = c.y; y1c = c.z; y2c = c.w; }   // for the ragged tail, if any
+        { const float4 c = S.c; x1c = c.x; x2c = c.y; y1c = c.z; y2c = c.w; }   // for the ragged tail, if any
         cp_async_wait<0>();
+        __syncwarp();
         while (tb < hi) { slow_tile(tb); tb += CH_TILE; }
     }
 }
