@@ -277,7 +277,7 @@ constexpr int CH_TPQ = DF_PER_THREAD / 4;          // quads per thread
 constexpr int CH_MIN_DELAY = 32;                   // shorter combs use the separate kernels
 
 __device__ __forceinline__ unsigned ch_qpos(unsigned q) { return q + (q >> 3); }
-__device__ __forceinline__ unsigned ch_fpos(unsigned m) { return (ch_qpos(m >> 2) << 2) | (m & 3u); }   // sample m of a tile
+__device__ __forceinline__ unsigned ch_fpos(unsigned m) { return m + ((m >> 5) << 2); }   // sample m of a tile (float index)
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {   // L2 only (.cg): coherent with this
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n"                         // warp's earlier global stores
@@ -300,6 +300,36 @@ __device__ __forceinline__ float4 comb_quad(const float4 y, const float4 a0, con
     const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
     return make_float4(__fadd_rn(y.x, __fmul_rn(g, a[SH])), __fadd_rn(y.y, __fmul_rn(g, a[SH + 1])),
                        __fadd_rn(y.z, __fmul_rn(g, a[SH + 2])), __fadd_rn(y.w, __fmul_rn(g, a[SH + 3])));
+}
+
+// Combs shorter than 128 samples: chunks of 32 E samples (<= D), E consecutive samples per thread.  y is read ahead of
+// the chunk loop, z goes straight to the ring (32 E contiguous floats per instruction) and into the tap window for the
+// chunks that follow; one barrier per chunk.
+template <int E>
+__device__ __forceinline__ void comb_small(const float* tf, float* wf, float* zdata, unsigned zb, unsigned zm, unsigned Du,
+                                           unsigned sh, float g, unsigned wl) {
+    constexpr int NC = CH_TILE / (32 * E);
+    float y[NC][E];
+#pragma unroll
+    for (int c = 0; c < NC; c++)
+#pragma unroll
+        for (int e = 0; e < E; e++) y[c][e] = tf[ch_fpos(32u * E * c + E * wl + e)];
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        const unsigned m = 32u * E * c + E * wl;
+        float z[E];
+#pragma unroll
+        for (int e = 0; e < E; e++) z[e] = __fadd_rn(y[c][e], __fmul_rn(g, wf[m + sh + e]));
+        const unsigned r = m + Du + sh;                             // a multiple of E: D + sh = 0 (mod 4)
+        if (E == 2) {
+            *reinterpret_cast<float2*>(zdata + ((zb + m) & zm)) = make_float2(z[0], z[E - 1]);
+            if (c + 1 < NC && r < (unsigned)CH_TILE + 4u) *reinterpret_cast<float2*>(wf + r) = make_float2(z[0], z[E - 1]);
+        } else {
+            zdata[(zb + m) & zm] = z[0];
+            if (c + 1 < NC && r < (unsigned)CH_TILE + 4u) wf[r] = z[0];
+        }
+        if (c + 1 < NC) __syncwarp();
+    }
 }
 
 __global__ void __launch_bounds__(DF_CTA_THREADS, 7)
@@ -411,9 +441,9 @@ dfcomb_kernel(const float* __restrict__ coef, const float* __restrict__ pw, cons
                     x[2 + 4 * jq] = v.x; x[3 + 4 * jq] = v.y; x[4 + 4 * jq] = v.z; x[5 + 4 * jq] = v.w;
                 }
                 // history (x[t0-2], x[t0-1]) = the quad before this thread's own; lane 0 reads the carry instead
-                const float4 vh = xs[ch_qpos(wl ? CH_TPQ * wl - 1u : 0u)];
-                x[0] = wl ? vh.z : cr.y;
-                x[1] = wl ? vh.w : cr.x;
+                const float2 vh = reinterpret_cast<const float2*>(xs + ch_qpos(wl ? CH_TPQ * wl - 1u : 0u))[1];
+                x[0] = wl ? vh.x : cr.y;
+                x[1] = wl ? vh.y : cr.x;
                 biquad_tile(x, cr.z, cr.w, Pk, b0, b1, b2, a1, a2, wl, yv, y1, y2);
                 __syncwarp();                                       // everyone has read its x (and the carry): y may overwrite them
                 if (wl == 31) {
@@ -432,7 +462,9 @@ dfcomb_kernel(const float* __restrict__ coef, const float* __restrict__ pw, cons
 #pragma unroll
                 for (int c = 0; c < CH_TQ / 32; c++) {
                     const unsigned q = 32u * c + wl;
-                    const float4 t0 = S.w[q], t1 = S.w[q + 1], y = xs[ch_qpos(q)];
+                    const float4 t0 = S.w[q], y = xs[ch_qpos(q)];
+                    float4 t1 = t0;
+                    if (sh) t1 = S.w[q + 1];
                     float4 z;
                     switch (sh) {                                   // warp-uniform
                         case 0: z = comb_quad<0>(y, t0, t1, g); break;
@@ -446,31 +478,10 @@ dfcomb_kernel(const float* __restrict__ coef, const float* __restrict__ pw, cons
                         __syncwarp();
                     }
                 }
+            } else if (Du >= 64u) {
+                comb_small<2>(reinterpret_cast<const float*>(xs), wf, zout.data, zb, zm, Du, sh, g, wl);
             } else {
-                float* tf = reinterpret_cast<float*>(xs);
-                if (Du >= 64u) {                                    // chunks of 64 samples, two per thread
-                    for (unsigned m = 2u * wl; m < (unsigned)CH_TILE; m += 64u) {
-                        const float2 y = *reinterpret_cast<const float2*>(tf + ch_fpos(m));
-                        const float z0 = __fadd_rn(y.x, __fmul_rn(g, wf[m + sh])), z1 = __fadd_rn(y.y, __fmul_rn(g, wf[m + sh + 1u]));
-                        *reinterpret_cast<float2*>(tf + ch_fpos(m)) = make_float2(z0, z1);
-                        const unsigned r = m + Du + sh;
-                        if (r < (unsigned)CH_TILE + 4u) *reinterpret_cast<float2*>(wf + r) = make_float2(z0, z1);
-                        __syncwarp();
-                    }
-                } else {                                            // chunks of 32 samples (D >= 32)
-                    for (unsigned m = wl; m < (unsigned)CH_TILE; m += 32u) {
-                        const float z = __fadd_rn(tf[ch_fpos(m)], __fmul_rn(g, wf[m + sh]));
-                        tf[ch_fpos(m)] = z;
-                        const unsigned r = m + Du + sh;
-                        if (r < (unsigned)CH_TILE + 4u) wf[r] = z;
-                        __syncwarp();
-                    }
-                }
-#pragma unroll
-                for (int c = 0; c < CH_TQ / 32; c++) {
-                    const unsigned q = 32u * c + wl;
-                    *reinterpret_cast<float4*>(zout.data + ((zb + 4u * q) & zm)) = xs[ch_qpos(q)];
-                }
+                comb_small<1>(reinterpret_cast<const float*>(xs), wf, zout.data, zb, zm, Du, sh, g, wl);
             }
             __syncwarp();                                           // the next tile's taps read these stores
             qb += CH_TILE; zb += CH_TILE;

@@ -23,6 +23,8 @@ def variant(name):
         v = np.arange(n_voices)
         if name == "ge256":
             delay = (300 + v % 700).astype(np.uint32)
+        elif name == "ge128":
+            delay = (128 + v % 872).astype(np.uint32)
         elif name == "ge512":
             delay = (600 + v % 400).astype(np.uint32)
         elif name == "shuffled":
