@@ -167,3 +167,47 @@ def test_redefine_bank_replaces_parameters():
     g.define_oscbank(7, **bank_a)
     again = g.fill_buffer(1, 2000, 0)
     assert_same_bits(again, first, "redefine")
+
+
+def one_partial_bank(n_voices, seed=11, sr=48000.0):
+    """One partial per voice (cfg3's exciters): both resonator classes, DC and near-Nyquist, with and without attack
+    ramp and decay, and two silent voices (no partials)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    counts = np.ones(n_voices, dtype=np.uint64)
+    counts[[3, n_voices - 2]] = 0
+    P = int(counts.sum())
+    f = rng.uniform(15.0, 23900.0, P)
+    f[:4] = [0.0, 11999.5, 12000.5, 23999.0]
+    attack = rng.uniform(0.0, 400.0, P).astype(np.float32)
+    attack[::5] = 0.0
+    tau = rng.uniform(2000.0, 90000.0, P).astype(np.float32)
+    tau[::7] = np.inf
+    return dict(sample_rate=sr, voice_offsets=np.concatenate([[0], np.cumsum(counts)]).astype(np.uint64), freq_hz=f,
+                amp=rng.uniform(0.1, 1.0, P).astype(np.float32), phase=rng.uniform(-3, 3, P).astype(np.float32),
+                attack=attack, tau=tau)
+
+
+@pytest.mark.parametrize("anchor", [0, 48, 64])
+def test_one_partial_voices_kernel_vs_fp64_and_block_invariance(anchor):
+    """The dedicated kernel for banks of one-partial voices (osc_one_kernel): fp64 oracle at t = 0 (attack ramps) and deep
+    into the render, an unaligned window, segment lengths that are not a multiple of the 32-sample hand-over (48), and
+    ragged block cuts giving the bits of one call."""
+    from libfriendship_b200 import B200Renderer, KIND_OSCBANK
+    nv = 70
+    bank = one_partial_bank(nv)
+    for idx, n in ((0, 3000), (1_000_003, 2049)):
+        gpu = render_bank(B200Renderer, bank, n, idx, n_voices=nv, osc_anchor=anchor)
+        ref = render_bank(OracleRenderer, bank, n, idx, n_voices=nv)
+        assert np.abs(gpu.astype(np.float64) - ref).max() <= TOL * full_scale(bank), (anchor, idx)
+        assert (gpu[3] == 0).all() and (gpu[nv - 2] == 0).all()
+    whole = render_bank(B200Renderer, bank, 4000, 0, n_voices=nv, osc_anchor=anchor)
+    r = B200Renderer(osc_anchor=anchor)
+    r.define_oscbank(5, **bank)
+    r.on_add_node(1, KIND_OSCBANK, 5)
+    for v in range(nv):
+        r.on_add_edge((1, 0, v, v))
+    parts, idx = [], 0
+    for n in (1, 31, 32, 33, 255, 1, 1000, 2647):
+        parts.append(r.fill_buffer(nv, n, idx))
+        idx += n
+    assert_same_bits(np.concatenate(parts, axis=1), whole, "one-partial voices, block invariance")
