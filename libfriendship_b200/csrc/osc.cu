@@ -32,6 +32,7 @@
 //  * Voices with many partials are split into partial ranges over CTAs (fixed per bank: the summation order never
 //    depends on the block size); the range planes are summed in fixed order by osc_reduce_kernel.
 #include "osc.cuh"
+#include "osc_one.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -585,83 +586,59 @@ __global__ void __launch_bounds__(OSC_THREADS) osc_kernel(OscLaunch p) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Banks of ONE-partial voices, unsplit (one exciter per voice: BASELINE configs[2]).  Same segments, same anchor, same
-// recurrence and therefore the same bits as osc_kernel<1, ATTACK>, but nothing of the multi-partial machinery: no
-// accumulator columns (there is nothing to accumulate), no record staging, no sign-flip passes.  The kernel is bound by
-// its ring writes; osc_kernel<1> spent 76% of its warp time waiting for the 48-byte record at the head of each CTA with
-// only 12 one-warp CTAs per SM (17 KB of accumulator columns each).  Here a thread hands its samples over 32 at a
-// time through a 4.5 KB transposition tile (32 CTAs per SM) and the warp writes them out as 128-byte rows.
-constexpr int ONE_SUB = 32;                  // samples per thread between write-outs
+// Banks of ONE-partial voices, unsplit (one exciter per voice: BASELINE configs[2]).  Nothing of the multi-partial
+// machinery: no accumulator columns (there is nothing to accumulate), no record staging, no sign-flip passes, no
+// separate attack kernel.  The oscillator is osc_one_group8 (osc_one.cuh): groups of 8 samples anchored at absolute
+// multiples of 8 — the very function the fused exciter -> biquad -> comb kernel (scan.cu) calls, so the two paths
+// agree bit for bit.  The kernel is bound by its ring writes (osc_kernel<1> spent 76% of its warp time waiting for the
+// 48-byte record at the head of each CTA, with only 12 one-warp CTAs per SM: 17 KB of accumulator columns each): one
+// warp per 4,096-sample span of a voice; a thread hands over 32 samples at a time through a 4.5 KB transposition tile
+// (32 CTAs per SM) and the warp writes them out as 128-byte rows.
+constexpr int ONE_SUB = 32;                  // samples per thread between write-outs (4 groups of 8)
 constexpr int ONE_ROW = ONE_SUB + 4;         // tile row stride in floats: 128-bit accesses by row and by column are conflict-free
+constexpr int ONE_ROUNDS = 4;                // write-outs per CTA
+constexpr int ONE_SPAN = OSC_THREADS * ONE_SUB * ONE_ROUNDS;   // samples per CTA, aligned to absolute multiples of it
 
-template <bool ATTACK>
-__global__ void __launch_bounds__(OSC_THREADS) osc_one_kernel(OscLaunch p) {
+__global__ void __launch_bounds__(OSC_THREADS) osc_one_kernel(OscOneSrc src, const BufferDesc* __restrict__ bufdesc, uint32_t first_buf,
+                                                              unsigned long long span0, unsigned long long lo, unsigned long long hi) {
     __shared__ __align__(16) float s_t[OSC_THREADS * ONE_ROW];
     const unsigned lane = threadIdx.x, v = blockIdx.y;
-    const unsigned seg_base = blockIdx.x * OSC_THREADS;
-    const int L = p.L;
-    const unsigned long long n0 = (p.seg0 + seg_base + lane) * (unsigned long long)L;
-    const float nf = (float)n0;
-    float x = 0.f, y = 0.f, a = 0.f, b = 0.f, cm1 = 0.f, invA = 0.f;
-    bool class1 = false;
-    if (p.n_grp[v]) {                                        // warp-uniform; a voice without partials is silent
-        const size_t r = p.grp_begin[v];                     // K = 1: one record per group
-        const float4 h = __ldg(p.hot + r);
-        const float4 an = __ldg(p.anc + r);
-        const uint4 ph = __ldg(p.ph + r);
-        a = h.x; b = h.y; cm1 = h.z; invA = an.w;
-        class1 = p.n_grp0[v] == 0;
-        // the anchor of osc_group, operation for operation
-        const unsigned n0_lo = (unsigned)n0, n0_hi = (unsigned)(n0 >> 32);
-        const unsigned turns_hi = __umulhi(ph.x, n0_lo) + ph.y * n0_lo + ph.x * n0_hi + ph.w;
-        const float th = (float)(int)turns_hi * 1.4629180792671596e-9f;
-        float sn, cs;
-        __sincosf(th, &sn, &cs);
-        float e;
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-an.z * nf));
-        e *= an.y;
-        y = e * sn;
-        x = e * fmaf(h.w, sn, an.x * cs);
-    }
-    const BufferDesc bd = p.bufdesc[p.first_buf + v];
-    const unsigned n_live = min((unsigned)OSC_THREADS, p.nseg > seg_base ? p.nseg - seg_base : 0u);
-    const unsigned long long cta_n0 = (p.seg0 + seg_base) * (unsigned long long)L;
-    for (int s0 = 0; s0 < L; s0 += ONE_SUB) {
-        const int ns = min(ONE_SUB, L - s0);                 // L is a multiple of 16: 32, or 16 at the end
+    const OscOneVoice o = osc_one_load(src, v);
+    const BufferDesc bd = bufdesc[first_buf + v];
+    const unsigned long long base = (span0 + blockIdx.x) * (unsigned long long)ONE_SPAN;
+    for (int rd = 0; rd < ONE_ROUNDS; rd++) {
+        const unsigned long long rb = base + (unsigned long long)rd * (OSC_THREADS * ONE_SUB);   // this round: 1,024 samples
+        if (rb >= hi || rb + OSC_THREADS * ONE_SUB <= lo) continue;                               // warp-uniform
 #pragma unroll
-        for (int q = 0; q < ONE_SUB / 4; q++) {
-            if (4 * q < ns) {
-                float r[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    // osc_group adds y to a zero accumulator (attack: fmaf(ramp, y, 0)); a class-1 partial runs in the
-                    // alternating-sign domain and the odd samples are flipped back on the way out
-                    r[u] = ATTACK ? fminf((nf + (float)(s0 + 4 * q + u)) * invA, 1.0f) * y : y;
-                    x = fmaf(-a, y, x);
-                    const float t = fmaf(cm1, y, y);
-                    y = fmaf(b, x, t);
-                }
-                if (class1) { r[1] = -r[1]; r[3] = -r[3]; }
-                *reinterpret_cast<float4*>(s_t + lane * ONE_ROW + 4 * q) = make_float4(r[0], r[1], r[2], r[3]);
-            }
+        for (int g = 0; g < ONE_SUB / 8; g++) {
+            float r[8];
+            osc_one_group8(o.h, o.an, o.ph, o.flags, rb + (unsigned long long)lane * ONE_SUB + 8u * g, src.max_attack, r);
+            *reinterpret_cast<float4*>(s_t + lane * ONE_ROW + 8 * g) = make_float4(r[0], r[1], r[2], r[3]);
+            *reinterpret_cast<float4*>(s_t + lane * ONE_ROW + 8 * g + 4) = make_float4(r[4], r[5], r[6], r[7]);
         }
         __syncwarp();
-        const unsigned sq = ns == ONE_SUB ? 3u : 2u;         // log2(quads per row)
-        for (unsigned i = lane; i < (n_live << sq); i += OSC_THREADS) {
-            const unsigned row = i >> sq, qq = i & ((1u << sq) - 1u);
-            const float4 o = *reinterpret_cast<const float4*>(s_t + row * ONE_ROW + 4 * qq);
-            const unsigned long long t = cta_n0 + (unsigned long long)row * L + s0 + 4 * qq;
-            if (t >= p.lo && t + 4 <= p.hi) {
-                *reinterpret_cast<float4*>(bd.data + (t & bd.mask)) = o;
+#pragma unroll
+        for (int it = 0; it < ONE_SUB / 4; it++) {                   // 8 quads per row: 4 rows per instruction
+            const unsigned row = 4u * it + (lane >> 3), qq = lane & 7u;
+            const float4 q = *reinterpret_cast<const float4*>(s_t + row * ONE_ROW + 4 * qq);
+            const unsigned long long t = rb + (unsigned long long)row * ONE_SUB + 4 * qq;
+            if (t >= lo && t + 4 <= hi) {
+                *reinterpret_cast<float4*>(bd.data + (t & bd.mask)) = q;
             } else {
-                const float rr[4] = {o.x, o.y, o.z, o.w};
+                const float rr[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
                 for (int u = 0; u < 4; u++)
-                    if (t + u >= p.lo && t + u < p.hi) bd.data[(t + u) & bd.mask] = rr[u];
+                    if (t + u >= lo && t + u < hi) bd.data[(t + u) & bd.mask] = rr[u];
             }
         }
         __syncwarp();
     }
+}
+
+bool osc_one_source(const OscBankDev& b, OscOneSrc* out) {
+    if (b.K != OSC_K_ONE || b.split != 1) return false;
+    if (out) *out = OscOneSrc{b.d_hot, b.d_anc, b.d_ph, b.d_grp_begin, b.d_n_grp0, b.d_n_grp, b.max_attack};
+    return true;
 }
 
 // sums the split planes in fixed order into the voices' rings
@@ -724,6 +701,13 @@ cudaError_t launch_osc(const OscBankDev& b, const BufferDesc* d_bufdesc, uint32_
 
 static cudaError_t launch_osc_range(const OscBankDev& b, const BufferDesc* d_bufdesc, uint32_t first_buf, uint64_t lo, uint64_t hi,
                                     uint32_t anchor, int sm_count, cudaStream_t stream, uint64_t* n_launches) {
+    OscOneSrc one;
+    if (osc_one_source(b, &one)) {                           // one-partial voices: their own kernel, anchors every 8 samples
+        const uint64_t span0 = lo / ONE_SPAN, n_span = (hi + ONE_SPAN - 1) / ONE_SPAN - span0;
+        osc_one_kernel<<<dim3((unsigned)n_span, b.n_voices), OSC_THREADS, 0, stream>>>(one, d_bufdesc, first_buf, span0, lo, hi);
+        if (n_launches) (*n_launches)++;
+        return cudaGetLastError();
+    }
     int L = anchor ? (int)anchor : 128;
     L = std::max(16, std::min(OSC_LMAX, (L / 16) * 16));
     OscLaunch p;
@@ -780,7 +764,6 @@ static cudaError_t launch_osc_range(const OscBankDev& b, const BufferDesc* d_buf
         dim3 grid((n_att + threads - 1) / threads, b.n_voices, p.split);
         if (b.K == OSC_K) osc_kernel<OSC_K, true><<<grid, threads, smem, st>>>(q);
         else if (b.K == OSC_K_SMALL) osc_kernel<OSC_K_SMALL, true><<<grid, threads, smem, st>>>(q);
-        else if (p.split == 1) osc_one_kernel<true><<<dim3(grid.x, grid.y), threads, 0, st>>>(q);
         else osc_kernel<OSC_K_ONE, true><<<grid, threads, smem, st>>>(q);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
@@ -794,7 +777,6 @@ static cudaError_t launch_osc_range(const OscBankDev& b, const BufferDesc* d_buf
         dim3 grid((q.nseg + threads - 1) / threads, b.n_voices, p.split);
         if (b.K == OSC_K) osc_kernel<OSC_K, false><<<grid, threads, smem, stream>>>(q);
         else if (b.K == OSC_K_SMALL) osc_kernel<OSC_K_SMALL, false><<<grid, threads, smem, stream>>>(q);
-        else if (p.split == 1) osc_one_kernel<false><<<dim3(grid.x, grid.y), threads, 0, stream>>>(q);
         else osc_kernel<OSC_K_ONE, false><<<grid, threads, smem, stream>>>(q);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;

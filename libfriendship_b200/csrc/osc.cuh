@@ -31,6 +31,11 @@ bool osc_usable(const OscBankDev& b);   // false for a bank whose allocations we
 
 cudaError_t osc_init_device();
 
+// Banks whose voices have at most one partial each (and no partial-range split) can also be evaluated inside another
+// kernel (osc_one.cuh): fills *out with the bank's device arrays and returns true for such a bank.
+struct OscOneSrc;
+bool osc_one_source(const OscBankDev& b, OscOneSrc* out);
+
 // Renders every voice of the bank over absolute times [lo, hi) into the voices' ring buffers
 // bufdesc[first_buf + v].  `anchor` = samples between exact re-anchors of each partial.
 cudaError_t launch_osc(const OscBankDev& b, const BufferDesc* d_bufdesc, uint32_t first_buf, uint64_t lo, uint64_t hi,
