@@ -2,6 +2,7 @@
 // block-wise rendering.  Follows the contract of Renderer::fill_buffer (reference src/render/renderer.rs:6-17)
 // and the bookkeeping of RefRenderer::fill_buffer (reference src/render/reference.rs:46-86).
 #include "renderer.hpp"
+#include "osc_one.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -157,6 +158,7 @@ void Renderer::define_oscbank(uint64_t key, const frb_oscbank_desc* d) {
     if (old) {
         // re-definition = new parameters for the same node (the per-render input of a synthesis graph)
         if (old_voices != d->n_voices) dirty_ = true;       // the lane count is part of the schedule
+        if (osc_one_source(*old, nullptr) != osc_one_source(*b, nullptr)) dirty_ = true;   // ... and so is whether a chain can evaluate it
         cache_valid_ = false;                               // rings hold the old bank's samples
     }
     osc_defs_[key] = b;
@@ -228,6 +230,8 @@ void Renderer::free_device_schedule() {
     h_bufdesc_.clear();
     for (auto p : d_ext_in_bufs_) if (p) cudaFree(p);
     d_ext_in_bufs_.clear();
+    for (auto p : d_exc_voice_) if (p) cudaFree(p);
+    d_exc_voice_.clear();
 }
 
 const Schedule& Renderer::schedule(uint32_t n_slots) {
@@ -327,11 +331,49 @@ void Renderer::upload_schedule() {
             chained_[i] = 1;
         }
     }
+    exc_of_.assign(sched_.ext.size(), -1);
+    exc_fused_.assign(sched_.ext.size(), 0);
+    d_exc_voice_.assign(sched_.ext.size(), nullptr);
+    if (!(cfg_.flags & FRB_FLAG_NO_CHAIN_FUSION)) {
+        const auto& V = sched_.values;
+        std::vector<uint32_t> uses(V.size(), 0);
+        for (const Value& x : V) {
+            if (x.op == V_DELAY || (x.op >= V_SUM2 && x.op <= V_MIN)) { uses[x.a]++; uses[x.b]++; }
+            if (x.op == V_TAP || x.op == V_GATE) uses[x.a]++;
+        }
+        for (uint32_t o : sched_.outputs) uses[o]++;
+        for (const auto& inst : sched_.ext) for (uint32_t in : inst.inputs) uses[in]++;
+        std::vector<uint32_t> used_voices(sched_.ext.size(), 0);   // per instance: lanes somebody reads
+        for (size_t k = 0; k < V.size(); k++) if (V[k].op == V_EXT && uses[k]) used_voices[V[k].a]++;
+        for (size_t j = 0; j < sched_.ext.size(); j++) {
+            if (chain_of_[j] < 0) continue;
+            const ExtInstance& df = sched_.ext[chain_of_[j]];
+            const Value& v0 = V[df.inputs[0]];
+            if (v0.op != V_EXT) continue;
+            const uint32_t o = v0.a;
+            const ExtInstance& bank = sched_.ext[o];
+            if (bank.kind != EXT_OSCBANK || exc_fused_[o] || used_voices[o] != df.n_lanes) continue;
+            const auto bank_def = osc_defs_.find(bank.key);
+            if (bank_def == osc_defs_.end() || !osc_one_source(*bank_def->second, nullptr)) continue;
+            std::vector<uint32_t> voice(df.n_lanes);
+            bool ok = true;
+            for (uint32_t l = 0; l < df.n_lanes && ok; l++) {
+                const Value& v = V[df.inputs[l]];
+                ok = v.op == V_EXT && v.a == o && uses[df.inputs[l]] == 1;
+                voice[l] = v.imm;
+            }
+            if (!ok) continue;
+            CU(cudaMalloc(&d_exc_voice_[j], voice.size() * sizeof(uint32_t)));
+            CU(cudaMemcpy(d_exc_voice_[j], voice.data(), voice.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            exc_of_[j] = (int32_t)o;
+            exc_fused_[o] = 1;
+        }
+    }
     // Block length: as long as the rings allow (more samples per launch = more parallelism for the stage kernels),
     // with the ring memory (<= 2 x block x 4 B per allocated ring) kept under ~8 GB.
     {
         uint64_t nb = 0;
-        for (const BufferInfo& bi : sched_.buffers) nb += !(bi.ext != ~0u && chained_[bi.ext]);
+        for (const BufferInfo& bi : sched_.buffers) nb += !(bi.ext != ~0u && (chained_[bi.ext] || exc_fused_[bi.ext]));
         nb = std::max<uint64_t>(nb, 1);
         uint64_t c = 1ull << 20;
         while (c > (1ull << 14) && 2 * c * nb > (1ull << 31)) c >>= 1;
@@ -354,7 +396,7 @@ void Renderer::ensure_rings(uint64_t t_end) {
     }
     for (auto& g : ring_groups_) {
         const BufferInfo& b = sched_.buffers[g.first];
-        if (b.ext != ~0u && chained_[b.ext]) continue;   // the biquad of a fused chain: its output stays in registers
+        if (b.ext != ~0u && (chained_[b.ext] || exc_fused_[b.ext])) continue;   // biquad / exciter of a fused chain: its output stays in registers
         const bool full = b.lookback == LOOKBACK_FULL;
         uint64_t need = full ? pow2_ceil(t_end + 8) : pow2_ceil(b.lookback + chunk_ + 8);
         if (need <= g.cap) continue;
@@ -553,7 +595,9 @@ void Renderer::run_range(uint64_t lo, uint64_t hi, float* d_out, uint64_t t0, ui
             for (uint32_t xi : st.ext) {
                 const ExtInstance& x = sched_.ext[xi];
                 uint64_t nl = 0;
-                if (x.kind == EXT_OSCBANK) {
+                if (x.kind == EXT_OSCBANK && exc_fused_[xi]) {
+                    continue;                                   // evaluated inside the chain kernel that reads it
+                } else if (x.kind == EXT_OSCBANK) {
                     timed(&frb_timing::osc_ms, [&] { CU(launch_osc(*osc_defs_.at(x.key), d_bufdesc_, x.first_out_buf, c0, c1, cfg_.osc_anchor, sm_count_, stream_, &nl)); });
                     stats.osc_launches += nl;
                 } else if (x.kind == EXT_DIRECTFORM && chained_[xi]) {
@@ -561,7 +605,10 @@ void Renderer::run_range(uint64_t lo, uint64_t hi, float* d_out, uint64_t t0, ui
                 } else if (x.kind == EXT_FBDELAY && chain_of_[xi] >= 0) {
                     const uint32_t di = (uint32_t)chain_of_[xi];
                     const ExtInstance& df = sched_.ext[di];
-                    timed(&frb_timing::scan_ms, [&] { CU(launch_dfcomb(*df_defs_.at(df.key), *fb_defs_.at(x.key), *chain_state_[xi], d_bufdesc_, d_ext_in_bufs_[di], x.first_out_buf, c0, c1, stream_, &nl)); });
+                    OscOneSrc exc;
+                    const bool has_exc = exc_of_[xi] >= 0 && osc_one_source(*osc_defs_.at(sched_.ext[exc_of_[xi]].key), &exc);
+                    if (exc_of_[xi] >= 0 && !has_exc) throw Error{FRB_E_INVALID, "oscillator bank changed shape under a fused chain"};
+                    timed(&frb_timing::scan_ms, [&] { CU(launch_dfcomb(*df_defs_.at(df.key), *fb_defs_.at(x.key), *chain_state_[xi], d_bufdesc_, d_ext_in_bufs_[di], x.first_out_buf, c0, c1, stream_, &nl, has_exc ? &exc : nullptr, d_exc_voice_[xi])); });
                     stats.scan_launches += nl;
                     stats.chain_launches += nl;
                 } else if (x.kind == EXT_DIRECTFORM) {

@@ -106,6 +106,12 @@ private:
     std::vector<int32_t> chain_of_;
     std::vector<uint8_t> chained_;
     std::vector<std::shared_ptr<ChainStateDev>> chain_state_;   // per fb instance
+    // Exciter fusion: a fused chain whose biquad lanes each read their own voice of a one-partial oscillator bank, when
+    // nothing else reads that bank, evaluates the oscillator inside the chain kernel (osc_one.cuh): exc_of_[fb instance] =
+    // the bank's instance, d_exc_voice_[fb instance] = voice per lane; exc_fused_[bank instance] = 1 (not launched, no rings)
+    std::vector<int32_t> exc_of_;
+    std::vector<uint8_t> exc_fused_;
+    std::vector<uint32_t*> d_exc_voice_;
     std::vector<BufferDesc> h_bufdesc_;
     struct RingGroup { uint32_t first, count; float* data; uint64_t cap; };   // consecutive buffers in one allocation
     std::vector<RingGroup> ring_groups_;

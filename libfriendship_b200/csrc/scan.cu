@@ -18,6 +18,7 @@
 //   lane steps through time D samples at a time, all D phases in parallel; every output is computed in the same
 //   order and with the same two roundings (mul, add) as a sequential f32 evaluation, so it is bit-exact to one.
 #include "scan.cuh"
+#include "osc_one.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -292,6 +293,8 @@ struct __align__(16) ChainWarpSmem {               // what one warp (= one lane 
     float4 w[CH_WQ];                               // tap window of the current tile
     float4 pw[5];                                  // A^(S * 2^k), k < 5 (read by broadcast)
     float4 c;                                      // carry between fast tiles {x[tb-1], x[tb-2], y[tb-1], y[tb-2]}
+    float4 rec_h, rec_an;                          // EXC: the lane's one-partial oscillator record (osc_one.cuh)
+    uint4 rec_ph;
 };
 
 // z of 4 samples: a[0..7] are two consecutive quads of the tap window, the taps are a[SH .. SH + 3]
@@ -332,17 +335,34 @@ __device__ __forceinline__ void comb_small(const float* tf, float* wf, float* zd
     }
 }
 
+// EXC: the biquad's input is not a ring but a one-partial oscillator voice (exc_voice[lane] of the bank `exc`), evaluated
+// in registers by osc_one_group8 — the function osc_one_kernel fills that voice's ring with when the chain is not fused,
+// so the bits are the same — and the chain's only HBM traffic is its output: 4 B per lane-sample.
+template <bool EXC>
 __global__ void __launch_bounds__(DF_CTA_THREADS, 7)
 dfcomb_kernel(const float* __restrict__ coef, const float* __restrict__ pw, const uint32_t* __restrict__ delay,
               const float* __restrict__ gain, const BufferDesc* __restrict__ bufdesc, const uint32_t* __restrict__ in_bufs,
-              uint32_t first_out_buf, float4* __restrict__ state, unsigned n_lanes, unsigned long long lo, unsigned long long hi) {
+              uint32_t first_out_buf, float4* __restrict__ state, unsigned n_lanes, unsigned long long lo, unsigned long long hi,
+              OscOneSrc exc, const uint32_t* __restrict__ exc_voice) {
     constexpr int NW = DF_CTA_THREADS / 32;
     __shared__ ChainWarpSmem s_all[NW];
     const unsigned wl = threadIdx.x & 31, wi = threadIdx.x >> 5;
     const unsigned lane = blockIdx.x * NW + wi;
     if (lane >= n_lanes) return;                                   // whole warp exits together
     ChainWarpSmem& S = s_all[wi];
-    const BufferDesc xin = bufdesc[in_bufs[lane]];
+    BufferDesc xin = {nullptr, 0};
+    unsigned exc_flags = 0;
+    if (EXC) {
+        const OscOneVoice o = osc_one_load(exc, exc_voice[lane]);
+        if (wl == 0) { S.rec_h = o.h; S.rec_an = o.an; S.rec_ph = o.ph; }
+        exc_flags = o.flags;
+    } else {
+        xin = bufdesc[in_bufs[lane]];
+    }
+    // EXC: the 8 samples from n8 (a multiple of 8) of this lane's exciter; the record is read by broadcast
+    auto exc8 = [&](unsigned long long n8, float (&r)[8]) {
+        osc_one_group8(S.rec_h, S.rec_an, S.rec_ph, exc_flags, n8, exc.max_attack, r);
+    };
     const BufferDesc zout = bufdesc[first_out_buf + lane];
     const float b0 = coef[lane * 5 + 0], b1 = coef[lane * 5 + 1], b2 = coef[lane * 5 + 2];
     const float a1 = coef[lane * 5 + 3], a2 = coef[lane * 5 + 4];
@@ -364,8 +384,27 @@ dfcomb_kernel(const float* __restrict__ coef, const float* __restrict__ pw, cons
         float* tf = reinterpret_cast<float*>(S.x[0]);
         {
             float x[DF_PER_THREAD + 2], yv[DF_PER_THREAD], y1, y2;
+            if (EXC) {
+                // the (at most two) groups of 8 this thread's samples fall into, through a private strip of the tile buffers
+                static_assert(DF_PER_THREAD == 8 && 2 * CH_QUADS * 4 >= 32 * 16, "exciter scratch");
+                float* sc = reinterpret_cast<float*>(S.x[0]) + 16u * wl;
+                const unsigned off = (unsigned)(t0 & 7ull);
+                float r[8];
+                exc8(t0 - off, r);
 #pragma unroll
-            for (int j = 0; j < DF_PER_THREAD; j++) x[2 + j] = (t0 + j < hi) ? xin.data[(t0 + j) & xin.mask] : 0.0f;
+                for (int u = 0; u < 8; u++) sc[u] = r[u];
+                if (off) {
+                    exc8(t0 - off + 8, r);
+#pragma unroll
+                    for (int u = 0; u < 8; u++) sc[8 + u] = r[u];
+                }
+#pragma unroll
+                for (int j = 0; j < DF_PER_THREAD; j++) x[2 + j] = (t0 + j < hi) ? sc[off + j] : 0.0f;
+                __syncwarp();                                       // the strips overlap the tile y is about to go into
+            } else {
+#pragma unroll
+                for (int j = 0; j < DF_PER_THREAD; j++) x[2 + j] = (t0 + j < hi) ? xin.data[(t0 + j) & xin.mask] : 0.0f;
+            }
             const float px1 = __shfl_up_sync(0xffffffffu, x[DF_PER_THREAD + 1], 1), px2 = __shfl_up_sync(0xffffffffu, x[DF_PER_THREAD], 1);
             x[1] = wl ? px1 : x1c;
             x[0] = wl ? px2 : x2c;
@@ -398,7 +437,7 @@ dfcomb_kernel(const float* __restrict__ coef, const float* __restrict__ pw, cons
         }
     };
 
-    const bool can_fast = (((xin.mask | zout.mask) >> 32) == 0) && (lo % 4 == 0);
+    const bool can_fast = (((xin.mask | zout.mask) >> 32) == 0) && (lo % (EXC ? 8 : 4) == 0);   // EXC: a thread = one group of 8
     unsigned long long tb = lo;
     while (tb < hi && !(can_fast && tb >= (unsigned long long)Du + 4 && tb + CH_TILE <= hi)) { slow_tile(tb); tb += CH_TILE; }
     if (tb < hi) {
@@ -411,9 +450,11 @@ dfcomb_kernel(const float* __restrict__ coef, const float* __restrict__ pw, cons
         const unsigned dq = (Du + sh) >> 2;                                     // window quad of the tile's first sample
         float* wf = reinterpret_cast<float*>(S.w);
         if (wl == 0) S.c = make_float4(x1c, x2c, y1c, y2c);
+        if (!EXC) {
 #pragma unroll
-        for (int c = 0; c < CH_TQ / 32; c++)
-            cp_async16(&S.x[0][ch_qpos(32u * c + wl)], xin.data + ((xb + 128u * c + 4u * wl) & xm));
+            for (int c = 0; c < CH_TQ / 32; c++)
+                cp_async16(&S.x[0][ch_qpos(32u * c + wl)], xin.data + ((xb + 128u * c + 4u * wl) & xm));
+        }
         cp_async_commit();
         for (unsigned long long k = 0; k < n_fast; k++) {
             const unsigned cur = (unsigned)k & 1u;
@@ -424,26 +465,38 @@ dfcomb_kernel(const float* __restrict__ coef, const float* __restrict__ pw, cons
             if (wl == 0) cp_async16(&S.w[CH_TQ], zout.data + ((qb + (unsigned)CH_TILE) & zm));
             cp_async_commit();                                      // group "taps of tile k"
             xb = (xb + CH_TILE) & xm;
-            if (k + 1 < n_fast) {
+            if (!EXC && k + 1 < n_fast) {
 #pragma unroll
                 for (int c = 0; c < CH_TQ / 32; c++)
                     cp_async16(&S.x[cur ^ 1][ch_qpos(32u * c + wl)], xin.data + ((xb + 128u * c + 4u * wl) & xm));
             }
             cp_async_commit();                                      // group "x of tile k + 1" (possibly empty)
-            cp_async_wait<2>();                                     // x of tile k has landed (every lane's share of it)
-            __syncwarp();
+            if (!EXC) {
+                cp_async_wait<2>();                                 // x of tile k has landed (every lane's share of it)
+                __syncwarp();
+            }
             {
                 float x[DF_PER_THREAD + 2], yv[DF_PER_THREAD], y1, y2;
                 const float4 cr = S.c;                              // broadcast read
+                if (EXC) {
+                    float r[8];
+                    exc8(tb + 8ull * wl, r);
 #pragma unroll
-                for (int jq = 0; jq < CH_TPQ; jq++) {
-                    const float4 v = xs[ch_qpos(CH_TPQ * wl + jq)];
-                    x[2 + 4 * jq] = v.x; x[3 + 4 * jq] = v.y; x[4 + 4 * jq] = v.z; x[5 + 4 * jq] = v.w;
+                    for (int j = 0; j < 8; j++) x[2 + j] = r[j];
+                    const float px1 = __shfl_up_sync(0xffffffffu, r[7], 1), px2 = __shfl_up_sync(0xffffffffu, r[6], 1);
+                    x[0] = wl ? px2 : cr.y;
+                    x[1] = wl ? px1 : cr.x;
+                } else {
+#pragma unroll
+                    for (int jq = 0; jq < CH_TPQ; jq++) {
+                        const float4 v = xs[ch_qpos(CH_TPQ * wl + jq)];
+                        x[2 + 4 * jq] = v.x; x[3 + 4 * jq] = v.y; x[4 + 4 * jq] = v.z; x[5 + 4 * jq] = v.w;
+                    }
+                    // history (x[t0-2], x[t0-1]) = the quad before this thread's own; lane 0 reads the carry instead
+                    const float2 vh = reinterpret_cast<const float2*>(xs + ch_qpos(wl ? CH_TPQ * wl - 1u : 0u))[1];
+                    x[0] = wl ? vh.x : cr.y;
+                    x[1] = wl ? vh.y : cr.x;
                 }
-                // history (x[t0-2], x[t0-1]) = the quad before this thread's own; lane 0 reads the carry instead
-                const float2 vh = reinterpret_cast<const float2*>(xs + ch_qpos(wl ? CH_TPQ * wl - 1u : 0u))[1];
-                x[0] = wl ? vh.x : cr.y;
-                x[1] = wl ? vh.y : cr.x;
                 biquad_tile(x, cr.z, cr.w, Pk, b0, b1, b2, a1, a2, wl, yv, y1, y2);
                 __syncwarp();                                       // everyone has read its x (and the carry): y may overwrite them
                 if (wl == 31) {
@@ -507,13 +560,18 @@ std::shared_ptr<ChainStateDev> chain_state_create(uint32_t n_lanes) {
 
 cudaError_t launch_dfcomb(const DirectFormDev& df, const FbDelayDev& fb, ChainStateDev& st, const BufferDesc* d_bufdesc,
                           const uint32_t* d_in_bufs, uint32_t first_out_buf, uint64_t lo, uint64_t hi, cudaStream_t stream,
-                          uint64_t* n_launches) {
+                          uint64_t* n_launches, const OscOneSrc* exciter, const uint32_t* d_exc_voice) {
     if (n_launches) *n_launches = 0;
     if (hi <= lo || df.n_lanes == 0) return cudaSuccess;
     if (lo != 0 && lo != st.time) return cudaErrorInvalidValue;    // the renderer restarts recurrences at t = 0 or continues
     const unsigned per_cta = DF_CTA_THREADS / 32;
-    dfcomb_kernel<<<(df.n_lanes + per_cta - 1) / per_cta, DF_CTA_THREADS, 0, stream>>>(
-        df.d_coef, df.d_pow, fb.d_delay, fb.d_gain, d_bufdesc, d_in_bufs, first_out_buf, st.d_state, df.n_lanes, lo, hi);
+    const unsigned grid = (df.n_lanes + per_cta - 1) / per_cta;
+    if (exciter)
+        dfcomb_kernel<true><<<grid, DF_CTA_THREADS, 0, stream>>>(df.d_coef, df.d_pow, fb.d_delay, fb.d_gain, d_bufdesc, nullptr,
+                                                                 first_out_buf, st.d_state, df.n_lanes, lo, hi, *exciter, d_exc_voice);
+    else
+        dfcomb_kernel<false><<<grid, DF_CTA_THREADS, 0, stream>>>(df.d_coef, df.d_pow, fb.d_delay, fb.d_gain, d_bufdesc, d_in_bufs,
+                                                                  first_out_buf, st.d_state, df.n_lanes, lo, hi, OscOneSrc{}, nullptr);
     st.time = hi;
     if (n_launches) *n_launches = 1;
     return cudaGetLastError();

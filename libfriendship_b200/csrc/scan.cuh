@@ -36,8 +36,12 @@ cudaError_t launch_fbdelay(const FbDelayDev& f, const BufferDesc* d_bufdesc, con
 // first_out_buf + lane (the comb's outputs).  lo must be 0 or the previous call's hi.
 bool chain_fusable(const DirectFormDev& df, const FbDelayDev& fb);
 std::shared_ptr<ChainStateDev> chain_state_create(uint32_t n_lanes);
+// `exciter` != nullptr: the biquad's input of lane l is voice d_exc_voice[l] of that one-partial oscillator bank, evaluated
+// inside the kernel (osc_one.cuh; same bits as the bank's own kernel): d_in_bufs is not read and the chain's only HBM
+// traffic is its output.
+struct OscOneSrc;
 cudaError_t launch_dfcomb(const DirectFormDev& df, const FbDelayDev& fb, ChainStateDev& st, const BufferDesc* d_bufdesc,
                           const uint32_t* d_in_bufs, uint32_t first_out_buf, uint64_t lo, uint64_t hi, cudaStream_t stream,
-                          uint64_t* n_launches);
+                          uint64_t* n_launches, const OscOneSrc* exciter = nullptr, const uint32_t* d_exc_voice = nullptr);
 
 }  // namespace frb

@@ -320,3 +320,96 @@ def test_random_graphs_around_chains(seed):
     ref = o.fill_buffer(n_out, sum(blocks), 0, x)
     scale = max(np.abs(ref).max(), 1e-3)
     assert np.abs(outs_all[0].astype(np.float64) - ref).max() <= 1e-4 * scale
+
+
+def _exciter_chain_graph(r, bank, voice_of_lane, coefs, delay, gain, tap_voice=None):
+    """OscBank (one partial per voice) -> DirectForm lane l reads voice voice_of_lane[l] -> FbDelay -> output slot l."""
+    from libfriendship_b200 import KIND_DIRECTFORM, KIND_FBDELAY, KIND_OSCBANK
+    lanes = len(delay)
+    r.define_oscbank(7, **bank)
+    r.define_directform(3, *coefs)
+    r.define_fbdelay(4, delay, gain)
+    r.on_add_node(5, KIND_OSCBANK, 7)
+    r.on_add_node(1, KIND_DIRECTFORM, 3)
+    r.on_add_node(2, KIND_FBDELAY, 4)
+    for l in range(lanes):
+        r.on_add_edge((5, 1, int(voice_of_lane[l]), l))
+        r.on_add_edge((1, 2, l, l))
+        r.on_add_edge((2, 0, l, l))
+    if tap_voice is not None:
+        r.on_add_edge((5, 0, tap_voice, lanes))   # a voice that is also an output: the bank keeps its own kernel and rings
+    return lanes + (1 if tap_voice is not None else 0)
+
+
+def _one_partial_bank(n_voices, seed=21):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    f = rng.uniform(30.0, 23000.0, n_voices)
+    attack = rng.uniform(0.0, 700.0, n_voices).astype(np.float32)
+    attack[::4] = 0.0
+    tau = rng.uniform(4000.0, 60000.0, n_voices).astype(np.float32)
+    tau[1::5] = np.inf
+    return dict(sample_rate=48000.0, voice_offsets=np.arange(n_voices + 1, dtype=np.uint64), freq_hz=f,
+                amp=rng.uniform(0.2, 1.0, n_voices).astype(np.float32), phase=rng.uniform(-3, 3, n_voices).astype(np.float32),
+                attack=attack, tau=tau)
+
+
+@pytest.mark.parametrize("blocks", [[20000], [8, 248, 256, 4096, 3, 5, 15384], [1000] * 20, [777] * 26])
+def test_exciter_fused_into_chain_equals_separate_kernels_bit_exact(blocks):
+    """A chain whose biquad lanes read one-partial oscillator voices evaluates the oscillator inside the chain kernel (no
+    exciter rings, no oscillator launch); same bits as bank kernel + biquad kernel + comb kernel, for aligned and unaligned
+    block cuts, with the lanes reading the voices in a scrambled order; fp64 oracle within 1e-4 of full scale."""
+    from libfriendship_b200 import FLAG_NO_CHAIN_FUSION
+    lanes = len(CHAIN_DELAYS)
+    bank = _one_partial_bank(lanes)
+    voice_of_lane = np.random.Generator(np.random.PCG64(4)).permutation(lanes)
+    coefs = rbj_lowpass(np.geomspace(60.0, 15000.0, lanes), np.linspace(0.707, 4.0, lanes))
+    gain = np.linspace(-0.95, 0.95, lanes).astype(np.float32)
+    n = sum(blocks)
+    outs, stats = [], []
+    for flags in (0, FLAG_NO_CHAIN_FUSION):
+        r = gpu_cls()(flags=flags)
+        _exciter_chain_graph(r, bank, voice_of_lane, coefs, CHAIN_DELAYS, gain)
+        parts, idx = [], 0
+        for m in blocks:
+            parts.append(r.fill_buffer(lanes, m, idx))
+            idx += m
+        outs.append(np.concatenate(parts, axis=1))
+        stats.append(r.stats())
+    assert stats[0]["chain_launches"] > 0 and stats[0]["osc_launches"] == 0
+    assert stats[1]["chain_launches"] == 0 and stats[1]["osc_launches"] > 0
+    assert_same_bits(outs[0], outs[1], "exciter fused into the chain vs separate kernels")
+    o = OracleRenderer()
+    _exciter_chain_graph(o, bank, voice_of_lane, coefs, CHAIN_DELAYS, gain)
+    ref = o.fill_buffer(lanes, n, 0)
+    assert np.abs(outs[0].astype(np.float64) - ref).max() <= 1e-4 * np.abs(ref).max()
+
+
+def test_exciter_not_fused_when_a_voice_is_read_elsewhere_or_the_bank_changes_shape():
+    """A voice that is also an output keeps the bank on its own kernel; re-defining the bank with two partials per voice
+    under a fused chain re-plans (the chain then reads rings again)."""
+    lanes = 4
+    bank = _one_partial_bank(lanes)
+    coefs = rbj_lowpass(np.array([200.0, 800.0, 3000.0, 9000.0]), np.array([0.8, 1.5, 3.0, 1.0]))
+    delay = np.array([64, 300, 700, 1500], dtype=np.uint32)
+    gain = np.full(lanes, 0.8, dtype=np.float32)
+    r, o = gpu_cls()(), OracleRenderer()
+    n_out = _exciter_chain_graph(r, bank, np.arange(lanes), coefs, delay, gain, tap_voice=2)
+    _exciter_chain_graph(o, bank, np.arange(lanes), coefs, delay, gain, tap_voice=2)
+    a, b = r.fill_buffer(n_out, 4000, 0), o.fill_buffer(n_out, 4000, 0)
+    assert r.stats()["osc_launches"] > 0 and r.stats()["chain_launches"] > 0
+    assert np.abs(a.astype(np.float64) - b).max() <= 1e-4 * np.abs(b).max()
+
+    r, o = gpu_cls()(), OracleRenderer()
+    _exciter_chain_graph(r, bank, np.arange(lanes), coefs, delay, gain)
+    _exciter_chain_graph(o, bank, np.arange(lanes), coefs, delay, gain)
+    a, b = r.fill_buffer(lanes, 3000, 0), o.fill_buffer(lanes, 3000, 0)
+    assert r.stats()["osc_launches"] == 0
+    assert np.abs(a.astype(np.float64) - b).max() <= 1e-4 * np.abs(b).max()
+    from banks import detuned_bank
+    bank2, _ = detuned_bank(lanes, 2, seed=8)
+    r.define_oscbank(7, **bank2)                                 # the node's parameters: retroactive, like any graph edit
+    o = OracleRenderer()
+    _exciter_chain_graph(o, bank2, np.arange(lanes), coefs, delay, gain)
+    a, b = r.fill_buffer(lanes, 3000, 3000), o.fill_buffer(lanes, 3000, 3000)
+    assert r.stats()["osc_launches"] > 0
+    assert np.abs(a.astype(np.float64) - b).max() <= 1e-4 * np.abs(b).max()

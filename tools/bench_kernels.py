@@ -91,7 +91,7 @@ def case_cfg3(n_voices=4096, n=480000, flags=0, osc_anchor=0):
     return {"case": "cfg3 osc->DirectForm->FbDelay->mix" + ("" if fused else " (chain fusion off)"), "voices": n_voices, "samples": n,
             "ms": t["total_ms"], "scan_ms": t["scan_ms"], "osc_ms": t["osc_ms"], "fold_ms": t["interp_ms"],
             "K4_algorithmic_GBs": alg / t["scan_ms"] / 1e6, "peak_GBs": HBM, "K4_frac": alg / t["scan_ms"] / 1e6 / HBM,
-            "K4_kernel_bytes_GBs": moved / t["scan_ms"] / 1e6, "osc_write_GBs": 4.0 * n_voices * n / t["osc_ms"] / 1e6,
+            "K4_kernel_bytes_GBs": moved / t["scan_ms"] / 1e6, "osc_write_GBs": (4.0 * n_voices * n / t["osc_ms"] / 1e6) if t["osc_ms"] > 0 else None,
             "fold_read_GBs": 4.0 * n_voices * n / t["interp_ms"] / 1e6, "voice_samples_per_s": n_voices * n / (t["total_ms"] * 1e-3)}
 
 
