@@ -77,6 +77,8 @@ typedef struct frb_config {
 #define FRB_FLAG_JIT_EAGER     4u  /* compile a stage program the first time it runs (default: once it is hot) */
 #define FRB_FLAG_NO_CHAIN_FUSION 8u /* run DirectForm -> FbDelay chains as two kernels (16 B per lane-sample) even where the
                                       fused kernel (8 B) applies; same bits either way (tests compare the two) */
+#define FRB_FLAG_NO_EXCITER_FUSION 16u /* keep one-partial oscillator banks on their own kernel and rings even where a fused
+                                      chain could evaluate them itself; same bits either way (tests compare the two) */
 
 /* Oscillator bank definition (extension).  Voice v owns partials [voice_offsets[v], voice_offsets[v+1]).
  *   out_v(t) = sum_p amp_p * min(t/attack_p, 1) * exp(-t/tau_p) * sin(2*pi*freq_p*t/sample_rate + phase_p)

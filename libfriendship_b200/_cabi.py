@@ -36,6 +36,7 @@ FLAG_SPARKLE_DELAY = 1
 FLAG_NO_JIT = 2
 FLAG_JIT_EAGER = 4
 FLAG_NO_CHAIN_FUSION = 8
+FLAG_NO_EXCITER_FUSION = 16
 
 
 class frb_edge(C.Structure):

@@ -334,7 +334,7 @@ void Renderer::upload_schedule() {
     exc_of_.assign(sched_.ext.size(), -1);
     exc_fused_.assign(sched_.ext.size(), 0);
     d_exc_voice_.assign(sched_.ext.size(), nullptr);
-    if (!(cfg_.flags & FRB_FLAG_NO_CHAIN_FUSION)) {
+    if (!(cfg_.flags & (FRB_FLAG_NO_CHAIN_FUSION | FRB_FLAG_NO_EXCITER_FUSION))) {
         const auto& V = sched_.values;
         std::vector<uint32_t> uses(V.size(), 0);
         for (const Value& x : V) {

@@ -131,27 +131,29 @@ __device__ __forceinline__ void biquad_tile(const float (&x)[DF_PER_THREAD + 2],
     for (int j = 0; j < DF_PER_THREAD; j++) u[j] = fmaf(b2, x[j], fmaf(b1, x[j + 1], b0 * x[j + 2]));
     const float s1 = wl ? 0.f : cy1, s2 = wl ? 0.f : cy2;
     float e1 = s1, e2 = s2;
+    // the y[n-2] term is folded in first: ONE FMA per step on the recurrence's critical path
 #pragma unroll
     for (int j = 0; j < DF_PER_THREAD; j++) {
-        const float y = fmaf(-a2, e2, fmaf(-a1, e1, u[j]));
+        const float y = fmaf(-a1, e1, fmaf(-a2, e2, u[j]));
         e2 = e1; e1 = y;
     }
     float v1 = e1, v2 = e2;
 #pragma unroll
     for (int k = 0; k < 5; k++) {
         const float4 Pk = P(k);
-        const float o1 = __shfl_up_sync(0xffffffffu, v1, 1u << k), o2 = __shfl_up_sync(0xffffffffu, v2, 1u << k);
-        if (wl >= (1u << k)) {
-            v1 += Pk.x * o1 + Pk.y * o2;
-            v2 += Pk.z * o1 + Pk.w * o2;
-        }
+        float o1 = __shfl_up_sync(0xffffffffu, v1, 1u << k), o2 = __shfl_up_sync(0xffffffffu, v2, 1u << k);
+        const bool on = wl >= (1u << k);                            // lanes below 2^k have nothing to their left at this level
+        o1 = on ? o1 : 0.f; o2 = on ? o2 : 0.f;
+        const float n1 = fmaf(Pk.x, o1, fmaf(Pk.y, o2, v1));
+        v2 = fmaf(Pk.z, o1, fmaf(Pk.w, o2, v2));
+        v1 = n1;
     }
     const float p1 = __shfl_up_sync(0xffffffffu, v1, 1), p2 = __shfl_up_sync(0xffffffffu, v2, 1);
     y1 = wl ? p1 : s1;                                              // (y[t0-1], y[t0-2])
     y2 = wl ? p2 : s2;
 #pragma unroll
     for (int j = 0; j < DF_PER_THREAD; j++) {
-        const float y = fmaf(-a2, y2, fmaf(-a1, y1, u[j]));
+        const float y = fmaf(-a1, y1, fmaf(-a2, y2, u[j]));
         yv[j] = y; y2 = y1; y1 = y;
     }
 }

@@ -358,7 +358,7 @@ def test_exciter_fused_into_chain_equals_separate_kernels_bit_exact(blocks):
     """A chain whose biquad lanes read one-partial oscillator voices evaluates the oscillator inside the chain kernel (no
     exciter rings, no oscillator launch); same bits as bank kernel + biquad kernel + comb kernel, for aligned and unaligned
     block cuts, with the lanes reading the voices in a scrambled order; fp64 oracle within 1e-4 of full scale."""
-    from libfriendship_b200 import FLAG_NO_CHAIN_FUSION
+    from libfriendship_b200 import FLAG_NO_CHAIN_FUSION, FLAG_NO_EXCITER_FUSION
     lanes = len(CHAIN_DELAYS)
     bank = _one_partial_bank(lanes)
     voice_of_lane = np.random.Generator(np.random.PCG64(4)).permutation(lanes)
@@ -366,7 +366,7 @@ def test_exciter_fused_into_chain_equals_separate_kernels_bit_exact(blocks):
     gain = np.linspace(-0.95, 0.95, lanes).astype(np.float32)
     n = sum(blocks)
     outs, stats = [], []
-    for flags in (0, FLAG_NO_CHAIN_FUSION):
+    for flags in (0, FLAG_NO_CHAIN_FUSION, FLAG_NO_EXCITER_FUSION):
         r = gpu_cls()(flags=flags)
         _exciter_chain_graph(r, bank, voice_of_lane, coefs, CHAIN_DELAYS, gain)
         parts, idx = [], 0
@@ -377,7 +377,9 @@ def test_exciter_fused_into_chain_equals_separate_kernels_bit_exact(blocks):
         stats.append(r.stats())
     assert stats[0]["chain_launches"] > 0 and stats[0]["osc_launches"] == 0
     assert stats[1]["chain_launches"] == 0 and stats[1]["osc_launches"] > 0
+    assert stats[2]["chain_launches"] > 0 and stats[2]["osc_launches"] > 0
     assert_same_bits(outs[0], outs[1], "exciter fused into the chain vs separate kernels")
+    assert_same_bits(outs[0], outs[2], "exciter fused into the chain vs bank kernel + fused chain")
     o = OracleRenderer()
     _exciter_chain_graph(o, bank, voice_of_lane, coefs, CHAIN_DELAYS, gain)
     ref = o.fill_buffer(lanes, n, 0)

@@ -143,7 +143,7 @@ def case_cfg1():
 if __name__ == "__main__":
     which = sys.argv[1:] or ["pure", "elementwise", "cfg3"]
     for w in which:
-        fn = {"pure": case_pure_elementwise, "elementwise": case_elementwise, "cfg3": case_cfg3, "cfg3_unfused": lambda: case_cfg3(flags=8), "cfg3_L64": lambda: case_cfg3(osc_anchor=64), "cfg3_L32": lambda: case_cfg3(osc_anchor=32),
+        fn = {"pure": case_pure_elementwise, "elementwise": case_elementwise, "cfg3": case_cfg3, "cfg3_unfused": lambda: case_cfg3(flags=8), "cfg3_ring": lambda: case_cfg3(flags=16), "cfg3_L64": lambda: case_cfg3(osc_anchor=64), "cfg3_L32": lambda: case_cfg3(osc_anchor=32),
           "cfg3_L128": lambda: case_cfg3(osc_anchor=128), "cfg3_L256": lambda: case_cfg3(osc_anchor=256), "cfg1": case_cfg1, "cfg2": case_cfg2, "cfg2_64": lambda: case_cfg2(64), "cfg2_32": lambda: case_cfg2(32)}[w]
         t0 = time.time()
         try:

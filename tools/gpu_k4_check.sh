@@ -1,6 +1,6 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_recurrences.py tests/test_oscbank.py tests/test_full_size.py -m gpu -x -q 2>&1 | tail -25 > gpurun_out/k4_tests.log
+timeout 900 python -m pytest tests/test_recurrences.py -m gpu -x -q 2>&1 | tail -25 > gpurun_out/k4_tests.log
 cat gpurun_out/k4_tests.log
-timeout 300 python tools/k4_probe.py base ge256 > gpurun_out/k4_probe.log 2>&1
+timeout 300 python tools/k4_probe.py base base+ring ge256 ge256+ring > gpurun_out/k4_probe.log 2>&1
 cat gpurun_out/k4_probe.log

@@ -35,7 +35,8 @@ def variant(name):
 
 if __name__ == "__main__":
     for name in sys.argv[1:] or ["base", "ge256", "shuffled"]:
-        filters.cfg3_filters = variant(name)
-        res = bench_kernels.case_cfg3()
+        ring = name.endswith("+ring")                         # exciters on their own kernel and rings (FRB_FLAG_NO_EXCITER_FUSION)
+        filters.cfg3_filters = variant(name.split("+")[0])
+        res = bench_kernels.case_cfg3(flags=16 if ring else 0)
         res["delays"] = name
         print(json.dumps({k: res[k] for k in ("delays", "ms", "scan_ms", "osc_ms", "fold_ms", "K4_frac")}), flush=True)
