@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 
 namespace frb {
@@ -369,14 +370,20 @@ void Renderer::upload_schedule() {
             exc_fused_[o] = 1;
         }
     }
-    // Block length: as long as the rings allow (more samples per launch = more parallelism for the stage kernels),
-    // with the ring memory (<= 2 x block x 4 B per allocated ring) kept under ~8 GB.
+    // Block length: as long as the rings allow (more samples per launch = more parallelism for the stage kernels — the
+    // ordered fold over an extension node's lanes is parallel across the samples of a block only: cfg3's mix takes 1.32 ms
+    // with 262,144-sample blocks, 1.50 ms with 65,536, 11.5 ms with 4,096), with the ring memory (<= 2 x block x 4 B per
+    // allocated ring) kept under ~16 GB of the 180.
     {
         uint64_t nb = 0;
         for (const BufferInfo& bi : sched_.buffers) nb += !(bi.ext != ~0u && (chained_[bi.ext] || exc_fused_[bi.ext]));
         nb = std::max<uint64_t>(nb, 1);
         uint64_t c = 1ull << 20;
-        while (c > (1ull << 14) && 2 * c * nb > (1ull << 31)) c >>= 1;
+        while (c > (1ull << 14) && 2 * c * nb > (1ull << 32)) c >>= 1;
+        if (const char* e = getenv("FRB_BLOCK_SAMPLES")) {           // measurement knob (tools/k4_probe.py): a power of two >= 1024
+            const uint64_t v = strtoull(e, nullptr, 10);
+            if (v >= 1024 && (v & (v - 1)) == 0) c = v;
+        }
         chunk_ = c;
     }
 }
