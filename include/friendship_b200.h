@@ -68,7 +68,8 @@ typedef struct frb_node {
 typedef struct frb_config {
     int32_t  device;          /* CUDA device ordinal */
     uint32_t flags;           /* FRB_FLAG_* */
-    uint32_t osc_anchor;      /* oscillator re-anchor interval in samples (0 = default) */
+    uint32_t osc_anchor;      /* oscillator re-anchor interval in samples (0 = default: 128; a multiple of 16, <= 256).
+                                 Banks whose voices have at most one partial each are always re-anchored every 8 */
     uint32_t reserved;
 } frb_config;
 #define FRB_FLAG_SPARKLE_DELAY 1u  /* negative / NaN delay amounts yield 0.0 (reference sparkle.rs:525-542)

@@ -189,9 +189,9 @@ def one_partial_bank(n_voices, seed=11, sr=48000.0):
 
 @pytest.mark.parametrize("anchor", [0, 48, 64])
 def test_one_partial_voices_kernel_vs_fp64_and_block_invariance(anchor):
-    """The dedicated kernel for banks of one-partial voices (osc_one_kernel): fp64 oracle at t = 0 (attack ramps) and deep
-    into the render, an unaligned window, segment lengths that are not a multiple of the 32-sample hand-over (48), and
-    ragged block cuts giving the bits of one call."""
+    """The dedicated kernel for banks of one-partial voices (osc_one_kernel, re-anchored every 8 samples whatever
+    osc_anchor says): fp64 oracle at t = 0 (attack ramps) and deep into the render, an unaligned window, and ragged block
+    cuts giving the bits of one call."""
     from libfriendship_b200 import B200Renderer, KIND_OSCBANK
     nv = 70
     bank = one_partial_bank(nv)
