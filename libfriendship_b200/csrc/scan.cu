@@ -29,7 +29,7 @@ namespace frb {
 
 constexpr int FB_THREADS = 128;
 constexpr int DF_CTA_THREADS = 128;   // 4 lanes per CTA, one warp each
-constexpr int DF_PER_THREAD = 8;
+constexpr int DF_PER_THREAD = 8;     // samples per thread of a tile (the exciter-fused chain kernel uses 16, see there)
 constexpr int DF_LEVELS = 8;      // stored powers A^(8*2^k), k < 8 (the warp scan uses k < 5)
 
 struct DirectFormDev {
@@ -122,18 +122,18 @@ __device__ __forceinline__ float ring_at(const BufferDesc& b, long long t) {
 // Every thread runs its 8 samples from a zero state — lane 0 from the carry — the end states are combined by a
 // Kogge-Stone scan with the operator "v_i <- v_i + A^(8*2^k) v_(i-2^k)", which leaves in lane i the true state at the end
 // of its run; its left neighbour's is the state it re-runs from.  Out: yv[0..7], (y1, y2) = (y[t0+7], y[t0+6]).
-template <class PF>
-__device__ __forceinline__ void biquad_tile(const float (&x)[DF_PER_THREAD + 2], float cy1, float cy2, PF P, float b0, float b1,
-                                            float b2, float a1, float a2, unsigned wl, float (&yv)[DF_PER_THREAD],
+template <int S, class PF>
+__device__ __forceinline__ void biquad_tile(const float (&x)[S + 2], float cy1, float cy2, PF P, float b0, float b1,
+                                            float b2, float a1, float a2, unsigned wl, float (&yv)[S],
                                             float& y1, float& y2) {
-    float u[DF_PER_THREAD];
+    float u[S];
 #pragma unroll
-    for (int j = 0; j < DF_PER_THREAD; j++) u[j] = fmaf(b2, x[j], fmaf(b1, x[j + 1], b0 * x[j + 2]));
+    for (int j = 0; j < S; j++) u[j] = fmaf(b2, x[j], fmaf(b1, x[j + 1], b0 * x[j + 2]));
     const float s1 = wl ? 0.f : cy1, s2 = wl ? 0.f : cy2;
     float e1 = s1, e2 = s2;
     // the y[n-2] term is folded in first: ONE FMA per step on the recurrence's critical path
 #pragma unroll
-    for (int j = 0; j < DF_PER_THREAD; j++) {
+    for (int j = 0; j < S; j++) {
         const float y = fmaf(-a1, e1, fmaf(-a2, e2, u[j]));
         e2 = e1; e1 = y;
     }
@@ -152,7 +152,7 @@ __device__ __forceinline__ void biquad_tile(const float (&x)[DF_PER_THREAD + 2],
     y1 = wl ? p1 : s1;                                              // (y[t0-1], y[t0-2])
     y2 = wl ? p2 : s2;
 #pragma unroll
-    for (int j = 0; j < DF_PER_THREAD; j++) {
+    for (int j = 0; j < S; j++) {
         const float y = fmaf(-a1, y1, fmaf(-a2, y2, u[j]));
         yv[j] = y; y2 = y1; y1 = y;
     }
@@ -200,7 +200,7 @@ directform_kernel(const float* __restrict__ coef, const float* __restrict__ pw, 
         x[1] = wl ? px1 : x1c;
         x[0] = wl ? px2 : x2c;
         float yv[DF_PER_THREAD], y1, y2;
-        biquad_tile(x, y1c, y2c, [&](int k) { return make_float4(P[k][0], P[k][1], P[k][2], P[k][3]); }, b0, b1, b2, a1, a2, wl, yv, y1, y2);
+        biquad_tile<DF_PER_THREAD>(x, y1c, y2c, [&](int k) { return make_float4(P[k][0], P[k][1], P[k][2], P[k][3]); }, b0, b1, b2, a1, a2, wl, yv, y1, y2);
         if (vec && t0 + DF_PER_THREAD <= hi) {
 #pragma unroll
             for (int jq = 0; jq < DF_PER_THREAD / 4; jq++)
@@ -272,11 +272,14 @@ fbdelay_kernel(const uint32_t* __restrict__ delay, const float* __restrict__ gai
 //     fbdelay_kernel: given the same y the bits are identical;
 //   * the biquad carry {x[n-1], x[n-2], y[n-1], y[n-2]} at the end of the block is kept in a per-lane state array (the
 //     y ring that directform_kernel re-reads it from does not exist here).
-constexpr int CH_TILE = 32 * DF_PER_THREAD;        // samples per tile
-constexpr int CH_TQ = CH_TILE / 4;                 // quads per tile
-constexpr int CH_QUADS = CH_TQ + CH_TQ / 8;        // ... skewed: quad q at position q + (q >> 3)
-constexpr int CH_WQ = CH_TQ + 2;                   // tap window: r < tile + 4 used, one more quad is read (and ignored)
-constexpr int CH_TPQ = DF_PER_THREAD / 4;          // quads per thread
+template <int S>
+struct ChainGeom {                                 // tile geometry for S samples per thread
+    static constexpr int TILE = 32 * S;            // samples per tile
+    static constexpr int TQ = TILE / 4;            // quads per tile
+    static constexpr int QUADS = TQ + TQ / 8;      // ... skewed: quad q at position q + (q >> 3)
+    static constexpr int WQ = TQ + 2;              // tap window: r < tile + 4 used, one more quad is read (and ignored)
+    static constexpr int TPQ = S / 4;              // quads per thread
+};
 constexpr int CH_MIN_DELAY = 32;                   // shorter combs use the separate kernels
 
 __device__ __forceinline__ unsigned ch_qpos(unsigned q) { return q + (q >> 3); }
@@ -290,9 +293,10 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory"); }
 
+template <int S>
 struct __align__(16) ChainWarpSmem {               // what one warp (= one lane of the chain) keeps in shared memory
-    float4 x[2][CH_QUADS];                         // x tiles in flight (double buffered); the current one becomes y, then z
-    float4 w[CH_WQ];                               // tap window of the current tile
+    float4 x[2][ChainGeom<S>::QUADS];              // x tiles in flight (double buffered); the current one becomes y
+    float4 w[ChainGeom<S>::WQ];                    // tap window of the current tile
     float4 pw[5];                                  // A^(S * 2^k), k < 5 (read by broadcast)
     float4 c;                                      // carry between fast tiles {x[tb-1], x[tb-2], y[tb-1], y[tb-2]}
     float4 rec_h, rec_an;                          // EXC: the lane's one-partial oscillator record (osc_one.cuh)
@@ -310,7 +314,7 @@ __device__ __forceinline__ float4 comb_quad(const float4 y, const float4 a0, con
 // Combs shorter than 128 samples: chunks of 32 E samples (<= D), E consecutive samples per thread.  y is read ahead of
 // the chunk loop, z goes straight to the ring (32 E contiguous floats per instruction) and into the tap window for the
 // chunks that follow; one barrier per chunk.
-template <int E>
+template <int CH_TILE, int E>
 __device__ __forceinline__ void comb_small(const float* tf, float* wf, float* zdata, unsigned zb, unsigned zm, unsigned Du,
                                            unsigned sh, float g, unsigned wl) {
     constexpr int NC = CH_TILE / (32 * E);
@@ -346,12 +350,18 @@ dfcomb_kernel(const float* __restrict__ coef, const float* __restrict__ pw, cons
               const float* __restrict__ gain, const BufferDesc* __restrict__ bufdesc, const uint32_t* __restrict__ in_bufs,
               uint32_t first_out_buf, float4* __restrict__ state, unsigned n_lanes, unsigned long long lo, unsigned long long hi,
               OscOneSrc exc, const uint32_t* __restrict__ exc_voice) {
+    // Samples per thread.  16 halves the per-sample cost of the scan and of everything that happens once per tile, which
+    // pays when the kernel is bound by issue slots (EXC: 3.20 -> 2.81 ms on cfg3) and not when it is bound by the LSU
+    // pipe (ring input: 3.26 -> 3.43 ms); the biquad's tiles — hence its roundings — therefore differ between the two.
+    constexpr int SPT = EXC ? 16 : DF_PER_THREAD;
+    constexpr int PSHIFT = EXC ? 1 : 0;                            // stored powers are A^(8 * 2^k): A^(SPT * 2^k) = entry k + PSHIFT
+    constexpr int CH_TILE = ChainGeom<SPT>::TILE, CH_TQ = ChainGeom<SPT>::TQ, CH_QUADS = ChainGeom<SPT>::QUADS, CH_TPQ = ChainGeom<SPT>::TPQ;
     constexpr int NW = DF_CTA_THREADS / 32;
-    __shared__ ChainWarpSmem s_all[NW];
+    __shared__ ChainWarpSmem<SPT> s_all[NW];
     const unsigned wl = threadIdx.x & 31, wi = threadIdx.x >> 5;
     const unsigned lane = blockIdx.x * NW + wi;
     if (lane >= n_lanes) return;                                   // whole warp exits together
-    ChainWarpSmem& S = s_all[wi];
+    ChainWarpSmem<SPT>& S = s_all[wi];
     BufferDesc xin = {nullptr, 0};
     unsigned exc_flags = 0;
     if (EXC) {
@@ -370,7 +380,7 @@ dfcomb_kernel(const float* __restrict__ coef, const float* __restrict__ pw, cons
     const float a1 = coef[lane * 5 + 3], a2 = coef[lane * 5 + 4];
     const unsigned Du = delay[lane];
     const float g = gain[lane];
-    if (wl < 5) S.pw[wl] = reinterpret_cast<const float4*>(pw + (size_t)lane * DF_LEVELS * 4)[wl];
+    if (wl < 5) S.pw[wl] = reinterpret_cast<const float4*>(pw + (size_t)lane * DF_LEVELS * 4)[wl + PSHIFT];
     __syncwarp();
     const float4* P = S.pw;                                         // warp-uniform: read by broadcast
     auto Pk = [&](int k) { return P[k]; };
@@ -382,47 +392,48 @@ dfcomb_kernel(const float* __restrict__ coef, const float* __restrict__ pw, cons
     // Any tile: ragged ends, an unaligned block start, the first D + 4 samples after t = 0, rings beyond 2^32 floats.
     // Same biquad_tile; the comb walks the tile in chunks of 32 samples (<= D) with its taps straight from the ring.
     auto slow_tile = [&](unsigned long long tb) {
-        const unsigned long long t0 = tb + (unsigned long long)wl * DF_PER_THREAD;
+        const unsigned long long t0 = tb + (unsigned long long)wl * SPT;
         float* tf = reinterpret_cast<float*>(S.x[0]);
         {
-            float x[DF_PER_THREAD + 2], yv[DF_PER_THREAD], y1, y2;
+            float x[SPT + 2], yv[SPT], y1, y2;
             if (EXC) {
                 // the (at most two) groups of 8 this thread's samples fall into, through a private strip of the tile buffers
-                static_assert(DF_PER_THREAD == 8 && 2 * CH_QUADS * 4 >= 32 * 16, "exciter scratch");
-                float* sc = reinterpret_cast<float*>(S.x[0]) + 16u * wl;
+                constexpr int NG = SPT / 8;               // whole groups per thread; one more when unaligned
+                static_assert(SPT % 8 == 0 && 2 * CH_QUADS * 4 >= 32 * 8 * (NG + 1), "exciter scratch");
+                float* sc = reinterpret_cast<float*>(S.x[0]) + 8u * (NG + 1) * wl;
                 const unsigned off = (unsigned)(t0 & 7ull);
-                float r[8];
-                exc8(t0 - off, r);
 #pragma unroll
-                for (int u = 0; u < 8; u++) sc[u] = r[u];
-                if (off) {
-                    exc8(t0 - off + 8, r);
+                for (int gi = 0; gi <= NG; gi++) {
+                    if (gi < NG || off) {
+                        float r[8];
+                        exc8(t0 - off + 8ull * gi, r);
 #pragma unroll
-                    for (int u = 0; u < 8; u++) sc[8 + u] = r[u];
+                        for (int u = 0; u < 8; u++) sc[8 * gi + u] = r[u];
+                    }
                 }
 #pragma unroll
-                for (int j = 0; j < DF_PER_THREAD; j++) x[2 + j] = (t0 + j < hi) ? sc[off + j] : 0.0f;
+                for (int j = 0; j < SPT; j++) x[2 + j] = (t0 + j < hi) ? sc[off + j] : 0.0f;
                 __syncwarp();                                       // the strips overlap the tile y is about to go into
             } else {
 #pragma unroll
-                for (int j = 0; j < DF_PER_THREAD; j++) x[2 + j] = (t0 + j < hi) ? xin.data[(t0 + j) & xin.mask] : 0.0f;
+                for (int j = 0; j < SPT; j++) x[2 + j] = (t0 + j < hi) ? xin.data[(t0 + j) & xin.mask] : 0.0f;
             }
-            const float px1 = __shfl_up_sync(0xffffffffu, x[DF_PER_THREAD + 1], 1), px2 = __shfl_up_sync(0xffffffffu, x[DF_PER_THREAD], 1);
+            const float px1 = __shfl_up_sync(0xffffffffu, x[SPT + 1], 1), px2 = __shfl_up_sync(0xffffffffu, x[SPT], 1);
             x[1] = wl ? px1 : x1c;
             x[0] = wl ? px2 : x2c;
-            biquad_tile(x, y1c, y2c, Pk, b0, b1, b2, a1, a2, wl, yv, y1, y2);
+            biquad_tile<SPT>(x, y1c, y2c, Pk, b0, b1, b2, a1, a2, wl, yv, y1, y2);
             if (tb + CH_TILE >= hi) {                               // the block's last two samples: carry of the next launch
 #pragma unroll
-                for (int j = 0; j < DF_PER_THREAD; j++) {
+                for (int j = 0; j < SPT; j++) {
                     if (t0 + j + 1 == hi) { state[lane].x = x[2 + j]; state[lane].z = yv[j]; }
                     if (t0 + j + 2 == hi) { state[lane].y = x[2 + j]; state[lane].w = yv[j]; }
                 }
                 if (wl == 0 && tb + 1 == hi) { state[lane].y = x1c; state[lane].w = y1c; }   // hi - 2 lies before the tile
             }
 #pragma unroll
-            for (int j = 0; j < DF_PER_THREAD; j++) tf[ch_fpos(wl * DF_PER_THREAD + j)] = yv[j];
+            for (int j = 0; j < SPT; j++) tf[ch_fpos(wl * SPT + j)] = yv[j];
             y1c = __shfl_sync(0xffffffffu, y1, 31); y2c = __shfl_sync(0xffffffffu, y2, 31);
-            x1c = __shfl_sync(0xffffffffu, x[DF_PER_THREAD + 1], 31); x2c = __shfl_sync(0xffffffffu, x[DF_PER_THREAD], 31);
+            x1c = __shfl_sync(0xffffffffu, x[SPT + 1], 31); x2c = __shfl_sync(0xffffffffu, x[SPT], 31);
         }
         __syncwarp();
         for (unsigned m = wl; m < (unsigned)CH_TILE; m += 32) {
@@ -478,14 +489,17 @@ dfcomb_kernel(const float* __restrict__ coef, const float* __restrict__ pw, cons
                 __syncwarp();
             }
             {
-                float x[DF_PER_THREAD + 2], yv[DF_PER_THREAD], y1, y2;
+                float x[SPT + 2], yv[SPT], y1, y2;
                 const float4 cr = S.c;                              // broadcast read
                 if (EXC) {
-                    float r[8];
-                    exc8(tb + 8ull * wl, r);
 #pragma unroll
-                    for (int j = 0; j < 8; j++) x[2 + j] = r[j];
-                    const float px1 = __shfl_up_sync(0xffffffffu, r[7], 1), px2 = __shfl_up_sync(0xffffffffu, r[6], 1);
+                    for (int gi = 0; gi < SPT / 8; gi++) {
+                        float r[8];
+                        exc8(tb + (unsigned long long)SPT * wl + 8ull * gi, r);
+#pragma unroll
+                        for (int j = 0; j < 8; j++) x[2 + 8 * gi + j] = r[j];
+                    }
+                    const float px1 = __shfl_up_sync(0xffffffffu, x[SPT + 1], 1), px2 = __shfl_up_sync(0xffffffffu, x[SPT], 1);
                     x[0] = wl ? px2 : cr.y;
                     x[1] = wl ? px1 : cr.x;
                 } else {
@@ -499,10 +513,10 @@ dfcomb_kernel(const float* __restrict__ coef, const float* __restrict__ pw, cons
                     x[0] = wl ? vh.x : cr.y;
                     x[1] = wl ? vh.y : cr.x;
                 }
-                biquad_tile(x, cr.z, cr.w, Pk, b0, b1, b2, a1, a2, wl, yv, y1, y2);
+                biquad_tile<SPT>(x, cr.z, cr.w, Pk, b0, b1, b2, a1, a2, wl, yv, y1, y2);
                 __syncwarp();                                       // everyone has read its x (and the carry): y may overwrite them
                 if (wl == 31) {
-                    const float4 c = make_float4(x[DF_PER_THREAD + 1], x[DF_PER_THREAD], y1, y2);
+                    const float4 c = make_float4(x[SPT + 1], x[SPT], y1, y2);
                     S.c = c;
                     if (k + 1 == n_fast && tb + CH_TILE == hi) state[lane] = c;
                 }
@@ -534,9 +548,9 @@ dfcomb_kernel(const float* __restrict__ coef, const float* __restrict__ pw, cons
                     }
                 }
             } else if (Du >= 64u) {
-                comb_small<2>(reinterpret_cast<const float*>(xs), wf, zout.data, zb, zm, Du, sh, g, wl);
+                comb_small<CH_TILE, 2>(reinterpret_cast<const float*>(xs), wf, zout.data, zb, zm, Du, sh, g, wl);
             } else {
-                comb_small<1>(reinterpret_cast<const float*>(xs), wf, zout.data, zb, zm, Du, sh, g, wl);
+                comb_small<CH_TILE, 1>(reinterpret_cast<const float*>(xs), wf, zout.data, zb, zm, Du, sh, g, wl);
             }
             __syncwarp();                                           // the next tile's taps read these stores
             qb += CH_TILE; zb += CH_TILE;
