@@ -255,11 +255,11 @@ fbdelay_kernel(const uint32_t* __restrict__ delay, const float* __restrict__ gai
 // ------------------------------------------------------------------------------------------------------------------
 // Fused chain: DirectForm lane l -> FbDelay lane l, when nothing else reads the biquad's output.  8 B per lane-sample of
 // HBM traffic (read x once, write z once) instead of 16 B for the two separate kernels: the biquad's y never leaves the
-// SM.  One warp per lane, tiles of 32 threads x DF_PER_THREAD samples:
+// SM.  One warp per lane, tiles of 32 threads x S samples (S = 8; 16 when the input is an oscillator, see the kernel):
 //   * tiles travel between HBM and shared memory as quads (4 samples) in coalesced rows — lane i moves quads i, 32 + i,
 //     ... : 512 contiguous bytes per instruction — with cp.async (no registers held): the x tile of the NEXT iteration
 //     and this tile's comb taps are in flight during the biquad;
-//   * the biquad is biquad_tile, shared with directform_kernel (same bits); a thread's own samples are consecutive quads
+//   * the biquad is biquad_tile, shared with directform_kernel (same bits at S = 8); a thread's own samples are consecutive quads
 //     of the tile, which sits in shared memory skewed (quad q at q + (q >> 3)) so that both this pattern and the
 //     coalesced one are free of bank conflicts; y goes back into the same tile;
 //   * the comb z[n] = y[n] + g z[n - D] runs as a second pass over the tile in the COALESCED mapping, in chunks of 32 E
