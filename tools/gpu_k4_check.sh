@@ -1,6 +1,6 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_recurrences.py -m gpu -x -q 2>&1 | tail -8 > gpurun_out/k4_tests.log
+timeout 600 python -m pytest tests/test_jit.py -m gpu -x -q 2>&1 | tail -5 > gpurun_out/k4_tests.log
 cat gpurun_out/k4_tests.log
-timeout 300 python tools/k4_probe.py base base+ring ge256 > gpurun_out/k4_probe.log 2>&1
-cat gpurun_out/k4_probe.log
+timeout 300 python tools/bench_kernels.py pure elementwise 2>&1 | cut -c1-420 > gpurun_out/k23.log
+cat gpurun_out/k23.log
