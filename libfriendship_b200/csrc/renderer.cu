@@ -378,7 +378,7 @@ void Renderer::upload_schedule() {
         uint64_t nb = 0;
         for (const BufferInfo& bi : sched_.buffers) nb += !(bi.ext != ~0u && (chained_[bi.ext] || exc_fused_[bi.ext]));
         nb = std::max<uint64_t>(nb, 1);
-        uint64_t c = 1ull << 20;
+        uint64_t c = 1ull << 22;
         while (c > (1ull << 14) && 2 * c * nb > (1ull << 32)) c >>= 1;
         if (const char* e = getenv("FRB_BLOCK_SAMPLES")) {           // measurement knob (tools/k4_probe.py): a power of two >= 1024
             const uint64_t v = strtoull(e, nullptr, 10);

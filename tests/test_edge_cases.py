@@ -95,3 +95,34 @@ def test_edge_from_a_missing_node_is_an_error_not_a_crash():
         with pytest.raises(RendererError) as e:
             r.fill_buffer(1, 4, 0)
         assert e.value.code == -1
+
+
+def test_internal_block_length_does_not_change_the_result(monkeypatch):
+    """One fill is cut into internal blocks (FRB_BLOCK_SAMPLES overrides their length): the primitive path and the
+    oscillator bank are pure functions of absolute time, so 1,024-sample blocks give the bits of one block; the
+    recurrences restart their scan tiles at every block start, so they agree within their tolerance."""
+    from banks import build_voice_mix_graph, detuned_bank
+    from filters import build_cfg3_graph
+    from libfriendship_b200 import B200Renderer
+    n = 20000
+    x = cfg1_input(n)
+    bank, ids = detuned_bank(3, 40)
+    bank1, _ = detuned_bank(5, 1, seed=5)
+    outs = {}
+    for blk in (None, "1024"):
+        if blk:
+            monkeypatch.setenv("FRB_BLOCK_SAMPLES", blk)
+        r = B200Renderer()
+        build_cfg1_graph(r)
+        a = r.fill_buffer(2, n, 0, [x])
+        r = B200Renderer()
+        build_voice_mix_graph(r, bank, ids, delay0=480.0)
+        b = r.fill_buffer(1, n, 0)
+        r = B200Renderer()
+        build_cfg3_graph(r, 5, excitation="osc", bank=bank1, mix_to_one=True)
+        c = r.fill_buffer(1, n, 0)
+        outs[blk] = (a, b, c)
+    assert_same_bits(outs[None][0], outs["1024"][0], "primitive graph, internal blocks")
+    assert_same_bits(outs[None][1], outs["1024"][1], "oscillator bank + delay + mix, internal blocks")
+    scale = np.abs(outs[None][2]).max()
+    assert np.abs(outs[None][2].astype(np.float64) - outs["1024"][2]).max() <= 1e-5 * scale
