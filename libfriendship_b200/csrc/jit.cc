@@ -127,16 +127,30 @@ std::string jit_generate_source(const Stage& st) {
         const uint32_t rep = shapes[k].strands[0];
         body << "  case " << k << ": {\n";
         body << "  const unsigned* q = frb_tab" << k << "[frb_idx_of[strand]];\n  (void)q;\n";
-        body << "  for (unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; g < p.n_groups;\n"
-                "       g += (unsigned long long)gridDim.x * blockDim.x) {\n";
-        body << "    const unsigned long long t_0 = p.t_begin + 8ull * g, t_1 = t_0 + 4ull;\n";
         uint32_t nreg = 0;
         for (uint32_t i = st.strand_offsets[rep]; i < st.strand_offsets[rep + 1]; i++) {
             const uint32_t op = st.program[i].w0 & 0xFFu;
             if (op == I_END) break;
             if (op != I_STBUF && op != I_STOUT) nreg = std::max(nreg, (st.program[i].w0 >> 16) + 1);
         }
-        for (uint32_t r = 0; r < nreg; r++) body << "    float4 " << reg(r, 0) << ", " << reg(r, 1) << ";\n";
+        // A stage is a stream and what bounds it is the bytes it keeps in flight: 12 resident CTAs x 128 threads x two
+        // 16-byte loads per input are 6 MB on the whole GPU, ~5 TB/s at the loaded DRAM latency (measured: 5.0).  A small
+        // program therefore walks TWO groups of 8 samples per iteration (one grid stride apart, so every load instruction
+        // still covers 512 contiguous bytes), instruction by instruction, which puts the second group's loads in front of
+        // the first group's stores.  Loads never alias this stage's stores (a stage reads what earlier stages wrote).
+        const int W = nreg <= 6 ? 4 : 2;            // float4 columns per thread and iteration
+        body << "  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;\n";
+        body << "  for (unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; g < p.n_groups; g += " << (W / 2) << "ull * stride) {\n";
+        body << "    const unsigned long long t_0 = p.t_begin + 8ull * g, t_1 = t_0 + 4ull;\n";
+        if (W == 4) {
+            body << "    const bool two = g + stride < p.n_groups;\n";       // the last iteration may have one group only:
+            body << "    const unsigned long long t_2 = p.t_begin + 8ull * (two ? g + stride : g), t_3 = t_2 + 4ull;\n";   // it loads the first twice and stores once
+        }
+        for (uint32_t r = 0; r < nreg; r++) {
+            body << "    float4 " << reg(r, 0);
+            for (int w = 1; w < W; w++) body << ", " << reg(r, w);
+            body << ";\n";
+        }
         uint32_t n_words = 0;
         const uint32_t len = st.strand_offsets[rep + 1] - st.strand_offsets[rep];
         for (uint32_t j = 0; j < len; j++) {
@@ -156,8 +170,9 @@ std::string jit_generate_source(const Stage& st) {
             if ((flags & IF_A_IMM) || tap) wa = word(0);
             if ((flags & IF_B_IMM) || tap || op == I_GATE) wb = word(1);
             if (op == I_LDIN || op == I_LDBUF || op == I_STBUF || op == I_STOUT || op == I_DLY_IN || op == I_DLY_BUF || tap || op == I_GATE) wx = word(2);
-            for (int w = 0; w < 2; w++) {
+            for (int w = 0; w < W; w++) {
                 const std::string t = "t_" + std::to_string(w);
+                const char* guard = w >= 2 ? "if (two) " : "";
                 const std::string a = (flags & IF_A_IMM) ? "f4splat(" + wa + ")" : reg(in.a, w);
                 const std::string b = (flags & IF_B_IMM) ? "f4splat(" + wb + ")" : reg(in.b, w);
                 const std::string sh = "(((unsigned long long)" + wb + " << 32) | " + wa + ")";
@@ -171,8 +186,8 @@ std::string jit_generate_source(const Stage& st) {
                     case I_MOV: body << reg(dst, w) << " = " << a << ";"; break;
                     case I_LDIN: body << reg(dst, w) << " = f4ld_in(p.inputs[" << wx << "], " << t << ");"; break;
                     case I_LDBUF: body << reg(dst, w) << " = f4ld_buf(p.buffers[" << wx << "], " << t << ");"; break;
-                    case I_STBUF: body << "f4st_buf(p.buffers[" << wx << "], " << t << ", " << a << ");"; break;
-                    case I_STOUT: body << "f4st_out(p, " << wx << ", " << t << ", " << a << ");"; break;
+                    case I_STBUF: body << guard << "f4st_buf(p.buffers[" << wx << "], " << t << ", " << a << ");"; break;
+                    case I_STOUT: body << guard << "f4st_out(p, " << wx << ", " << t << ", " << a << ");"; break;
                     case I_TAP_IN: body << reg(dst, w) << " = f4tap_in(p.inputs[" << wx << "], " << t << ", " << sh << ");"; break;
                     case I_TAP_BUF: body << reg(dst, w) << " = f4tap_buf(p.buffers[" << wx << "], " << t << ", " << sh << ");"; break;
                     case I_GATE: body << reg(dst, w) << " = f4gate(" << a << ", " << t << ", (((unsigned long long)" << wx << " << 32) | " << wb << "));"; break;

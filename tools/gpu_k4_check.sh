@@ -1,5 +1,6 @@
+set -x
 mkdir -p gpurun_out
-for c in 262144 1048576 4194304; do
-  echo "block $c"; FRB_BLOCK_SAMPLES=$c timeout 200 python tools/bench_kernels.py pure elementwise 2>&1 | cut -c1-330
-done > gpurun_out/k23_blocks.log 2>&1
-cat gpurun_out/k23_blocks.log
+timeout 600 python -m pytest tests/test_jit.py tests/test_random_dags.py tests/test_edge_cases.py -m gpu -x -q 2>&1 | tail -5 > gpurun_out/k4_tests.log
+cat gpurun_out/k4_tests.log
+timeout 300 python tools/bench_kernels.py pure elementwise 2>&1 | cut -c1-330 > gpurun_out/k23.log
+cat gpurun_out/k23.log
