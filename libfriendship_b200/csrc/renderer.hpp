@@ -129,6 +129,8 @@ private:
     size_t d_indesc_cap_ = 0;
     float* d_in_stage_ = nullptr;
     size_t d_in_stage_cap_ = 0;
+    void* d_ingest_ = nullptr;                  // row descriptors of a batched ingest (renderer.cu ingest_rows_kernel)
+    size_t d_ingest_cap_ = 0;
 
     // output staging
     float* d_out_ = nullptr;

@@ -126,3 +126,29 @@ def test_internal_block_length_does_not_change_the_result(monkeypatch):
     assert_same_bits(outs[None][1], outs["1024"][1], "oscillator bank + delay + mix, internal blocks")
     scale = np.abs(outs[None][2]).max()
     assert np.abs(outs[None][2].astype(np.float64) - outs["1024"][2]).max() <= 1e-5 * scale
+
+
+def test_many_long_input_rows_ragged_and_unaligned():
+    """Five input rows of > 200,000 samples each take the batched ingest (one kernel for all rows): rows of different
+    lengths (the short ones are padded with their last value, reference.rs:72-73), a row of odd length (so the rows after
+    it start at unaligned offsets), a Delay reaching back into the previous call's rows; bit-exact against the oracle."""
+    from graphs import GraphBuilder
+    from libfriendship_b200 import B200Renderer, KIND_DELAY, KIND_SUM2
+    rng = np.random.Generator(np.random.PCG64(8))
+    n = 262144
+    lens = [n, n - 1, n - 4097, 7, n]
+    outs = []
+    for cls in (B200Renderer, OracleRenderer):
+        r = cls()
+        g = GraphBuilder(r)
+        for s in range(5):
+            d = g.node(KIND_DELAY, g.input(s), g.const(float(1000 + 37 * s)))
+            g.output(s, g.node(KIND_SUM2, g.input(s), d))
+        got = []
+        for call in range(2):
+            rows = [rng.uniform(-1, 1, m).astype(np.float32) for m in lens] if cls is B200Renderer else saved[call]
+            got.append((rows, r.fill_buffer(5, n, call * n, rows)))
+        if cls is B200Renderer:
+            saved = [rows for rows, _ in got]
+        outs.append(np.concatenate([o for _, o in got], axis=1))
+    assert_same_bits(outs[0], outs[1], "batched ingest of ragged, unaligned rows")
