@@ -544,7 +544,7 @@ void Renderer::ingest_inputs(uint32_t n_slots, uint64_t n_times, uint64_t idx, c
             d_rows = d_in_stage_ - offs[0];
         }
         // many long rows: one kernel for all of them instead of a device-to-device copy each
-        const bool batched = n_fed >= 4 && total >= (1ull << 20);
+        const bool batched = n_fed >= 4 && n_fed <= 65535 && total >= (1ull << 20);   // rows are grid.y
         std::vector<IngestRow> batch;
         for (size_t r = 0; r < n_fed; r++) {
             materialise_slot(r);
