@@ -420,3 +420,40 @@ def test_exciter_not_fused_when_a_voice_is_read_elsewhere_or_the_bank_changes_sh
     a, b = r.fill_buffer(lanes, 3000, 3000), o.fill_buffer(lanes, 3000, 3000)
     assert r.stats()["osc_launches"] > 0
     assert np.abs(a.astype(np.float64) - b).max() <= 1e-4 * np.abs(b).max()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_exciter_fusion_randomized(seed):
+    """Random lane counts (a partly filled CTA, several CTAs), voice maps that leave voices of the bank unused, delays
+    over every comb path (32 .. 1,200), random block cuts (multiples of 8 and odd ones): the exciter-fused chain against
+    bank kernel + fused chain and against the fp64 oracle."""
+    from libfriendship_b200 import FLAG_NO_EXCITER_FUSION
+    rng = np.random.Generator(np.random.PCG64(100 + seed))
+    lanes = [1, 3, 5, 37, 64, 130][seed]
+    n_voices = lanes + int(rng.integers(0, 4))
+    bank = _one_partial_bank(n_voices, seed=30 + seed)
+    voice_of_lane = rng.permutation(n_voices)[:lanes]
+    coefs = rbj_lowpass(rng.uniform(80.0, 12000.0, lanes), rng.uniform(0.7, 3.0, lanes))
+    delay = rng.integers(32, 1200, lanes).astype(np.uint32)
+    gain = rng.uniform(-0.9, 0.9, lanes).astype(np.float32)
+    blocks, left = [], 6000
+    while left > 0:
+        m = int(min(left, rng.choice([8, 64, 256, 512, 1000, 1024, 333, 1])))
+        blocks.append(m)
+        left -= m
+    outs = []
+    for flags in (0, FLAG_NO_EXCITER_FUSION):
+        r = gpu_cls()(flags=flags)
+        _exciter_chain_graph(r, bank, voice_of_lane, coefs, delay, gain)
+        parts, idx = [], 0
+        for m in blocks:
+            parts.append(r.fill_buffer(lanes, m, idx))
+            idx += m
+        outs.append(np.concatenate(parts, axis=1))
+        assert (r.stats()["osc_launches"] == 0) == (flags == 0)
+    o = OracleRenderer()
+    _exciter_chain_graph(o, bank, voice_of_lane, coefs, delay, gain)
+    ref = o.fill_buffer(lanes, 6000, 0)
+    scale = np.abs(ref).max()
+    assert np.abs(outs[0].astype(np.float64) - outs[1]).max() <= 1e-5 * scale
+    assert np.abs(outs[0].astype(np.float64) - ref).max() <= 1e-4 * scale
