@@ -107,6 +107,9 @@ Renderer::~Renderer() {
     if (d_indesc_) cudaFree(d_indesc_);
     if (d_in_stage_) cudaFree(d_in_stage_);
     if (d_ingest_) cudaFree(d_ingest_);
+    for (int i = 0; i < 2; i++) { if (h_pin_indesc_[i]) cudaFreeHost(h_pin_indesc_[i]); if (ev_indesc_[i]) cudaEventDestroy(ev_indesc_[i]); }
+    if (h_pin_in_) cudaFreeHost(h_pin_in_);
+    if (h_pin_out_) cudaFreeHost(h_pin_out_);
     if (d_out_) cudaFree(d_out_);
     if (d_bufdesc_) cudaFree(d_bufdesc_);
     for (auto& st : sstage_) {
@@ -532,16 +535,26 @@ void Renderer::ingest_inputs(uint32_t n_slots, uint64_t n_times, uint64_t idx, c
     }
     if (n_fed > 0) {
         const float* d_rows = in_data;
+        cudaMemcpyKind rows_kind = cudaMemcpyDeviceToDevice;
         uint64_t total = offs[n_fed] - offs[0];
         if (!in_on_device && total > 0) {
-            if (d_in_stage_cap_ < total) {
-                if (d_in_stage_) { CU(cudaStreamSynchronize(stream_)); CU(cudaFree(d_in_stage_)); }
-                d_in_stage_cap_ = pow2_ceil(total);
-                CU(cudaMalloc(&d_in_stage_, d_in_stage_cap_ * sizeof(float)));
+            if (total * sizeof(float) <= kPinBytes) {
+                // short call: the rows go through pinned memory (no stream wait) straight into their history slots
+                if (!h_pin_in_) CU(cudaMallocHost(&h_pin_in_, kPinBytes));
+                CU(cudaStreamSynchronize(stream_));                        // the previous call's copies out of h_pin_in_ (idle stream: free)
+                memcpy(h_pin_in_, in_data + offs[0], total * sizeof(float));
+                rows_kind = cudaMemcpyHostToDevice;
+                d_rows = h_pin_in_ - offs[0];
+            } else {
+                if (d_in_stage_cap_ < total) {
+                    if (d_in_stage_) { CU(cudaStreamSynchronize(stream_)); CU(cudaFree(d_in_stage_)); }
+                    d_in_stage_cap_ = pow2_ceil(total);
+                    CU(cudaMalloc(&d_in_stage_, d_in_stage_cap_ * sizeof(float)));
+                }
+                CU(cudaMemcpyAsync(d_in_stage_, in_data + offs[0], total * sizeof(float), cudaMemcpyHostToDevice, stream_));
+                d_rows = d_in_stage_ - offs[0];
             }
-            CU(cudaMemcpyAsync(d_in_stage_, in_data + offs[0], total * sizeof(float), cudaMemcpyHostToDevice, stream_));
             stats.h2d_bytes += total * sizeof(float);
-            d_rows = d_in_stage_ - offs[0];
         }
         // many long rows: one kernel for all of them instead of a device-to-device copy each
         const bool batched = n_fed >= 4 && n_fed <= 65535 && total >= (1ull << 20);   // rows are grid.y
@@ -552,7 +565,7 @@ void Renderer::ingest_inputs(uint32_t n_slots, uint64_t n_times, uint64_t idx, c
             uint64_t row_len = offs[r + 1] - offs[r];
             grow_slot(s, idx + n_times);
             if (row_len && batched) batch.push_back(IngestRow{s.d_data + (idx - s.base), d_rows + offs[r], row_len});
-            else if (row_len) CU(cudaMemcpyAsync(s.d_data + (idx - s.base), d_rows + offs[r], row_len * sizeof(float), cudaMemcpyDeviceToDevice, stream_));
+            else if (row_len) CU(cudaMemcpyAsync(s.d_data + (idx - s.base), d_rows + offs[r], row_len * sizeof(float), rows_kind, stream_));
         }
         if (!batch.empty()) {
             const size_t bytes = batch.size() * sizeof(IngestRow);
@@ -725,6 +738,8 @@ void Renderer::fill(float* out, bool out_on_device, uint32_t n_slots, uint64_t n
     ingest_inputs(n_slots, n_times, idx, in_data, in_on_device, offs, n_rows);
 
     const uint64_t t1 = idx + n_times;
+    bool pinned_out = false;
+    uint64_t n_out_host = 0;
     if (n_times > 0 && n_slots > 0) {
         // input descriptor table for the slots the schedule reads
         uint32_t nin = sched_.n_input_slots;
@@ -740,11 +755,25 @@ void Renderer::fill(float* out, bool out_on_device, uint32_t n_slots, uint64_t n
                 CU(cudaMalloc(&d_indesc_, d_indesc_cap_ * sizeof(InputDesc)));
                 h_indesc_.clear();
             }
-            // the table is re-uploaded only when it changed (the copy below is waited for, so h_indesc_ is free to rewrite)
+            // the table is re-uploaded only when it changed — when streaming, every call (the history's end moves) —
+            // from one of two pinned buffers: asynchronous, no wait on the stream
             if (h_indesc_.size() != nin || memcmp(h_indesc_.data(), h.data(), nin * sizeof(InputDesc)) != 0) {
                 h_indesc_ = h;
-                CU(cudaMemcpyAsync(d_indesc_, h_indesc_.data(), nin * sizeof(InputDesc), cudaMemcpyHostToDevice, stream_));
-                CU(cudaStreamSynchronize(stream_));
+                if (h_pin_indesc_cap_ < nin) {
+                    CU(cudaStreamSynchronize(stream_));
+                    for (int i = 0; i < 2; i++) {
+                        if (h_pin_indesc_[i]) CU(cudaFreeHost(h_pin_indesc_[i]));
+                        h_pin_indesc_[i] = nullptr;
+                        CU(cudaMallocHost(&h_pin_indesc_[i], d_indesc_cap_ * sizeof(InputDesc)));
+                        if (!ev_indesc_[i]) CU(cudaEventCreateWithFlags(&ev_indesc_[i], cudaEventDisableTiming));
+                    }
+                    h_pin_indesc_cap_ = d_indesc_cap_;
+                }
+                const unsigned b = pin_indesc_next_++ & 1u;
+                CU(cudaEventSynchronize(ev_indesc_[b]));                   // the copy that last read this buffer (two uploads ago)
+                memcpy(h_pin_indesc_[b], h.data(), nin * sizeof(InputDesc));
+                CU(cudaMemcpyAsync(d_indesc_, h_pin_indesc_[b], nin * sizeof(InputDesc), cudaMemcpyHostToDevice, stream_));
+                CU(cudaEventRecord(ev_indesc_[b], stream_));
             }
         }
         ensure_rings(t1);
@@ -769,8 +798,11 @@ void Renderer::fill(float* out, bool out_on_device, uint32_t n_slots, uint64_t n
         cache_valid_ = true;
         cache_head_ = t1;
         if (!out_on_device) {
-            CU(cudaMemcpyAsync(out, d_out, n_out * sizeof(float), cudaMemcpyDeviceToHost, stream_));
+            pinned_out = n_out * sizeof(float) <= kPinBytes;
+            if (pinned_out && !h_pin_out_) CU(cudaMallocHost(&h_pin_out_, kPinBytes));
+            CU(cudaMemcpyAsync(pinned_out ? h_pin_out_ : out, d_out, n_out * sizeof(float), cudaMemcpyDeviceToHost, stream_));
             stats.d2h_bytes += n_out * sizeof(float);
+            n_out_host = n_out;
         }
     }
     head_ = t1;                           // reference.rs:84
@@ -779,7 +811,10 @@ void Renderer::fill(float* out, bool out_on_device, uint32_t n_slots, uint64_t n
         CU(cudaEventSynchronize(ev_[1]));
         CU(cudaEventElapsedTime(&timing.total_ms, ev_[0], ev_[1]));
     }
-    if (!out_on_device) CU(cudaStreamSynchronize(stream_));
+    if (!out_on_device) {
+        CU(cudaStreamSynchronize(stream_));
+        if (pinned_out) memcpy(out, h_pin_out_, n_out_host * sizeof(float));
+    }
 }
 
 // N4 (include/friendship_b200.h): consecutive fill_buffer calls of `block` samples, two blocks in flight.

@@ -136,6 +136,16 @@ private:
     float* d_out_ = nullptr;
     size_t d_out_cap_ = 0;
     std::vector<InputDesc> h_indesc_;                              // what d_indesc_ currently holds
+    // Pinned staging for short calls through host buffers (a pageable cudaMemcpyAsync synchronises the stream before it
+    // copies: three of them per call made three waits out of one): the descriptor table (two buffers, an event each),
+    // the input rows and the output of calls up to kPinBytes.
+    static constexpr size_t kPinBytes = 256 * 1024;
+    InputDesc* h_pin_indesc_[2] = {nullptr, nullptr};
+    size_t h_pin_indesc_cap_ = 0;
+    cudaEvent_t ev_indesc_[2] = {nullptr, nullptr};
+    unsigned pin_indesc_next_ = 0;
+    float* h_pin_in_ = nullptr;
+    float* h_pin_out_ = nullptr;
 
     // streaming render (N4): two blocks in flight
     struct StreamStage { float* d_out = nullptr; float* h_out = nullptr; float* h_in = nullptr;
