@@ -266,7 +266,7 @@ cudaError_t launch_interp(const InterpParams& p_in, unsigned n_regs, int sm_coun
     unsigned long long per_sm = 227ull * 1024ull / (smem + 1024);
     if (per_sm > 12) per_sm = 12;
     if (per_sm < 1) per_sm = 1;
-    unsigned long long cap = ((unsigned long long)sm_count * per_sm + p.n_strands - 1) / p.n_strands;
+    unsigned long long cap = (unsigned long long)sm_count * per_sm / p.n_strands;   // rounded down: never a second wave of a few CTAs
     if (cap < 1) cap = 1;
     if (blocks > cap) blocks = cap;
     interp_kernel<<<dim3((unsigned)blocks, p.n_strands), threads, smem, stream>>>(p);

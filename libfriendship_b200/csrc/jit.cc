@@ -282,7 +282,7 @@ bool jit_launch(JitKernel* k, const InterpParams& p, int sm_count, cudaStream_t 
     if (!a.ok || !k) return false;
     if (p.n_groups == 0) return true;
     unsigned long long blocks = (p.n_groups + 127) / 128;
-    unsigned long long cap = ((unsigned long long)sm_count * 16 + p.n_strands - 1) / p.n_strands;
+    unsigned long long cap = (unsigned long long)sm_count * 16 / p.n_strands;   // rounded down: never a second wave of a few CTAs
     if (cap < 1) cap = 1;
     if (blocks > cap) blocks = cap;
     InterpParams pp = p;

@@ -577,7 +577,7 @@ void Renderer::ingest_inputs(uint32_t n_slots, uint64_t n_times, uint64_t idx, c
             CU(cudaMemcpyAsync(d_ingest_, batch.data(), bytes, cudaMemcpyHostToDevice, stream_));   // pageable: staged before the call returns
             uint64_t longest = 0;
             for (const IngestRow& b : batch) longest = std::max<uint64_t>(longest, b.n);
-            const unsigned per_row = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((longest / 4 + 1023) / 1024, ((uint64_t)sm_count_ * 8 + batch.size() - 1) / batch.size()));
+            const unsigned per_row = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((longest / 4 + 1023) / 1024, (uint64_t)sm_count_ * 8 / batch.size()));   // rounded down: the grid fits in one wave (8 CTAs of 256 threads per SM)
             ingest_rows_kernel<<<dim3(per_row, (unsigned)batch.size()), 256, 0, stream_>>>(static_cast<const IngestRow*>(d_ingest_));
             CU(cudaGetLastError());
             stats.kernel_launches++;

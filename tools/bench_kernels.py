@@ -34,6 +34,40 @@ def timed_fill(r, d_out, n_slots, n, idx, d_in=0, offs=None, reps=5):
     return best
 
 
+def case_pure_continuing(n_slots=64, n=1 << 22, reps=5):
+    """The pure elementwise graph in consecutive calls (idx advances: no seek, so none of the per-slot history resets
+    a seek costs): what the ingest kernel itself takes = total_ms - interp_ms of the best call."""
+    from libfriendship_b200 import KIND_MINIMUM
+    r = B200Renderer()
+    g = GraphBuilder(r)
+    for s in range(n_slots):
+        x = g.input(s)
+        a = g.node(KIND_MULTIPLY, x, g.const(0.5))
+        b = g.node(KIND_SUM2, a, g.const(0.25))
+        g.output(s, g.node(KIND_MINIMUM, b, x))
+    x = torch.rand((n_slots, n), dtype=torch.float32, device="cuda")
+    out = torch.empty((n_slots, n), dtype=torch.float32, device="cuda")
+    offs = np.arange(n_slots + 1, dtype=np.uint64) * n
+    idx = 0
+    for _ in range(2):
+        r.fill_buffer_device(out.data_ptr(), n_slots, n, idx, x.data_ptr(), offs)
+        idx += n
+    r.sync()
+    r.set_profiling(True)
+    calls = []
+    for _ in range(reps):
+        r.fill_buffer_device(out.data_ptr(), n_slots, n, idx, x.data_ptr(), offs)
+        r.sync()
+        idx += n
+        calls.append(r.timing())
+    r.set_profiling(False)
+    t = min(calls, key=lambda c: c["total_ms"])      # a call in which no history buffer had to grow
+    ingest = t["total_ms"] - t["interp_ms"]
+    return {"case": "K2 pure elementwise, consecutive calls (no seek)", "slots": n_slots, "samples": n, "ms": t["total_ms"],
+            "interp_ms": t["interp_ms"], "ingest_ms": ingest, "ingest_GBs": 8.0 * n_slots * n / ingest / 1e6, "peak_GBs": HBM,
+            "all_calls_ms": [c["total_ms"] for c in calls]}
+
+
 def case_elementwise(n_slots=64, n=1 << 22):
     """out_s = 0.5*in_s + 0.35*Delay(0.5*in_s, 12000)  for s in slots: reads one input plane, writes one output plane
     (+ the materialised delay source: one ring write + one ring read).  Algorithmic: 8 B/sample (in + out)."""
@@ -144,7 +178,7 @@ def case_cfg1():
 if __name__ == "__main__":
     which = sys.argv[1:] or ["pure", "elementwise", "cfg3"]
     for w in which:
-        fn = {"pure": case_pure_elementwise, "elementwise": case_elementwise, "cfg3": case_cfg3, "cfg3_unfused": lambda: case_cfg3(flags=8), "cfg3_ring": lambda: case_cfg3(flags=16), "cfg3_L64": lambda: case_cfg3(osc_anchor=64), "cfg3_L32": lambda: case_cfg3(osc_anchor=32),
+        fn = {"pure": case_pure_elementwise, "pure_continuing": case_pure_continuing, "elementwise": case_elementwise, "cfg3": case_cfg3, "cfg3_unfused": lambda: case_cfg3(flags=8), "cfg3_ring": lambda: case_cfg3(flags=16), "cfg3_L64": lambda: case_cfg3(osc_anchor=64), "cfg3_L32": lambda: case_cfg3(osc_anchor=32),
           "cfg3_L128": lambda: case_cfg3(osc_anchor=128), "cfg3_L256": lambda: case_cfg3(osc_anchor=256), "cfg1": case_cfg1, "cfg2": case_cfg2, "cfg2_64": lambda: case_cfg2(64), "cfg2_32": lambda: case_cfg2(32)}[w]
         t0 = time.time()
         try:
