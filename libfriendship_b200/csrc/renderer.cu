@@ -94,6 +94,7 @@ Renderer::Renderer(const frb_config& cfg) : cfg_(cfg) {
     CU(cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, device_));
     CU(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     for (auto& ev : ev_) CU(cudaEventCreate(&ev));
+    if (const char* e = getenv("FRB_NO_ALIGN_SPLIT")) align_split_ = !(e[0] == '1');   // measurement knob (tools/align_probe.py)
     CU(interp_init_device());
     CU(osc_init_device());
 }
@@ -655,9 +656,17 @@ void Renderer::run_range(uint64_t lo, uint64_t hi, float* d_out, uint64_t t0, ui
         }
     };
     const int out_vec_ok = d_out && (t0 % 4 == 0) && (out_stride % 4 == 0) && ((uintptr_t)d_out % 16 == 0);
+    // The recurrence kernels move 128-bit quads only from a block start that is a multiple of 4 (8 when the chain
+    // evaluates its exciters); an unaligned start would cost them the fast tiles of the whole chunk (2.2x at
+    // 4,097-sample blocks).  The at most 7 samples up to the next multiple of 8 are therefore rendered as a range of
+    // their own — the same thing as two consecutive calls — when the rest is long enough to pay for the launches.
+    bool has_recurrence = false;
+    for (const ExtInstance& x : sched_.ext) has_recurrence |= (x.kind == EXT_DIRECTFORM || x.kind == EXT_FBDELAY);
+    constexpr uint64_t kAlignSplitMin = 2048;
     uint64_t c0 = lo;
     while (c0 < hi) {
         uint64_t c1 = std::min(hi, (c0 / chunk_ + 1) * chunk_);
+        if (has_recurrence && align_split_ && (c0 & 7) && c1 - c0 >= kAlignSplitMin) c1 = (c0 | 7) + 1;
         for (size_t sg = 0; sg < sched_.stages.size(); sg++) {
             const Stage& st = sched_.stages[sg];
             for (uint32_t xi : st.ext) {

@@ -119,6 +119,7 @@ private:
     size_t d_bufdesc_cap_ = 0;
     bool bufdesc_dirty_ = true;
     uint64_t chunk_ = 1ull << 16;
+    bool align_split_ = true;                                      // run_range: unaligned heads rendered on their own
 
     // external-input history
     std::vector<InputSlot> inputs_;

@@ -221,6 +221,38 @@ def test_fused_chain_equals_separate_kernels_bit_exact(blocks):
     assert np.abs(outs[0].astype(np.float64) - ref).max() <= 1e-4 * scale
 
 
+def test_unaligned_block_start_is_split_off_and_both_ways_are_the_recurrence(monkeypatch):
+    """A long block whose start is not a multiple of 8: run_range renders the head up to the next multiple of 8 as a
+    range of its own (renderer.cu), so the chain's fast tiles apply to the rest.  With the split and without it
+    (FRB_NO_ALIGN_SPLIT=1, the measurement knob) the tiles fall differently — both are the recurrence within the north
+    star's 1e-4 of full scale, and the split is what two consecutive calls cut at the same place give, bit for bit."""
+    lanes = len(CHAIN_DELAYS)
+    coefs = rbj_lowpass(np.geomspace(60.0, 15000.0, lanes), np.linspace(0.707, 4.0, lanes))
+    gain = np.linspace(-0.95, 0.95, lanes).astype(np.float32)
+    cuts = {"split": [3, 20000], "two_calls": [3, 5, 19995], "no_split": [3, 20000]}
+    n = 20003
+    x = noise(lanes, n, seed=21)
+    outs = {}
+    for name, blocks in cuts.items():
+        if name == "no_split":
+            monkeypatch.setenv("FRB_NO_ALIGN_SPLIT", "1")
+        r = gpu_cls()()
+        _chain_graph(r, coefs, CHAIN_DELAYS, gain)
+        parts, idx = [], 0
+        for m in blocks:
+            parts.append(r.fill_buffer(lanes, m, idx, [row[idx:idx + m] for row in x]))
+            idx += m
+        assert r.stats()["chain_launches"] > 0
+        outs[name] = np.concatenate(parts, axis=1)
+    assert_same_bits(outs["split"], outs["two_calls"], "split head vs two calls")
+    o = OracleRenderer()
+    _chain_graph(o, coefs, CHAIN_DELAYS, gain)
+    ref = o.fill_buffer(lanes, n, 0, x)
+    scale = np.abs(ref).max()
+    for name in ("split", "no_split"):
+        assert np.abs(outs[name].astype(np.float64) - ref).max() <= 1e-4 * scale, name
+
+
 def test_chain_not_fused_when_biquad_is_tapped_or_comb_is_short():
     lanes = 3
     coefs = rbj_lowpass(np.array([300.0, 1000.0, 5000.0]), np.array([1.0, 2.0, 0.8]))

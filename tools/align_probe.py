@@ -16,9 +16,13 @@ from libfriendship_b200 import B200Renderer
 from banks import detuned_bank
 from filters import build_cfg3_graph
 
+# argv: [n_voices [block ...]]; FRB_NO_ALIGN_SPLIT=1 in the environment renders unaligned heads inside the block (the
+# behaviour before run_range split them off)
+N_VOICES = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+BLOCKS = tuple(int(a) for a in sys.argv[2:]) or (448, 441, 4096, 4097)
 for flags, name in ((0, "exciters inside the chain kernel"), (16, "exciters on rings")):
-    for block in (448, 441, 4096, 4097):
-        n_voices = 1024
+    for block in BLOCKS:
+        n_voices = N_VOICES
         r = B200Renderer(flags=flags)
         bank, _ = detuned_bank(n_voices, 1, seed=5)
         build_cfg3_graph(r, n_voices, excitation="osc", bank=bank, mix_to_one=True)
@@ -28,8 +32,8 @@ for flags, name in ((0, "exciters inside the chain kernel"), (16, "exciters on r
             r.fill_buffer_device(out.data_ptr(), 1, block, idx, 0, None); idx += block
         r.sync()
         t0 = time.perf_counter()
-        nb = 100
+        nb = 100 if block * n_voices < (1 << 24) else 20
         for _ in range(nb):
             r.fill_buffer_device(out.data_ptr(), 1, block, idx, 0, None); idx += block
         r.sync()
-        print(json.dumps({"case": name, "block": block, "ms_per_block": (time.perf_counter() - t0) * 1e3 / nb}), flush=True)
+        print(json.dumps({"case": name, "voices": n_voices, "block": block, "align_split": os.environ.get("FRB_NO_ALIGN_SPLIT") != "1", "ms_per_block": (time.perf_counter() - t0) * 1e3 / nb}), flush=True)
