@@ -100,6 +100,8 @@ void* frb_stream(frb_renderer* r) { return r ? (void*)r->impl.stream() : nullptr
 
 int frb_device_alloc(frb_renderer* r, uint64_t bytes, void** d_ptr_out) {
     return guarded(r, [&] {
+        if (!d_ptr_out) throw Error{FRB_E_INVALID, "d_ptr_out is NULL"};
+        r->impl.use_device();
         cudaError_t e = cudaMalloc(d_ptr_out, bytes);
         if (e == cudaSuccess) e = cudaMemset(*d_ptr_out, 0, bytes);
         if (e != cudaSuccess) throw Error{FRB_E_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e)};
@@ -107,6 +109,7 @@ int frb_device_alloc(frb_renderer* r, uint64_t bytes, void** d_ptr_out) {
 }
 int frb_device_free(frb_renderer* r, void* d_ptr) {
     return guarded(r, [&] {
+        r->impl.use_device();
         cudaError_t e = cudaFree(d_ptr);
         if (e != cudaSuccess) throw Error{FRB_E_CUDA, std::string("cudaFree: ") + cudaGetErrorString(e)};
     });
@@ -114,6 +117,8 @@ int frb_device_free(frb_renderer* r, void* d_ptr) {
 int frb_ipc_export(frb_renderer* r, const void* d_ptr, unsigned char handle[64]) {
     return guarded(r, [&] {
         static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        if (!d_ptr || !handle) throw Error{FRB_E_INVALID, "null argument"};
+        r->impl.use_device();
         cudaIpcMemHandle_t h;
         cudaError_t e = cudaIpcGetMemHandle(&h, const_cast<void*>(d_ptr));
         if (e != cudaSuccess) throw Error{FRB_E_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)};
@@ -122,6 +127,8 @@ int frb_ipc_export(frb_renderer* r, const void* d_ptr, unsigned char handle[64])
 }
 int frb_ipc_open(frb_renderer* r, const unsigned char handle[64], void** d_ptr_out) {
     return guarded(r, [&] {
+        if (!handle || !d_ptr_out) throw Error{FRB_E_INVALID, "null argument"};
+        r->impl.use_device();
         cudaIpcMemHandle_t h;
         memcpy(&h, handle, 64);
         cudaError_t e = cudaIpcOpenMemHandle(d_ptr_out, h, cudaIpcMemLazyEnablePeerAccess);
@@ -130,6 +137,7 @@ int frb_ipc_open(frb_renderer* r, const unsigned char handle[64], void** d_ptr_o
 }
 int frb_ipc_close(frb_renderer* r, void* d_ptr) {
     return guarded(r, [&] {
+        r->impl.use_device();
         cudaError_t e = cudaIpcCloseMemHandle(d_ptr);
         if (e != cudaSuccess) throw Error{FRB_E_CUDA, std::string("cudaIpcCloseMemHandle: ") + cudaGetErrorString(e)};
     });

@@ -129,6 +129,11 @@ void Renderer::require_device() const {
     if (host_only_) throw Error{FRB_E_NO_DEVICE, "renderer was created without a CUDA device (planning only); there is no CPU fallback"};
 }
 
+void Renderer::use_device() const {
+    require_device();
+    CU(cudaSetDevice(device_));
+}
+
 // ------------------------------------------------------------------------------------------------ definitions
 
 GraphNode Renderer::make_node(uint32_t kind, uint64_t key) const {

@@ -55,6 +55,7 @@ public:
 
     const Schedule& schedule(uint32_t n_slots);   // (re)builds if needed
     cudaStream_t stream() const { return stream_; }
+    void use_device() const;                      // makes the renderer's device current (throws when planning only)
 
     std::string last_error;
     std::string last_jit_error;
