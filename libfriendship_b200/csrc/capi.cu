@@ -58,7 +58,10 @@ void frb_destroy(frb_renderer* r) { delete r; }
 const char* frb_last_error(const frb_renderer* r) { return r ? r->impl.last_error.c_str() : g_create_error.c_str(); }
 
 int frb_define_effect(frb_renderer* r, uint64_t key, const frb_node* nodes, uint32_t n_nodes, const frb_edge* edges, uint32_t n_edges) {
-    return guarded(r, [&] { r->impl.define_effect(key, nodes, n_nodes, edges, n_edges); });
+    return guarded(r, [&] {
+        if ((n_nodes && !nodes) || (n_edges && !edges)) throw Error{FRB_E_INVALID, "null array"};
+        r->impl.define_effect(key, nodes, n_nodes, edges, n_edges);
+    });
 }
 int frb_define_oscbank(frb_renderer* r, uint64_t key, const frb_oscbank_desc* d) {
     return guarded(r, [&] { if (!d) throw Error{FRB_E_INVALID, "null desc"}; r->impl.define_oscbank(key, d); });

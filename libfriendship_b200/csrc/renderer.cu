@@ -211,6 +211,7 @@ void Renderer::define_directform(uint64_t key, const frb_directform_desc* d) {
 void Renderer::define_fbdelay(uint64_t key, const frb_fbdelay_desc* d) {
     if (host_only_) {
         uint64_t mx = 0;
+        if (d->n_lanes && (!d->delay || !d->gain)) throw Error{FRB_E_INVALID, "fbdelay: null array"};
         for (uint32_t i = 0; i < d->n_lanes; i++) {
             if (d->delay[i] < 1) throw Error{FRB_E_INVALID, "fbdelay: delay must be >= 1"};
             mx = std::max<uint64_t>(mx, d->delay[i]);

@@ -49,6 +49,28 @@ def test_no_cpu_fallback_without_device():
         assert e.code == L._cabi.FRB_E_NO_DEVICE
 
 
+def test_null_arguments_are_refused_not_dereferenced():
+    """Raw C callers: NULL arrays / out-pointers come back as FRB_E_INVALID (or FRB_E_NO_DEVICE for the device helpers
+    of a planning-only handle), never as a crash."""
+    import ctypes as C
+    import libfriendship_b200 as L
+    lib = L._lib
+    r = L.B200Renderer(device=-1)
+    h = r._h
+    assert lib.frb_define_effect(h, C.c_uint64(7), None, C.c_uint32(2), None, C.c_uint32(0)) == L._cabi.FRB_E_INVALID
+    assert lib.frb_define_effect(h, C.c_uint64(7), None, C.c_uint32(0), None, C.c_uint32(3)) == L._cabi.FRB_E_INVALID
+    assert lib.frb_define_effect(h, C.c_uint64(7), None, C.c_uint32(0), None, C.c_uint32(0)) == 0     # an empty effect is fine
+    for fn in (lib.frb_define_oscbank, lib.frb_define_directform, lib.frb_define_fbdelay):
+        assert fn(h, C.c_uint64(9), None) == L._cabi.FRB_E_INVALID
+
+    d = L._cabi.frb_fbdelay_desc(4, 0, None, None)
+    assert lib.frb_define_fbdelay(h, C.c_uint64(9), C.byref(d)) == L._cabi.FRB_E_INVALID
+    assert lib.frb_device_alloc(h, C.c_uint64(16), None) == L._cabi.FRB_E_INVALID
+    out = C.c_void_p()
+    assert lib.frb_device_alloc(h, C.c_uint64(16), C.byref(out)) == L._cabi.FRB_E_NO_DEVICE   # planning only: no device
+    assert lib.frb_fill_buffer(None, None, 1, 4, 0, None, None, 0) == L._cabi.FRB_E_INVALID
+
+
 def test_product_does_not_link_or_import_oracle():
     import subprocess
     import libfriendship_b200 as L
