@@ -152,6 +152,29 @@ class Dispatch:
         except Exception:
             pass
 
+    # ---- OscToplevel: the one entry point of the reference, `Dispatch::dispatch(msg)` (dispatch.rs:109-160) ----
+    _ROUTES = {
+        "/routegraph/add_node": "add_node", "/routegraph/add_edge": "add_edge", "/routegraph/del_node": "del_node",
+        "/routegraph/del_edge": "del_edge", "/routegraph/query_meta": "query_meta", "/routegraph/query_id": "query_id",
+        "/renderer/render": "_render_msg", "/resman/add_dir": "add_dir",
+    }
+
+    def dispatch(self, address, *args):
+        """One OSC message by its address — the `#[osc_address]` paths of `OscToplevel` / `OscRouteGraph` /
+        `OscRenderer` / `OscResMan` (dispatch.rs:31-84) — with the message's argument tuple:
+        `/routegraph/add_node (handle, EffectId)`, `/routegraph/add_edge (edge,)`, `/routegraph/del_node (handle,)`,
+        `/routegraph/del_edge (edge,)`, `/routegraph/query_meta (handle,)`, `/routegraph/query_id (handle,)`,
+        `/renderer/render (range, num_slots, inputs)`, `/resman/add_dir (dir,)`.  The byte encoding of OSC packets
+        (the reference derives it with an external macro crate) is not part of this layer."""
+        name = self._ROUTES.get("/" + "/".join(p for p in address.split("/") if p))
+        if name is None:
+            raise DispatchError(-108, f"no such OSC address: {address}")
+        return getattr(self, name)(*args)
+
+    def _render_msg(self, rng, n_slots, inputs=None):
+        start, end = (rng.start, rng.stop) if isinstance(rng, range) else rng
+        return self.render_range(start, end, n_slots, inputs)
+
     # ---- OscRouteGraph ----
     def add_node(self, handle, effect_id):
         self._check(_lib.frd_add_node(self._h, handle, effect_id.to_json().encode()))

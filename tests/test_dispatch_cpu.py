@@ -183,3 +183,40 @@ def test_render_without_a_device_fails_loudly():
     with pytest.raises(DispatchError) as e:
         d.render_range(0, 4, 1)
     assert e.value.code == -9
+
+
+def test_messages_by_osc_address(tmp_path):
+    """`Dispatch::dispatch(OscToplevel)` (dispatch.rs:109-160): every message through the one entry point, by the
+    address its `#[osc_address]` attributes spell (dispatch.rs:31-84)."""
+    (tmp_path / "mulby2.fnd").write_text(json.dumps(mulby_desc()))
+    got = []
+
+    class C(Client):
+        def node_meta(self, handle, meta):
+            got.append(("meta", handle, meta["id"]["name"]))
+
+        def node_id(self, handle, id):
+            got.append(("id", handle, id["name"]))
+
+    d = planner(C())
+    d.dispatch("/resman/add_dir", tmp_path)
+    d.dispatch("/routegraph/add_node", 1, EffectId("MulBy2"))
+    d.dispatch("/routegraph/add_node", 2, EffectId.primitive("Delay"))
+    d.dispatch("/routegraph/add_edge", (0, 1, 0, 0))
+    d.dispatch("routegraph/add_edge/", (1, 2, 0, 0))                          # leading / trailing separators do not matter
+    d.dispatch("/routegraph/query_meta", 1)
+    d.dispatch("/routegraph/query_id", 2)
+    assert got == [("meta", 1, "MulBy2"), ("id", 2, "Delay")]
+    with pytest.raises(DispatchError) as e:
+        d.dispatch("/routegraph/del_node", 1)
+    assert e.value.variant == "NodeInUse"
+    d.dispatch("/routegraph/del_edge", (1, 2, 0, 0))
+    d.dispatch("/routegraph/del_edge", (0, 1, 0, 0))
+    d.dispatch("/routegraph/del_node", 1)
+    assert [n[0]["node_handle"] for n in d.adjlist()["nodes"]] == [2]
+    with pytest.raises(DispatchError) as e:
+        d.dispatch("/renderer/render", range(0, 4), 1, None)                  # planning only: refused, not emulated
+    assert e.value.code == -9
+    with pytest.raises(DispatchError) as e:
+        d.dispatch("/renderer/stop")
+    assert e.value.variant == "BadMessage"

@@ -11,8 +11,9 @@ pytestmark = pytest.mark.gpu
 KIND_NAME = {0: "Delay", 1: "F32Constant", 2: "Sum2", 3: "Multiply", 4: "Divide", 5: "Modulo", 6: "Minimum"}
 
 
+@pytest.mark.parametrize("via", ["methods", "osc_address"])
 @pytest.mark.parametrize("test", load_golden(), ids=lambda t: t["name"])
-def test_dispatch_replays_reference_tests(test, tmp_path):
+def test_dispatch_replays_reference_tests(test, via, tmp_path):
     from libfriendship_b200.dispatch import Client, Dispatch, EffectId, sha256_file
     from test_dispatch_cpu import bits  # noqa: F401
 
@@ -23,6 +24,16 @@ def test_dispatch_replays_reference_tests(test, tmp_path):
             rendered.append(buffer)
 
     d = Dispatch(MyClient())
+    if via == "osc_address":
+        # the same messages through the one entry point, by address (Dispatch::dispatch, dispatch.rs:109-160)
+        disp = d
+
+        class ByAddress:
+            add_dir = staticmethod(lambda p: disp.dispatch("/resman/add_dir", p))
+            add_node = staticmethod(lambda h, eid: disp.dispatch("/routegraph/add_node", h, eid))
+            add_edge = staticmethod(lambda e: disp.dispatch("/routegraph/add_edge", e))
+            render_range = staticmethod(lambda a, b, n, inputs: disp.dispatch("/renderer/render", range(a, b), n, inputs))
+        d = ByAddress
     effect_ids = {}
     for step in test["steps"]:
         op = step["op"]
