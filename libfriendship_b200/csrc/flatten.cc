@@ -16,11 +16,16 @@
 #include <cmath>
 #include <cstring>
 #include <functional>
+#include <exception>
 #include <map>
+
+#include <pthread.h>
 
 namespace frb {
 
 namespace {
+
+constexpr int kMaxDepthGuard = 500000;            // levels of recursion the walk's own stack is sized for (flatten() below)
 
 struct Ctx {
     const Graph* g;
@@ -119,7 +124,7 @@ struct Flattener {
     }
 
     uint32_t resolve(int ctx, const frb_edge& e) {
-        if (++depth > 100000) throw Error{FRB_E_UNSUPPORTED, "graph too deep to flatten"};
+        if (++depth > kMaxDepthGuard) throw Error{FRB_E_UNSUPPORTED, "graph too deep to flatten (longest path over 500,000 nodes)"};
         struct Guard { int& d; ~Guard() { --d; } } guard{depth};
         const Ctx c = ctxs[ctx];
         if (e.from == 0) {
@@ -250,7 +255,39 @@ uint64_t sat_add(uint64_t a, uint64_t b) {
 
 }  // namespace
 
+namespace {
+Schedule flatten_here(const Graph& top, uint32_t n_slots, const FlattenEnv& env);
+}
+
+// The depth-first walk recurses once per node of the longest path (about 600 B of stack per level): a Sum2 chain of
+// 15,000 nodes overflows the 8 MB of a default thread — the reference's per-sample recursion (reference.rs:178-266)
+// has the same limit.  The walk therefore runs on a thread of its own whose stack (reserved, committed only as far as
+// it is touched) holds kMaxDepthGuard (500,000) levels, and deeper graphs are refused with FRB_E_UNSUPPORTED instead of crashing
+// the host process.
+constexpr size_t kFlattenStack = 512ull << 20;
+
 Schedule flatten(const Graph& top, uint32_t n_slots, const FlattenEnv& env) {
+    struct Job { const Graph* top; uint32_t n_slots; const FlattenEnv* env; Schedule out; std::exception_ptr err; } job{&top, n_slots, &env, {}, nullptr};
+    auto body = [](void* p) -> void* {
+        Job& j = *static_cast<Job*>(p);
+        try { j.out = flatten_here(*j.top, j.n_slots, *j.env); } catch (...) { j.err = std::current_exception(); }
+        return nullptr;
+    };
+    pthread_attr_t attr;
+    pthread_t th;
+    bool started = false;
+    if (pthread_attr_init(&attr) == 0) {
+        if (pthread_attr_setstacksize(&attr, kFlattenStack) == 0) started = pthread_create(&th, &attr, body, &job) == 0;
+        pthread_attr_destroy(&attr);
+    }
+    if (!started) throw Error{FRB_E_UNSUPPORTED, "cannot reserve the stack for the graph walk"};
+    pthread_join(th, nullptr);
+    if (job.err) std::rethrow_exception(job.err);
+    return std::move(job.out);
+}
+
+namespace {
+Schedule flatten_here(const Graph& top, uint32_t n_slots, const FlattenEnv& env) {
     Schedule s;
     Flattener f(env, s);
     f.ctxs.push_back(Ctx{&top, -1, nullptr});
@@ -436,7 +473,7 @@ Schedule flatten(const Graph& top, uint32_t n_slots, const FlattenEnv& env) {
         std::vector<int64_t> vreg_of(nv, -1);
         uint32_t n_vreg = 0;
         auto new_vreg = [&]() { return n_vreg++; };
-        const uint32_t NOREG = 0xFFFFu;
+        const uint32_t NOREG = 0xFFFFFFFFu;   // not a virtual register (a stage may have more than 65,535); packs as 0xFFFF in Instr::make
 
         // operand: immediate for constants, register otherwise (loading leaves / planes on first use)
         auto operand = [&](uint32_t u, uint32_t imm_flag, uint32_t* flags) -> uint32_t {
@@ -608,6 +645,7 @@ Schedule flatten(const Graph& top, uint32_t n_slots, const FlattenEnv& env) {
     }
     return s;
 }
+}  // namespace
 
 std::vector<uint32_t> Schedule::dump() const {
     std::vector<uint32_t> w;

@@ -98,7 +98,7 @@ struct Json {
     // ---- parse ----
     static Json parse(const std::string& text) {
         size_t p = 0;
-        Json j = parse_value(text, p);
+        Json j = parse_value(text, p, 0);
         skip_ws(text, p);
         if (p != text.size()) throw std::runtime_error("trailing characters after JSON value");
         return j;
@@ -108,7 +108,11 @@ private:
     static void skip_ws(const std::string& t, size_t& p) {
         while (p < t.size() && (t[p] == ' ' || t[p] == '\n' || t[p] == '\r' || t[p] == '\t')) p++;
     }
-    static Json parse_value(const std::string& t, size_t& p) {
+    // nesting is bounded like serde_json's parser, which the reference loads effect files with (recursion limit 128):
+    // a hostile file must not overflow the stack
+    static constexpr int kMaxDepth = 128;
+    static Json parse_value(const std::string& t, size_t& p, int depth) {
+        if (depth > kMaxDepth) throw std::runtime_error("recursion limit exceeded");
         skip_ws(t, p);
         if (p >= t.size()) throw std::runtime_error("unexpected end of JSON");
         char c = t[p];
@@ -124,7 +128,7 @@ private:
                 skip_ws(t, p);
                 if (p >= t.size() || t[p] != ':') throw std::runtime_error("expected ':'");
                 p++;
-                j.o.emplace_back(k, parse_value(t, p));
+                j.o.emplace_back(k, parse_value(t, p, depth + 1));
                 skip_ws(t, p);
                 if (p < t.size() && t[p] == ',') { p++; continue; }
                 if (p < t.size() && t[p] == '}') { p++; return j; }
@@ -137,7 +141,7 @@ private:
             skip_ws(t, p);
             if (p < t.size() && t[p] == ']') { p++; return j; }
             for (;;) {
-                j.a.push_back(parse_value(t, p));
+                j.a.push_back(parse_value(t, p, depth + 1));
                 skip_ws(t, p);
                 if (p < t.size() && t[p] == ',') { p++; continue; }
                 if (p < t.size() && t[p] == ']') { p++; return j; }

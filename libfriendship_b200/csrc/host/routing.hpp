@@ -21,6 +21,7 @@
 #include <optional>
 #include <set>
 #include <sstream>
+#include <unordered_set>
 #include <string>
 #include <vector>
 
@@ -346,8 +347,7 @@ public:
         for (auto& ef : nodes_.at(0).outbound) {
             if (ef.from_slot != in_slot) continue;
             if (ef.to == 0) { if (ef.to_slot == out_slot) return true; continue; }          // direct pass-through edge
-            std::set<Edge> seen;
-            if (reaches(ef, 0, out_slot, seen)) return true;
+            if (reaches(ef, 0, out_slot)) return true;
         }
         return false;
     }
@@ -382,19 +382,27 @@ private:
     // From edge `from` (already at node from.to, slot from.to_slot): can a chain of internally connected slots reach
     // node `target`, arriving at an edge that leaves through... (for target == toplevel: an edge into output `slot`;
     // for a real node: an edge into `target` whose to_slot is internally connected to output `slot` of `target`).
-    bool reaches(const Edge& from, uint32_t target, uint32_t slot, std::set<Edge>& seen) const {
-        if (from.to == 0) return false;
-        if (!seen.insert(from).second) return false;
-        auto it = nodes_.find(from.to);
-        if (it == nodes_.end()) return false;
-        const Node& n = it->second;
-        if (from.to == target && target != 0) {
-            if (!n.data || n.data->are_slots_connected(from.to_slot, slot)) return true;
-        }
-        for (auto& cand : n.outbound) {
-            if (n.data && !n.data->are_slots_connected(from.to_slot, cand.from_slot)) continue;   // :239-243
-            if (target == 0 && cand.to == 0 && cand.to_slot == slot) return true;
-            if (reaches(cand, target, slot, seen)) return true;
+    // Iterative (a chain of tens of thousands of nodes must not be a stack depth), and a state is the (node, input slot)
+    // an edge arrives at: two edges into the same slot continue the same way.
+    bool reaches(const Edge& start, uint32_t target, uint32_t slot) const {
+        std::unordered_set<uint64_t> seen;
+        std::vector<Edge> todo{start};
+        while (!todo.empty()) {
+            const Edge from = todo.back();
+            todo.pop_back();
+            if (from.to == 0) continue;
+            if (!seen.insert(((uint64_t)from.to << 32) | from.to_slot).second) continue;
+            auto it = nodes_.find(from.to);
+            if (it == nodes_.end()) continue;
+            const Node& n = it->second;
+            if (from.to == target && target != 0) {
+                if (!n.data || n.data->are_slots_connected(from.to_slot, slot)) return true;
+            }
+            for (auto& cand : n.outbound) {
+                if (n.data && !n.data->are_slots_connected(from.to_slot, cand.from_slot)) continue;   // :239-243
+                if (target == 0 && cand.to == 0 && cand.to_slot == slot) return true;
+                todo.push_back(cand);
+            }
         }
         return false;
     }
@@ -404,8 +412,7 @@ private:
             auto it = nodes_.find(e.to);
             return !it->second.data || it->second.data->are_slots_connected(e.to_slot, e.from_slot);
         }
-        std::set<Edge> seen;
-        return reaches(e, e.from, e.from_slot, seen);
+        return reaches(e, e.from, e.from_slot);
     }
     std::map<uint32_t, Node> nodes_;
 };
@@ -423,7 +430,16 @@ inline std::shared_ptr<const Effect> Effect::from_id(const EffectId& id, const R
         e->primitive = prim;
         return e;
     }
+    // Files whose sub-nodes are being resolved right now, innermost last.  An effect file that names itself (or a file
+    // that is loading it) by name only would recurse without end — the reference overflows its stack on such a file;
+    // a library inside someone else's process skips the candidate instead, and the id ends up NoMatchingEffect.
+    static thread_local std::vector<std::string> loading;
+    struct Loading {
+        explicit Loading(const std::string& p) { loading.push_back(p); }
+        ~Loading() { loading.pop_back(); }
+    };
     for (auto& path : resman.find_effect(id)) {                                             // effect.rs:158-216
+        if (loading.size() >= 256 || std::find(loading.begin(), loading.end(), path) != loading.end()) continue;
         std::string text;
         if (!ResMan::read_file(path, &text)) continue;
         EffectDesc desc;
@@ -431,6 +447,7 @@ inline std::shared_ptr<const Effect> Effect::from_id(const EffectId& id, const R
         if (desc.meta.id.name != id.name) continue;                                         // :163, :209-211
         desc.update_id();
         RgError sub = RgError::None;
+        Loading in_progress(path);
         auto graph = RouteGraph::from_adjlist(desc.adjlist, resman, &sub);
         if (!graph) continue;                                                               // :207 warn, next
         // all declared outputs driven, exactly (:168-175)

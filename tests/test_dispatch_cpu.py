@@ -220,3 +220,32 @@ def test_messages_by_osc_address(tmp_path):
     with pytest.raises(DispatchError) as e:
         d.dispatch("/renderer/stop")
     assert e.value.variant == "BadMessage"
+
+
+def test_hostile_effect_files_are_rejected_not_crashed_on(tmp_path):
+    """Effect files come from disk (resman.rs:64-97): nesting deeper than serde_json's recursion limit, numbers out of
+    range, and effects that contain themselves (directly, or through another file, by name only) end up as
+    NoMatchingEffect — the reference's parser errors out on the first two and overflows its stack on the third."""
+    d = planner()
+    d.add_dir(tmp_path)
+    hostile = {"deep_arr": "[" * 200000, "deep_obj": '{"a":' * 100000, "big_num": '{"meta": 1e999999}',
+               "huge_handle": json.dumps(mulby_desc()).replace('"node_handle": 2', '"node_handle": 99999999999999999999')}
+    for name, payload in hostile.items():
+        f = tmp_path / "a.fnd"
+        f.write_text(payload)
+        with pytest.raises(DispatchError) as e:
+            d.add_node(1, EffectId("MulBy2"))
+        assert e.value.variant == "NoMatchingEffect", name
+        f.unlink()
+    nested = lambda name, inner: dict(mulby_desc(name=name), adjlist=dict(
+        mulby_desc()["adjlist"], nodes=mulby_desc()["adjlist"]["nodes"] + [[{"node_handle": 3}, {"name": inner, "sha256": None, "urls": []}]]))
+    (tmp_path / "a.fnd").write_text(json.dumps(nested("A", "A")))
+    (tmp_path / "b.fnd").write_text(json.dumps(nested("B", "C")))
+    (tmp_path / "c.fnd").write_text(json.dumps(nested("C", "B")))
+    for name in ("A", "B", "C"):
+        with pytest.raises(DispatchError) as e:
+            d.add_node(1, EffectId(name))
+        assert e.value.variant == "NoMatchingEffect", name
+    # depth within the limit still loads: 100 nested arrays are not an effect, but they parse (the error is the shape's)
+    (tmp_path / "ok.fnd").write_text(json.dumps(mulby_desc(name="Fine")))
+    d.add_node(1, EffectId("Fine"))

@@ -121,3 +121,42 @@ def test_shared_subgraph_is_evaluated_once():
     rec.on_add_edge((2, 0, 0, 1))        # and also an output
     got, _ = check(rec, 2)
     assert sum(1 for v in got["values"] if v[0] == 5) == 1
+
+
+def _sum_chain(r, n):
+    """out0 = (...((in0 + 1) + 1) ... + 1), n Sum2 nodes in a row: the longest path has n nodes."""
+    r.on_add_node(1, 1)
+    prev = 0
+    for i in range(n):
+        h = 2 + i
+        r.on_add_node(h, 2)
+        r.on_add_edge((prev, h, 0, 0))
+        r.on_add_edge((1, h, 0x3F800000, 1))
+        prev = h
+    r.on_add_edge((prev, 0, 0, 0))
+
+
+def test_long_chains_flatten_on_their_own_stack_and_may_have_more_than_65535_registers():
+    """A Sum2 chain of 70,000 nodes — what a bank of partials written in the reference's own primitives looks like:
+    the depth-first walk needs about 600 B of stack per node (it runs on a 512 MB stack of its own), and the stage has
+    more than 65,535 virtual registers (0xFFFF once doubled as 'no register')."""
+    from libfriendship_b200 import RendererError
+    n = 70000
+    r = planner()
+    _sum_chain(r, n)
+    got = parse_dump(r.dump_schedule(1))
+    assert sum(1 for v in got["values"] if v[0] == 4) == n                 # V_SUM2, one per node
+    assert len(set(got["stage"])) == 1 and len(got["stages"]) == 1       # one fused elementwise stage
+    st = got["stages"][0]
+    assert st["n_regs"] <= 2                                               # a chain keeps one value live
+    assert n + 2 <= len(st["instrs"]) <= n + 6                             # load, n sums, store, end markers
+
+
+def test_graphs_deeper_than_the_walk_allows_are_refused_not_crashed_on():
+    from libfriendship_b200 import RendererError
+    from libfriendship_b200._cabi import FRB_E_UNSUPPORTED
+    r = planner()
+    _sum_chain(r, 500100)
+    with pytest.raises(RendererError) as e:
+        r.dump_schedule(1)
+    assert e.value.code == FRB_E_UNSUPPORTED
