@@ -13,8 +13,8 @@ pytestmark = pytest.mark.gpu
 
 
 def _chain(n):
-    from libfriendship_b200 import B200Renderer, KIND_F32CONSTANT, KIND_SUM2
-    r = B200Renderer()
+    from libfriendship_b200 import B200Renderer, FLAG_NO_JIT, KIND_F32CONSTANT, KIND_SUM2
+    r = B200Renderer(flags=FLAG_NO_JIT)        # the interpreter is what is under test
     r.on_add_node(1, KIND_F32CONSTANT)
     prev = 0
     for i in range(n):
@@ -42,8 +42,7 @@ def test_program_read_from_global_memory_is_bit_exact(n_nodes, n_times):
     r = _chain(n_nodes)
     rng = np.random.Generator(np.random.PCG64(n_nodes + n_times))
     x = rng.uniform(-1, 1, 2 * n_times).astype(np.float32)
-    # two consecutive blocks (the second starts at an odd time for n_times = 1001): both on the interpreter, the stage
-    # JIT only takes over at a stage's 4th launch
+    # two consecutive blocks (the second starts at an odd time for n_times = 1001)
     got0 = r.fill_buffer(1, n_times, 0, [x[:n_times]])
     got1 = r.fill_buffer(1, n_times, n_times, [x[n_times:]])
     st = r.stats()
