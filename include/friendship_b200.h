@@ -196,6 +196,12 @@ int64_t frb_dump_schedule(frb_renderer* r, uint32_t n_slots, uint32_t* words, ui
  * the length needed. */
 int64_t frb_jit_source(frb_renderer* r, uint32_t n_slots, uint32_t stage, char* out, uint64_t cap);
 int64_t frb_jit_cubin_size(frb_renderer* r, uint32_t n_slots, uint32_t stage);
+/* Instructions that stage holds as straight-line code once compiled (one body per distinct strand shape).  NVRTC's time
+ * grows faster than linearly in it, so the renderer compiles a stage on the render thread only up to 192 of them (above:
+ * beside the render loop, the interpreter serving meanwhile) and not at all above 512 (interpreted for good). */
+#define FRB_JIT_MAX_SYNC_CODE 192
+#define FRB_JIT_MAX_CODE 512
+int64_t frb_jit_code_instructions(frb_renderer* r, uint32_t n_slots, uint32_t stage);
 
 /* Counters since creation: kernel launches, bytes H2D, bytes D2H. */
 typedef struct frb_stats {

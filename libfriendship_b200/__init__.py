@@ -132,6 +132,14 @@ class B200Renderer(_cabi.CRendererBase):
             self._check(int(n))
         return int(n)
 
+    def jit_code_instructions(self, n_slots, stage):
+        """Straight-line instructions the compiled stage would hold (one body per distinct strand shape); the renderer
+        compiles up to FRB_JIT_MAX_CODE = 512 of them, on the render thread only up to FRB_JIT_MAX_SYNC_CODE = 192."""
+        n = _lib.frb_jit_code_instructions(self._h, n_slots, stage)
+        if n < 0:
+            self._check(int(n))
+        return int(n)
+
     # ---- K5: CUDA-IPC plumbing for the cross-GPU mix (see include/friendship_b200.h) ----
     def device_alloc(self, nbytes):
         out = _C.c_void_p()

@@ -85,7 +85,7 @@ EXPORTS = [
     "frb_create", "frb_destroy", "frb_last_error", "frb_define_effect", "frb_define_oscbank",
     "frb_define_directform", "frb_define_fbdelay", "frb_add_node", "frb_del_node", "frb_add_edge", "frb_del_edge",
     "frb_fill_buffer", "frb_fill_buffer_device", "frb_sync", "frb_stream", "frb_dump_schedule", "frb_get_stats",
-    "frb_set_profiling", "frb_get_timing", "frb_version", "frb_jit_source", "frb_jit_cubin_size", "frb_device_alloc", "frb_device_free", "frb_ipc_export", "frb_ipc_open", "frb_ipc_close", "frb_sum_rows",
+    "frb_set_profiling", "frb_get_timing", "frb_version", "frb_jit_source", "frb_jit_cubin_size", "frb_jit_code_instructions", "frb_device_alloc", "frb_device_free", "frb_ipc_export", "frb_ipc_open", "frb_ipc_close", "frb_sum_rows",
     "frb_render_stream",
 ]
 
@@ -114,6 +114,7 @@ def declare(lib, prefix):
         "get_timing": ([vp, C.POINTER(frb_timing)], C.c_int),
         "jit_source": ([vp, C.c_uint32, C.c_uint32, C.c_char_p, C.c_uint64], C.c_int64),
         "jit_cubin_size": ([vp, C.c_uint32, C.c_uint32], C.c_int64),
+        "jit_code_instructions": ([vp, C.c_uint32, C.c_uint32], C.c_int64),
     }
     for name, (args, res) in sig.items():
         fn = getattr(lib, f"{prefix}_{name}", None)

@@ -187,6 +187,16 @@ int64_t frb_jit_cubin_size(frb_renderer* r, uint32_t n_slots, uint32_t stage) {
     return rc == FRB_OK ? n : (int64_t)rc;
 }
 
+int64_t frb_jit_code_instructions(frb_renderer* r, uint32_t n_slots, uint32_t stage) {
+    int64_t n = 0;
+    int rc = guarded(r, [&] {
+        const frb::Schedule& s = r->impl.schedule(n_slots);
+        if (stage >= s.stages.size()) throw Error{FRB_E_INVALID, "no such stage"};
+        n = (int64_t)frb::jit_code_instructions(s.stages[stage]);
+    });
+    return rc == FRB_OK ? n : (int64_t)rc;
+}
+
 int frb_get_stats(const frb_renderer* r, frb_stats* out) {
     if (!r || !out) return FRB_E_INVALID;
     *out = r->impl.stats;

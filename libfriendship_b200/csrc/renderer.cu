@@ -619,17 +619,26 @@ void Renderer::poll_stage_jit(size_t sg, uint64_t n_groups) {
     const Stage& st = sched_.stages[sg];
     StageJit& sj = stage_jit_[sg];
     sj.uses++;
-    const bool eager = (cfg_.flags & FRB_FLAG_JIT_EAGER) || n_groups >= (1ull << 15);
-    if (sj.state == 0 && !(cfg_.flags & FRB_FLAG_NO_JIT) && st.program.size() <= 65536 &&   // bound the generated source
+    const bool asked = (cfg_.flags & FRB_FLAG_JIT_EAGER) != 0;
+    const bool eager = asked || n_groups >= (1ull << 15);
+    if (sj.state == 0 && !(cfg_.flags & FRB_FLAG_NO_JIT) && st.program.size() <= 65536 &&   // bound the generated tables
         (eager || sj.uses >= 4)) {
-        if (eager) {
+        // NVRTC's time grows faster than linearly in the straight-line code it is given (jit.cc, jit_code_instructions:
+        // 200 instructions 2 s, 500 16 s, 2,000 more than 5 minutes): a stage above JIT_MAX_CODE stays on the
+        // interpreter for good, and one above JIT_MAX_SYNC_CODE is never compiled on the render thread unless the
+        // caller asked for that with FRB_FLAG_JIT_EAGER
+        if (sj.code_instrs == ~0ull) sj.code_instrs = jit_code_instructions(st);
+        if (sj.code_instrs > JIT_MAX_CODE) {
+            sj.state = 2;
+            last_jit_error = "stage program too long for the JIT; interpreted";
+        } else if (eager && (asked || sj.code_instrs <= JIT_MAX_SYNC_CODE)) {
             // a long block (or an explicit request) pays for the ~0.2 s of NVRTC right away
             std::string jerr;
             sj.k = jit_build(st, &jerr);
             sj.state = sj.k ? 1 : 2;
             if (!sj.k) last_jit_error = jerr;
         } else {
-            // streaming in short blocks: compile beside the render loop, never stall a block for it
+            // streaming in short blocks (or a long body): compile beside the render loop, never stall a block for it
             const std::string src = jit_generate_source(st);
             sj.cubin = std::async(std::launch::async, [src]() {
                 std::string cubin, log;

@@ -99,7 +99,10 @@ private:
     // device-resident schedule
     std::vector<uint32_t*> d_programs_;         // per stage
     // state: 0 untried, 1 ready, 2 failed, 3 compiling in the background (the stage keeps being interpreted meanwhile)
-    struct StageJit { JitKernel* k = nullptr; int state = 0; uint64_t uses = 0; std::future<std::string> cubin; };
+    // code_instrs: jit_code_instructions of the stage, computed when the stage first qualifies (~0 = not yet)
+    struct StageJit { JitKernel* k = nullptr; int state = 0; uint64_t uses = 0; uint64_t code_instrs = ~0ull; std::future<std::string> cubin; };
+    static constexpr uint64_t JIT_MAX_CODE = FRB_JIT_MAX_CODE;        // above: interpreted for good (NVRTC needs minutes)
+    static constexpr uint64_t JIT_MAX_SYNC_CODE = FRB_JIT_MAX_SYNC_CODE;   // above: compiled only beside the render loop (NVRTC needs > 2 s)
     std::vector<StageJit> stage_jit_;
     std::vector<uint32_t*> d_ext_in_bufs_;      // per extension instance: input ring ids per lane
     // Fused DirectForm -> FbDelay chains (scan.cu dfcomb_kernel): chain_of_[fb instance] = df instance whose lanes feed it

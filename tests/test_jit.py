@@ -94,3 +94,48 @@ def test_hot_stage_gets_compiled_in_the_background():
     s = g.stats()
     assert switched_at is not None and switched_at > 4, (switched_at, s)
     assert 0 < s["jit_launches"] < s["interp_launches"]
+
+
+def test_code_size_the_jit_is_bounded_by_counts_one_body_per_strand_shape():
+    """NVRTC's time grows faster than linearly in straight-line code (a 500-node Sum2 chain: 16 s, 2,000 nodes: more
+    than 5 minutes), so the renderer bounds what it compiles by `jit_code_instructions` (FRB_JIT_MAX_CODE; on the
+    render thread FRB_JIT_MAX_SYNC_CODE): strands of one shape count once, however many there are."""
+    from libfriendship_b200 import B200Renderer, KIND_F32CONSTANT, KIND_SUM2
+    # 1) one long chain: every node is code
+    r = B200Renderer(device=-1)
+    r.on_add_node(1, KIND_F32CONSTANT)
+    prev = 0
+    for i in range(3000):
+        r.on_add_node(2 + i, KIND_SUM2)
+        r.on_add_edge((prev, 2 + i, 0, 0))
+        r.on_add_edge((1, 2 + i, 0x3F800000, 1))
+        prev = 2 + i
+    r.on_add_edge((prev, 0, 0, 0))
+    assert 3000 <= r.jit_code_instructions(1, 0) <= 3004            # load, 3,000 sums, store: far above the 512 compiled
+    # 2) the same short chain on 48 slots: 48 strands, one body
+    r = B200Renderer(device=-1)
+    r.on_add_node(1, KIND_F32CONSTANT)
+    h = 2
+    for slot in range(48):
+        prev = None
+        for i in range(5):
+            r.on_add_node(h, KIND_SUM2)
+            if prev is None:
+                r.on_add_edge((0, h, slot, 0))
+            else:
+                r.on_add_edge((prev, h, 0, 0))
+            r.on_add_edge((1, h, 0x3F800000 + slot, 1))
+            prev = h
+            h += 1
+        r.on_add_edge((prev, 0, 0, slot))
+    one = B200Renderer(device=-1)
+    one.on_add_node(1, KIND_F32CONSTANT)
+    prev = 0
+    for i in range(5):
+        one.on_add_node(2 + i, KIND_SUM2)
+        one.on_add_edge((prev, 2 + i, 0, 0))
+        one.on_add_edge((1, 2 + i, 0x3F800000, 1))
+        prev = 2 + i
+    one.on_add_edge((prev, 0, 0, 0))
+    assert r.jit_code_instructions(48, 0) == one.jit_code_instructions(1, 0) <= 8
+    assert r.jit_cubin_size(48, 0) > 1000
