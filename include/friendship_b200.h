@@ -197,9 +197,12 @@ int64_t frb_dump_schedule(frb_renderer* r, uint32_t n_slots, uint32_t* words, ui
 int64_t frb_jit_source(frb_renderer* r, uint32_t n_slots, uint32_t stage, char* out, uint64_t cap);
 int64_t frb_jit_cubin_size(frb_renderer* r, uint32_t n_slots, uint32_t stage);
 /* Instructions that stage holds as straight-line code once compiled (one body per distinct strand shape).  NVRTC's time
- * grows faster than linearly in it, so the renderer compiles a stage on the render thread only up to 192 of them (above:
- * beside the render loop, the interpreter serving meanwhile) and not at all above 512 (interpreted for good). */
-#define FRB_JIT_MAX_SYNC_CODE 192
+ * grows faster than linearly in it (200: 2 s, 500: 16 s, 2,000: more than 5 minutes), so a stage above
+ * FRB_JIT_MAX_CODE is never compiled (interpreted for good).  FRB_JIT_MAX_SYNC_CODE bounds what a long block compiles on
+ * the render thread without FRB_FLAG_JIT_EAGER (above: beside the render loop, the interpreter serving meanwhile);
+ * it equals FRB_JIT_MAX_CODE for now: the 64-voice mix stage of the cfg4 bench is 320 instructions and the measured
+ * numbers of round 1 have it compiled in the first call. */
+#define FRB_JIT_MAX_SYNC_CODE 512
 #define FRB_JIT_MAX_CODE 512
 int64_t frb_jit_code_instructions(frb_renderer* r, uint32_t n_slots, uint32_t stage);
 

@@ -134,7 +134,7 @@ class B200Renderer(_cabi.CRendererBase):
 
     def jit_code_instructions(self, n_slots, stage):
         """Straight-line instructions the compiled stage would hold (one body per distinct strand shape); the renderer
-        compiles up to FRB_JIT_MAX_CODE = 512 of them, on the render thread only up to FRB_JIT_MAX_SYNC_CODE = 192."""
+        compiles a stage only up to FRB_JIT_MAX_CODE = 512 of them (include/friendship_b200.h)."""
         n = _lib.frb_jit_code_instructions(self._h, n_slots, stage)
         if n < 0:
             self._check(int(n))

@@ -102,7 +102,7 @@ private:
     // code_instrs: jit_code_instructions of the stage, computed when the stage first qualifies (~0 = not yet)
     struct StageJit { JitKernel* k = nullptr; int state = 0; uint64_t uses = 0; uint64_t code_instrs = ~0ull; std::future<std::string> cubin; };
     static constexpr uint64_t JIT_MAX_CODE = FRB_JIT_MAX_CODE;        // above: interpreted for good (NVRTC needs minutes)
-    static constexpr uint64_t JIT_MAX_SYNC_CODE = FRB_JIT_MAX_SYNC_CODE;   // above: compiled only beside the render loop (NVRTC needs > 2 s)
+    static constexpr uint64_t JIT_MAX_SYNC_CODE = FRB_JIT_MAX_SYNC_CODE;   // above: compiled only beside the render loop (see the header: = JIT_MAX_CODE for now)
     std::vector<StageJit> stage_jit_;
     std::vector<uint32_t*> d_ext_in_bufs_;      // per extension instance: input ring ids per lane
     // Fused DirectForm -> FbDelay chains (scan.cu dfcomb_kernel): chain_of_[fb instance] = df instance whose lanes feed it

@@ -99,7 +99,7 @@ def test_hot_stage_gets_compiled_in_the_background():
 def test_code_size_the_jit_is_bounded_by_counts_one_body_per_strand_shape():
     """NVRTC's time grows faster than linearly in straight-line code (a 500-node Sum2 chain: 16 s, 2,000 nodes: more
     than 5 minutes), so the renderer bounds what it compiles by `jit_code_instructions` (FRB_JIT_MAX_CODE; on the
-    render thread FRB_JIT_MAX_SYNC_CODE): strands of one shape count once, however many there are."""
+    render thread FRB_JIT_MAX_SYNC_CODE, the same number for now): strands of one shape count once, however many there are."""
     from libfriendship_b200 import B200Renderer, KIND_F32CONSTANT, KIND_SUM2
     # 1) one long chain: every node is code
     r = B200Renderer(device=-1)
