@@ -21,7 +21,6 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np
 
@@ -83,8 +82,8 @@ class ClockSampler(threading.Thread):
 def cpu_baseline(n_threads=None, budget_s=12.0):
     """The CPU oracle (reference-style f32 per-sample evaluation, as RefRenderer would do it) on a bounded sample of
     the same workload: voice 0, its first `p` partials, `n` samples, through the same per-voice delay/mix graph."""
-    from banks import build_voice_mix_graph, detuned_bank
-    from oracle_binding import OracleRenderer
+    from workloads.banks import build_voice_mix_graph, detuned_bank
+    from oracle.binding import OracleRenderer
     n_threads = n_threads or os.cpu_count() or 1
     p, n = 4096, 2400
     bank, ids = detuned_bank(1, p)
@@ -178,7 +177,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from banks import build_voice_mix_graph, detuned_bank
+    from workloads.banks import build_voice_mix_graph, detuned_bank
     from libfriendship_b200.sharded import ShardedRenderer
 
     torch.cuda.set_device(local_rank)

@@ -74,6 +74,9 @@ typedef struct frb_config {
 } frb_config;
 #define FRB_FLAG_SPARKLE_DELAY 1u  /* negative / NaN delay amounts yield 0.0 (reference sparkle.rs:525-542)
                                       instead of clamping to delay 0 (reference.rs:205-210, the default) */
+#define FRB_FLAG_SPARKLE_MIN  32u  /* Minimum as the reference's JIT renderer computes it, select(a ULT b, a, b): a NaN in either
+                                      operand yields a (reference sparkle.rs:492-498), instead of f32::min = minNum, which
+                                      yields the operand that is not NaN (reference.rs:242-248, the default) */
 #define FRB_FLAG_NO_JIT        2u  /* always interpret stage programs; never compile them (see frb_jit_cubin_size) */
 #define FRB_FLAG_JIT_EAGER     4u  /* compile a stage program the first time it runs (default: once it is hot) */
 #define FRB_FLAG_NO_CHAIN_FUSION 8u /* run DirectForm -> FbDelay chains as two kernels (16 B per lane-sample) even where the

@@ -1,7 +1,7 @@
 """ctypes declarations for the C ABI in include/friendship_b200.h.
 
-The same struct layouts and call shapes are reused by tests/oracle_binding.py for the CPU oracle's `orc_*`
-mirror (test infrastructure); this module itself never loads or references the oracle.
+The same struct layouts and call shapes are reused by the test infrastructure's CPU restatement of the reference
+renderer (its `orc_*` mirror of this ABI loads this file by path); this module never loads or references it.
 """
 import ctypes as C
 
@@ -37,6 +37,7 @@ FLAG_NO_JIT = 2
 FLAG_JIT_EAGER = 4
 FLAG_NO_CHAIN_FUSION = 8
 FLAG_NO_EXCITER_FUSION = 16
+FLAG_SPARKLE_MIN = 32
 
 
 class frb_edge(C.Structure):

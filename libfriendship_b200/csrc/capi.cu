@@ -180,7 +180,7 @@ int64_t frb_jit_cubin_size(frb_renderer* r, uint32_t n_slots, uint32_t stage) {
         const frb::Schedule& s = r->impl.schedule(n_slots);
         if (stage >= s.stages.size()) throw Error{FRB_E_INVALID, "no such stage"};
         std::string cubin, log;
-        if (!frb::jit_compile_to_cubin(frb::jit_generate_source(s.stages[stage]), &cubin, &log))
+        if (!frb::jit_compile_to_cubin(frb::jit_generate(s.stages[stage]).source, &cubin, &log))
             throw Error{FRB_E_UNSUPPORTED, "NVRTC: " + log};
         n = (int64_t)cubin.size();
     });

@@ -18,6 +18,7 @@
 #include <functional>
 #include <exception>
 #include <map>
+#include <set>
 
 #include <pthread.h>
 
@@ -156,6 +157,22 @@ struct Flattener {
                 uint32_t amt = resolve_maybe(ctx, n.inbound, 1);
                 // Delay of the constant-zero signal is zero at every t (exactly +0.0f either way).
                 if (s.values[src].op == V_ZERO) { v = src; break; }
+                {
+                    // Delay of a stored signal (an external input, an extension lane, or one of those already shifted)
+                    // by a constant amount is that signal read at t - d, 0 before t = d: a TAP — 128-bit reads wherever
+                    // t - d is a multiple of 4 — instead of the general Delay with its per-sample clamps.
+                    const Value sv = s.values[src];
+                    const Value amtv = s.values[amt];
+                    uint64_t d = 0;
+                    if ((sv.op == V_INPUT || sv.op == V_EXT || sv.op == V_TAP) && (amtv.op == V_CONST || amtv.op == V_ZERO)) {
+                        if (!const_delay_of(amtv, &d)) { v = zero(); break; }              // never reads its source
+                        const uint64_t base = sv.op == V_TAP ? shift_of(sv) : 0;
+                        if (d < (1ull << 40) && base < (1ull << 40)) {
+                            v = mk64(V_TAP, sv.op == V_TAP ? sv.a : src, base + d);
+                            break;
+                        }
+                    }
+                }
                 {
                     const uint8_t sop = s.values[src].op;
                     const bool computed = (sop >= V_SUM2 && sop <= V_MIN) || sop == V_GATE;
@@ -607,8 +624,11 @@ Schedule flatten_here(const Graph& top, uint32_t n_slots, const FlattenEnv& env)
                 if (uses_a(sc[i])) last_use[sc[i].a] = (int64_t)i;
                 if (uses_b(sc[i])) last_use[sc[i].b] = (int64_t)i;
             }
+            // lowest free register first: the allocator's state after a group of instructions depends only on which
+            // values are live, so a repeated group (a term of a Sum2 chain, a voice of a mix) gets the same registers
+            // every time — which is what lets the stage JIT fold the repetition into a loop (jit.cc)
             std::map<uint32_t, uint32_t> phys;
-            std::vector<uint32_t> free_list;
+            std::set<uint32_t> free_list;
             uint32_t n_phys = 0;
             for (size_t i = 0; i < sc.size(); i++) {
                 VI c = sc[i];
@@ -616,16 +636,16 @@ Schedule flatten_here(const Graph& top, uint32_t n_slots, const FlattenEnv& env)
                 const uint32_t va = c.a, vb = c.b;
                 if (a_reg) c.a = phys.at(va);
                 if (b_reg) c.b = phys.at(vb);
-                if (a_reg && last_use[va] == (int64_t)i) free_list.push_back(phys.at(va));
-                if (b_reg && last_use[vb] == (int64_t)i && !(a_reg && vb == va)) free_list.push_back(phys.at(vb));
+                if (a_reg && last_use[va] == (int64_t)i) free_list.insert(phys.at(va));
+                if (b_reg && last_use[vb] == (int64_t)i && !(a_reg && vb == va)) free_list.insert(phys.at(vb));
                 if (c.dst != NOREG) {
                     const uint32_t vd = c.dst;
                     uint32_t pr;
-                    if (!free_list.empty()) { pr = free_list.back(); free_list.pop_back(); }
+                    if (!free_list.empty()) { pr = *free_list.begin(); free_list.erase(free_list.begin()); }
                     else pr = n_phys++;
                     phys[vd] = pr;
                     c.dst = pr;
-                    if (!last_use.count(vd)) free_list.push_back(pr);   // dead value
+                    if (!last_use.count(vd)) free_list.insert(pr);   // dead value
                 }
                 stage.program.push_back(Instr::make(c.op, c.flags, c.dst, c.a, c.b, c.aux));
             }

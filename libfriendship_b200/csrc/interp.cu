@@ -82,7 +82,7 @@ interp_kernel(InterpParams p) {
                     break;
                 case I_MIN:
 #pragma unroll
-                    for (int w = 0; w < VW; w++) REG(dst, w) = make_float4(fminf(a[w].x, b[w].x), fminf(a[w].y, b[w].y), fminf(a[w].z, b[w].z), fminf(a[w].w, b[w].w));
+                    for (int w = 0; w < VW; w++) REG(dst, w) = f4min(a[w], b[w], p.sparkle_min);
                     break;
                 case I_MOV:
 #pragma unroll

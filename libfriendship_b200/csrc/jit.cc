@@ -1,4 +1,4 @@
-// jit.cc — stage JIT: one flattened stage program -> one fused, straight-line sm_100a kernel through NVRTC.
+// jit.cc — stage JIT: one flattened stage program -> one fused sm_100a kernel through NVRTC.
 //
 // The reference's fast renderer is itself a JIT (`SparkleRenderer`, LLVM MCJIT: one function per effect,
 // src/render/sparkle.rs:169-243, finalised lazily at the next render, :271-288).  This is its B200 counterpart for the
@@ -16,10 +16,14 @@
 #include <nvrtc.h>
 
 #include <algorithm>
+#include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <sstream>
+#include <thread>
 
 namespace frb {
 
@@ -81,173 +85,316 @@ Api& api(bool need_driver) {
 
 std::string reg(uint32_t r, int w) { return "r" + std::to_string(r) + "_" + std::to_string(w); }
 
-}  // namespace
-
 // ------------------------------------------------------------------------------------------------------------------
-// Strands with the same SHAPE (same operations on the same registers; only slot / buffer indices, immediates, shifts
-// and thresholds differ) share one code body; what differs comes from a per-strand row of a constant table.  A stage
-// that applies the same chain to 64 slots compiles one body, not 64.
-// what makes two strands share a code body; *n_ops = instructions before the strand's I_END
-static std::string strand_shape_key(const Stage& st, size_t sd, size_t* n_ops) {
-    std::string key;
-    size_t n = 0;
+// Loops, not straight lines.  A strand is a straight-line register program; what the reference's vocabulary builds out
+// of it is mostly REPETITION: a Sum2 chain over 2,000 partial terms is the same three instructions 2,000 times, the
+// 64-voice mix of the cfg4 graph the same five 64 times.  NVRTC's time grows faster than linearly in the straight-line
+// code it is handed (500 instructions 16 s, 2,000 more than 5 minutes), so the generator folds every run of like
+// instruction groups (a tandem repeat of the instruction SHAPES: same operation on the same registers) into one loop
+// whose trip count and per-iteration operands (slot / buffer indices, immediates, shifts, thresholds) come from a
+// device-resident operand table.  Runs of like loops fold again (a chain per voice, 64 voices: two levels).  The
+// generated code therefore depends on the program's structure only — not on its constants or its repeat counts — so
+// two strands of the same structure share one body, and a graph edit that adds a partial or changes a constant finds
+// its cubin in the cache.
+struct Node {
+    bool loop = false;
+    uint32_t instr = 0;                        // leaf: index into Stage::program
+    uint32_t sym = 0;                          // structure symbol: leaves by shape, loops by their body's symbols
+    std::vector<std::vector<Node>> iters;      // loop: every iteration (equal symbol sequences); code comes from iters[0]
+};
+
+struct Interner {
+    std::map<std::string, uint32_t> ids;
+    uint32_t get(const std::string& k) {
+        auto it = ids.find(k);
+        if (it != ids.end()) return it->second;
+        const uint32_t id = (uint32_t)ids.size();
+        ids.emplace(k, id);
+        return id;
+    }
+};
+
+bool reads_a_reg(uint32_t op, uint32_t flags) { return !(flags & IF_A_IMM) && op != I_LDIN && op != I_LDBUF && op != I_TAP_IN && op != I_TAP_BUF; }
+bool reads_b_reg(uint32_t op, uint32_t flags) { return !(flags & IF_B_IMM) && (op <= I_MIN || op == I_DLY_TI); }
+
+std::string leaf_shape(const Instr& in) {
+    const uint32_t op = in.w0 & 0xFFu, flags = (in.w0 >> 8) & 0xFFu;
+    char buf[64];
+    snprintf(buf, sizeof buf, "%x.%x.%x", in.w0, reads_a_reg(op, flags) ? in.a : 0xffffu, reads_b_reg(op, flags) ? in.b : 0xffffu);
+    return buf;
+}
+
+constexpr size_t kMaxPeriod = 96;              // longest loop body looked for, in symbols
+constexpr size_t kMinSaved = 6;                // a loop must remove at least this many symbols
+
+// One pass of tandem-repeat folding over a symbol sequence: greedy from the left, at every position the SHORTEST period
+// (up to max_period) that removes at least kMinSaved symbols.  `work` bounds
+// the comparisons (adversarial programs stay straight-line).
+std::vector<Node> fold_pass(std::vector<Node>& seq, Interner& syms, size_t max_period, bool* changed, size_t* work) {
+    std::vector<Node> out;
+    const size_t n = seq.size();
+    size_t i = 0;
+    while (i < n) {
+        size_t best_p = 0, best_r = 0;
+        if (*work < (200u << 20)) {
+            for (size_t P = 1; P <= max_period && i + 2 * P <= n; P++) {
+                if (seq[i].sym != seq[i + P].sym) continue;
+                size_t m = 0;
+                while (i + P + m < n && seq[i + m].sym == seq[i + P + m].sym) m++;
+                *work += m + 1;
+                const size_t R = 1 + m / P;
+                if (R >= 2 && (R - 1) * P >= kMinSaved) { best_p = P; best_r = R; break; }
+            }
+        }
+        if (!best_p) { out.push_back(std::move(seq[i])); i++; continue; }
+        Node L;
+        L.loop = true;
+        std::string key = "L";
+        for (size_t j = 0; j < best_p; j++) key += ":" + std::to_string(seq[i + j].sym);
+        L.sym = syms.get(key);
+        L.iters.resize(best_r);
+        for (size_t r = 0; r < best_r; r++)
+            for (size_t j = 0; j < best_p; j++) L.iters[r].push_back(std::move(seq[i + r * best_p + j]));
+        out.push_back(std::move(L));
+        i += best_p * best_r;
+        *changed = true;
+    }
+    return out;
+}
+
+std::vector<Node> fold_strand(const Stage& st, size_t sd, Interner& syms) {
+    std::vector<Node> seq;
     for (uint32_t i = st.strand_offsets[sd]; i < st.strand_offsets[sd + 1]; i++) {
         const Instr& in = st.program[i];
-        const uint32_t op = in.w0 & 0xFFu, flags = (in.w0 >> 8) & 0xFFu;
-        if (op == I_END) break;
-        const bool a_reg = !(flags & IF_A_IMM) && op != I_LDIN && op != I_LDBUF && op != I_TAP_IN && op != I_TAP_BUF;
-        const bool b_reg = !(flags & IF_B_IMM) && (op <= I_MIN || op == I_DLY_TI);
-        char buf[64];
-        snprintf(buf, sizeof buf, "%x.%x.%x.%x;", in.w0, a_reg ? in.a : 0xffffu, b_reg ? in.b : 0xffffu, 0u);
-        key += buf;
-        n++;
+        if ((in.w0 & 0xFFu) == I_END) break;
+        Node nd;
+        nd.instr = i;
+        nd.sym = syms.get(leaf_shape(in));
+        seq.push_back(std::move(nd));
     }
-    if (n_ops) *n_ops = n;
-    return key;
+    // short periods everywhere first (a long period found early would swallow the short runs inside it unrolled),
+    // then longer ones over what the earlier passes left: loops count as one symbol whatever their trip count
+    size_t work = 0;
+    for (size_t cap : {(size_t)4, (size_t)12, (size_t)32, kMaxPeriod}) {
+        for (int again = 0; again < 3; again++) {
+            bool changed = false;
+            seq = fold_pass(seq, syms, cap, &changed, &work);
+            if (!changed) break;
+        }
+    }
+    return seq;
 }
 
-// Instructions the generated kernel holds as straight-line code: one body per distinct shape.  NVRTC's time grows faster
-// than linearly in it (sm_100a, CUDA 12.9, a Sum2 chain: 50 -> 0.5 s, 100 -> 0.8 s, 200 -> 1.9 s, 500 -> 16 s,
-// 2,000 -> more than 5 minutes), so the renderer bounds what it compiles by this number (renderer.cu, poll_stage_jit).
-size_t jit_code_instructions(const Stage& st) {
-    const size_t n_strands = st.strand_offsets.empty() ? 0 : st.strand_offsets.size() - 1;
-    std::vector<std::string> keys;
-    size_t total = 0;
-    for (size_t sd = 0; sd < n_strands; sd++) {
-        size_t n = 0;
-        std::string key = strand_shape_key(st, sd, &n);
-        bool seen = false;
-        for (const std::string& k : keys) if (k == key) { seen = true; break; }
-        if (!seen) { keys.push_back(std::move(key)); total += n; }
-    }
-    return total;
+// operand-table words of one instruction, in the order the generated code reads them: [a][b][aux]
+void leaf_words(const Instr& in, std::vector<uint32_t>* w, int* n_a, int* n_b, int* n_x) {
+    const uint32_t op = in.w0 & 0xFFu, flags = (in.w0 >> 8) & 0xFFu;
+    const bool tap = op == I_TAP_IN || op == I_TAP_BUF;
+    const bool wa = (flags & IF_A_IMM) || tap;
+    const bool wb = (flags & IF_B_IMM) || tap || op == I_GATE;
+    const bool wx = op == I_LDIN || op == I_LDBUF || op == I_STBUF || op == I_STOUT || op == I_DLY_IN || op == I_DLY_BUF || tap || op == I_GATE;
+    if (w) { if (wa) w->push_back(in.a); if (wb) w->push_back(in.b); if (wx) w->push_back(in.aux); }
+    if (n_a) { *n_a = wa; *n_b = wb; *n_x = wx; }
 }
 
-std::string jit_generate_source(const Stage& st) {
+void emit_words(const Stage& st, const std::vector<Node>& seq, std::vector<uint32_t>* w) {
+    for (const Node& nd : seq) {
+        if (!nd.loop) { leaf_words(st.program[nd.instr], w, nullptr, nullptr, nullptr); continue; }
+        w->push_back((uint32_t)nd.iters.size());
+        for (const auto& it : nd.iters) emit_words(st, it, w);
+    }
+}
+
+size_t count_leaves(const std::vector<Node>& seq) {
+    size_t n = 0;
+    for (const Node& nd : seq) n += nd.loop ? count_leaves(nd.iters[0]) : 1;
+    return n;
+}
+bool has_loop(const std::vector<Node>& seq) {
+    for (const Node& nd : seq) if (nd.loop) return true;
+    return false;
+}
+// how often the compiler is asked to unroll an innermost loop: enough iterations side by side that their loads are in
+// flight together (a loop iteration is a dependent chain operand word -> descriptor -> samples), small enough that the
+// unrolled body stays a few dozen instructions
+unsigned unroll_of(const Node& loop) {
+    if (has_loop(loop.iters[0])) return 1;
+    const size_t n = std::max<size_t>(count_leaves(loop.iters[0]), 1);
+    return (unsigned)std::max<size_t>(1, std::min<size_t>(8, 32 / n));
+}
+// statements the compiler sees (unrolled bodies counted as often as they are unrolled): what NVRTC's time depends on
+size_t code_size(const std::vector<Node>& seq) {
+    size_t n = 0;
+    for (const Node& nd : seq) n += nd.loop ? unroll_of(nd) * code_size(nd.iters[0]) + 1 : 1;
+    return n;
+}
+
+struct Emitter {
+    const Stage& st;
+    std::ostringstream& o;
+    int W;
+    int next_id = 0;
+
+    void leaf(const Instr& in, const std::string& cur, size_t* off, const std::string& ind) {
+        const uint32_t op = in.w0 & 0xFFu, flags = (in.w0 >> 8) & 0xFFu, dst = in.w0 >> 16;
+        int na, nb, nx;
+        leaf_words(in, nullptr, &na, &nb, &nx);
+        auto word = [&]() { return cur + "[" + std::to_string((*off)++) + "]"; };
+        std::string wa, wb, wx;
+        if (na) wa = word();
+        if (nb) wb = word();
+        if (nx) wx = word();
+        for (int w = 0; w < W; w++) {
+            const std::string t = "t_" + std::to_string(w);
+            const char* guard = w >= 2 ? "if (two) " : "";
+            const std::string a = (flags & IF_A_IMM) ? "f4splat(" + wa + ")" : reg(in.a, w);
+            const std::string b = (flags & IF_B_IMM) ? "f4splat(" + wb + ")" : reg(in.b, w);
+            const std::string sh = "(((unsigned long long)" + wb + " << 32) | " + wa + ")";
+            o << ind;
+            switch (op) {
+                case I_ADD: o << reg(dst, w) << " = f4add(" << a << ", " << b << ");"; break;
+                case I_MUL: o << reg(dst, w) << " = f4mul(" << a << ", " << b << ");"; break;
+                case I_DIV: o << reg(dst, w) << " = f4div(" << a << ", " << b << ");"; break;
+                case I_MOD: o << reg(dst, w) << " = f4mod(" << a << ", " << b << ");"; break;
+                case I_MIN: o << reg(dst, w) << " = f4min(" << a << ", " << b << ", p.sparkle_min);"; break;
+                case I_MOV: o << reg(dst, w) << " = " << a << ";"; break;
+                case I_LDIN: o << reg(dst, w) << " = f4ld_in(p.inputs[" << wx << "], " << t << ");"; break;
+                case I_LDBUF: o << reg(dst, w) << " = f4ld_buf(p.buffers[" << wx << "], " << t << ");"; break;
+                case I_STBUF: o << guard << "f4st_buf(p.buffers[" << wx << "], " << t << ", " << a << ");"; break;
+                case I_STOUT: o << guard << "f4st_out(p, " << wx << ", " << t << ", " << a << ");"; break;
+                case I_TAP_IN: o << reg(dst, w) << " = f4tap_in(p.inputs[" << wx << "], " << t << ", " << sh << ");"; break;
+                case I_TAP_BUF: o << reg(dst, w) << " = f4tap_buf(p.buffers[" << wx << "], " << t << ", " << sh << ");"; break;
+                case I_GATE: o << reg(dst, w) << " = f4gate(" << a << ", " << t << ", (((unsigned long long)" << wx << " << 32) | " << wb << "));"; break;
+                case I_DLY_IN: o << reg(dst, w) << " = f4delay<0>(p.inputs[" << wx << "], no_buf, " << a << ", z4, " << t << ", p.sparkle_delay);"; break;
+                case I_DLY_BUF: o << reg(dst, w) << " = f4delay<1>(no_in, p.buffers[" << wx << "], " << a << ", z4, " << t << ", p.sparkle_delay);"; break;
+                case I_DLY_TI: o << reg(dst, w) << " = f4delay<2>(no_in, no_buf, " << a << ", " << b << ", " << t << ", p.sparkle_delay);"; break;
+                default: o << "/* unknown op " << op << " */"; break;
+            }
+            o << "\n";
+        }
+    }
+
+    // `cur` is the operand cursor (a `const unsigned*` variable); on return it has been advanced past everything seq read
+    void seq(const std::vector<Node>& nodes, const std::string& cur, const std::string& ind) {
+        size_t off = 0;
+        for (const Node& nd : nodes) {
+            if (!nd.loop) { leaf(st.program[nd.instr], cur, &off, ind); continue; }
+            const std::string id = std::to_string(next_id++);
+            o << ind << "const unsigned n_" << id << " = " << cur << "[" << off << "];\n";
+            o << ind << "const unsigned* q_" << id << " = " << cur << " + " << (off + 1) << ";\n";
+            o << ind << "#pragma unroll " << unroll_of(nd) << "\n";
+            o << ind << "for (unsigned i_" << id << " = 0; i_" << id << " < n_" << id << "; i_" << id << "++) {\n";
+            seq(nd.iters[0], "q_" + id, ind + "  ");
+            o << ind << "}\n";
+            o << ind << cur << " = q_" << id << ";\n";
+            off = 0;
+        }
+        if (off) o << ind << cur << " += " << off << ";\n";
+    }
+};
+
+}  // namespace
+
+// The generated kernel of a stage: CUDA source (a function of the program's structure), the operand table it reads
+// (per strand: shape, row offset; then the rows) and the statements the compiler sees.
+JitProgram jit_generate(const Stage& st) {
     const size_t n_strands = st.strand_offsets.empty() ? 0 : st.strand_offsets.size() - 1;
-    struct Shape { std::string key; std::vector<uint32_t> strands; };
+    Interner syms;
+    struct Shape { std::vector<uint32_t> key; std::vector<Node> code; uint32_t nreg = 0; };
     std::vector<Shape> shapes;
-    std::vector<uint32_t> shape_of(n_strands), idx_of(n_strands);
+    JitProgram out;
+    out.table.assign(2 * std::max<size_t>(n_strands, 1), 0);
     for (size_t sd = 0; sd < n_strands; sd++) {
-        const std::string key = strand_shape_key(st, sd, nullptr);
+        std::vector<Node> seq = fold_strand(st, sd, syms);
+        std::vector<uint32_t> key;
+        for (const Node& nd : seq) key.push_back(nd.sym);
         size_t k = 0;
         for (; k < shapes.size(); k++) if (shapes[k].key == key) break;
-        if (k == shapes.size()) shapes.push_back(Shape{key, {}});
-        shape_of[sd] = (uint32_t)k;
-        idx_of[sd] = (uint32_t)shapes[k].strands.size();
-        shapes[k].strands.push_back((uint32_t)sd);
+        out.table[2 * sd] = (uint32_t)k;
+        out.table[2 * sd + 1] = (uint32_t)out.table.size();
+        emit_words(st, seq, &out.table);
+        out.table.push_back(0);                                   // a row is never empty
+        if (k == shapes.size()) {
+            Shape sh;
+            sh.key = std::move(key);
+            for (uint32_t i = st.strand_offsets[sd]; i < st.strand_offsets[sd + 1]; i++) {
+                const uint32_t op = st.program[i].w0 & 0xFFu;
+                if (op == I_END) break;
+                if (op != I_STBUF && op != I_STOUT) sh.nreg = std::max(sh.nreg, (st.program[i].w0 >> 16) + 1);
+            }
+            sh.code = std::move(seq);
+            shapes.push_back(std::move(sh));
+        }
     }
 
-    std::ostringstream o, tables;
+    std::ostringstream o;
     o << kInterpDeviceSource << "\n";
-    std::ostringstream body;
-    body << "extern \"C\" __global__ void __launch_bounds__(128) frb_stage(const InterpParams p) {\n";
-    body << "  const InputDesc no_in = {nullptr, 0ull, 0ull};\n  const BufferDesc no_buf = {nullptr, 0ull};\n";
-    body << "  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);\n";
-    body << "  (void)no_in; (void)no_buf; (void)z4;\n";
-    body << "  const unsigned strand = blockIdx.y;\n";
-    body << "  switch (frb_shape_of[strand]) {\n";
+    o << "extern \"C\" __global__ void __launch_bounds__(128) frb_stage(const InterpParams p, const unsigned* __restrict__ tab) {\n";
+    o << "  const InputDesc no_in = {nullptr, 0ull, 0ull};\n  const BufferDesc no_buf = {nullptr, 0ull};\n";
+    o << "  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);\n";
+    o << "  (void)no_in; (void)no_buf; (void)z4;\n";
+    o << "  const unsigned strand = blockIdx.y;\n";
+    o << "  const unsigned* const row = tab + tab[2 * strand + 1];\n";
+    o << "  switch (tab[2 * strand]) {\n";
     for (size_t k = 0; k < shapes.size(); k++) {
-        // the varying words of every strand of this shape, in instruction order
-        std::vector<std::vector<uint32_t>> rows(shapes[k].strands.size());
-        const uint32_t rep = shapes[k].strands[0];
-        body << "  case " << k << ": {\n";
-        body << "  const unsigned* q = frb_tab" << k << "[frb_idx_of[strand]];\n  (void)q;\n";
-        uint32_t nreg = 0;
-        for (uint32_t i = st.strand_offsets[rep]; i < st.strand_offsets[rep + 1]; i++) {
-            const uint32_t op = st.program[i].w0 & 0xFFu;
-            if (op == I_END) break;
-            if (op != I_STBUF && op != I_STOUT) nreg = std::max(nreg, (st.program[i].w0 >> 16) + 1);
-        }
+        const Shape& sh = shapes[k];
+        out.code_instrs += code_size(sh.code);
+        o << "  case " << k << ": {\n";
         // A stage is a stream and what bounds it is the bytes it keeps in flight: 12 resident CTAs x 128 threads x two
         // 16-byte loads per input are 6 MB on the whole GPU, ~5 TB/s at the loaded DRAM latency (measured: 5.0).  A small
         // program therefore walks TWO groups of 8 samples per iteration (one grid stride apart, so every load instruction
         // still covers 512 contiguous bytes), instruction by instruction, which puts the second group's loads in front of
         // the first group's stores.  Loads never alias this stage's stores (a stage reads what earlier stages wrote).
-        const int W = nreg <= 6 ? 4 : 2;            // float4 columns per thread and iteration
-        body << "  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;\n";
-        body << "  for (unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; g < p.n_groups; g += " << (W / 2) << "ull * stride) {\n";
-        body << "    const unsigned long long t_0 = p.t_begin + 8ull * g, t_1 = t_0 + 4ull;\n";
+        const int W = sh.nreg <= 6 ? 4 : 2;            // float4 columns per thread and iteration
+        o << "  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;\n";
+        o << "  for (unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; g < p.n_groups; g += " << (W / 2) << "ull * stride) {\n";
+        o << "    const unsigned long long t_0 = p.t_begin + 8ull * g, t_1 = t_0 + 4ull;\n";
         if (W == 4) {
-            body << "    const bool two = g + stride < p.n_groups;\n";       // the last iteration may have one group only:
-            body << "    const unsigned long long t_2 = p.t_begin + 8ull * (two ? g + stride : g), t_3 = t_2 + 4ull;\n";   // it loads the first twice and stores once
+            o << "    const bool two = g + stride < p.n_groups;\n";       // the last iteration may have one group only:
+            o << "    const unsigned long long t_2 = p.t_begin + 8ull * (two ? g + stride : g), t_3 = t_2 + 4ull;\n";   // it loads the first twice and stores once
         }
-        for (uint32_t r = 0; r < nreg; r++) {
-            body << "    float4 " << reg(r, 0);
-            for (int w = 1; w < W; w++) body << ", " << reg(r, w);
-            body << ";\n";
+        for (uint32_t r = 0; r < sh.nreg; r++) {
+            o << "    float4 " << reg(r, 0);
+            for (int w = 1; w < W; w++) o << ", " << reg(r, w);
+            o << ";\n";
         }
-        uint32_t n_words = 0;
-        const uint32_t len = st.strand_offsets[rep + 1] - st.strand_offsets[rep];
-        for (uint32_t j = 0; j < len; j++) {
-            const Instr& in = st.program[st.strand_offsets[rep] + j];
-            const uint32_t op = in.w0 & 0xFFu, flags = (in.w0 >> 8) & 0xFFu, dst = in.w0 >> 16;
-            if (op == I_END) break;
-            // table words for this instruction: [a if immediate / shift-lo][b if immediate / shift-hi][aux]
-            auto word = [&](int which) {   // 0: a, 1: b, 2: aux
-                for (size_t m = 0; m < rows.size(); m++) {
-                    const Instr& im = st.program[st.strand_offsets[shapes[k].strands[m]] + j];
-                    rows[m].push_back(which == 0 ? im.a : which == 1 ? im.b : im.aux);
-                }
-                return "q[" + std::to_string(n_words++) + "]";
-            };
-            const bool tap = op == I_TAP_IN || op == I_TAP_BUF;
-            std::string wa, wb, wx;
-            if ((flags & IF_A_IMM) || tap) wa = word(0);
-            if ((flags & IF_B_IMM) || tap || op == I_GATE) wb = word(1);
-            if (op == I_LDIN || op == I_LDBUF || op == I_STBUF || op == I_STOUT || op == I_DLY_IN || op == I_DLY_BUF || tap || op == I_GATE) wx = word(2);
-            for (int w = 0; w < W; w++) {
-                const std::string t = "t_" + std::to_string(w);
-                const char* guard = w >= 2 ? "if (two) " : "";
-                const std::string a = (flags & IF_A_IMM) ? "f4splat(" + wa + ")" : reg(in.a, w);
-                const std::string b = (flags & IF_B_IMM) ? "f4splat(" + wb + ")" : reg(in.b, w);
-                const std::string sh = "(((unsigned long long)" + wb + " << 32) | " + wa + ")";
-                body << "    ";
-                switch (op) {
-                    case I_ADD: body << reg(dst, w) << " = f4add(" << a << ", " << b << ");"; break;
-                    case I_MUL: body << reg(dst, w) << " = f4mul(" << a << ", " << b << ");"; break;
-                    case I_DIV: body << reg(dst, w) << " = f4div(" << a << ", " << b << ");"; break;
-                    case I_MOD: body << reg(dst, w) << " = f4mod(" << a << ", " << b << ");"; break;
-                    case I_MIN: body << reg(dst, w) << " = f4min(" << a << ", " << b << ");"; break;
-                    case I_MOV: body << reg(dst, w) << " = " << a << ";"; break;
-                    case I_LDIN: body << reg(dst, w) << " = f4ld_in(p.inputs[" << wx << "], " << t << ");"; break;
-                    case I_LDBUF: body << reg(dst, w) << " = f4ld_buf(p.buffers[" << wx << "], " << t << ");"; break;
-                    case I_STBUF: body << guard << "f4st_buf(p.buffers[" << wx << "], " << t << ", " << a << ");"; break;
-                    case I_STOUT: body << guard << "f4st_out(p, " << wx << ", " << t << ", " << a << ");"; break;
-                    case I_TAP_IN: body << reg(dst, w) << " = f4tap_in(p.inputs[" << wx << "], " << t << ", " << sh << ");"; break;
-                    case I_TAP_BUF: body << reg(dst, w) << " = f4tap_buf(p.buffers[" << wx << "], " << t << ", " << sh << ");"; break;
-                    case I_GATE: body << reg(dst, w) << " = f4gate(" << a << ", " << t << ", (((unsigned long long)" << wx << " << 32) | " << wb << "));"; break;
-                    case I_DLY_IN: body << reg(dst, w) << " = f4delay<0>(p.inputs[" << wx << "], no_buf, " << a << ", z4, " << t << ", p.sparkle_delay);"; break;
-                    case I_DLY_BUF: body << reg(dst, w) << " = f4delay<1>(no_in, p.buffers[" << wx << "], " << a << ", z4, " << t << ", p.sparkle_delay);"; break;
-                    case I_DLY_TI: body << reg(dst, w) << " = f4delay<2>(no_in, no_buf, " << a << ", " << b << ", " << t << ", p.sparkle_delay);"; break;
-                    default: body << "/* unknown op " << op << " */"; break;
-                }
-                body << "\n";
-            }
-        }
-        body << "  }\n  } break;\n";
-        tables << "__device__ const unsigned frb_tab" << k << "[" << rows.size() << "][" << std::max<uint32_t>(n_words, 1) << "] = {";
-        for (size_t m = 0; m < rows.size(); m++) {
-            tables << (m ? ",{" : "{");
-            if (rows[m].empty()) tables << "0u";
-            for (size_t j = 0; j < rows[m].size(); j++) tables << (j ? "," : "") << rows[m][j] << "u";
-            tables << "}";
-        }
-        tables << "};\n";
+        o << "    const unsigned* q = row;\n";
+        Emitter em{st, o, W};
+        em.seq(sh.code, "q", "    ");
+        o << "  }\n  } break;\n";
     }
-    body << "  default: break;\n  }\n}\n";
-    tables << "__device__ const unsigned frb_shape_of[" << std::max<size_t>(n_strands, 1) << "] = {";
-    for (size_t sd = 0; sd < n_strands; sd++) tables << (sd ? "," : "") << shape_of[sd] << "u";
-    if (!n_strands) tables << "0u";
-    tables << "};\n__device__ const unsigned frb_idx_of[" << std::max<size_t>(n_strands, 1) << "] = {";
-    for (size_t sd = 0; sd < n_strands; sd++) tables << (sd ? "," : "") << idx_of[sd] << "u";
-    if (!n_strands) tables << "0u";
-    tables << "};\n";
-    o << tables.str() << body.str();
-    return o.str();
+    o << "  default: break;\n  }\n}\n";
+    out.source = o.str();
+    return out;
+}
+
+std::string jit_generate_source(const Stage& st) { return jit_generate(st).source; }
+size_t jit_code_instructions(const Stage& st) { return jit_generate(st).code_instrs; }
+
+// Compiled cubins by source text, process-wide: the source is a function of the program's structure only, so a graph
+// edit that changes constants or repeat counts — and every renderer that builds the same graph — compiles nothing.
+namespace {
+std::mutex g_cache_mu;
+std::map<std::string, std::shared_ptr<const std::string>> g_cubin_cache;
+size_t g_cache_bytes = 0;
+std::mutex g_jobs_mu;
+std::condition_variable g_jobs_cv;
+int g_jobs_in_flight = 0;
+}  // namespace
+
+std::shared_ptr<const std::string> jit_cache_lookup(const std::string& source) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    auto it = g_cubin_cache.find(source);
+    return it == g_cubin_cache.end() ? nullptr : it->second;
+}
+
+static void cache_store(const std::string& source, const std::string& cubin) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    if (g_cache_bytes > (256u << 20)) { g_cubin_cache.clear(); g_cache_bytes = 0; }
+    if (g_cubin_cache.emplace(source, std::make_shared<const std::string>(cubin)).second) g_cache_bytes += source.size() + cubin.size();
 }
 
 bool jit_compile_to_cubin(const std::string& source, std::string* cubin, std::string* log) {
+    if (auto hit = jit_cache_lookup(source)) { *cubin = *hit; return true; }
     Api& a = api(false);
     if (!a.ok) { if (log) *log = a.why; return false; }
     nvrtcProgram prog;
@@ -258,7 +405,15 @@ bool jit_compile_to_cubin(const std::string& source, std::string* cubin, std::st
     // same arithmetic contract as the nvcc-built interpreter: no FMA contraction, IEEE division, no flush-to-zero
     const char* opts[] = {"--gpu-architecture=sm_100a", "--fmad=false", "--prec-div=true", "--prec-sqrt=true", "--ftz=false",
                           "-std=c++17", "-lineinfo"};
-    nvrtcResult rc = a.CompileProgram(prog, (int)(sizeof(opts) / sizeof(opts[0])), opts);
+    std::vector<const char*> optv(opts, opts + sizeof(opts) / sizeof(opts[0]));
+    if (getenv("FRB_JIT_NO_LINEINFO")) optv.pop_back();
+    std::vector<std::string> extra;
+    if (const char* e = getenv("FRB_JIT_NVRTC_OPTS")) {            // measurement knob: extra NVRTC options, space separated
+        std::istringstream is(e);
+        for (std::string w; is >> w;) extra.push_back(w);
+        for (const std::string& w : extra) optv.push_back(w.c_str());
+    }
+    nvrtcResult rc = a.CompileProgram(prog, (int)optv.size(), optv.data());
     size_t ls = 0;
     a.GetProgramLogSize(prog, &ls);
     if (log && ls > 1) { log->resize(ls); a.GetProgramLog(prog, &(*log)[0]); }
@@ -269,21 +424,53 @@ bool jit_compile_to_cubin(const std::string& source, std::string* cubin, std::st
         if (ok) { cubin->resize(n); ok = a.GetCUBIN(prog, &(*cubin)[0]) == NVRTC_SUCCESS; }
     }
     a.DestroyProgram(&prog);
+    if (ok) cache_store(source, *cubin);
     return ok;
+}
+
+// A compile beside the render loop.  The thread owns a reference to the job, so a renderer that no longer wants the
+// result (graph edit, n_slots change) just drops its own: nothing waits for NVRTC, and the cubin still lands in the cache.
+std::shared_ptr<JitJob> jit_compile_async(std::string source) {
+    auto job = std::make_shared<JitJob>();
+    {
+        std::lock_guard<std::mutex> lk(g_jobs_mu);
+        g_jobs_in_flight++;
+    }
+    std::thread([job, src = std::move(source)]() {
+        std::string cubin, log;
+        const bool ok = jit_compile_to_cubin(src, &cubin, &log);
+        job->cubin = ok ? std::move(cubin) : std::string();
+        job->log = std::move(log);
+        job->done.store(ok ? 1 : -1, std::memory_order_release);
+        {
+            std::lock_guard<std::mutex> lk(g_jobs_mu);
+            g_jobs_in_flight--;
+        }
+        g_jobs_cv.notify_all();
+    }).detach();
+    return job;
+}
+
+// Called when the last renderer of a process goes away (and by tests): no compile thread outlives the library's users.
+void jit_wait_idle() {
+    std::unique_lock<std::mutex> lk(g_jobs_mu);
+    g_jobs_cv.wait(lk, [] { return g_jobs_in_flight == 0; });
 }
 
 struct JitKernel {
     CUmodule mod = nullptr;
     CUfunction fn = nullptr;
+    unsigned* d_tab = nullptr;      // operand table (device)
 };
 
 JitKernel* jit_build(const Stage& st, std::string* err) {
+    const JitProgram prog = jit_generate(st);
     std::string cubin, log;
-    if (!jit_compile_to_cubin(jit_generate_source(st), &cubin, &log)) { if (err) *err = "NVRTC: " + log; return nullptr; }
-    return jit_load(cubin, err);
+    if (!jit_compile_to_cubin(prog.source, &cubin, &log)) { if (err) *err = "NVRTC: " + log; return nullptr; }
+    return jit_load(cubin, prog.table, err);
 }
 
-JitKernel* jit_load(const std::string& cubin, std::string* err) {
+JitKernel* jit_load(const std::string& cubin, const std::vector<uint32_t>& table, std::string* err) {
     Api& a = api(true);
     if (!a.ok) { if (err) *err = a.why; return nullptr; }
     auto* k = new JitKernel();
@@ -293,12 +480,20 @@ JitKernel* jit_load(const std::string& cubin, std::string* err) {
         if (err) *err = "cuModuleLoadData failed";
         return nullptr;
     }
+    const size_t bytes = std::max<size_t>(table.size(), 1) * sizeof(uint32_t);
+    if (cudaMalloc(&k->d_tab, bytes) != cudaSuccess ||
+        (!table.empty() && cudaMemcpy(k->d_tab, table.data(), table.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess)) {
+        if (err) *err = "operand table upload failed";
+        jit_free(k);
+        return nullptr;
+    }
     return k;
 }
 
 void jit_free(JitKernel* k) {
     if (!k) return;
     Api& a = api(true);
+    if (k->d_tab) cudaFree(k->d_tab);
     if (a.ok && k->mod) a.ModuleUnload(k->mod);
     delete k;
 }
@@ -312,7 +507,8 @@ bool jit_launch(JitKernel* k, const InterpParams& p, int sm_count, cudaStream_t 
     if (cap < 1) cap = 1;
     if (blocks > cap) blocks = cap;
     InterpParams pp = p;
-    void* args[] = {&pp};
+    const unsigned* tab = k->d_tab;
+    void* args[] = {&pp, &tab};
     return a.LaunchKernel(k->fn, (unsigned)blocks, p.n_strands, 1, 128, 1, 1, 0, (CUstream)stream, args, nullptr) == CUDA_SUCCESS;
 }
 

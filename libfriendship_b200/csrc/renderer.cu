@@ -104,6 +104,7 @@ Renderer::~Renderer() {
     cudaSetDevice(device_);
     if (stream_) cudaStreamSynchronize(stream_);
     free_device_schedule();
+    jit_wait_idle();                      // no compile thread outlives the renderers (a sub-second wait at most)
     for (auto& s : inputs_) if (s.d_data) cudaFree(s.d_data);
     if (d_indesc_) cudaFree(d_indesc_);
     if (d_in_stage_) cudaFree(d_in_stage_);
@@ -256,10 +257,8 @@ void Renderer::del_edge(const frb_edge& e) {                               // re
 void Renderer::free_device_schedule() {
     for (auto p : d_programs_) if (p) cudaFree(p);
     d_programs_.clear();
-    for (auto& j : stage_jit_) {
-        if (j.state == 3 && j.cubin.valid()) j.cubin.wait();   // never leave a compile thread behind
-        jit_free(j.k);
-    }
+    // a compile still running beside the loop is simply dropped: its thread owns the job, the cubin goes to the cache
+    for (auto& j : stage_jit_) jit_free(j.k);
     stage_jit_.clear();
     for (auto& g : ring_groups_) if (g.data) cudaFree(g.data);
     ring_groups_.clear();
@@ -309,7 +308,7 @@ void Renderer::ensure_schedule(uint32_t n_slots) { (void)schedule(n_slots); }
 
 void Renderer::upload_schedule() {
     d_programs_.assign(sched_.stages.size(), nullptr);
-    stage_jit_ = std::vector<StageJit>(sched_.stages.size());   // StageJit holds a future: not copyable
+    stage_jit_ = std::vector<StageJit>(sched_.stages.size());
     for (size_t i = 0; i < sched_.stages.size(); i++) {
         // device layout: [strand offsets, padded to a multiple of 4 words][instructions]
         const Stage& stg = sched_.stages[i];
@@ -621,38 +620,45 @@ void Renderer::poll_stage_jit(size_t sg, uint64_t n_groups) {
     sj.uses++;
     const bool asked = (cfg_.flags & FRB_FLAG_JIT_EAGER) != 0;
     const bool eager = asked || n_groups >= (1ull << 15);
-    if (sj.state == 0 && !(cfg_.flags & FRB_FLAG_NO_JIT) && st.program.size() <= 65536 &&   // bound the generated tables
-        (eager || sj.uses >= 4)) {
-        // NVRTC's time grows faster than linearly in the straight-line code it is given (jit.cc, jit_code_instructions:
-        // 200 instructions 2 s, 500 16 s, 2,000 more than 5 minutes): a stage above JIT_MAX_CODE stays on the
-        // interpreter for good, and one above JIT_MAX_SYNC_CODE is never compiled on the render thread unless the
-        // caller asked for that with FRB_FLAG_JIT_EAGER
-        if (sj.code_instrs == ~0ull) sj.code_instrs = jit_code_instructions(st);
-        if (sj.code_instrs > JIT_MAX_CODE) {
+    if (sj.state == 0 && !(cfg_.flags & FRB_FLAG_NO_JIT) && (eager || sj.uses >= 4)) {
+        // What NVRTC is handed is bounded (jit.cc: runs of like instruction groups are loops, so this is the program's
+        // STRUCTURE, not its length; straight-line code costs 2 s at 200 statements, 16 s at 500): a stage above
+        // JIT_MAX_CODE stays on the interpreter for good, and one above JIT_MAX_SYNC_CODE is never compiled on the
+        // render thread unless the caller asked for that with FRB_FLAG_JIT_EAGER.  A cubin the process has compiled
+        // before (same structure: other constants, other repeat counts, another renderer) is loaded right away.
+        JitProgram prog = jit_generate(st);
+        sj.code_instrs = prog.code_instrs;
+        sj.table = std::move(prog.table);
+        std::string jerr;
+        if (auto hit = jit_cache_lookup(prog.source)) {
+            sj.k = jit_load(*hit, sj.table, &jerr);
+            sj.state = sj.k ? 1 : 2;
+            if (!sj.k) last_jit_error = jerr;
+        } else if (sj.code_instrs > JIT_MAX_CODE) {
             sj.state = 2;
             last_jit_error = "stage program too long for the JIT; interpreted";
         } else if (eager && (asked || sj.code_instrs <= JIT_MAX_SYNC_CODE)) {
-            // a long block (or an explicit request) pays for the ~0.2 s of NVRTC right away
-            std::string jerr;
-            sj.k = jit_build(st, &jerr);
+            // a long block (or an explicit request) pays for the NVRTC call right away
+            std::string cubin, log;
+            if (jit_compile_to_cubin(prog.source, &cubin, &log)) sj.k = jit_load(cubin, sj.table, &jerr);
+            else jerr = "NVRTC: " + log;
             sj.state = sj.k ? 1 : 2;
             if (!sj.k) last_jit_error = jerr;
         } else {
             // streaming in short blocks (or a long body): compile beside the render loop, never stall a block for it
-            const std::string src = jit_generate_source(st);
-            sj.cubin = std::async(std::launch::async, [src]() {
-                std::string cubin, log;
-                return jit_compile_to_cubin(src, &cubin, &log) ? cubin : std::string();
-            });
+            sj.job = jit_compile_async(std::move(prog.source));
             sj.state = 3;
         }
+        if (sj.state != 3) std::vector<uint32_t>().swap(sj.table);
     }
-    if (sj.state == 3 && sj.cubin.wait_for(std::chrono::seconds(0)) == std::future_status::ready) {
-        const std::string cubin = sj.cubin.get();
+    if (sj.state == 3 && sj.job->done.load(std::memory_order_acquire) != 0) {
         std::string jerr;
-        sj.k = cubin.empty() ? nullptr : jit_load(cubin, &jerr);
+        const bool ok = sj.job->done.load(std::memory_order_acquire) > 0;
+        sj.k = ok ? jit_load(sj.job->cubin, sj.table, &jerr) : nullptr;
         sj.state = sj.k ? 1 : 2;
-        if (!sj.k) last_jit_error = cubin.empty() ? "NVRTC compile failed" : jerr;
+        if (!sj.k) last_jit_error = ok ? jerr : "NVRTC: " + sj.job->log;
+        sj.job.reset();
+        std::vector<uint32_t>().swap(sj.table);
     }
 }
 
@@ -735,6 +741,7 @@ void Renderer::run_range(uint64_t lo, uint64_t hi, float* d_out, uint64_t t0, ui
             p.t1 = d_out ? t1 : t0;                  // warm-up ranges write no output
             p.out_vec_ok = out_vec_ok;
             p.sparkle_delay = (cfg_.flags & FRB_FLAG_SPARKLE_DELAY) ? 1 : 0;
+            p.sparkle_min = (cfg_.flags & FRB_FLAG_SPARKLE_MIN) ? 1 : 0;
             // Tiered like the reference's JIT renderer (sparkle.rs:271-288 compiles lazily at the next render): a stage
             // program is interpreted until it is hot (4th launch, or a block of >= 256 Ki samples), then compiled
             // once by NVRTC into a fused kernel.  A stage that fails to compile stays on the interpreter.

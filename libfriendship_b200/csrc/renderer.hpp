@@ -4,7 +4,6 @@
 #pragma once
 #include <cuda_runtime.h>
 
-#include <future>
 #include <map>
 #include <memory>
 #include <string>
@@ -100,9 +99,11 @@ private:
     std::vector<uint32_t*> d_programs_;         // per stage
     // state: 0 untried, 1 ready, 2 failed, 3 compiling in the background (the stage keeps being interpreted meanwhile)
     // code_instrs: jit_code_instructions of the stage, computed when the stage first qualifies (~0 = not yet)
-    struct StageJit { JitKernel* k = nullptr; int state = 0; uint64_t uses = 0; uint64_t code_instrs = ~0ull; std::future<std::string> cubin; };
+    // job: the compile running beside the render loop (jit.hpp; dropped, never waited for, when the schedule goes away)
+    struct StageJit { JitKernel* k = nullptr; int state = 0; uint64_t uses = 0; uint64_t code_instrs = ~0ull;
+                      std::shared_ptr<JitJob> job; std::vector<uint32_t> table; };
     static constexpr uint64_t JIT_MAX_CODE = FRB_JIT_MAX_CODE;        // above: interpreted for good (NVRTC needs minutes)
-    static constexpr uint64_t JIT_MAX_SYNC_CODE = FRB_JIT_MAX_SYNC_CODE;   // above: compiled only beside the render loop (see the header: = JIT_MAX_CODE for now)
+    static constexpr uint64_t JIT_MAX_SYNC_CODE = FRB_JIT_MAX_SYNC_CODE;   // above: compiled only beside the render loop
     std::vector<StageJit> stage_jit_;
     std::vector<uint32_t*> d_ext_in_bufs_;      // per extension instance: input ring ids per lane
     // Fused DirectForm -> FbDelay chains (scan.cu dfcomb_kernel): chain_of_[fb instance] = df instance whose lanes feed it

@@ -1,13 +1,20 @@
-"""ctypes binding of the CPU oracle (oracle/_build/liboracle.so) — TEST INFRASTRUCTURE ONLY.
+"""ctypes binding of the CPU oracle (oracle/_build/liboracle.so) — TEST INFRASTRUCTURE ONLY: imported by tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs, never by the product package.
 
 Same Python surface as libfriendship_b200.B200Renderer so parity tests drive both with the same calls.
 """
 import ctypes as C
 import os
 
-from libfriendship_b200 import _cabi
+import importlib.util
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# The oracle's C shim mirrors include/friendship_b200.h (orc_* for frb_*), so it shares the ctypes declarations of that
+# header — loaded BY PATH: importing the package would map the product library, and bench.py's reference arm must run
+# on oracle/_build/liboracle.so alone.
+_spec = importlib.util.spec_from_file_location("_frb_cabi_decls", os.path.join(ROOT, "libfriendship_b200", "_cabi.py"))
+_cabi = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(_cabi)
 _LIB_PATH = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
 _lib = C.CDLL(_LIB_PATH)
 _cabi.declare(_lib, "orc")
@@ -27,6 +34,8 @@ class OracleRenderer(_cabi.CRendererBase):
         _lib.orc_set_ext_mode(self._h, 0 if ext_mode == "fp64" else 1)
         _lib.orc_set_sparkle_delay.argtypes = [C.c_void_p, C.c_int]
         _lib.orc_set_sparkle_delay(self._h, 1 if flags & _cabi.FLAG_SPARKLE_DELAY else 0)
+        _lib.orc_set_sparkle_min.argtypes = [C.c_void_p, C.c_int]
+        _lib.orc_set_sparkle_min(self._h, 1 if flags & _cabi.FLAG_SPARKLE_MIN else 0)
 
     def fill_buffer_mt(self, n_slots, n_times, idx, n_threads):
         """CPU-baseline helper: multi-threaded evaluation of the current graph (inputs already fed)."""

@@ -30,6 +30,7 @@ const char* orc_last_error(const orc_renderer* h) { return h ? h->err.c_str() : 
 int orc_set_ext_mode(orc_renderer* h, int mode) { h->r.ext_mode = mode ? ExtMode::F32_REFSTYLE : ExtMode::FP64; return 0; }
 
 int orc_set_sparkle_delay(orc_renderer* h, int on) { h->r.sparkle_delay = on != 0; return 0; }
+int orc_set_sparkle_min(orc_renderer* h, int on) { h->r.sparkle_min = on != 0; return 0; }
 
 int orc_define_effect(orc_renderer* h, uint64_t key, const frb_node* nodes, uint32_t n_nodes,
                       const frb_edge* edges, uint32_t n_edges) {

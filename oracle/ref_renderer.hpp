@@ -88,6 +88,7 @@ struct NodeMap {
     std::vector<std::optional<Edge>> output_edges;
     ExtMode ext_mode = ExtMode::FP64;
     bool sparkle_delay = false;
+    bool sparkle_min = false;
 
     // reference.rs:141-153
     void add_edge(const Edge& e) {
@@ -169,6 +170,9 @@ struct NodeMap {
             case Minimum: {                                                     // :242-248  f32::min == IEEE minNum
                 if (from_slot != 0) throw Panic(-4, "Minimum: from_slot != 0 (reference.rs:244)");
                 float l = in(0, time), r = in(1, time);
+                // SparkleRenderer's variant (reference sparkle.rs:492-498): select(fcmp ULT l r, l, r) — ULT is
+                // "unordered or less than", so a NaN in either operand yields l
+                if (sparkle_min) return !(l >= r) ? l : r;
                 return std::fmin(l, r);
             }
             case Modulo: {                                                      // :249-262
@@ -284,6 +288,10 @@ struct NodeMap {
         sparkle_delay = f;
         for (auto& kv : nodes) if (kv.second.user) kv.second.user->set_sparkle_delay(f);
     }
+    void set_sparkle_min(bool f) {
+        sparkle_min = f;
+        for (auto& kv : nodes) if (kv.second.user) kv.second.user->set_sparkle_min(f);
+    }
 };
 
 // One external-input slot vector of the reference (`inputs[slot]: Vec<f32>`, reference.rs:22-25), stored as
@@ -308,6 +316,7 @@ public:
     uint64_t head = 0;                                          // reference.rs:26-28
     ExtMode ext_mode = ExtMode::FP64;
     bool sparkle_delay = false;      // evaluate Delay the way SparkleRenderer does (sparkle.rs:525-542)
+    bool sparkle_min = false;        // evaluate Minimum the way SparkleRenderer does (sparkle.rs:492-498)
 
     // definitions registry (the reference passes Rc<Effect>; the C ABI passes keys)
     std::unordered_map<uint64_t, std::shared_ptr<NodeMap>> effect_defs;
@@ -393,6 +402,7 @@ public:
                      const std::vector<std::vector<float>>& rows) {
         nodes.set_ext_mode(ext_mode);
         nodes.set_sparkle_delay(sparkle_delay);
+        nodes.set_sparkle_min(sparkle_min);
         nodes.clear_memo();
         if (idx != head) {                                                      // :52-58 seek: every slot := idx zeros
             for (auto& slot : inputs) { slot.base = idx; slot.data.clear(); }

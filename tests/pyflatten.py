@@ -184,6 +184,14 @@ def flatten(top, n_slots):
                 sop = values[src][0]
                 computed = (V_SUM2 <= sop <= V_MIN) or sop == V_GATE
                 v = None
+                if sop in (V_INPUT, V_EXT, V_TAP) and values[amt][0] in (V_CONST, V_ZERO):
+                    # a stored signal delayed by a constant: read at t - d (a TAP)
+                    d = const_delay_of(amt)
+                    base = shift_of(values[src]) if sop == V_TAP else 0
+                    if d is None:
+                        v = mk(V_ZERO)
+                    elif d < (1 << 40) and base < (1 << 40):
+                        v = mk64(V_TAP, values[src][1] if sop == V_TAP else src, base + d)
                 if computed and values[amt][0] in (V_CONST, V_ZERO):
                     d = const_delay_of(amt)
                     if d is not None and d < (1 << 40) and clone_cost(src, CLONE_MAX_OPS) is not None and not is_ti(src):

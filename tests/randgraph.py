@@ -2,7 +2,7 @@
 sequence of GraphWatcher calls is applied to any renderer object."""
 import numpy as np
 
-from graphs import f32_bits
+from workloads.graphs import f32_bits
 from libfriendship_b200 import (KIND_DELAY, KIND_DIVIDE, KIND_EFFECT, KIND_F32CONSTANT, KIND_MINIMUM, KIND_MODULO,
                                 KIND_MULTIPLY, KIND_SUM2)
 

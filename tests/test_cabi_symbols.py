@@ -95,3 +95,16 @@ def test_rust_build_script_lists_every_translation_unit():
     listed = set(re.findall(r'\("([\w./]+\.(?:cu|cc))",', src))
     want = {u for u in g.CU_SOURCES + g.CC_SOURCES if not u.startswith("host/")}
     assert listed == want, (sorted(listed), sorted(want))
+
+
+def test_workload_kinds_match_the_header_constants():
+    """workloads/kinds.py restates the node kinds and flags so that the builders never import the product package."""
+    import libfriendship_b200 as L
+    from workloads import kinds
+    for name in dir(kinds):
+        if name.startswith(("KIND_", "FLAG_")):
+            assert getattr(kinds, name) == getattr(L._cabi, name), name
+    hdr = open(os.path.join(ROOT, "include", "friendship_b200.h")).read()
+    import re
+    for name, val in re.findall(r"#define FRB_((?:KIND|FLAG)_\w+)\s+(\d+)u", hdr):
+        assert getattr(kinds, name) == int(val), name

@@ -3,8 +3,8 @@ src/render/reference.rs), oracle vs CUDA, bit-exact."""
 import numpy as np
 import pytest
 
-from graphs import build_cfg1_graph, cfg1_input, f32_bits
-from oracle_binding import OracleRenderer
+from workloads.graphs import build_cfg1_graph, cfg1_input, f32_bits
+from oracle.binding import OracleRenderer
 from replay import assert_same_bits
 
 pytestmark = pytest.mark.gpu
@@ -28,7 +28,7 @@ def test_seek_far_beyond_2_pow_32():
 
 
 def test_oscillator_phase_is_exact_beyond_2_pow_32():
-    from banks import full_scale, harmonic_bank
+    from workloads.banks import full_scale, harmonic_bank
     from libfriendship_b200 import KIND_OSCBANK
     bank = harmonic_bank(64)
     bank["tau"] = np.full(64, np.inf, dtype=np.float32)          # keep it audible at t = 2^32
@@ -101,8 +101,8 @@ def test_internal_block_length_does_not_change_the_result(monkeypatch):
     """One fill is cut into internal blocks (FRB_BLOCK_SAMPLES overrides their length): the primitive path and the
     oscillator bank are pure functions of absolute time, so 1,024-sample blocks give the bits of one block; the
     recurrences restart their scan tiles at every block start, so they agree within their tolerance."""
-    from banks import build_voice_mix_graph, detuned_bank
-    from filters import build_cfg3_graph
+    from workloads.banks import build_voice_mix_graph, detuned_bank
+    from workloads.filters import build_cfg3_graph
     from libfriendship_b200 import B200Renderer
     n = 20000
     x = cfg1_input(n)
@@ -132,7 +132,7 @@ def test_many_long_input_rows_ragged_and_unaligned():
     """Five input rows of > 200,000 samples each take the batched ingest (one kernel for all rows): rows of different
     lengths (the short ones are padded with their last value, reference.rs:72-73), a row of odd length (so the rows after
     it start at unaligned offsets), a Delay reaching back into the previous call's rows; bit-exact against the oracle."""
-    from graphs import GraphBuilder
+    from workloads.graphs import GraphBuilder
     from libfriendship_b200 import B200Renderer, KIND_DELAY, KIND_SUM2
     rng = np.random.Generator(np.random.PCG64(8))
     n = 262144

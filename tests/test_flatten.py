@@ -38,7 +38,7 @@ def test_schedule_matches_python_restatement(seed):
 def test_delay_line_offsets_and_stage_cut():
     """in0 -> *0.5 -> Delay(12000) -> ... : the Delay source is a computed signal, so it is materialised with a
     lookback of exactly 12000 samples and the Delay lands in the next stage."""
-    from graphs import build_cfg1_graph
+    from workloads.graphs import build_cfg1_graph
     from randgraph import Recorder
     rec = Recorder()
     build_cfg1_graph(rec)
@@ -53,7 +53,7 @@ def test_delay_line_offsets_and_stage_cut():
 
 def test_expensive_delay_source_is_materialised_with_exact_lookback():
     """A Delay source with more than 8 operations is materialised: ring lookback = the delay, Delay in the next stage."""
-    from graphs import GraphBuilder
+    from workloads.graphs import GraphBuilder
     from randgraph import Recorder
     from libfriendship_b200 import KIND_DELAY, KIND_MULTIPLY, KIND_SUM2
     rec = Recorder()

@@ -4,8 +4,8 @@ because the render is a pure function of absolute time)."""
 import numpy as np
 import pytest
 
-from banks import build_voice_mix_graph, detuned_bank, full_scale, harmonic_bank
-from oracle_binding import OracleRenderer
+from workloads.banks import build_voice_mix_graph, detuned_bank, full_scale, harmonic_bank
+from oracle.binding import OracleRenderer
 from replay import assert_same_bits
 
 pytestmark = pytest.mark.gpu
@@ -86,7 +86,7 @@ def test_cfg3_full_voice_count_selected_voices_vs_fp64():
     """cfg3: 4,096 voices, biquad + feedback delay each, excited by a 1-partial oscillator per voice, 1 s of audio
     at the full voice count; eight voices spread over the range are also routed to their own output slots and
     compared with the fp64 oracle, which renders just those voices."""
-    from filters import build_cfg3_graph, cfg3_filters
+    from workloads.filters import build_cfg3_graph, cfg3_filters
     from libfriendship_b200 import KIND_DIRECTFORM, KIND_FBDELAY, KIND_OSCBANK
     n_voices, n = 4096, 48000
     bank, _ = detuned_bank(n_voices, 1, seed=5)
@@ -151,7 +151,7 @@ def test_cfg5_shape_one_voice_of_a_million_partials_at_the_end_of_a_minute():
 def test_device_resident_inputs_and_outputs_match_the_host_path():
     """frb_fill_buffer_device: inputs and outputs stay in HBM (what bench.py's `value` times)."""
     import torch
-    from graphs import build_cfg1_graph, cfg1_input
+    from workloads.graphs import build_cfg1_graph, cfg1_input
     n = 20000
     x = cfg1_input(n)
     host = gpu()

@@ -2,7 +2,7 @@
 (tests/golden/make_reference_tests.py cites each test's file:line)."""
 import pytest
 
-from oracle_binding import OracleRenderer
+from oracle.binding import OracleRenderer
 from replay import load_golden, replay
 
 

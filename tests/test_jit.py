@@ -3,7 +3,7 @@ kernel per stage — the B200 counterpart of the reference's LLVM JIT renderer (
 import numpy as np
 import pytest
 
-from graphs import build_cfg1_graph, cfg1_input
+from workloads.graphs import build_cfg1_graph, cfg1_input
 from randgraph import random_graph, random_inputs
 from replay import assert_same_bits, load_golden, replay
 
@@ -11,7 +11,7 @@ from replay import assert_same_bits, load_golden, replay
 def test_generated_source_compiles_for_sm_100a_without_a_gpu():
     """CPU: codegen + NVRTC (--gpu-architecture=sm_100a --fmad=false): the cfg1 graph (single stage: the Delay
     source is re-evaluated at t - 12000) and a graph whose Delay source is materialised (two stages)."""
-    from graphs import GraphBuilder
+    from workloads.graphs import GraphBuilder
     from libfriendship_b200 import B200Renderer, KIND_DELAY, KIND_MULTIPLY, KIND_SUM2
     r = B200Renderer(device=-1)
     build_cfg1_graph(r)
@@ -46,7 +46,7 @@ def test_random_programs_compile(seed):
 def test_jit_equals_interpreter_equals_oracle(seed):
     """Bit-exact three ways on seeded random graphs over several calls (ragged inputs, seek)."""
     from libfriendship_b200 import B200Renderer, FLAG_JIT_EAGER, FLAG_NO_JIT
-    from oracle_binding import OracleRenderer
+    from oracle.binding import OracleRenderer
     rec = random_graph(900 + seed, n_inputs=2, n_nodes=10 + seed % 11, n_outputs=2, nested_levels=1 + seed % 2)
     jit, itp, orc = B200Renderer(flags=FLAG_JIT_EAGER), B200Renderer(flags=FLAG_NO_JIT), OracleRenderer()
     for r in (jit, itp, orc):
@@ -74,7 +74,7 @@ def test_hot_stage_gets_compiled_in_the_background():
     render loop and the compiled kernel takes over without ever stalling a block — same bits before and after."""
     import time
     from libfriendship_b200 import B200Renderer
-    from oracle_binding import OracleRenderer
+    from oracle.binding import OracleRenderer
     n = 512
     g, o = B200Renderer(), OracleRenderer()
     build_cfg1_graph(g, delay=100.0)
@@ -96,46 +96,78 @@ def test_hot_stage_gets_compiled_in_the_background():
     assert 0 < s["jit_launches"] < s["interp_launches"]
 
 
-def test_code_size_the_jit_is_bounded_by_counts_one_body_per_strand_shape():
-    """NVRTC's time grows faster than linearly in straight-line code (a 500-node Sum2 chain: 16 s, 2,000 nodes: more
-    than 5 minutes), so the renderer bounds what it compiles by `jit_code_instructions` (FRB_JIT_MAX_CODE; on the
-    render thread FRB_JIT_MAX_SYNC_CODE, the same number for now): strands of one shape count once, however many there are."""
-    from libfriendship_b200 import B200Renderer, KIND_F32CONSTANT, KIND_SUM2
-    # 1) one long chain: every node is code
+def _const_chain(r, n, slot_in=0, slot_out=0, first_handle=2, c=0x3F800000):
+    """out[slot_out] = (...((in[slot_in] + c) + c) ... + c), n Sum2 nodes; constants from node 1"""
+    from libfriendship_b200 import KIND_SUM2
+    prev = None
+    h = first_handle
+    for i in range(n):
+        r.on_add_node(h, KIND_SUM2)
+        r.on_add_edge((0, h, slot_in, 0) if prev is None else (prev, h, 0, 0))
+        r.on_add_edge((1, h, c, 1))
+        prev = h
+        h += 1
+    r.on_add_edge((prev, 0, 0, slot_out))
+    return h
+
+
+def test_code_size_depends_on_structure_not_on_length():
+    """NVRTC's time grows faster than linearly in straight-line code (500 statements: 16 s, 2,000: more than 5 minutes),
+    so the generator folds runs of like instruction groups into loops whose trip counts and operands come from a table
+    (csrc/jit.cc): what the compiler sees — `jit_code_instructions`, bounded by FRB_JIT_MAX_CODE — is the program's
+    structure.  Strands of one structure share a body, whatever their length."""
+    import time
+    from libfriendship_b200 import B200Renderer, KIND_F32CONSTANT
+    # 1) one long chain: a load, ONE loop, a store
     r = B200Renderer(device=-1)
     r.on_add_node(1, KIND_F32CONSTANT)
-    prev = 0
-    for i in range(3000):
-        r.on_add_node(2 + i, KIND_SUM2)
-        r.on_add_edge((prev, 2 + i, 0, 0))
-        r.on_add_edge((1, 2 + i, 0x3F800000, 1))
-        prev = 2 + i
-    r.on_add_edge((prev, 0, 0, 0))
-    assert 3000 <= r.jit_code_instructions(1, 0) <= 3004            # load, 3,000 sums, store: far above the 512 compiled
-    # 2) the same short chain on 48 slots: 48 strands, one body
+    _const_chain(r, 3000)
+    assert r.jit_code_instructions(1, 0) <= 16
+    src = r.jit_source(1, 0)
+    assert src.count("for (unsigned i_") == 1 and "3000" not in src[src.index("frb_stage"):]
+    t0 = time.time()
+    assert r.jit_cubin_size(1, 0) > 1000
+    first = time.time() - t0
+    # 2) another length, other constants: the same source text, so the cubin comes from the cache
+    r2 = B200Renderer(device=-1)
+    r2.on_add_node(1, KIND_F32CONSTANT)
+    _const_chain(r2, 9000, c=0x40000000)
+    assert r2.jit_source(1, 0) == src
+    t0 = time.time()
+    assert r2.jit_cubin_size(1, 0) > 1000
+    assert time.time() - t0 < max(0.1, first / 2)
+    # 3) chains of different lengths on 48 slots: 48 strands, one body
     r = B200Renderer(device=-1)
     r.on_add_node(1, KIND_F32CONSTANT)
     h = 2
     for slot in range(48):
-        prev = None
-        for i in range(5):
-            r.on_add_node(h, KIND_SUM2)
-            if prev is None:
-                r.on_add_edge((0, h, slot, 0))
-            else:
-                r.on_add_edge((prev, h, 0, 0))
-            r.on_add_edge((1, h, 0x3F800000 + slot, 1))
-            prev = h
-            h += 1
-        r.on_add_edge((prev, 0, 0, slot))
+        h = _const_chain(r, 20 + slot, slot_in=slot, slot_out=slot, first_handle=h, c=0x3F800000 + slot)
     one = B200Renderer(device=-1)
     one.on_add_node(1, KIND_F32CONSTANT)
-    prev = 0
-    for i in range(5):
-        one.on_add_node(2 + i, KIND_SUM2)
-        one.on_add_edge((prev, 2 + i, 0, 0))
-        one.on_add_edge((1, 2 + i, 0x3F800000, 1))
-        prev = 2 + i
-    one.on_add_edge((prev, 0, 0, 0))
-    assert r.jit_code_instructions(48, 0) == one.jit_code_instructions(1, 0) <= 8
+    _const_chain(one, 20)
+    assert r.jit_code_instructions(48, 0) == one.jit_code_instructions(1, 0) <= 16
     assert r.jit_cubin_size(48, 0) > 1000
+
+
+def test_repeated_groups_fold_on_two_levels():
+    """A chain per voice, voices summed: the inner chains are loops, and the run of like (loop + glue) groups is a loop
+    again — the operand cursor walks the table, so inner trip counts may differ per voice."""
+    from workloads.graphs import GraphBuilder
+    from libfriendship_b200 import B200Renderer, KIND_MULTIPLY, KIND_SUM2
+    r = B200Renderer(device=-1)
+    g = GraphBuilder(r)
+    total, slot = None, 0
+    for v in range(24):
+        voice = None
+        for p in range(12 + (v % 5)):
+            term = g.node(KIND_MULTIPLY, g.input(slot), g.const(1.0 / (1 + p)))
+            slot += 1
+            voice = term if voice is None else g.node(KIND_SUM2, voice, term)
+        voice = g.node(KIND_MULTIPLY, voice, g.const(0.5 + v))
+        total = voice if total is None else g.node(KIND_SUM2, total, voice)
+    g.output(0, total)
+    src = r.jit_source(1, 0)
+    body = src[src.index("frb_stage"):]
+    assert body.count("for (unsigned i_") >= 2 and "#pragma unroll 1\n" in body       # an outer loop around an inner one
+    assert r.jit_code_instructions(1, 0) < 120                                          # ~1,000 instructions in the program
+    assert r.jit_cubin_size(1, 0) > 1000

@@ -4,8 +4,8 @@ Tolerance (BASELINE.json north_star): max abs error <= 1e-5 of full scale, full 
 import numpy as np
 import pytest
 
-from banks import build_voice_mix_graph, detuned_bank, full_scale, harmonic_bank
-from oracle_binding import OracleRenderer
+from workloads.banks import build_voice_mix_graph, detuned_bank, full_scale, harmonic_bank
+from oracle.binding import OracleRenderer
 from replay import assert_same_bits
 
 pytestmark = pytest.mark.gpu

@@ -20,7 +20,7 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_PORT"] = str(port)
     import torch.distributed as dist
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from banks import build_voice_mix_graph, detuned_bank
+    from workloads.banks import build_voice_mix_graph, detuned_bank
     from libfriendship_b200.sharded import ShardedRenderer
     sr = ShardedRenderer(rank=rank, world_size=world, device=0, exchange="p2p")
     mine = sr.voices_of_rank(N_VOICES)
@@ -47,7 +47,7 @@ def test_two_ranks_store_into_rank0_slab_and_sum_in_rank_order():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    from banks import build_voice_mix_graph, detuned_bank, full_scale
+    from workloads.banks import build_voice_mix_graph, detuned_bank, full_scale
     from libfriendship_b200 import B200Renderer
     bank, ids = detuned_bank(N_VOICES, N_PARTIALS)
     r = B200Renderer()

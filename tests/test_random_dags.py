@@ -5,7 +5,7 @@ ragged inputs, seeks and graph edits between calls."""
 import numpy as np
 import pytest
 
-from oracle_binding import OracleRenderer
+from oracle.binding import OracleRenderer
 from randgraph import random_graph, random_inputs
 from replay import assert_same_bits
 
@@ -63,7 +63,7 @@ def test_random_graph_seek_and_edit(seed):
 def test_cfg1_one_call_equals_blocks():
     """BASELINE configs[0]: 440 Hz sine through Multiply/Sum/Delay, 48 kHz x 1 s — one call and 94 x 512-sample
     calls are identical, and both equal the oracle bit for bit."""
-    from graphs import build_cfg1_graph, cfg1_input
+    from workloads.graphs import build_cfg1_graph, cfg1_input
     n = 48000
     x = cfg1_input(n)
     gpu, orc = both()
@@ -128,3 +128,40 @@ def test_sparkle_delay_flag_matches_sparkle_semantics(seed):
         outs.append(r.fill_buffer(2, 200, 0, rows))
     assert_same_bits(outs[0], outs[2], f"sparkle interp seed {seed}")
     assert_same_bits(outs[1], outs[2], f"sparkle jit seed {seed}")
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_sparkle_min_flag_matches_sparkle_semantics(seed):
+    """FRB_FLAG_SPARKLE_MIN: Minimum as select(a ULT b, a, b) — a NaN in either operand yields a (reference
+    sparkle.rs:492-498) — instead of f32::min = minNum (reference.rs:242-248).  Random graphs rich in Minimum nodes,
+    NaN constants and NaN-producing operations (0/0, x mod 0), interpreter and JIT against the oracle; the two
+    semantics must actually differ on these graphs."""
+    from libfriendship_b200 import B200Renderer, FLAG_JIT_EAGER, FLAG_SPARKLE_MIN, KIND_DIVIDE, KIND_MINIMUM, KIND_MODULO, KIND_SUM2
+    from workloads.graphs import GraphBuilder
+    rng = np.random.RandomState(7000 + seed)
+    pool = [float("nan"), 0.0, -0.0, 1.0, -2.5, float("inf"), -float("inf"), 3.0]
+
+    def build(r):
+        g = GraphBuilder(r)
+        rs = np.random.RandomState(100 + seed)
+        vals = [g.input(0), g.input(1)] + [g.const(c) for c in pool]
+        for k in range(24):
+            kind = [KIND_MINIMUM, KIND_MINIMUM, KIND_DIVIDE, KIND_MODULO, KIND_SUM2][rs.randint(5)]
+            a, b = vals[rs.randint(len(vals))], vals[rs.randint(len(vals))]
+            vals.append(g.node(kind, a, b))
+        mins = [v for v in vals[len(pool) + 2:]]
+        g.output(0, g.node(KIND_MINIMUM, mins[-1], mins[-2]))
+        g.output(1, g.node(KIND_MINIMUM, g.input(0), g.node(KIND_DIVIDE, g.input(1), g.input(1))))   # b = NaN where in1 == 0
+        g.output(2, g.node(KIND_MINIMUM, g.node(KIND_DIVIDE, g.input(1), g.input(1)), g.input(0)))   # a = NaN where in1 == 0
+
+    rows = [(rng.randn(200) * 2).astype(np.float32) for _ in range(2)]
+    rows[1][::3] = 0.0
+    outs = []
+    for r in (B200Renderer(flags=FLAG_SPARKLE_MIN), B200Renderer(flags=FLAG_SPARKLE_MIN | FLAG_JIT_EAGER),
+              OracleRenderer(flags=FLAG_SPARKLE_MIN), OracleRenderer()):
+        build(r)
+        outs.append(r.fill_buffer(3, 200, 0, rows))
+    assert_same_bits(outs[0], outs[2], f"sparkle-min interp seed {seed}")
+    assert_same_bits(outs[1], outs[2], f"sparkle-min jit seed {seed}")
+    # slot 1: Sparkle keeps a (a number) where b is NaN, like minNum; slot 2: Sparkle yields NaN where a is NaN, minNum the number
+    assert np.isnan(outs[2][2][::3]).all() and not np.isnan(outs[3][2][::3]).any()

@@ -4,8 +4,8 @@ feedback delay, bit-exact against the sequential f32 evaluation."""
 import numpy as np
 import pytest
 
-from filters import build_cfg3_graph, cfg3_filters, rbj_lowpass
-from oracle_binding import OracleRenderer
+from workloads.filters import build_cfg3_graph, cfg3_filters, rbj_lowpass
+from oracle.binding import OracleRenderer
 from replay import assert_same_bits
 
 pytestmark = pytest.mark.gpu
@@ -116,7 +116,7 @@ def test_ten_seconds_feedback_chain_error_bound():
 
 
 def test_osc_excited_chain_mixed_to_one_slot():
-    from banks import detuned_bank
+    from workloads.banks import detuned_bank
     n_voices, n = 4, 2500
     bank, _ = detuned_bank(n_voices, 32, seed=3)
     outs = []
@@ -296,7 +296,7 @@ def test_random_graphs_around_chains(seed):
     decides, the fused build must equal the unfused build bit for bit, and both the fp64 oracle within 1e-4."""
     from libfriendship_b200 import (FLAG_NO_CHAIN_FUSION, KIND_DELAY, KIND_DIRECTFORM, KIND_FBDELAY, KIND_MINIMUM,
                                     KIND_MULTIPLY, KIND_SUM2)
-    from graphs import GraphBuilder
+    from workloads.graphs import GraphBuilder
     rng = np.random.RandomState(900 + seed)
     lanes = int(rng.randint(1, 6))
     fc = rng.uniform(100.0, 12000.0, lanes)
@@ -444,7 +444,7 @@ def test_exciter_not_fused_when_a_voice_is_read_elsewhere_or_the_bank_changes_sh
     a, b = r.fill_buffer(lanes, 3000, 0), o.fill_buffer(lanes, 3000, 0)
     assert r.stats()["osc_launches"] == 0
     assert np.abs(a.astype(np.float64) - b).max() <= 1e-4 * np.abs(b).max()
-    from banks import detuned_bank
+    from workloads.banks import detuned_bank
     bank2, _ = detuned_bank(lanes, 2, seed=8)
     r.define_oscbank(7, **bank2)                                 # the node's parameters: retroactive, like any graph edit
     o = OracleRenderer()

@@ -20,9 +20,9 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from banks import build_voice_mix_graph, detuned_bank
+    from workloads.banks import build_voice_mix_graph, detuned_bank
     from libfriendship_b200.sharded import ShardedRenderer
-    from oracle_binding import OracleRenderer
+    from oracle.binding import OracleRenderer
     sr = ShardedRenderer(rank=rank, world_size=world, renderer=OracleRenderer())
     mine = sr.voices_of_rank(N_VOICES)
     bank, ids = detuned_bank(N_VOICES, N_PARTIALS, voices=mine)
@@ -53,8 +53,8 @@ def test_two_rank_voice_shards_reduce_to_the_full_render():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    from banks import build_voice_mix_graph, detuned_bank, full_scale
-    from oracle_binding import OracleRenderer
+    from workloads.banks import build_voice_mix_graph, detuned_bank, full_scale
+    from oracle.binding import OracleRenderer
     bank, ids = detuned_bank(N_VOICES, N_PARTIALS)
     r = OracleRenderer()
     build_voice_mix_graph(r, bank, ids, delay0=100.0)

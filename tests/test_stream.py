@@ -3,9 +3,9 @@ give the same bits as the plain fill_buffer calls they stand for, which in turn 
 import numpy as np
 import pytest
 
-from banks import build_voice_mix_graph, detuned_bank
-from graphs import build_cfg1_graph, cfg1_input
-from oracle_binding import OracleRenderer
+from workloads.banks import build_voice_mix_graph, detuned_bank
+from workloads.graphs import build_cfg1_graph, cfg1_input
+from oracle.binding import OracleRenderer
 from replay import assert_same_bits
 
 pytestmark = pytest.mark.gpu
@@ -80,7 +80,7 @@ def test_dispatch_render_stream_to_wav(tmp_path):
     """Dispatch -> RouteGraph -> renderer -> WavClient: the file holds the bits the oracle renders."""
     import struct
     from libfriendship_b200.dispatch import Dispatch, EffectId, WavClient
-    from graphs import f32_bits
+    from workloads.graphs import f32_bits
     path = tmp_path / "const.wav"
     client = WavClient(path, 1, 48000)
     d = Dispatch(client)

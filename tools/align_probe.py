@@ -8,13 +8,12 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import torch
 
 from libfriendship_b200 import B200Renderer
-from banks import detuned_bank
-from filters import build_cfg3_graph
+from workloads.banks import detuned_bank
+from workloads.filters import build_cfg3_graph
 
 # argv: [n_voices [block ...]]; FRB_NO_ALIGN_SPLIT=1 in the environment renders unaligned heads inside the block (the
 # behaviour before run_range split them off)

@@ -7,13 +7,12 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np
 import torch
 
 from libfriendship_b200 import (B200Renderer, KIND_DELAY, KIND_F32CONSTANT, KIND_MULTIPLY, KIND_SUM2)
-from graphs import GraphBuilder, f32_bits
+from workloads.graphs import GraphBuilder, f32_bits
 
 HBM = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6535.7) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6535.7
 
@@ -112,8 +111,8 @@ def case_cfg3(n_voices=4096, n=480000, flags=0, osc_anchor=0):
     """cfg3: per voice 1-partial oscillator -> biquad -> feedback delay, mixed to one slot.  K4 algorithmic traffic
     (SURVEY.md §8d): 8 B per voice-sample for the fused biquad -> comb chain (read x, write y); the two separate kernels
     (FLAG_NO_CHAIN_FUSION) move 16 B."""
-    from banks import detuned_bank
-    from filters import build_cfg3_graph
+    from workloads.banks import detuned_bank
+    from workloads.filters import build_cfg3_graph
     r = B200Renderer(flags=flags, osc_anchor=osc_anchor)
     bank, _ = detuned_bank(n_voices, 1, seed=5)
     build_cfg3_graph(r, n_voices, excitation="osc", bank=bank, mix_to_one=True)
@@ -132,7 +131,7 @@ def case_cfg3(n_voices=4096, n=480000, flags=0, osc_anchor=0):
 
 def case_cfg2(anchor=0):
     """cfg2: 1,024 harmonic partials x 1 voice, 48 kHz x 10 s (one voice: parallelism only along time)."""
-    from banks import harmonic_bank
+    from workloads.banks import harmonic_bank
     from libfriendship_b200 import KIND_OSCBANK
     n = 480000
     r = B200Renderer(osc_anchor=anchor)
@@ -149,7 +148,7 @@ def case_cfg2(anchor=0):
 def case_cfg1():
     """cfg1: 440 Hz sine through Multiply/Sum/Delay (+ Min/Mod/Div side chain), 48 kHz x 1 s, host in/out through
     frb_fill_buffer: one call, and 94 x 512-sample streaming calls.  Latency-bound: reported as us per block."""
-    from graphs import build_cfg1_graph, cfg1_input
+    from workloads.graphs import build_cfg1_graph, cfg1_input
     n = 48000
     x = cfg1_input(n)
     r = B200Renderer()

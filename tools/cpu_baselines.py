@@ -9,14 +9,13 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np
 
-from banks import build_voice_mix_graph, detuned_bank, harmonic_bank
-from filters import build_cfg3_graph
-from graphs import build_cfg1_graph, cfg1_input
-from oracle_binding import OracleRenderer
+from workloads.banks import build_voice_mix_graph, detuned_bank, harmonic_bank
+from workloads.filters import build_cfg3_graph
+from workloads.graphs import build_cfg1_graph, cfg1_input
+from oracle.binding import OracleRenderer
 
 NT = os.cpu_count() or 1
 

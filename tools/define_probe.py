@@ -1,10 +1,9 @@
 """Times frb_define_oscbank for the cfg4 bank (pinned vs pageable host arrays); FRB_TRACE=1 prints the phases."""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
-import numpy as np
+sys.path.insert(0, ROOT); import numpy as np
 import torch
-from banks import detuned_bank
+from workloads.banks import detuned_bank
 from libfriendship_b200 import B200Renderer
 
 nv, npart = int(sys.argv[1]) if len(sys.argv) > 1 else 64, int(sys.argv[2]) if len(sys.argv) > 2 else 65536

@@ -1,8 +1,8 @@
 import sys, time
-sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
+sys.path.insert(0, '.')
 import numpy as np
 from libfriendship_b200 import B200Renderer
-from graphs import build_cfg1_graph, cfg1_input
+from workloads.graphs import build_cfg1_graph, cfg1_input
 n = 48000
 x = cfg1_input(n)
 r = B200Renderer()

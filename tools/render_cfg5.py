@@ -11,13 +11,12 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np
 import torch
 import torch.distributed as dist
 
-from banks import build_voice_mix_graph, detuned_bank
+from workloads.banks import build_voice_mix_graph, detuned_bank
 from libfriendship_b200.sharded import ShardedRenderer
 
 SR, N_VOICES, N_PARTIALS, N_SAMPLES = 192000.0, 256, 1 << 20, 11_520_000

@@ -1,8 +1,8 @@
 """Synthetic oscillator banks of the BASELINE.json shapes, at any scale."""
 import numpy as np
 
-from libfriendship_b200 import KIND_DELAY, KIND_MULTIPLY, KIND_OSCBANK, KIND_SUM2
-from graphs import GraphBuilder
+from .kinds import KIND_DELAY, KIND_MULTIPLY, KIND_OSCBANK, KIND_SUM2
+from .graphs import GraphBuilder
 
 
 def harmonic_bank(n_partials, sr=48000.0, f0=20.0):

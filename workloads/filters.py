@@ -30,7 +30,7 @@ def cfg3_filters(n_voices, sr=48000.0):
 def build_cfg3_graph(r, n_voices, excitation="input", bank=None, mix_to_one=False):
     """excitation 'input': external input slot v feeds voice v; 'osc': OscBank voice v.  Each voice:
     excitation -> DirectForm (biquad) -> FbDelay -> output slot v (or a Sum2 chain to slot 0)."""
-    from libfriendship_b200 import KIND_DIRECTFORM, KIND_FBDELAY, KIND_OSCBANK, KIND_SUM2
+    from .kinds import KIND_DIRECTFORM, KIND_FBDELAY, KIND_OSCBANK, KIND_SUM2
     (b0, b1, b2, a1, a2), delay, gain = cfg3_filters(n_voices)
     r.define_directform(11, b0, b1, b2, a1, a2)
     r.define_fbdelay(12, delay, gain)

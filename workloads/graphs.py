@@ -4,7 +4,7 @@ import struct
 
 import numpy as np
 
-from libfriendship_b200 import (KIND_DELAY, KIND_DIVIDE, KIND_F32CONSTANT, KIND_MINIMUM, KIND_MODULO, KIND_MULTIPLY,
+from .kinds import (KIND_DELAY, KIND_DIVIDE, KIND_F32CONSTANT, KIND_MINIMUM, KIND_MODULO, KIND_MULTIPLY,
                                 KIND_SUM2)
 
 
