@@ -70,7 +70,14 @@ typedef struct frb_config {
     uint32_t flags;           /* FRB_FLAG_* */
     uint32_t osc_anchor;      /* oscillator re-anchor interval in samples (0 = default: 128; a multiple of 16, <= 256).
                                  Banks whose voices have at most one partial each are always re-anchored every 8 */
-    uint32_t reserved;
+    uint32_t n_devices;       /* 0 or 1: one B200.  N > 1: devices device .. device + N - 1 behind this one handle — the
+                                 oscillator-bank voices are sharded round-robin over them (voice v on device v mod N), each
+                                 device renders the sub-graph of its voices and stores its mix block straight into a slab in
+                                 the first device's HBM over NVLink, where the rows are summed in device order (K5).  Every
+                                 output slot must then be linear in the bank lanes (sums, gains, delays, linear filters) or
+                                 use no lane at all; otherwise frb_fill_buffer returns FRB_E_UNSUPPORTED.  Output and
+                                 device-resident inputs live on the first device.  The reference's caller owns ONE renderer
+                                 (dispatch.rs:99-106): this keeps it that way. */
 } frb_config;
 #define FRB_FLAG_SPARKLE_DELAY 1u  /* negative / NaN delay amounts yield 0.0 (reference sparkle.rs:525-542)
                                       instead of clamping to delay 0 (reference.rs:205-210, the default) */
@@ -86,7 +93,8 @@ typedef struct frb_config {
 
 /* Oscillator bank definition (extension).  Voice v owns partials [voice_offsets[v], voice_offsets[v+1]).
  *   out_v(t) = sum_p amp_p * min(t/attack_p, 1) * exp(-t/tau_p) * sin(2*pi*freq_p*t/sample_rate + phase_p)
- * attack_p <= 0 means no attack ramp; tau_p <= 0 or +inf means no decay.  t is the absolute sample index. */
+ * attack_p <= 0 means no attack ramp; tau_p <= 0 or +inf means no decay.  t is the absolute sample index.
+ * At most 65,535 voices per bank (FRB_E_UNSUPPORTED above; any number of banks). */
 typedef struct frb_oscbank_desc {
     uint32_t        n_voices;
     uint32_t        reserved;
@@ -108,7 +116,8 @@ typedef struct frb_directform_desc {
     const float* b0; const float* b1; const float* b2; const float* a1; const float* a2;  /* n_lanes each */
 } frb_directform_desc;
 
-/* Feedback delay bank (extension): per lane  y[n] = x[n] + g * y[n - D],  D >= 1, y == 0 for n < 0. */
+/* Feedback delay bank (extension): per lane  y[n] = x[n] + g * y[n - D],  D >= 1, y == 0 for n < 0.
+ * At most 65,535 lanes per bank (FRB_E_UNSUPPORTED above). */
 typedef struct frb_fbdelay_desc {
     uint32_t        n_lanes;
     uint32_t        reserved;
@@ -193,19 +202,26 @@ int frb_sum_rows(frb_renderer* r, float* d_out, const float* d_rows, uint32_t n_
  * schedule needs (may exceed cap; nothing is written beyond cap), or a negative status. */
 int64_t frb_dump_schedule(frb_renderer* r, uint32_t n_slots, uint32_t* words, uint64_t cap);
 
+/* Voice sharding (frb_config::n_devices): how the outputs of the graph depend on the oscillator-bank lanes —
+ * 0: linearly (sums, gains, delays, linear filters: the voices may be rendered on different devices and added),
+ * 1: not at all, 2: otherwise (n_devices > 1 refuses such a graph) — and the schedule device `rank` of `world` would run:
+ * the graph restricted to the voices it owns (v mod world == rank), which are lanes 0, 1, ... of its compact bank. */
+int frb_lane_use(frb_renderer* r, uint32_t n_slots);
+int64_t frb_dump_schedule_shard(frb_renderer* r, uint32_t n_slots, uint32_t rank, uint32_t world, uint32_t* words, uint64_t cap);
+
 /* The stage JIT (the B200 counterpart of the reference's LLVM JIT, src/render/sparkle.rs): CUDA source generated for
  * stage `stage` of the schedule for `n_slots` outputs, and the size of the sm_100a cubin NVRTC builds from it
  * (negative status on failure; needs no GPU).  frb_jit_source writes at most cap bytes (NUL-terminated) and returns
  * the length needed. */
 int64_t frb_jit_source(frb_renderer* r, uint32_t n_slots, uint32_t stage, char* out, uint64_t cap);
 int64_t frb_jit_cubin_size(frb_renderer* r, uint32_t n_slots, uint32_t stage);
-/* Instructions that stage holds as straight-line code once compiled (one body per distinct strand shape).  NVRTC's time
- * grows faster than linearly in it (200: 2 s, 500: 16 s, 2,000: more than 5 minutes), so a stage above
- * FRB_JIT_MAX_CODE is never compiled (interpreted for good).  FRB_JIT_MAX_SYNC_CODE bounds what a long block compiles on
- * the render thread without FRB_FLAG_JIT_EAGER (above: beside the render loop, the interpreter serving meanwhile);
- * it equals FRB_JIT_MAX_CODE for now: the 64-voice mix stage of the cfg4 bench is 320 instructions and the measured
- * numbers of round 1 have it compiled in the first call. */
-#define FRB_JIT_MAX_SYNC_CODE 512
+/* Statements the compiler sees for that stage.  Runs of like instruction groups in a stage program (the terms of a
+ * Sum2 chain, the voices of a mix) are compiled as loops whose trip counts and operands come from a device table, so
+ * this is a measure of the program's STRUCTURE, not of its length: a 9,000-node chain is 11.  NVRTC's time grows faster
+ * than linearly in it (100: 1 s, 200: 2 s, 400: 8 s), so a stage above FRB_JIT_MAX_CODE is never compiled (interpreted
+ * for good), and one above FRB_JIT_MAX_SYNC_CODE is compiled beside the render loop — the interpreter serving meanwhile
+ * — rather than on the render thread (unless FRB_FLAG_JIT_EAGER asks for that). */
+#define FRB_JIT_MAX_SYNC_CODE 128
 #define FRB_JIT_MAX_CODE 512
 int64_t frb_jit_code_instructions(frb_renderer* r, uint32_t n_slots, uint32_t stage);
 

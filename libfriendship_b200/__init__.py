@@ -49,8 +49,9 @@ class B200Renderer(_cabi.CRendererBase):
     _lib = _lib
     _prefix = "frb"
 
-    def __init__(self, device=0, flags=0, osc_anchor=0):
-        cfg = _cabi.frb_config(device, flags, osc_anchor, 0)
+    def __init__(self, device=0, flags=0, osc_anchor=0, n_devices=0):
+        """n_devices > 1: devices device .. device + n_devices - 1 behind this one renderer (voices sharded v mod N)."""
+        cfg = _cabi.frb_config(device, flags, osc_anchor, n_devices)
         h = _lib.frb_create(_C.byref(cfg))
         if not h:
             msg = _lib.frb_last_error(None)
@@ -116,6 +117,23 @@ class B200Renderer(_cabi.CRendererBase):
         assert n2 == n
         return w
 
+    def dump_schedule_shard(self, n_slots, rank, world):
+        """The schedule device `rank` of `world` would run (n_devices = world): the graph restricted to its voices."""
+        import numpy as np
+        n = _lib.frb_dump_schedule_shard(self._h, n_slots, rank, world, None, 0)
+        if n < 0:
+            self._check(int(n))
+        w = np.zeros(n, dtype=np.uint32)
+        _lib.frb_dump_schedule_shard(self._h, n_slots, rank, world, w.ctypes.data_as(_C.POINTER(_C.c_uint32)), n)
+        return w
+
+    def lane_use(self, n_slots):
+        """0: outputs linear in the oscillator-bank lanes (shardable), 1: no lane used, 2: otherwise."""
+        u = _lib.frb_lane_use(self._h, n_slots)
+        if u < 0:
+            self._check(int(u))
+        return int(u)
+
     def jit_source(self, n_slots, stage):
         """CUDA source the stage JIT generates for `stage` (see csrc/jit.cc)."""
         n = _lib.frb_jit_source(self._h, n_slots, stage, None, 0)
@@ -133,8 +151,8 @@ class B200Renderer(_cabi.CRendererBase):
         return int(n)
 
     def jit_code_instructions(self, n_slots, stage):
-        """Straight-line instructions the compiled stage would hold (one body per distinct strand shape); the renderer
-        compiles a stage only up to FRB_JIT_MAX_CODE = 512 of them (include/friendship_b200.h)."""
+        """Statements the compiled stage would hold (loops over repeated groups count once per unrolled copy, one body
+        per distinct strand structure); the renderer compiles a stage only up to FRB_JIT_MAX_CODE = 512 of them."""
         n = _lib.frb_jit_code_instructions(self._h, n_slots, stage)
         if n < 0:
             self._check(int(n))

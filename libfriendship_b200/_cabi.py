@@ -49,7 +49,7 @@ class frb_node(C.Structure):
 
 
 class frb_config(C.Structure):
-    _fields_ = [("device", C.c_int32), ("flags", C.c_uint32), ("osc_anchor", C.c_uint32), ("reserved", C.c_uint32)]
+    _fields_ = [("device", C.c_int32), ("flags", C.c_uint32), ("osc_anchor", C.c_uint32), ("n_devices", C.c_uint32)]
 
 
 class frb_oscbank_desc(C.Structure):
@@ -87,7 +87,7 @@ EXPORTS = [
     "frb_define_directform", "frb_define_fbdelay", "frb_add_node", "frb_del_node", "frb_add_edge", "frb_del_edge",
     "frb_fill_buffer", "frb_fill_buffer_device", "frb_sync", "frb_stream", "frb_dump_schedule", "frb_get_stats",
     "frb_set_profiling", "frb_get_timing", "frb_version", "frb_jit_source", "frb_jit_cubin_size", "frb_jit_code_instructions", "frb_device_alloc", "frb_device_free", "frb_ipc_export", "frb_ipc_open", "frb_ipc_close", "frb_sum_rows",
-    "frb_render_stream",
+    "frb_render_stream", "frb_lane_use", "frb_dump_schedule_shard",
 ]
 
 
@@ -110,6 +110,8 @@ def declare(lib, prefix):
         "destroy": ([vp], None),
         "last_error": ([vp], C.c_char_p),
         "dump_schedule": ([vp, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint64], C.c_int64),
+        "dump_schedule_shard": ([vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint64], C.c_int64),
+        "lane_use": ([vp, C.c_uint32], C.c_int),
         "get_stats": ([vp, C.POINTER(frb_stats)], C.c_int),
         "set_profiling": ([vp, C.c_int], C.c_int),
         "get_timing": ([vp, C.POINTER(frb_timing)], C.c_int),

@@ -131,7 +131,7 @@ struct Flattener {
         if (e.from == 0) {
             // reading an input of this graph level
             if (c.parent < 0) {
-                s.n_input_slots = std::max(s.n_input_slots, e.from_slot + 1);
+                s.n_input_slots = std::max<uint64_t>(s.n_input_slots, (uint64_t)e.from_slot + 1);
                 return mk(V_INPUT, 0, 0, e.from_slot);
             }
             return resolve_maybe(c.parent, c.pnode->inbound, e.from_slot);
@@ -193,6 +193,15 @@ struct Flattener {
                 uint32_t b = resolve_maybe(ctx, n.inbound, 1);
                 uint8_t op = n.kind == FRB_KIND_SUM2 ? V_SUM2 : n.kind == FRB_KIND_MULTIPLY ? V_MUL
                            : n.kind == FRB_KIND_DIVIDE ? V_DIV : n.kind == FRB_KIND_MODULO ? V_MOD : V_MIN;
+                if (env.shard_world > 1) {
+                    // the lanes of other ranks are zero signals here: a sum keeps its other operand, a product or a
+                    // quotient of a zero lane is that rank's (zero) share of a linear output
+                    const bool za = s.values[a].op == V_ZERO, zb = s.values[b].op == V_ZERO;
+                    if (op == V_SUM2 && za) { v = b; break; }
+                    if (op == V_SUM2 && zb) { v = a; break; }
+                    if (op == V_MUL && (za || zb)) { v = zero(); break; }
+                    if (op == V_DIV && za) { v = zero(); break; }
+                }
                 v = mk(op, a, b, 0);
                 break;
             }
@@ -231,7 +240,16 @@ struct Flattener {
                 } else {
                     inst = xit->second;
                 }
+                if (env.shard_world > 1 && n.kind == FRB_KIND_OSCBANK) {
+                    // this rank's bank holds the voices it owns, compacted: global voice = shard_rank + lane * shard_world
+                    // (osc_create); everybody else's voice is the zero signal here
+                    const uint32_t lane = e.from_slot / env.shard_world;
+                    v = (e.from_slot % env.shard_world == env.shard_rank && lane < s.ext[inst].n_lanes) ? mk(V_EXT, inst, 0, lane) : zero();
+                    break;
+                }
                 v = (e.from_slot < s.ext[inst].n_lanes) ? mk(V_EXT, inst, 0, e.from_slot) : zero();
+                if (env.shard_world > 1 && s.values[v].op == V_EXT && s.values[s.ext[inst].inputs[e.from_slot]].op == V_ZERO)
+                    v = zero();                              // a zero-state linear filter of silence
                 break;
             }
             default: throw Error{FRB_E_INVALID, "unknown node kind " + std::to_string(n.kind)};
@@ -667,6 +685,52 @@ Schedule flatten_here(const Graph& top, uint32_t n_slots, const FlattenEnv& env)
 }
 }  // namespace
 
+LaneUse lane_use_of_outputs(const Schedule& s) {
+    enum : uint8_t { ZERO = 0, IND = 1, LIN = 2, BAD = 3 };      // independent of the lanes / linear in them / neither
+    const auto& V = s.values;
+    std::vector<uint8_t> c(V.size(), BAD);
+    for (size_t v = 0; v < V.size(); v++) {
+        const Value& x = V[v];
+        switch (x.op) {
+            case V_ZERO: c[v] = ZERO; break;
+            case V_CONST: case V_INPUT: c[v] = IND; break;
+            case V_EXT: {
+                const ExtInstance& inst = s.ext[x.a];
+                c[v] = inst.kind == EXT_OSCBANK ? LIN : c[inst.inputs[x.imm]];   // DirectForm / FbDelay: linear, zero state
+                break;
+            }
+            case V_SUM2: {
+                const uint8_t a = c[x.a], b = c[x.b];
+                c[v] = a == ZERO ? b : b == ZERO ? a : (a == b && a != BAD) ? a : BAD;
+                break;
+            }
+            case V_MUL: {
+                const uint8_t a = c[x.a], b = c[x.b];
+                c[v] = (a == ZERO || b == ZERO) ? (a == BAD || b == BAD ? BAD : ZERO) : (a == IND && b == IND) ? IND
+                     : ((a == LIN && b == IND) || (a == IND && b == LIN)) ? LIN : BAD;
+                break;
+            }
+            case V_DIV: {
+                const uint8_t a = c[x.a], b = c[x.b];
+                c[v] = b != IND ? BAD : a;                   // x / (lane-independent): the class of x
+                break;
+            }
+            case V_MOD: case V_MIN: c[v] = (c[x.a] <= IND && c[x.b] <= IND) ? IND : BAD; break;
+            case V_DELAY: c[v] = c[x.b] <= IND ? c[x.a] : BAD; break;          // the amount must not depend on a lane
+            case V_TAP: case V_GATE: c[v] = c[x.a]; break;
+            default: c[v] = BAD;
+        }
+    }
+    bool lin = false, ind = false;
+    for (uint32_t o : s.outputs) {
+        if (c[o] == BAD) return LANES_OTHER;
+        lin |= c[o] == LIN;
+        ind |= c[o] == IND;
+    }
+    if (!lin) return LANES_UNUSED;
+    return ind ? LANES_OTHER : LANES_LINEAR;
+}
+
 std::vector<uint32_t> Schedule::dump() const {
     std::vector<uint32_t> w;
     w.push_back(0x53425246u);   // 'FRBS'
@@ -675,7 +739,7 @@ std::vector<uint32_t> Schedule::dump() const {
     w.push_back((uint32_t)buffers.size());
     w.push_back((uint32_t)stages.size());
     w.push_back((uint32_t)ext.size());
-    w.push_back(n_input_slots);
+    w.push_back((uint32_t)std::min<uint64_t>(n_input_slots, 0xFFFFFFFFull));
     w.push_back((from_zero ? 1u : 0u) | (full_history ? 2u : 0u));
     for (size_t v = 0; v < values.size(); v++) {
         w.push_back(values[v].op); w.push_back(values[v].a); w.push_back(values[v].b); w.push_back(values[v].imm);

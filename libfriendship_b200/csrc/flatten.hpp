@@ -14,9 +14,24 @@ struct FlattenEnv {
     std::function<uint64_t(uint64_t key)> ext_max_delay;
     bool sparkle_delay = false;   // FRB_FLAG_SPARKLE_DELAY: a negative / NaN constant amount makes the Delay output 0
     uint32_t max_regs = 48;   // registers (8 samples each) per thread the interpreter kernel can hold in shared memory
+    // Voice sharding over the devices of one renderer (multi.cu): with shard_world > 1 this schedule evaluates the graph
+    // RESTRICTED to the oscillator-bank lanes this rank owns (lane mod shard_world == shard_rank) — every other bank lane
+    // is the zero signal, and zeros fold through Sum2 / Multiply / Divide / Delay — so the sum of the ranks' outputs is the
+    // whole graph's output wherever that output is linear in the bank lanes (lane_use_of_outputs checks it).
+    uint32_t shard_rank = 0, shard_world = 1;
 };
 
 // Throws frb::Error.
 Schedule flatten(const Graph& top, uint32_t n_slots, const FlattenEnv& env);
+
+// How the outputs of `s` (flattened with shard_world == 1) depend on the oscillator-bank lanes:
+//   LANES_LINEAR  every output slot is zero or a homogeneous linear function of the lanes — sums, gains and divisions
+//                 by lane-independent signals, delays, zero-state linear filters — so rendering the lanes on different
+//                 devices and adding the results is exact up to f32 summation order;
+//   LANES_UNUSED  no output depends on a lane (one device renders everything);
+//   LANES_OTHER   anything else (a lane through Minimum / Modulo / a product of lanes, or lanes mixed with
+//                 lane-independent signals in one output).
+enum LaneUse { LANES_LINEAR = 0, LANES_UNUSED = 1, LANES_OTHER = 2 };
+LaneUse lane_use_of_outputs(const Schedule& s);
 
 }  // namespace frb

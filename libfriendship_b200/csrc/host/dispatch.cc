@@ -110,14 +110,17 @@ int frd_add_node(frd_dispatch* d, uint32_t handle, const char* effect_id_json) {
     if (err != RgError::None) { d->err = std::string("RouteGraphError(") + rg_name(err) + ")"; return rg_code(err); }
     uint32_t kind; uint64_t key;
     int rc = kind_of(d, data, &kind, &key);
-    if (rc != FRB_OK) return rc;
-    return renderer_rc(d, frb_add_node(d->renderer, handle, kind, key));                // on_add_node, dispatch.rs:202-204
+    if (rc == FRB_OK) rc = renderer_rc(d, frb_add_node(d->renderer, handle, kind, key));    // on_add_node, dispatch.rs:202-204
+    if (rc != FRB_OK) d->routegraph.del_node(handle);      // the renderer refused: the two graphs stay in step
+    return rc;
 }
 int frd_add_edge(frd_dispatch* d, frb_edge e) {                                          // dispatch.rs:120-123
     if (!d) return FRD_E_BAD_MESSAGE;
     RgError err = d->routegraph.add_edge(Edge{e.from, e.to, e.from_slot, e.to_slot});
     if (err != RgError::None) { d->err = std::string("RouteGraphError(") + rg_name(err) + ")"; return rg_code(err); }
-    return renderer_rc(d, frb_add_edge(d->renderer, e));
+    const int rc = renderer_rc(d, frb_add_edge(d->renderer, e));
+    if (rc != FRB_OK) d->routegraph.del_edge(Edge{e.from, e.to, e.from_slot, e.to_slot});   // refused (e.g. to_slot out of the renderer's range)
+    return rc;
 }
 int frd_del_node(frd_dispatch* d, uint32_t handle) {                                     // dispatch.rs:124-127
     if (!d) return FRD_E_BAD_MESSAGE;

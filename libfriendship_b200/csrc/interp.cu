@@ -89,7 +89,7 @@ interp_kernel(InterpParams p) {
                     for (int w = 0; w < VW; w++) REG(dst, w) = a[w];
                     break;
                 case I_LDIN: {
-                    const InputDesc in = p.inputs[ins.w];
+                    const InputDesc in = input_desc(p, ins.w);
 #pragma unroll
                     for (int w = 0; w < VW; w++) {
                         const unsigned long long t = t0g + 4 * w;
@@ -110,7 +110,7 @@ interp_kernel(InterpParams p) {
                     break;
                 }
                 case I_TAP_IN: {
-                    const InputDesc in = p.inputs[ins.w];
+                    const InputDesc in = input_desc(p, ins.w);
                     const unsigned long long shift = ((unsigned long long)ins.z << 32) | ins.y;
 #pragma unroll
                     for (int w = 0; w < VW; w++) REG(dst, w) = f4tap_in(in, t0g + 4 * w, shift);
@@ -153,7 +153,7 @@ interp_kernel(InterpParams p) {
                     break;
                 }
                 case I_DLY_IN: case I_DLY_BUF: case I_DLY_TI: {
-                    const InputDesc in = (op == I_DLY_IN) ? p.inputs[ins.w] : InputDesc{nullptr, 0, 0};
+                    const InputDesc in = (op == I_DLY_IN) ? input_desc(p, ins.w) : InputDesc{nullptr, 0, 0};
                     const BufferDesc bd = (op == I_DLY_BUF) ? p.buffers[ins.w] : BufferDesc{nullptr, 0};
 #pragma unroll
                     for (int w = 0; w < VW; w++) {

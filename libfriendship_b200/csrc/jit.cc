@@ -257,14 +257,14 @@ struct Emitter {
                 case I_MOD: o << reg(dst, w) << " = f4mod(" << a << ", " << b << ");"; break;
                 case I_MIN: o << reg(dst, w) << " = f4min(" << a << ", " << b << ", p.sparkle_min);"; break;
                 case I_MOV: o << reg(dst, w) << " = " << a << ";"; break;
-                case I_LDIN: o << reg(dst, w) << " = f4ld_in(p.inputs[" << wx << "], " << t << ");"; break;
+                case I_LDIN: o << reg(dst, w) << " = f4ld_in(input_desc(p, " << wx << "), " << t << ");"; break;
                 case I_LDBUF: o << reg(dst, w) << " = f4ld_buf(p.buffers[" << wx << "], " << t << ");"; break;
                 case I_STBUF: o << guard << "f4st_buf(p.buffers[" << wx << "], " << t << ", " << a << ");"; break;
                 case I_STOUT: o << guard << "f4st_out(p, " << wx << ", " << t << ", " << a << ");"; break;
-                case I_TAP_IN: o << reg(dst, w) << " = f4tap_in(p.inputs[" << wx << "], " << t << ", " << sh << ");"; break;
+                case I_TAP_IN: o << reg(dst, w) << " = f4tap_in(input_desc(p, " << wx << "), " << t << ", " << sh << ");"; break;
                 case I_TAP_BUF: o << reg(dst, w) << " = f4tap_buf(p.buffers[" << wx << "], " << t << ", " << sh << ");"; break;
                 case I_GATE: o << reg(dst, w) << " = f4gate(" << a << ", " << t << ", (((unsigned long long)" << wx << " << 32) | " << wb << "));"; break;
-                case I_DLY_IN: o << reg(dst, w) << " = f4delay<0>(p.inputs[" << wx << "], no_buf, " << a << ", z4, " << t << ", p.sparkle_delay);"; break;
+                case I_DLY_IN: o << reg(dst, w) << " = f4delay<0>(input_desc(p, " << wx << "), no_buf, " << a << ", z4, " << t << ", p.sparkle_delay);"; break;
                 case I_DLY_BUF: o << reg(dst, w) << " = f4delay<1>(no_in, p.buffers[" << wx << "], " << a << ", z4, " << t << ", p.sparkle_delay);"; break;
                 case I_DLY_TI: o << reg(dst, w) << " = f4delay<2>(no_in, no_buf, " << a << ", " << b << ", " << t << ", p.sparkle_delay);"; break;
                 default: o << "/* unknown op " << op << " */"; break;

@@ -49,6 +49,7 @@ constexpr int OSC_K_SMALL = 4;      // banks whose voices have <= 8 partials: le
 constexpr int OSC_K_ONE = 1;        // banks of one-partial voices (one exciter per voice, BASELINE configs[2]): no padding
 constexpr int OSC_THREADS = 32;     // threads (= time segments) per CTA: one warp, so the per-group barrier couples no warps
 constexpr int OSC_LMAX = 256;       // max segment length (shared memory: L * THREADS * 4 B)
+constexpr uint32_t kOscMinGroupsPerCta = 8;   // a partial-range split leaves every CTA at least this many groups of K partials
 
 struct OscBankDev {
     uint32_t n_voices = 0;
@@ -221,7 +222,7 @@ __global__ void osc_setup_kernel(unsigned n_voices, const unsigned long long* __
 }
 
 std::shared_ptr<OscBankDev> osc_create(const frb_oscbank_desc* d, cudaStream_t stream, std::string* err,
-                                       const std::shared_ptr<OscBankDev>& recycle) {
+                                       const std::shared_ptr<OscBankDev>& recycle, uint32_t shard_rank, uint32_t shard_world) {
     std::shared_ptr<OscBankDev> b;
     bool stolen = false;
     auto fail = [&](const std::string& m) {
@@ -233,20 +234,43 @@ std::shared_ptr<OscBankDev> osc_create(const frb_oscbank_desc* d, cudaStream_t s
         return fail("oscbank: null array");
     if (!(d->sample_rate > 0.0)) return fail("oscbank: sample_rate must be positive");
     if (d->voice_offsets[0] != 0 || d->voice_offsets[d->n_voices] != d->n_partials) return fail("oscbank: voice_offsets must span [0, n_partials]");
-    uint64_t mx = 0;
-    for (uint32_t v = 0; v < d->n_voices; v++) {
+    // A renderer that shards voices over several devices (multi.cu) defines on every device the COMPACT bank of the
+    // voices that device owns (global voice v = shard_rank + lane * shard_world becomes lane `lane`; the flattener maps
+    // the graph's lane numbers the same way): only their parameters travel — straight from the caller's arrays, one
+    // copy per run of owned voices — and nothing downstream knows about the other ranks' voices.
+    if (shard_world == 0) shard_world = 1;
+    for (uint32_t v = 0; v < d->n_voices; v++)
         if (d->voice_offsets[v + 1] < d->voice_offsets[v]) return fail("oscbank: voice_offsets must be non-decreasing");
-        mx = std::max<uint64_t>(mx, d->voice_offsets[v + 1] - d->voice_offsets[v]);
+    const uint32_t nv = d->n_voices > shard_rank ? (d->n_voices - shard_rank + shard_world - 1) / shard_world : 0;
+    std::vector<uint64_t> vo((size_t)nv + 1, 0);
+    struct Run { uint64_t src, dst, n; };
+    std::vector<Run> runs;
+    uint64_t mx = 0;
+    for (uint32_t l = 0; l < nv; l++) {
+        const uint32_t v = shard_rank + l * shard_world;
+        const uint64_t len = d->voice_offsets[v + 1] - d->voice_offsets[v];
+        vo[l + 1] = vo[l] + len;
+        if (len) {
+            if (!runs.empty() && runs.back().src + runs.back().n == d->voice_offsets[v]) runs.back().n += len;
+            else runs.push_back(Run{d->voice_offsets[v], vo[l], len});
+        }
+        mx = std::max<uint64_t>(mx, len);
     }
     if (mx >= (1ull << 31)) return fail("oscbank: more than 2^31 partials in one voice");
     b = std::make_shared<OscBankDev>();
-    b->n_voices = d->n_voices;
-    b->n_partials = d->n_partials;
+    b->n_voices = nv;
+    b->n_partials = vo[nv];
     b->sample_rate = d->sample_rate;
     b->K = (mx <= 1) ? OSC_K_ONE : (mx <= 8) ? OSC_K_SMALL : OSC_K;
     const int K = b->K;
-    const uint64_t np = d->n_partials;
-    const uint32_t nv = d->n_voices;
+    const uint64_t np = vo[nv];
+    auto upload = [&](void* dst, const void* src, size_t esz) -> cudaError_t {
+        for (const Run& r : runs) {
+            cudaError_t e = cudaMemcpyAsync((char*)dst + r.dst * esz, (const char*)src + r.src * esz, r.n * esz, cudaMemcpyHostToDevice, stream);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    };
 
 #define OC(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(std::string("oscbank: ") + cudaGetErrorString(e_)); } while (0)
     const bool trace = getenv("FRB_TRACE") != nullptr;      // tuning aid: host-clock phases of a definition on stderr
@@ -281,12 +305,12 @@ std::shared_ptr<OscBankDev> osc_create(const frb_oscbank_desc* d, cudaStream_t s
     unsigned* d_cnt0 = reinterpret_cast<unsigned*>(d_offs + nvp);
     unsigned* d_maxatt = d_cnt0 + nvp;
     lap("alloc raw");
-    OC(cudaMemcpyAsync(d_offs, d->voice_offsets, ((size_t)nv + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
+    OC(cudaMemcpyAsync(d_offs, vo.data(), ((size_t)nv + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
     OC(cudaMemsetAsync(d_maxatt, 0, 4, stream));
     if (np) {
-        OC(cudaMemcpyAsync(d_freq, d->freq_hz, np * sizeof(double), cudaMemcpyHostToDevice, stream));
-        OC(cudaMemcpyAsync(d_amp, d->amp, np * sizeof(float), cudaMemcpyHostToDevice, stream));
-        OC(cudaMemcpyAsync(d_attack, d->attack, np * sizeof(float), cudaMemcpyHostToDevice, stream));
+        OC(upload(d_freq, d->freq_hz, sizeof(double)));
+        OC(upload(d_amp, d->amp, sizeof(float)));
+        OC(upload(d_attack, d->attack, sizeof(float)));
     }
     lap("h2d freq/amp/att");
     std::vector<uint32_t> cnt0(nv, 0);
@@ -298,8 +322,8 @@ std::shared_ptr<OscBankDev> osc_create(const frb_oscbank_desc* d, cudaStream_t s
     }
     OC(cudaMemcpyAsync(&max_attack_bits, d_maxatt, 4, cudaMemcpyDeviceToHost, stream));
     if (np) {   // the remaining parameters travel while the host waits for the counts
-        OC(cudaMemcpyAsync(d_phase, d->phase, np * sizeof(float), cudaMemcpyHostToDevice, stream));
-        OC(cudaMemcpyAsync(d_tau, d->tau, np * sizeof(float), cudaMemcpyHostToDevice, stream));
+        OC(upload(d_phase, d->phase, sizeof(float)));
+        OC(upload(d_tau, d->tau, sizeof(float)));
     }
     OC(cudaStreamSynchronize(stream));
     lap("rank + h2d rest");
@@ -309,7 +333,7 @@ std::shared_ptr<OscBankDev> osc_create(const frb_oscbank_desc* d, cudaStream_t s
     std::vector<uint32_t> grp_begin(nv), n_grp0(nv), n_grp(nv);
     uint64_t groups = 0;
     for (uint32_t v = 0; v < nv; v++) {
-        const uint64_t len = d->voice_offsets[v + 1] - d->voice_offsets[v];
+        const uint64_t len = vo[v + 1] - vo[v];
         const uint64_t g0 = (cnt0[v] + K - 1) / K, g1 = (len - cnt0[v] + K - 1) / K;
         if (groups + g0 + g1 >= (1ull << 32)) return fail("oscbank: too many partial groups");
         grp_begin[v] = (uint32_t)groups;
@@ -328,10 +352,13 @@ std::shared_ptr<OscBankDev> osc_create(const frb_oscbank_desc* d, cudaStream_t s
     // 4096 costs 4% at 8 voices in plane traffic, 256 costs 3% in tail) — and long blocks do the rest.
     // Fixed per bank, so the order of summation (and hence the result) never depends on the block size of a render.
     {
-        uint64_t target = d->n_voices >= 32 ? 2048 : 1024;
-        if (const char* ev = getenv("FRB_OSC_SPLIT_TARGET")) target = std::max<uint64_t>(1, strtoull(ev, nullptr, 10));   // tuning aid
+        const uint32_t live_voices = std::max<uint32_t>(nv, 1);
+        uint64_t target = live_voices >= 32 ? 2048 : 1024;
+        uint32_t min_groups = kOscMinGroupsPerCta;
+        if (const char* ev = getenv("FRB_OSC_SPLIT_TARGET")) target = std::max<uint64_t>(1, strtoull(ev, nullptr, 10));   // tuning aids
+        if (const char* ev = getenv("FRB_OSC_MIN_GROUPS")) min_groups = (uint32_t)std::max<uint64_t>(1, strtoull(ev, nullptr, 10));
         uint32_t s = 1;
-        while (s < 512 && (uint64_t)d->n_voices * s < target && b->max_groups / (s * 2) >= 8) s *= 2;
+        while (s < 512 && (uint64_t)live_voices * s < target && b->max_groups / (s * 2) >= min_groups) s *= 2;
         b->split = s;
     }
 
@@ -753,18 +780,29 @@ static cudaError_t launch_osc_range(const OscBankDev& b, const BufferDesc* d_buf
         if (e != cudaSuccess) return e;
     }
     if (n_att) {
+        // The attack region is a few hundred samples: at the main kernel's L it is a handful of live threads in one warp
+        // per (voice, split) walking every group of the split — the longest CTA of the launch (the ramp loop is slower),
+        // and for a bank of few voices, whose launch is a single wave, the whole kernel's duration.  It therefore runs in
+        // SHORTER segments (32 samples, anchored at absolute multiples of 32 like every segment): four times the live
+        // threads, a quarter of the critical path.  A function of the bank and of absolute time only, so results still
+        // do not depend on how a render is cut into blocks.
         OscLaunch q = p;
-        q.nseg = n_att;
+        const int La = (L % 32 == 0 && !getenv("FRB_OSC_ATTACK_SAME_L")) ? 32 : L;
+        const unsigned r = (unsigned)(L / La);
+        q.L = La;
+        q.seg0 = p.seg0 * r;
+        q.nseg = n_att * r;
         cudaStream_t st = stream;
         if (fork) {   // a handful of warps walking every partial: overlap it with the main kernel instead of serialising
             cudaEventRecord(b.ev_fork, stream);
             cudaStreamWaitEvent(b.side, b.ev_fork, 0);
             st = b.side;
         }
-        dim3 grid((n_att + threads - 1) / threads, b.n_voices, p.split);
-        if (b.K == OSC_K) osc_kernel<OSC_K, true><<<grid, threads, smem, st>>>(q);
-        else if (b.K == OSC_K_SMALL) osc_kernel<OSC_K_SMALL, true><<<grid, threads, smem, st>>>(q);
-        else osc_kernel<OSC_K_ONE, true><<<grid, threads, smem, st>>>(q);
+        const size_t smem_a = (size_t)La * (threads + (b.K < OSC_K ? 1 : 0)) * sizeof(float);
+        dim3 grid((q.nseg + threads - 1) / threads, b.n_voices, p.split);
+        if (b.K == OSC_K) osc_kernel<OSC_K, true><<<grid, threads, smem_a, st>>>(q);
+        else if (b.K == OSC_K_SMALL) osc_kernel<OSC_K_SMALL, true><<<grid, threads, smem_a, st>>>(q);
+        else osc_kernel<OSC_K_ONE, true><<<grid, threads, smem_a, st>>>(q);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         if (n_launches) (*n_launches)++;

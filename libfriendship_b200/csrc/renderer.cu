@@ -176,24 +176,34 @@ void Renderer::define_effect(uint64_t key, const frb_node* nodes, uint32_t n_nod
     effect_defs_[key] = g;
 }
 
+// the bank and comb kernels put voices / lanes on grid.y: refuse what a launch could not hold at definition time,
+// not in the middle of a render
+static constexpr uint32_t kMaxGridY = 65535;
+
 void Renderer::define_oscbank(uint64_t key, const frb_oscbank_desc* d) {
-    if (host_only_) { meta_lanes_[{FRB_KIND_OSCBANK, key}] = {d->n_voices, 0}; return; }   // planning only: shape
+    if (d->n_voices > kMaxGridY) throw Error{FRB_E_UNSUPPORTED, "oscbank: at most 65,535 voices per bank (use several banks)"};
+    if (host_only_) {                                        // planning only: shape
+        auto& m = meta_lanes_[{FRB_KIND_OSCBANK, key}];
+        if (m.first != d->n_voices) dirty_ = true;
+        m = {d->n_voices, 0};
+        return;
+    }
     require_device();
     CU(cudaSetDevice(device_));
     std::string err;
     std::shared_ptr<OscBankDev> old;
     if (auto it = osc_defs_.find(key); it != osc_defs_.end()) old = it->second;
-    const uint32_t old_voices = old ? osc_info(*old).n_voices : d->n_voices;
-    auto b = osc_create(d, stream_, &err, old);
+    const uint32_t old_voices = old ? osc_info(*old).n_voices : 0;
+    auto b = osc_create(d, stream_, &err, old, shard_rank_, shard_world_);
     if (!b) {
         if (old && !osc_usable(*old)) { osc_defs_.erase(key); dirty_ = true; }   // its allocations went into the failed attempt
         throw Error{FRB_E_INVALID, err};
     }
-    stats.h2d_bytes += d->n_partials * (sizeof(double) + 4 * sizeof(float)) + ((uint64_t)d->n_voices + 1) * sizeof(uint64_t);
+    stats.h2d_bytes += osc_info(*b).n_partials * (sizeof(double) + 4 * sizeof(float)) + ((uint64_t)osc_info(*b).n_voices + 1) * sizeof(uint64_t);
     stats.kernel_launches += 3;   // rank, fill, setup
     if (old) {
         // re-definition = new parameters for the same node (the per-render input of a synthesis graph)
-        if (old_voices != d->n_voices) dirty_ = true;       // the lane count is part of the schedule
+        if (old_voices != osc_info(*b).n_voices) dirty_ = true;   // the lane count is part of the schedule
         if (osc_one_source(*old, nullptr) != osc_one_source(*b, nullptr)) dirty_ = true;   // ... and so is whether a chain can evaluate it
         cache_valid_ = false;                               // rings hold the old bank's samples
     }
@@ -210,6 +220,7 @@ void Renderer::define_directform(uint64_t key, const frb_directform_desc* d) {
     df_defs_[key] = b;
 }
 void Renderer::define_fbdelay(uint64_t key, const frb_fbdelay_desc* d) {
+    if (d->n_lanes > kMaxGridY) throw Error{FRB_E_UNSUPPORTED, "fbdelay: at most 65,535 lanes per bank (use several banks)"};
     if (host_only_) {
         uint64_t mx = 0;
         if (d->n_lanes && (!d->delay || !d->gain)) throw Error{FRB_E_INVALID, "fbdelay: null array"};
@@ -269,25 +280,43 @@ void Renderer::free_device_schedule() {
     d_exc_voice_.clear();
 }
 
+FlattenEnv Renderer::flatten_env(uint32_t rank, uint32_t world, bool compact_banks) const {
+    FlattenEnv env;
+    env.ext_lanes = [this, rank, world, compact_banks](uint32_t kind, uint64_t key) -> int64_t {
+        int64_t n = -1;
+        auto mit = meta_lanes_.find({kind, key});
+        if (mit != meta_lanes_.end()) n = (int64_t)mit->second.first;
+        else if (kind == FRB_KIND_OSCBANK) { auto it = osc_defs_.find(key); n = it == osc_defs_.end() ? -1 : (int64_t)osc_info(*it->second).n_voices; }
+        else if (kind == FRB_KIND_DIRECTFORM) { auto it = df_defs_.find(key); n = it == df_defs_.end() ? -1 : (int64_t)directform_lanes(*it->second); }
+        else if (kind == FRB_KIND_FBDELAY) { auto it = fb_defs_.find(key); n = it == fb_defs_.end() ? -1 : (int64_t)fbdelay_lanes(*it->second); }
+        // the whole bank's lane count -> the lanes rank `rank` owns (osc_create keeps voices rank, rank + world, ...)
+        if (compact_banks && kind == FRB_KIND_OSCBANK && n >= 0 && world > 1) n = n > (int64_t)rank ? (n - rank + world - 1) / world : 0;
+        return n;
+    };
+    env.ext_max_delay = [this](uint64_t key) -> uint64_t {
+        auto mit = meta_lanes_.find({FRB_KIND_FBDELAY, key});
+        if (mit != meta_lanes_.end()) return mit->second.second;
+        auto it = fb_defs_.find(key);
+        return it == fb_defs_.end() ? 0 : fbdelay_max_delay(*it->second);
+    };
+    env.max_regs = 48;
+    env.sparkle_delay = (cfg_.flags & FRB_FLAG_SPARKLE_DELAY) != 0;
+    env.shard_rank = rank;
+    env.shard_world = world ? world : 1;
+    return env;
+}
+
+Schedule Renderer::schedule_for_shard(uint32_t n_slots, uint32_t rank, uint32_t world) const {
+    if (world == 0 || rank >= world) throw Error{FRB_E_INVALID, "shard rank out of range"};
+    // a renderer that is itself a shard already holds compact banks; any other (planning handles included) holds whole ones
+    return flatten(graph_, n_slots, flatten_env(rank, world, shard_world_ <= 1));
+}
+
 const Schedule& Renderer::schedule(uint32_t n_slots) {
     if (dirty_ || sched_slots_ != n_slots) {
-        FlattenEnv env;
-        env.ext_lanes = [this](uint32_t kind, uint64_t key) -> int64_t {
-            auto mit = meta_lanes_.find({kind, key});
-            if (mit != meta_lanes_.end()) return (int64_t)mit->second.first;
-            if (kind == FRB_KIND_OSCBANK) { auto it = osc_defs_.find(key); return it == osc_defs_.end() ? -1 : (int64_t)osc_info(*it->second).n_voices; }
-            if (kind == FRB_KIND_DIRECTFORM) { auto it = df_defs_.find(key); return it == df_defs_.end() ? -1 : (int64_t)directform_lanes(*it->second); }
-            if (kind == FRB_KIND_FBDELAY) { auto it = fb_defs_.find(key); return it == fb_defs_.end() ? -1 : (int64_t)fbdelay_lanes(*it->second); }
-            return -1;
-        };
-        env.ext_max_delay = [this](uint64_t key) -> uint64_t {
-            auto mit = meta_lanes_.find({FRB_KIND_FBDELAY, key});
-            if (mit != meta_lanes_.end()) return mit->second.second;
-            auto it = fb_defs_.find(key);
-            return it == fb_defs_.end() ? 0 : fbdelay_max_delay(*it->second);
-        };
-        env.max_regs = 48;
-        env.sparkle_delay = (cfg_.flags & FRB_FLAG_SPARKLE_DELAY) != 0;
+        // this renderer's banks already hold only the voices it owns (set_shard), so their lane counts are the compact ones
+        const bool sharded = shard_world_ > 1 && flatten_sharded_;
+        FlattenEnv env = flatten_env(sharded ? shard_rank_ : 0, sharded ? shard_world_ : 1, false);
         Schedule s = flatten(graph_, n_slots, env);   // throws on malformed graphs; state unchanged then
         if (!host_only_) {
             CU(cudaSetDevice(device_));
@@ -295,11 +324,21 @@ const Schedule& Renderer::schedule(uint32_t n_slots) {
             free_device_schedule();
         }
         sched_ = std::move(s);
-        sched_slots_ = n_slots;
-        dirty_ = false;
+        sched_slots_ = ~0u;                  // not valid until the upload below succeeded
+        dirty_ = true;
         cache_valid_ = false;
         stats.schedule_builds++;
-        if (!host_only_) upload_schedule();
+        if (!host_only_) {
+            try {
+                upload_schedule();
+            } catch (...) {
+                cudaStreamSynchronize(stream_);
+                free_device_schedule();      // nothing half-uploaded is ever launched: the next call rebuilds
+                throw;
+            }
+        }
+        sched_slots_ = n_slots;
+        dirty_ = false;
     }
     return sched_;
 }
@@ -732,6 +771,7 @@ void Renderer::run_range(uint64_t lo, uint64_t hi, float* d_out, uint64_t t0, ui
             for (size_t k = 0; k + 1 < st.strand_offsets.size(); k++)
                 p.n_instr = std::max(p.n_instr, st.strand_offsets[k + 1] - st.strand_offsets[k]);   // longest strand
             p.inputs = d_indesc_;
+            p.n_inputs = n_indesc_;
             p.buffers = d_bufdesc_;
             p.out = d_out;
             p.out_stride = out_stride;
@@ -766,6 +806,13 @@ void Renderer::fill(float* out, bool out_on_device, uint32_t n_slots, uint64_t n
     if (idx + n_times < idx) throw Error{FRB_E_INVALID, "idx + n_times overflows"};
     ensure_schedule(n_slots);            // may throw on a malformed graph, before any state changes
     if (profiling) { timing = frb_timing{}; CU(cudaEventRecord(ev_[0], stream_)); }
+    // From here on state changes (input history, rings, recurrence carries).  A failure half-way (out of device memory,
+    // a launch error) leaves the history ahead of the playhead, so the next call is made a seek whatever its idx: the
+    // reference's seek rule (renderer.rs:12-15) then resets every slot and the rings are rebuilt — consistent again.
+    struct FailGuard {
+        Renderer* r; bool armed = true;
+        ~FailGuard() { if (armed) { r->cache_valid_ = false; r->head_ = ~0ull; } }
+    } guard{this};
     ingest_inputs(n_slots, n_times, idx, in_data, in_on_device, offs, n_rows);
 
     const uint64_t t1 = idx + n_times;
@@ -773,7 +820,10 @@ void Renderer::fill(float* out, bool out_on_device, uint32_t n_slots, uint64_t n
     uint64_t n_out_host = 0;
     if (n_times > 0 && n_slots > 0) {
         // input descriptor table for the slots the schedule reads
-        uint32_t nin = sched_.n_input_slots;
+        // table of the slots that exist: a slot the graph reads but no call ever fed has no entry and reads as 0
+        // (input_desc, interp_device.inc) — the graph may name any u32 slot, the table stays as small as the history
+        const uint32_t nin = (uint32_t)std::min<uint64_t>(sched_.n_input_slots, inputs_.size());
+        n_indesc_ = nin;
         if (nin) {
             std::vector<InputDesc> h(nin);
             for (uint32_t s = 0; s < nin; s++) {
@@ -846,6 +896,7 @@ void Renderer::fill(float* out, bool out_on_device, uint32_t n_slots, uint64_t n
         CU(cudaStreamSynchronize(stream_));
         if (pinned_out) memcpy(out, h_pin_out_, n_out_host * sizeof(float));
     }
+    guard.armed = false;
 }
 
 // N4 (include/friendship_b200.h): consecutive fill_buffer calls of `block` samples, two blocks in flight.

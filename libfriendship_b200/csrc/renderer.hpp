@@ -50,9 +50,18 @@ public:
     void render_stream(uint32_t n_slots, uint64_t idx, uint64_t n_total, uint64_t block, uint32_t n_in_rows,
                        frb_source_fn source, frb_sink_fn sink, void* user);
     void sync();
+    // Voice sharding (multi.cu): this renderer is rank `rank` of `world` devices.  Bank definitions keep only the voices
+    // the rank owns (fixed for the renderer's life); `flatten_sharded` says whether the next schedules evaluate the
+    // graph restricted to those voices (linear mixes) or whole (graphs that use no bank lane: rank 0 alone renders).
+    void set_shard(uint32_t rank, uint32_t world) { shard_rank_ = rank; shard_world_ = world ? world : 1; dirty_ = true; }
+    void set_flatten_sharded(bool on) { if (on != flatten_sharded_) { flatten_sharded_ = on; dirty_ = true; } }
+    void invalidate() { cache_valid_ = false; head_ = ~0ull; }        // the next call is a seek whatever its idx
+    int device() const { return device_; }
     void sum_rows(float* d_out, const float* d_rows, uint32_t n_rows, uint64_t row_stride, uint64_t n);
 
     const Schedule& schedule(uint32_t n_slots);   // (re)builds if needed
+    // what rank `rank` of `world` devices would flatten this graph to (host only: nothing is uploaded; for tests and tools)
+    Schedule schedule_for_shard(uint32_t n_slots, uint32_t rank, uint32_t world) const;
     cudaStream_t stream() const { return stream_; }
     void use_device() const;                      // makes the renderer's device current (throws when planning only)
 
@@ -75,6 +84,7 @@ private:
     void run_range(uint64_t lo, uint64_t hi, float* d_out, uint64_t t0, uint64_t t1, uint64_t out_stride);
     void poll_stage_jit(size_t sg, uint64_t n_groups);
     void free_device_schedule();
+    FlattenEnv flatten_env(uint32_t rank, uint32_t world, bool compact_banks) const;
 
     frb_config cfg_;
     int device_ = -1;
@@ -92,6 +102,8 @@ private:
     std::map<std::pair<uint32_t, uint64_t>, std::pair<uint32_t, uint64_t>> meta_lanes_;
 
     bool dirty_ = true;
+    uint32_t shard_rank_ = 0, shard_world_ = 1;
+    bool flatten_sharded_ = true;
     Schedule sched_;
     uint32_t sched_slots_ = ~0u;
 
@@ -133,6 +145,7 @@ private:
     uint64_t head_ = 0;                                            // reference.rs:26-28
     InputDesc* d_indesc_ = nullptr;
     size_t d_indesc_cap_ = 0;
+    uint32_t n_indesc_ = 0;                                        // entries of d_indesc_ in use (slots that exist)
     float* d_in_stage_ = nullptr;
     size_t d_in_stage_cap_ = 0;
     void* d_ingest_ = nullptr;                  // row descriptors of a batched ingest (renderer.cu ingest_rows_kernel)

@@ -109,7 +109,7 @@ struct Schedule {
     std::vector<int32_t> value_buffer;    // buffer id per value or -1
     std::vector<BufferInfo> buffers;
     std::vector<Stage> stages;
-    uint32_t n_input_slots = 0;           // 1 + highest external input slot read
+    uint64_t n_input_slots = 0;           // 1 + highest external input slot read (slot 0xFFFFFFFF is legal: u64)
     uint64_t max_lookback = 0;            // finite part
     bool from_zero = false;               // a recurrence or a signal-driven delay: non-contiguous fills restart at t = 0
     bool full_history = false;            // at least one buffer with LOOKBACK_FULL

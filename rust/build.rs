@@ -9,7 +9,7 @@ fn main() {
     let csrc = PathBuf::from("friendship-b200/libfriendship_b200/csrc");
     // the same translation units as __graft_entry__.py (the C++ Dispatch restatement host/dispatch.cc is not needed:
     // Dispatch stays in Rust).  interp_device_src.cc is generated from interp_device.inc by __graft_entry__.py.
-    let units = [("capi.cu", false), ("renderer.cu", false), ("interp.cu", false), ("flatten.cc", false),
+    let units = [("capi.cu", false), ("renderer.cu", false), ("multi.cu", false), ("interp.cu", false), ("flatten.cc", false),
                  ("jit.cc", false), ("interp_device_src.cc", false), ("osc.cu", true), ("scan.cu", true)];
     let mut objs = vec![];
     for (src, fmad) in units.iter() {

@@ -21,7 +21,7 @@ struct FrbEdge { from: u32, to: u32, from_slot: u32, to_slot: u32 }
 #[repr(C)] #[derive(Copy, Clone)]
 struct FrbNode { handle: u32, kind: u32, key: u64 }
 #[repr(C)]
-struct FrbConfig { device: i32, flags: u32, osc_anchor: u32, reserved: u32 }
+struct FrbConfig { device: i32, flags: u32, osc_anchor: u32, n_devices: u32 }
 enum FrbRenderer {}
 
 extern "C" {
@@ -61,7 +61,10 @@ pub struct B200Renderer {
 
 impl Default for B200Renderer {
     fn default() -> Self {
-        let cfg = FrbConfig { device: 0, flags: 0, osc_anchor: 0, reserved: 0 };
+        // FRB_N_DEVICES=8: the eight B200s of a box behind this one renderer (voices sharded v mod N inside the library);
+        // `Dispatch<B200Renderer, C>` and its callers do not change
+        let n_devices = std::env::var("FRB_N_DEVICES").ok().and_then(|s| s.parse().ok()).unwrap_or(0);
+        let cfg = FrbConfig { device: 0, flags: 0, osc_anchor: 0, n_devices };
         let raw = unsafe { frb_create(&cfg) };
         assert!(!raw.is_null(), "frb_create failed: no CUDA device (there is no CPU fallback)");
         B200Renderer { raw, keys: HashMap::new(), next_key: 1 }

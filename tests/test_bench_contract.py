@@ -3,6 +3,8 @@ shadowed method), and the bench line's static parts follow the driver's contract
 import ast
 import inspect
 import os
+import subprocess
+import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -70,3 +72,33 @@ def test_reference_arm_prints_exactly_one_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["value"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "cfg4" in d["config"]["workload"]
+
+
+def test_reference_arm_never_maps_the_product_library():
+    """VERDICT r1 'weak' 8: the reference arm's imports (workloads/, oracle/binding.py) must not load libfriendship_b200.so —
+    the oracle binding shares the ctypes declarations of the C header by loading that one file by path."""
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "import bench\n"
+            "from oracle.binding import OracleRenderer\n"
+            "from workloads.banks import build_voice_mix_graph, detuned_bank\n"
+            "bank, ids = detuned_bank(1, 8)\n"
+            "r = OracleRenderer(ext_mode='f32'); build_voice_mix_graph(r, bank, ids); r.fill_buffer(1, 8, 0)\n"
+            "maps = open('/proc/self/maps').read()\n"
+            "assert 'liboracle.so' in maps, 'oracle not loaded'\n"
+            "assert 'libfriendship_b200.so' not in maps, 'product library mapped by the reference arm'\n"
+            "assert 'libfriendship_b200' not in sys.modules\n") % ROOT
+    r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-2000:]
+
+
+def test_parity_windows_cover_start_taps_middle_and_end():
+    sys.path.insert(0, ROOT)
+    import bench
+    wins = bench.parity_windows(480000, 64)
+    assert len(wins) >= 4
+    starts = [w[0] for w in wins]
+    assert 0 in starts and any(4790 <= s <= 4800 for s in starts) and any(7120 <= s <= 7131 for s in starts)
+    assert any(s == 240000 for s in starts) and wins[-1] == (480000 - 32, 32)
+    for s0, n in wins:
+        assert 0 <= s0 and s0 + n <= 480000
+    assert all(s0 + n <= 600 for s0, n in bench.parity_windows(600, 4))      # a debug-sized run stays in range

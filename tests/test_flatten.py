@@ -160,3 +160,12 @@ def test_graphs_deeper_than_the_walk_allows_are_refused_not_crashed_on():
     with pytest.raises(RendererError) as e:
         r.dump_schedule(1)
     assert e.value.code == FRB_E_UNSUPPORTED
+
+
+def test_input_slot_count_does_not_wrap():
+    """slot 0xFFFFFFFF + 1 used to wrap to 0 in u32: the count is kept in 64 bits and the dump saturates."""
+    from libfriendship_b200 import B200Renderer
+    r = B200Renderer(device=-1)
+    r.on_add_edge((0, 0, 0xFFFFFFFF, 0))
+    w = r.dump_schedule(1)
+    assert int(w[6]) == 0xFFFFFFFF

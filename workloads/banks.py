@@ -68,3 +68,33 @@ def build_voice_mix_graph(r, bank, voice_ids, key=7, delay0=4800.0, delay_step=3
         total = voice if total is None else g.node(KIND_SUM2, total, voice)
     g.output(0, total)
     return g
+
+
+def partial_signals(bank, n_times, idx=0, voice=0):
+    """One voice of a bank spelled out in the reference's own vocabulary: the only way a time-varying signal enters the
+    reference is as an external input, so every partial's unit-amplitude signal
+        min(t/attack_p, 1) * exp(-t/tau_p) * sin(2*pi*f_p*t/sr + phase_p)          (include/friendship_b200.h)
+    is evaluated here in fp64, rounded once to f32, and becomes input row p."""
+    vo = bank["voice_offsets"].astype(np.int64)
+    lo, hi = int(vo[voice]), int(vo[voice + 1])
+    t = np.arange(idx, idx + n_times, dtype=np.float64)[None, :]
+    f = bank["freq_hz"][lo:hi].astype(np.float64)[:, None]
+    ph = bank["phase"][lo:hi].astype(np.float64)[:, None]
+    att = bank["attack"][lo:hi].astype(np.float64)[:, None]
+    tau = bank["tau"][lo:hi].astype(np.float64)[:, None]
+    env = np.where(att > 0, np.minimum(t / np.where(att > 0, att, 1.0), 1.0), 1.0)
+    env = env * np.where((tau > 0) & np.isfinite(tau), np.exp(-t / np.where(tau > 0, tau, 1.0)), 1.0)
+    return (env * np.sin(2.0 * np.pi * f * t / bank["sample_rate"] + ph)).astype(np.float32)
+
+
+def build_partial_sum_graph(r, amps):
+    """out0 = (((in0*a0 + in1*a1) + in2*a2) + ...): Multiply(in_p, C(amp_p)) terms in a left Sum2 chain — the additive
+    bank as a graph of the reference's seven primitives (reference.rs:221-234)."""
+    from .kinds import KIND_MULTIPLY, KIND_SUM2
+    g = GraphBuilder(r)
+    total = None
+    for p, a in enumerate(amps):
+        term = g.node(KIND_MULTIPLY, g.input(p), g.const(a))
+        total = term if total is None else g.node(KIND_SUM2, total, term)
+    g.output(0, total)
+    return g
