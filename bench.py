@@ -334,6 +334,8 @@ def main():
     sr.r.set_profiling(False)
     # what was rendered, for the parity check below (outside every timed region)
     dev_block = step_dev()
+    sr.r.sync()                                  # the block is complete on the renderer's stream, which torch's .cpu() does not know
+    torch.cuda.synchronize()
     host_dev = dev_block.cpu().numpy().copy() if rank == 0 else None
     host_e2e = step_e2e()
     host_e2e = host_e2e.copy() if rank == 0 else None

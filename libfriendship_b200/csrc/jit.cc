@@ -221,10 +221,35 @@ unsigned unroll_of(const Node& loop) {
     const size_t n = std::max<size_t>(count_leaves(loop.iters[0]), 1);
     return (unsigned)std::max<size_t>(1, std::min<size_t>(8, 32 / n));
 }
+bool is_pure_load(const Instr& in) {
+    const uint32_t op = in.w0 & 0xFFu;
+    return op == I_LDIN || op == I_LDBUF || op == I_TAP_IN || op == I_TAP_BUF;
+}
+// Unroll factor of the loads-first form (Emitter::seq) for an innermost loop of W-column code, or 1 when the loop does not
+// qualify: it must load something, and store nothing (a store may alias a later iteration's load: nothing moves across it).
+unsigned hoist_unroll(const Stage& st, const Node& loop, int W) {
+    if (has_loop(loop.iters[0])) return 1;
+    size_t loads = 0;
+    for (const Node& b : loop.iters[0]) {
+        const Instr& in = st.program[b.instr];
+        const uint32_t op = in.w0 & 0xFFu;
+        if (op == I_STBUF || op == I_STOUT) return 1;
+        loads += is_pure_load(in);
+    }
+    if (!loads || loads * (size_t)W > 16) return 1;
+    size_t U = std::min<size_t>(8, 16 / (loads * (size_t)W));              // ~16 quads (256 B) in flight per thread
+    U = std::min<size_t>(U, std::max<size_t>(1, 64 / loop.iters[0].size()));   // ... and an unrolled body of a few dozen instructions
+    return (unsigned)std::max<size_t>(U, 2);
+}
 // statements the compiler sees (unrolled bodies counted as often as they are unrolled): what NVRTC's time depends on
-size_t code_size(const std::vector<Node>& seq) {
+size_t code_size(const Stage& st, const std::vector<Node>& seq, int W) {
     size_t n = 0;
-    for (const Node& nd : seq) n += nd.loop ? unroll_of(nd) * code_size(nd.iters[0]) + 1 : 1;
+    for (const Node& nd : seq) {
+        if (!nd.loop) { n++; continue; }
+        const unsigned U = hoist_unroll(st, nd, W);
+        const size_t body = code_size(st, nd.iters[0], W);
+        n += (U > 1 ? (U + 1) * body : unroll_of(nd) * body) + 1;         // loads-first form: U copies + the remainder loop
+    }
     return n;
 }
 
@@ -233,16 +258,36 @@ struct Emitter {
     std::ostringstream& o;
     int W;
     int next_id = 0;
+    int next_desc = 0;
 
-    void leaf(const Instr& in, const std::string& cur, size_t* off, const std::string& ind) {
+    // hoist: "" = emit the instruction where it stands.  Otherwise the name of a temporary for a PURE LOAD (an instruction
+    // whose address depends on the time and the operand table only): phase 0 declares the temporary and issues the load,
+    // phase 1 emits everything else in program order, the load's place taken by a copy from the temporary.
+    void leaf(const Instr& in, const std::string& cur, size_t* off, const std::string& ind, const std::string& hoist = "", int phase = 1) {
         const uint32_t op = in.w0 & 0xFFu, flags = (in.w0 >> 8) & 0xFFu, dst = in.w0 >> 16;
         int na, nb, nx;
         leaf_words(in, nullptr, &na, &nb, &nx);
+        const bool pure_load = is_pure_load(in);
+        if (!hoist.empty() && phase == 0 && !pure_load) { *off += (size_t)(na + nb + nx); return; }
+        if (!hoist.empty() && phase == 1 && pure_load) {
+            *off += (size_t)(na + nb + nx);
+            for (int w = 0; w < W; w++) o << ind << reg(dst, w) << " = " << hoist << "_" << w << ";\n";
+            return;
+        }
         auto word = [&]() { return cur + "[" + std::to_string((*off)++) + "]"; };
         std::string wa, wb, wx;
         if (na) wa = word();
         if (nb) wb = word();
         if (nx) wx = word();
+        // the descriptor of the slot / ring this instruction addresses: loaded once, not once per column
+        const bool uses_in = op == I_LDIN || op == I_TAP_IN || op == I_DLY_IN;
+        const bool uses_buf = op == I_LDBUF || op == I_STBUF || op == I_TAP_BUF || op == I_DLY_BUF;
+        std::string desc;
+        if (uses_in || uses_buf) {
+            desc = "d" + std::to_string(next_desc++);
+            o << ind << (uses_in ? "const InputDesc " : "const BufferDesc ") << desc << " = "
+              << (uses_in ? "input_desc(p, " + wx + ")" : "p.buffers[" + wx + "]") << ";\n";
+        }
         for (int w = 0; w < W; w++) {
             const std::string t = "t_" + std::to_string(w);
             const char* guard = w >= 2 ? "if (two) " : "";
@@ -250,6 +295,7 @@ struct Emitter {
             const std::string b = (flags & IF_B_IMM) ? "f4splat(" + wb + ")" : reg(in.b, w);
             const std::string sh = "(((unsigned long long)" + wb + " << 32) | " + wa + ")";
             o << ind;
+            const std::string dreg = (!hoist.empty() && phase == 0) ? "const float4 " + hoist + "_" + std::to_string(w) : reg(dst, w);
             switch (op) {
                 case I_ADD: o << reg(dst, w) << " = f4add(" << a << ", " << b << ");"; break;
                 case I_MUL: o << reg(dst, w) << " = f4mul(" << a << ", " << b << ");"; break;
@@ -257,15 +303,15 @@ struct Emitter {
                 case I_MOD: o << reg(dst, w) << " = f4mod(" << a << ", " << b << ");"; break;
                 case I_MIN: o << reg(dst, w) << " = f4min(" << a << ", " << b << ", p.sparkle_min);"; break;
                 case I_MOV: o << reg(dst, w) << " = " << a << ";"; break;
-                case I_LDIN: o << reg(dst, w) << " = f4ld_in(input_desc(p, " << wx << "), " << t << ");"; break;
-                case I_LDBUF: o << reg(dst, w) << " = f4ld_buf(p.buffers[" << wx << "], " << t << ");"; break;
-                case I_STBUF: o << guard << "f4st_buf(p.buffers[" << wx << "], " << t << ", " << a << ");"; break;
+                case I_LDIN: o << dreg << " = f4ld_in(" << desc << ", " << t << ");"; break;
+                case I_LDBUF: o << dreg << " = f4ld_buf(" << desc << ", " << t << ");"; break;
+                case I_STBUF: o << guard << "f4st_buf(" << desc << ", " << t << ", " << a << ");"; break;
                 case I_STOUT: o << guard << "f4st_out(p, " << wx << ", " << t << ", " << a << ");"; break;
-                case I_TAP_IN: o << reg(dst, w) << " = f4tap_in(input_desc(p, " << wx << "), " << t << ", " << sh << ");"; break;
-                case I_TAP_BUF: o << reg(dst, w) << " = f4tap_buf(p.buffers[" << wx << "], " << t << ", " << sh << ");"; break;
+                case I_TAP_IN: o << dreg << " = f4tap_in(" << desc << ", " << t << ", " << sh << ");"; break;
+                case I_TAP_BUF: o << dreg << " = f4tap_buf(" << desc << ", " << t << ", " << sh << ");"; break;
                 case I_GATE: o << reg(dst, w) << " = f4gate(" << a << ", " << t << ", (((unsigned long long)" << wx << " << 32) | " << wb << "));"; break;
-                case I_DLY_IN: o << reg(dst, w) << " = f4delay<0>(input_desc(p, " << wx << "), no_buf, " << a << ", z4, " << t << ", p.sparkle_delay);"; break;
-                case I_DLY_BUF: o << reg(dst, w) << " = f4delay<1>(no_in, p.buffers[" << wx << "], " << a << ", z4, " << t << ", p.sparkle_delay);"; break;
+                case I_DLY_IN: o << reg(dst, w) << " = f4delay<0>(" << desc << ", no_buf, " << a << ", z4, " << t << ", p.sparkle_delay);"; break;
+                case I_DLY_BUF: o << reg(dst, w) << " = f4delay<1>(no_in, " << desc << ", " << a << ", z4, " << t << ", p.sparkle_delay);"; break;
                 case I_DLY_TI: o << reg(dst, w) << " = f4delay<2>(no_in, no_buf, " << a << ", " << b << ", " << t << ", p.sparkle_delay);"; break;
                 default: o << "/* unknown op " << op << " */"; break;
             }
@@ -281,8 +327,31 @@ struct Emitter {
             const std::string id = std::to_string(next_id++);
             o << ind << "const unsigned n_" << id << " = " << cur << "[" << off << "];\n";
             o << ind << "const unsigned* q_" << id << " = " << cur << " + " << (off + 1) << ";\n";
-            o << ind << "#pragma unroll " << unroll_of(nd) << "\n";
-            o << ind << "for (unsigned i_" << id << " = 0; i_" << id << " < n_" << id << "; i_" << id << "++) {\n";
+            const unsigned U = hoist_unroll(st, nd, W);
+            if (U > 1) {
+                // Innermost loop that only loads and computes (the terms of a Sum2 chain): an iteration is a dependent
+                // chain operand word -> descriptor -> samples -> arithmetic, and the compiler will not move a load across
+                // the branches of the iterations before it.  So U iterations at a time, ALL their loads first (into
+                // temporaries), then their arithmetic in program order: U x loads x W quads in flight per thread.
+                const std::vector<Node>& body = nd.iters[0];
+                size_t wpp = 0;
+                for (const Node& b : body) { int a, bb, x; leaf_words(st.program[b.instr], nullptr, &a, &bb, &x); wpp += (size_t)(a + bb + x); }
+                o << ind << "unsigned i_" << id << " = 0;\n";
+                o << ind << "for (; i_" << id << " + " << U << " <= n_" << id << "; i_" << id << " += " << U << ") {\n";
+                for (int phase = 0; phase < 2; phase++) {
+                    for (unsigned k = 0; k < U; k++) {
+                        size_t o2 = (size_t)k * wpp;
+                        for (size_t j = 0; j < body.size(); j++)
+                            leaf(st.program[body[j].instr], "q_" + id, &o2, ind + "  ", "h" + id + "_" + std::to_string(k) + "_" + std::to_string(j), phase);
+                    }
+                }
+                o << ind << "  q_" << id << " += " << (size_t)U * wpp << ";\n";
+                o << ind << "}\n";
+                o << ind << "for (; i_" << id << " < n_" << id << "; i_" << id << "++) {\n";
+            } else {
+                o << ind << "#pragma unroll " << unroll_of(nd) << "\n";
+                o << ind << "for (unsigned i_" << id << " = 0; i_" << id << " < n_" << id << "; i_" << id << "++) {\n";
+            }
             seq(nd.iters[0], "q_" + id, ind + "  ");
             o << ind << "}\n";
             o << ind << cur << " = q_" << id << ";\n";
@@ -337,7 +406,8 @@ JitProgram jit_generate(const Stage& st) {
     o << "  switch (tab[2 * strand]) {\n";
     for (size_t k = 0; k < shapes.size(); k++) {
         const Shape& sh = shapes[k];
-        out.code_instrs += code_size(sh.code);
+        out.code_instrs += code_size(st, sh.code, sh.nreg <= 6 ? 4 : 2);
+        if (k == 0 || (sh.nreg <= 6 ? 2u : 1u) < out.groups_per_thread) out.groups_per_thread = sh.nreg <= 6 ? 2u : 1u;
         o << "  case " << k << ": {\n";
         // A stage is a stream and what bounds it is the bytes it keeps in flight: 12 resident CTAs x 128 threads x two
         // 16-byte loads per input are 6 MB on the whole GPU, ~5 TB/s at the loaded DRAM latency (measured: 5.0).  A small
@@ -425,6 +495,10 @@ bool jit_compile_to_cubin(const std::string& source, std::string* cubin, std::st
     }
     a.DestroyProgram(&prog);
     if (ok) cache_store(source, *cubin);
+    if (const char* dir = getenv("FRB_JIT_DUMP")) {                // tuning aid: the last compiled stage's source and cubin
+        if (FILE* f = fopen((std::string(dir) + "/frb_stage.cu").c_str(), "w")) { fwrite(source.data(), 1, source.size(), f); fclose(f); }
+        if (ok) if (FILE* f = fopen((std::string(dir) + "/frb_stage.cubin").c_str(), "wb")) { fwrite(cubin->data(), 1, cubin->size(), f); fclose(f); }
+    }
     return ok;
 }
 
@@ -461,19 +535,21 @@ struct JitKernel {
     CUmodule mod = nullptr;
     CUfunction fn = nullptr;
     unsigned* d_tab = nullptr;      // operand table (device)
+    unsigned groups_per_thread = 1;
 };
 
 JitKernel* jit_build(const Stage& st, std::string* err) {
     const JitProgram prog = jit_generate(st);
     std::string cubin, log;
     if (!jit_compile_to_cubin(prog.source, &cubin, &log)) { if (err) *err = "NVRTC: " + log; return nullptr; }
-    return jit_load(cubin, prog.table, err);
+    return jit_load(cubin, prog.table, prog.groups_per_thread, err);
 }
 
-JitKernel* jit_load(const std::string& cubin, const std::vector<uint32_t>& table, std::string* err) {
+JitKernel* jit_load(const std::string& cubin, const std::vector<uint32_t>& table, unsigned groups_per_thread, std::string* err) {
     Api& a = api(true);
     if (!a.ok) { if (err) *err = a.why; return nullptr; }
     auto* k = new JitKernel();
+    k->groups_per_thread = groups_per_thread ? groups_per_thread : 1;
     if (a.ModuleLoadData(&k->mod, cubin.data()) != CUDA_SUCCESS || a.ModuleGetFunction(&k->fn, k->mod, "frb_stage") != CUDA_SUCCESS) {
         if (k->mod) a.ModuleUnload(k->mod);
         delete k;
@@ -502,7 +578,8 @@ bool jit_launch(JitKernel* k, const InterpParams& p, int sm_count, cudaStream_t 
     Api& a = api(true);
     if (!a.ok || !k) return false;
     if (p.n_groups == 0) return true;
-    unsigned long long blocks = (p.n_groups + 127) / 128;
+    const unsigned long long per_block = 128ull * k->groups_per_thread;          // every thread gets its two groups when the body walks two
+    unsigned long long blocks = (p.n_groups + per_block - 1) / per_block;
     unsigned long long cap = (unsigned long long)sm_count * 16 / p.n_strands;   // rounded down: never a second wave of a few CTAs
     if (cap < 1) cap = 1;
     if (blocks > cap) blocks = cap;

@@ -22,6 +22,7 @@ struct JitProgram {
     std::string source;
     std::vector<uint32_t> table;
     size_t code_instrs = 0;
+    unsigned groups_per_thread = 1;   // 8-sample groups a thread walks per iteration (2 for small programs): sizes the grid
 };
 JitProgram jit_generate(const Stage& st);
 std::string jit_generate_source(const Stage& st);
@@ -40,7 +41,7 @@ void jit_wait_idle();
 // compile + load into the current context; nullptr on failure
 JitKernel* jit_build(const Stage& st, std::string* err);
 // load an already compiled cubin (jit_compile_to_cubin) and its operand table into the current context
-JitKernel* jit_load(const std::string& cubin, const std::vector<uint32_t>& table, std::string* err);
+JitKernel* jit_load(const std::string& cubin, const std::vector<uint32_t>& table, unsigned groups_per_thread, std::string* err);
 void jit_free(JitKernel* k);
 bool jit_launch(JitKernel* k, const InterpParams& p, int sm_count, cudaStream_t stream);
 

@@ -197,9 +197,9 @@ void MultiRenderer::fill(float* out, bool out_on_device, uint32_t n_slots, uint6
     }
     const uint64_t row = (n_out + 3) & ~3ull;                // rows stay 16-byte aligned
     const size_t need = (size_t)row * (n_dev + 1);
-    CU(cudaSetDevice(kids_[0]->device()));
     if (slab_cap_ < need) {
-        sync();
+        sync();                                              // leaves the LAST device current
+        CU(cudaSetDevice(kids_[0]->device()));               // the slab lives in the first device's HBM
         if (d_slab_) CU(cudaFree(d_slab_));
         d_slab_ = nullptr; slab_cap_ = 0;
         CU(cudaMalloc(&d_slab_, need * sizeof(float)));

@@ -779,6 +779,20 @@ static cudaError_t launch_osc_range(const OscBankDev& b, const BufferDesc* d_buf
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b.ev_join, cudaEventDisableTiming);
         if (e != cudaSuccess) return e;
     }
+    if (fork) cudaEventRecord(b.ev_fork, stream);            // what the side stream must wait for: everything before this range
+    if (nseg_total > n_att) {
+        OscLaunch q = p;
+        q.seg0 = p.seg0 + n_att;
+        q.nseg = nseg_total - n_att;
+        q.plane_off = (unsigned long long)n_att * L;
+        dim3 grid((q.nseg + threads - 1) / threads, b.n_voices, p.split);
+        if (b.K == OSC_K) osc_kernel<OSC_K, false><<<grid, threads, smem, stream>>>(q);
+        else if (b.K == OSC_K_SMALL) osc_kernel<OSC_K_SMALL, false><<<grid, threads, smem, stream>>>(q);
+        else osc_kernel<OSC_K_ONE, false><<<grid, threads, smem, stream>>>(q);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        if (n_launches) (*n_launches)++;
+    }
     if (n_att) {
         // The attack region is a few hundred samples: at the main kernel's L it is a handful of live threads in one warp
         // per (voice, split) walking every group of the split — the longest CTA of the launch (the ramp loop is slower),
@@ -793,8 +807,7 @@ static cudaError_t launch_osc_range(const OscBankDev& b, const BufferDesc* d_buf
         q.seg0 = p.seg0 * r;
         q.nseg = n_att * r;
         cudaStream_t st = stream;
-        if (fork) {   // a handful of warps walking every partial: overlap it with the main kernel instead of serialising
-            cudaEventRecord(b.ev_fork, stream);
+        if (fork) {   // a handful of warps walking every partial: beside the main kernel (launched above), not before it
             cudaStreamWaitEvent(b.side, b.ev_fork, 0);
             st = b.side;
         }
@@ -803,19 +816,6 @@ static cudaError_t launch_osc_range(const OscBankDev& b, const BufferDesc* d_buf
         if (b.K == OSC_K) osc_kernel<OSC_K, true><<<grid, threads, smem_a, st>>>(q);
         else if (b.K == OSC_K_SMALL) osc_kernel<OSC_K_SMALL, true><<<grid, threads, smem_a, st>>>(q);
         else osc_kernel<OSC_K_ONE, true><<<grid, threads, smem_a, st>>>(q);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-        if (n_launches) (*n_launches)++;
-    }
-    if (nseg_total > n_att) {
-        OscLaunch q = p;
-        q.seg0 = p.seg0 + n_att;
-        q.nseg = nseg_total - n_att;
-        q.plane_off = (unsigned long long)n_att * L;
-        dim3 grid((q.nseg + threads - 1) / threads, b.n_voices, p.split);
-        if (b.K == OSC_K) osc_kernel<OSC_K, false><<<grid, threads, smem, stream>>>(q);
-        else if (b.K == OSC_K_SMALL) osc_kernel<OSC_K_SMALL, false><<<grid, threads, smem, stream>>>(q);
-        else osc_kernel<OSC_K_ONE, false><<<grid, threads, smem, stream>>>(q);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         if (n_launches) (*n_launches)++;

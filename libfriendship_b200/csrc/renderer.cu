@@ -668,9 +668,10 @@ void Renderer::poll_stage_jit(size_t sg, uint64_t n_groups) {
         JitProgram prog = jit_generate(st);
         sj.code_instrs = prog.code_instrs;
         sj.table = std::move(prog.table);
+        sj.groups_per_thread = prog.groups_per_thread;
         std::string jerr;
         if (auto hit = jit_cache_lookup(prog.source)) {
-            sj.k = jit_load(*hit, sj.table, &jerr);
+            sj.k = jit_load(*hit, sj.table, sj.groups_per_thread, &jerr);
             sj.state = sj.k ? 1 : 2;
             if (!sj.k) last_jit_error = jerr;
         } else if (sj.code_instrs > JIT_MAX_CODE) {
@@ -679,7 +680,7 @@ void Renderer::poll_stage_jit(size_t sg, uint64_t n_groups) {
         } else if (eager && (asked || sj.code_instrs <= JIT_MAX_SYNC_CODE)) {
             // a long block (or an explicit request) pays for the NVRTC call right away
             std::string cubin, log;
-            if (jit_compile_to_cubin(prog.source, &cubin, &log)) sj.k = jit_load(cubin, sj.table, &jerr);
+            if (jit_compile_to_cubin(prog.source, &cubin, &log)) sj.k = jit_load(cubin, sj.table, sj.groups_per_thread, &jerr);
             else jerr = "NVRTC: " + log;
             sj.state = sj.k ? 1 : 2;
             if (!sj.k) last_jit_error = jerr;
@@ -693,7 +694,7 @@ void Renderer::poll_stage_jit(size_t sg, uint64_t n_groups) {
     if (sj.state == 3 && sj.job->done.load(std::memory_order_acquire) != 0) {
         std::string jerr;
         const bool ok = sj.job->done.load(std::memory_order_acquire) > 0;
-        sj.k = ok ? jit_load(sj.job->cubin, sj.table, &jerr) : nullptr;
+        sj.k = ok ? jit_load(sj.job->cubin, sj.table, sj.groups_per_thread, &jerr) : nullptr;
         sj.state = sj.k ? 1 : 2;
         if (!sj.k) last_jit_error = ok ? jerr : "NVRTC: " + sj.job->log;
         sj.job.reset();

@@ -113,7 +113,7 @@ private:
     // code_instrs: jit_code_instructions of the stage, computed when the stage first qualifies (~0 = not yet)
     // job: the compile running beside the render loop (jit.hpp; dropped, never waited for, when the schedule goes away)
     struct StageJit { JitKernel* k = nullptr; int state = 0; uint64_t uses = 0; uint64_t code_instrs = ~0ull;
-                      std::shared_ptr<JitJob> job; std::vector<uint32_t> table; };
+                      std::shared_ptr<JitJob> job; std::vector<uint32_t> table; unsigned groups_per_thread = 1; };
     static constexpr uint64_t JIT_MAX_CODE = FRB_JIT_MAX_CODE;        // above: interpreted for good (NVRTC needs minutes)
     static constexpr uint64_t JIT_MAX_SYNC_CODE = FRB_JIT_MAX_SYNC_CODE;   // above: compiled only beside the render loop
     std::vector<StageJit> stage_jit_;

@@ -28,6 +28,8 @@ class ShardedRenderer:
         self.exchange = exchange if (self.on_gpu and world_size > 1) else "nccl"
         self._out = None
         self._host = None
+        self._stream = None
+        self._ev = None
         self._slabs = None          # p2p: (shape, [slab tensors on rank 0], [row pointers of this rank], step counter)
 
     def voices_of_rank(self, n_voices):
@@ -42,15 +44,28 @@ class ShardedRenderer:
     def _reduce(self, out):
         if self.world_size > 1:
             import torch.distributed as dist
-            dist.reduce(out, dst=0, op=dist.ReduceOp.SUM)   # the path's single exchange step
             if self.on_gpu:
-                # the next render (renderer stream) overwrites this block: the collective must have read it first
-                torch.cuda.current_stream(self.device).synchronize()
+                # Stream order on the device, no host round trip on either side (round 1 had two per step: r.sync() before
+                # the collective, current_stream().synchronize() after): torch's current stream — the one the collective
+                # is ordered on — waits for the render through an event, and the renderer's stream waits for the
+                # collective the same way before the next render overwrites this block.
+                ext, cur = self.cuda_stream(), torch.cuda.current_stream(self.device)
+                if self._ev is None:
+                    self._ev = (torch.cuda.Event(), torch.cuda.Event())
+                self._ev[0].record(ext)
+                cur.wait_event(self._ev[0])
+                dist.reduce(out, dst=0, op=dist.ReduceOp.SUM)   # the path's single exchange step
+                self._ev[1].record(cur)
+                ext.wait_event(self._ev[1])
+            else:
+                dist.reduce(out, dst=0, op=dist.ReduceOp.SUM)
         return out
 
     def cuda_stream(self):
-        """The CUDA stream the renderer launches on, as a torch stream (for CUDA-event timing)."""
-        return torch.cuda.ExternalStream(self.r.stream(), device=f"cuda:{self.device}")
+        """The CUDA stream the renderer launches on, as a torch stream (CUDA-event timing; the collective is ordered on it)."""
+        if self._stream is None:
+            self._stream = torch.cuda.ExternalStream(self.r.stream(), device=f"cuda:{self.device}")
+        return self._stream
 
     def _p2p_setup(self, n_slots, n_times):
         import torch.distributed as dist
@@ -90,15 +105,15 @@ class ShardedRenderer:
         return out
 
     def fill_buffer_device(self, n_slots, n_times, idx, inputs=None):
-        """Renders this rank's shard and reduces onto rank 0.  Returns the block tensor (valid on rank 0)."""
+        """Renders this rank's shard and reduces onto rank 0.  Returns the block tensor (valid on rank 0) with the work
+        ENQUEUED on the renderer's stream (`cuda_stream()`): order later device work on that stream, or `r.sync()`."""
         if self.exchange == "p2p":
             assert not inputs
             return self._fill_p2p(n_slots, n_times, idx)
         out = self._block(n_slots, n_times)
         if self.on_gpu:
             assert not inputs, "device path: feed external inputs through B200Renderer.fill_buffer_device directly"
-            self.r.fill_buffer_device(out.data_ptr(), n_slots, n_times, idx)
-            self.r.sync()                               # renderer stream -> visible to the collective's stream
+            self.r.fill_buffer_device(out.data_ptr(), n_slots, n_times, idx)      # enqueued on the renderer's stream
         else:
             out.copy_(torch.from_numpy(self.r.fill_buffer(n_slots, n_times, idx, inputs)))
         return self._reduce(out)
@@ -114,6 +129,8 @@ class ShardedRenderer:
             return None
         if self._host is None or tuple(self._host.shape) != (n_slots, n_times):
             self._host = torch.empty((n_slots, n_times), dtype=torch.float32, pin_memory=True)
+        if self.world_size == 1:
+            self.r.sync()                              # no collective ordered the copy's stream behind the render
         self._host.copy_(out, non_blocking=True)
         torch.cuda.synchronize(self.device)
         return self._host.numpy()
@@ -157,7 +174,9 @@ class ShardedRenderer:
             n = min(block, idx + n_total - t)
             # dflat[b] was last read by the copy of block k-2, delivered (hence complete) during iteration k-1
             self._out = dflat[b][:n_slots * n].view(n_slots, n)
-            out = self.fill_buffer_device(n_slots, n, t)        # render + exchange; complete on return
+            out = self.fill_buffer_device(n_slots, n, t)        # render + exchange, enqueued on the renderer's stream
+            copy_stream.wait_stream(self.cuda_stream())
+            copy_stream.wait_stream(torch.cuda.current_stream(self.device))
             if self.rank == 0:
                 with torch.cuda.stream(copy_stream):
                     hflat[b][:n_slots * n].view(n_slots, n).copy_(out, non_blocking=True)

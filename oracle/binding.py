@@ -5,6 +5,7 @@ Same Python surface as libfriendship_b200.B200Renderer so parity tests drive bot
 """
 import ctypes as C
 import os
+import sys
 
 import importlib.util
 
@@ -12,9 +13,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # The oracle's C shim mirrors include/friendship_b200.h (orc_* for frb_*), so it shares the ctypes declarations of that
 # header — loaded BY PATH: importing the package would map the product library, and bench.py's reference arm must run
 # on oracle/_build/liboracle.so alone.
-_spec = importlib.util.spec_from_file_location("_frb_cabi_decls", os.path.join(ROOT, "libfriendship_b200", "_cabi.py"))
-_cabi = importlib.util.module_from_spec(_spec)
-_spec.loader.exec_module(_cabi)
+if "libfriendship_b200._cabi" in sys.modules:
+    # a test process that drives both renderers: one set of classes (RendererError raised by either is the same type)
+    _cabi = sys.modules["libfriendship_b200._cabi"]
+else:
+    _spec = importlib.util.spec_from_file_location("_frb_cabi_decls", os.path.join(ROOT, "libfriendship_b200", "_cabi.py"))
+    _cabi = importlib.util.module_from_spec(_spec)
+    _spec.loader.exec_module(_cabi)
 _LIB_PATH = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
 _lib = C.CDLL(_LIB_PATH)
 _cabi.declare(_lib, "orc")

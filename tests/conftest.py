@@ -16,6 +16,9 @@ def pytest_configure(config):
     orc = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
     if not (os.path.exists(lib) and os.path.exists(orc)):
         subprocess.check_call([sys.executable, os.path.join(ROOT, "__graft_entry__.py")])
+    # The product package first: oracle/binding.py then shares its ABI declaration module (one RendererError class for
+    # both renderers) instead of loading a private copy by path, as it does for bench.py's reference arm.
+    import libfriendship_b200  # noqa: F401
 
 
 def _has_gpu():

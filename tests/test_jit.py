@@ -75,14 +75,19 @@ def test_hot_stage_gets_compiled_in_the_background():
     import time
     from libfriendship_b200 import B200Renderer
     from oracle.binding import OracleRenderer
+    from libfriendship_b200 import KIND_DIVIDE, KIND_MINIMUM, KIND_MODULO, KIND_SUM2
     n = 512
     g, o = B200Renderer(), OracleRenderer()
-    build_cfg1_graph(g, delay=100.0)
-    build_cfg1_graph(o, delay=100.0)
+    for r in (g, o):
+        # a program structure no other test compiles (cubins are cached by structure process-wide: a cache hit loads at
+        # once and there would be no background compile to watch)
+        b = build_cfg1_graph(r, delay=100.0)
+        x = b.node(KIND_MODULO, b.node(KIND_DIVIDE, b.node(KIND_MINIMUM, b.input(0), b.const(0.3)), b.const(0.7)), b.const(0.11))
+        b.output(2, b.node(KIND_SUM2, b.node(KIND_MINIMUM, x, b.input(0)), b.node(KIND_DIVIDE, x, b.const(1.5))))
     k, deadline, switched_at = 0, time.time() + 60.0, None
     while time.time() < deadline:
         blk = [cfg1_input(n * (k + 1))[k * n:]]
-        assert_same_bits(g.fill_buffer(2, n, k * n, blk), o.fill_buffer(2, n, k * n, blk), f"block {k}")
+        assert_same_bits(g.fill_buffer(3, n, k * n, blk), o.fill_buffer(3, n, k * n, blk), f"block {k}")
         k += 1
         s = g.stats()
         if s["jit_launches"] > 0 and switched_at is None:
@@ -124,7 +129,7 @@ def test_code_size_depends_on_structure_not_on_length():
     _const_chain(r, 3000)
     assert r.jit_code_instructions(1, 0) <= 16
     src = r.jit_source(1, 0)
-    assert src.count("for (unsigned i_") == 1 and "3000" not in src[src.index("frb_stage"):]
+    assert src.count("const unsigned n_") == 1 and "3000" not in src[src.index("frb_stage"):]
     t0 = time.time()
     assert r.jit_cubin_size(1, 0) > 1000
     first = time.time() - t0
@@ -168,6 +173,7 @@ def test_repeated_groups_fold_on_two_levels():
     g.output(0, total)
     src = r.jit_source(1, 0)
     body = src[src.index("frb_stage"):]
-    assert body.count("for (unsigned i_") >= 2 and "#pragma unroll 1\n" in body       # an outer loop around an inner one
+    assert body.count("const unsigned n_") >= 2 and "#pragma unroll 1\n" in body       # an outer loop around an inner one
+    assert "const float4 h" in body                                                     # inner loop: loads first, then arithmetic
     assert r.jit_code_instructions(1, 0) < 120                                          # ~1,000 instructions in the program
     assert r.jit_cubin_size(1, 0) > 1000

@@ -107,6 +107,29 @@ def case_pure_elementwise(n_slots=64, n=1 << 22):
             "algorithmic_GBs": alg / t["interp_ms"] / 1e6, "peak_GBs": HBM, "frac": alg / t["interp_ms"] / 1e6 / HBM}
 
 
+def case_refbank(n_partials=1024, n=1 << 19, flags=0):
+    """An additive bank in the reference's own vocabulary: n_partials external inputs, Multiply(in_p, C(amp_p)), left Sum2
+    chain — ONE stage of 3 x n_partials instructions, which the stage JIT compiles as one loop (csrc/jit.cc).
+    Algorithmic: 4 B x (n_partials reads + 1 write) per sample."""
+    from workloads.banks import build_partial_sum_graph
+    r = B200Renderer(flags=flags)
+    build_partial_sum_graph(r, [1.0 / (p + 1) for p in range(n_partials)])
+    x = torch.rand((n_partials, n), dtype=torch.float32, device="cuda")
+    out = torch.empty((1, n), dtype=torch.float32, device="cuda")
+    offs = np.arange(n_partials + 1, dtype=np.uint64) * n
+    t0 = time.perf_counter()
+    r.fill_buffer_device(out.data_ptr(), 1, n, 0, x.data_ptr(), offs)
+    r.sync()
+    first = time.perf_counter() - t0
+    t = timed_fill(r, out, 1, n, 0, x.data_ptr(), offs, reps=3)
+    alg = 4.0 * (n_partials + 1) * n
+    st = r.stats()
+    return {"case": "reference-vocabulary additive bank (Multiply + Sum2 chain over external inputs)", "partials": n_partials, "samples": n,
+            "first_call_s": first, "ms": t["total_ms"], "stage_ms": t["interp_ms"], "algorithmic_GBs": alg / t["interp_ms"] / 1e6, "peak_GBs": HBM,
+            "frac": alg / t["interp_ms"] / 1e6 / HBM, "jit_launches": st["jit_launches"], "interp_launches": st["interp_launches"],
+            "code_instructions": r.jit_code_instructions(1, 0)}
+
+
 def case_cfg3(n_voices=4096, n=480000, flags=0, osc_anchor=0):
     """cfg3: per voice 1-partial oscillator -> biquad -> feedback delay, mixed to one slot.  K4 algorithmic traffic
     (SURVEY.md §8d): 8 B per voice-sample for the fused biquad -> comb chain (read x, write y); the two separate kernels
@@ -178,7 +201,7 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["pure", "elementwise", "cfg3"]
     for w in which:
         fn = {"pure": case_pure_elementwise, "pure_continuing": case_pure_continuing, "elementwise": case_elementwise, "cfg3": case_cfg3, "cfg3_unfused": lambda: case_cfg3(flags=8), "cfg3_ring": lambda: case_cfg3(flags=16), "cfg3_L64": lambda: case_cfg3(osc_anchor=64), "cfg3_L32": lambda: case_cfg3(osc_anchor=32),
-          "cfg3_L128": lambda: case_cfg3(osc_anchor=128), "cfg3_L256": lambda: case_cfg3(osc_anchor=256), "cfg1": case_cfg1, "cfg2": case_cfg2, "cfg2_64": lambda: case_cfg2(64), "cfg2_32": lambda: case_cfg2(32)}[w]
+          "cfg3_L128": lambda: case_cfg3(osc_anchor=128), "cfg3_L256": lambda: case_cfg3(osc_anchor=256), "cfg1": case_cfg1, "cfg2": case_cfg2, "refbank": case_refbank, "refbank_nojit": lambda: case_refbank(flags=2), "refbank256": lambda: case_refbank(256, 1 << 21), "cfg2_64": lambda: case_cfg2(64), "cfg2_32": lambda: case_cfg2(32)}[w]
         t0 = time.time()
         try:
             res = fn()
