@@ -22,6 +22,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <type_traits>
 #include <vector>
 
@@ -281,6 +282,7 @@ struct ChainGeom {                                 // tile geometry for S sample
     static constexpr int TPQ = S / 4;              // quads per thread
 };
 constexpr int CH_MIN_DELAY = 32;                   // shorter combs use the separate kernels
+constexpr int kChainBulkDefault = 0;               // see dfcomb_kernel: which of the chain's tiles travel by bulk copy (UBLKCP)
 
 __device__ __forceinline__ unsigned ch_qpos(unsigned q) { return q + (q >> 3); }
 __device__ __forceinline__ unsigned ch_fpos(unsigned m) { return m + ((m >> 5) << 2); }   // sample m of a tile (float index)
@@ -293,6 +295,37 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory"); }
 
+// ---- bulk copies (TMA engine, SASS UBLKCP) completing on an mbarrier (SASS SYNCS): the copy engine moves the tile, the
+// LSU pipe — this kernel's limiter with per-thread cp.async (LDGSTS: 17 of 84 shared-memory wavefronts per tile) — does not.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 :: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_LOOP:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra WAIT_DONE;\n\t"
+                 "bra WAIT_LOOP;\n\tWAIT_DONE:\n\t}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// what the generic proxy did to memory (y into the tile, z into the window and the ring) is ordered before what the
+// async proxy does next (the bulk copies that overwrite the tile buffers / read the ring)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+// `count` floats (a multiple of 4) from ring position `pos` (a multiple of 4) of a ring of `mask + 1` floats into shared
+// memory: one bulk copy, two where the ring wraps (both parts stay multiples of 16 bytes)
+__device__ __forceinline__ void bulk_ring_g2s(float* smem_dst, const float* ring, unsigned pos, unsigned mask, unsigned count, unsigned long long* bar) {
+    pos &= mask;
+    const unsigned first = min(count, mask + 1u - pos);
+    bulk_g2s(smem_dst, ring + pos, first * 4u, bar);
+    if (first < count) bulk_g2s(smem_dst + first, ring, (count - first) * 4u, bar);
+}
+
 template <int S>
 struct __align__(16) ChainWarpSmem {               // what one warp (= one lane of the chain) keeps in shared memory
     float4 x[2][ChainGeom<S>::QUADS];              // x tiles in flight (double buffered); the current one becomes y
@@ -301,6 +334,8 @@ struct __align__(16) ChainWarpSmem {               // what one warp (= one lane 
     float4 c;                                      // carry between fast tiles {x[tb-1], x[tb-2], y[tb-1], y[tb-2]}
     float4 rec_h, rec_an;                          // EXC: the lane's one-partial oscillator record (osc_one.cuh)
     uint4 rec_ph;
+    unsigned long long bar_x[2], bar_w;            // BULK: mbarriers of the two x tiles and of the tap window
+    unsigned long long pad_;
 };
 
 // z of 4 samples: a[0..7] are two consecutive quads of the tap window, the taps are a[SH .. SH + 3]
@@ -314,7 +349,7 @@ __device__ __forceinline__ float4 comb_quad(const float4 y, const float4 a0, con
 // Combs shorter than 128 samples: chunks of 32 E samples (<= D), E consecutive samples per thread.  y is read ahead of
 // the chunk loop, z goes straight to the ring (32 E contiguous floats per instruction) and into the tap window for the
 // chunks that follow; one barrier per chunk.
-template <int CH_TILE, int E>
+template <int CH_TILE, int E, bool SKEW>
 __device__ __forceinline__ void comb_small(const float* tf, float* wf, float* zdata, unsigned zb, unsigned zm, unsigned Du,
                                            unsigned sh, float g, unsigned wl) {
     constexpr int NC = CH_TILE / (32 * E);
@@ -322,7 +357,7 @@ __device__ __forceinline__ void comb_small(const float* tf, float* wf, float* zd
 #pragma unroll
     for (int c = 0; c < NC; c++)
 #pragma unroll
-        for (int e = 0; e < E; e++) y[c][e] = tf[ch_fpos(32u * E * c + E * wl + e)];
+        for (int e = 0; e < E; e++) { const unsigned m = 32u * E * c + E * wl + e; y[c][e] = tf[SKEW ? ch_fpos(m) : m]; }
 #pragma unroll
     for (int c = 0; c < NC; c++) {
         const unsigned m = 32u * E * c + E * wl;
@@ -344,7 +379,14 @@ __device__ __forceinline__ void comb_small(const float* tf, float* wf, float* zd
 // EXC: the biquad's input is not a ring but a one-partial oscillator voice (exc_voice[lane] of the bank `exc`), evaluated
 // in registers by osc_one_group8 — the function osc_one_kernel fills that voice's ring with when the chain is not fused,
 // so the bits are the same — and the chain's only HBM traffic is its output: 4 B per lane-sample.
-template <bool EXC>
+// BULK: the x tile and the tap window travel by bulk copy (one elected lane, an mbarrier per buffer) instead of per-thread
+// cp.async.  A bulk copy lands linearly, so the ring-fed instance keeps its x tile unskewed (own-sample reads then take
+// a 2-way bank conflict: +4 wavefronts per tile against the 17 the LDGSTS copies cost).
+// BULK = 0: cp.async for both; 1: the x tile by bulk copy, the tap window by cp.async; 2: both by bulk copy.  The window
+// is z this very warp stored to the ring a moment ago: reading it through the async proxy needs the full
+// fence.proxy.async (SASS: MEMBAR.ALL.GPU + FENCE.VIEW.ASYNC) every tile, where the x tile (written by an earlier kernel)
+// needs only the shared-memory flavour for the buffer it overwrites.
+template <bool EXC, int BULK>
 __global__ void __launch_bounds__(DF_CTA_THREADS, 7)
 dfcomb_kernel(const float* __restrict__ coef, const float* __restrict__ pw, const uint32_t* __restrict__ delay,
               const float* __restrict__ gain, const BufferDesc* __restrict__ bufdesc, const uint32_t* __restrict__ in_bufs,
@@ -357,6 +399,10 @@ dfcomb_kernel(const float* __restrict__ coef, const float* __restrict__ pw, cons
     constexpr int PSHIFT = EXC ? 1 : 0;                            // stored powers are A^(8 * 2^k): A^(SPT * 2^k) = entry k + PSHIFT
     constexpr int CH_TILE = ChainGeom<SPT>::TILE, CH_TQ = ChainGeom<SPT>::TQ, CH_QUADS = ChainGeom<SPT>::QUADS, CH_TPQ = ChainGeom<SPT>::TPQ;
     constexpr int NW = DF_CTA_THREADS / 32;
+    constexpr bool BX = BULK >= 1 && !EXC;                         // x tile by bulk copy
+    constexpr bool BW = BULK == 2;                                 // tap window by bulk copy
+    constexpr bool SKEW = !BX;                                     // layout of the fast tiles' x / y buffer
+    auto XQ = [](unsigned q) { return SKEW ? ch_qpos(q) : q; };
     __shared__ ChainWarpSmem<SPT> s_all[NW];
     const unsigned wl = threadIdx.x & 31, wi = threadIdx.x >> 5;
     const unsigned lane = blockIdx.x * NW + wi;
@@ -463,29 +509,64 @@ dfcomb_kernel(const float* __restrict__ coef, const float* __restrict__ pw, cons
         const unsigned dq = (Du + sh) >> 2;                                     // window quad of the tile's first sample
         float* wf = reinterpret_cast<float*>(S.w);
         if (wl == 0) S.c = make_float4(x1c, x2c, y1c, y2c);
-        if (!EXC) {
+        if (BX || BW) {
+            if (wl == 0) {
+                mbar_init(&S.bar_x[0], 1); mbar_init(&S.bar_x[1], 1); mbar_init(&S.bar_w, 1);
+                asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+                if (BW) fence_proxy_async();                        // the slow tiles above wrote these buffers and the ring
+                else fence_proxy_async_smem();
+                if (BX) {
+                    mbar_expect_tx(&S.bar_x[0], CH_TILE * 4u);
+                    bulk_ring_g2s(reinterpret_cast<float*>(S.x[0]), xin.data, xb, xm, CH_TILE, &S.bar_x[0]);
+                }
+            }
+            __syncwarp();
+        }
+        if (!BX && !EXC) {
 #pragma unroll
             for (int c = 0; c < CH_TQ / 32; c++)
                 cp_async16(&S.x[0][ch_qpos(32u * c + wl)], xin.data + ((xb + 128u * c + 4u * wl) & xm));
         }
-        cp_async_commit();
+        if (!BX) cp_async_commit();                                 // group "x of tile 0" (empty with EXC)
         for (unsigned long long k = 0; k < n_fast; k++) {
             const unsigned cur = (unsigned)k & 1u;
             float4* xs = S.x[cur];
-#pragma unroll
-            for (int c = 0; c < CH_TQ / 32; c++)
-                cp_async16(&S.w[32u * c + wl], zout.data + ((qb + 128u * c + 4u * wl) & zm));
-            if (wl == 0) cp_async16(&S.w[CH_TQ], zout.data + ((qb + (unsigned)CH_TILE) & zm));
-            cp_async_commit();                                      // group "taps of tile k"
-            xb = (xb + CH_TILE) & xm;
-            if (!EXC && k + 1 < n_fast) {
+            // ---- taps of tile k
+            if (!BW) {
 #pragma unroll
                 for (int c = 0; c < CH_TQ / 32; c++)
-                    cp_async16(&S.x[cur ^ 1][ch_qpos(32u * c + wl)], xin.data + ((xb + 128u * c + 4u * wl) & xm));
+                    cp_async16(&S.w[32u * c + wl], zout.data + ((qb + 128u * c + 4u * wl) & zm));
+                if (wl == 0) cp_async16(&S.w[CH_TQ], zout.data + ((qb + (unsigned)CH_TILE) & zm));
+                cp_async_commit();                                  // group "taps of tile k"
             }
-            cp_async_commit();                                      // group "x of tile k + 1" (possibly empty)
-            if (!EXC) {
-                cp_async_wait<2>();                                 // x of tile k has landed (every lane's share of it)
+            // ---- x of tile k + 1
+            xb = (xb + CH_TILE) & xm;
+            if (BX || BW) {
+                if (wl == 0) {
+                    if (BW) fence_proxy_async();                    // tile k - 1: y / z written by the generic proxy, z stored to the ring
+                    else fence_proxy_async_smem();                  // tile k - 1: y written into the buffer the copy below overwrites
+                    if (BW) {
+                        mbar_expect_tx(&S.bar_w, (CH_TILE + 4) * 4u);
+                        bulk_ring_g2s(wf, zout.data, qb, zm, CH_TILE + 4, &S.bar_w);
+                    }
+                    if (BX && k + 1 < n_fast) {
+                        mbar_expect_tx(&S.bar_x[cur ^ 1], CH_TILE * 4u);
+                        bulk_ring_g2s(reinterpret_cast<float*>(S.x[cur ^ 1]), xin.data, xb, xm, CH_TILE, &S.bar_x[cur ^ 1]);
+                    }
+                }
+            }
+            if (!BX) {
+                if (!EXC && k + 1 < n_fast) {
+#pragma unroll
+                    for (int c = 0; c < CH_TQ / 32; c++)
+                        cp_async16(&S.x[cur ^ 1][ch_qpos(32u * c + wl)], xin.data + ((xb + 128u * c + 4u * wl) & xm));
+                }
+                cp_async_commit();                                  // group "x of tile k + 1" (possibly empty)
+            }
+            // ---- x of tile k has landed
+            if (BX) mbar_wait(&S.bar_x[cur], (unsigned)(k >> 1) & 1u);
+            else if (!EXC) {
+                if (BW) cp_async_wait<1>(); else cp_async_wait<2>();   // groups still allowed in flight: x of k + 1 (and the taps of k)
                 __syncwarp();
             }
             {
@@ -505,11 +586,11 @@ dfcomb_kernel(const float* __restrict__ coef, const float* __restrict__ pw, cons
                 } else {
 #pragma unroll
                     for (int jq = 0; jq < CH_TPQ; jq++) {
-                        const float4 v = xs[ch_qpos(CH_TPQ * wl + jq)];
+                        const float4 v = xs[XQ(CH_TPQ * wl + jq)];
                         x[2 + 4 * jq] = v.x; x[3 + 4 * jq] = v.y; x[4 + 4 * jq] = v.z; x[5 + 4 * jq] = v.w;
                     }
                     // history (x[t0-2], x[t0-1]) = the quad before this thread's own; lane 0 reads the carry instead
-                    const float2 vh = reinterpret_cast<const float2*>(xs + ch_qpos(wl ? CH_TPQ * wl - 1u : 0u))[1];
+                    const float2 vh = reinterpret_cast<const float2*>(xs + XQ(wl ? CH_TPQ * wl - 1u : 0u))[1];
                     x[0] = wl ? vh.x : cr.y;
                     x[1] = wl ? vh.y : cr.x;
                 }
@@ -522,16 +603,18 @@ dfcomb_kernel(const float* __restrict__ coef, const float* __restrict__ pw, cons
                 }
 #pragma unroll
                 for (int jq = 0; jq < CH_TPQ; jq++)
-                    xs[ch_qpos(CH_TPQ * wl + jq)] = make_float4(yv[4 * jq], yv[4 * jq + 1], yv[4 * jq + 2], yv[4 * jq + 3]);
+                    xs[XQ(CH_TPQ * wl + jq)] = make_float4(yv[4 * jq], yv[4 * jq + 1], yv[4 * jq + 2], yv[4 * jq + 3]);
             }
-            cp_async_wait<1>();                                     // the taps have landed
+            if (BW) mbar_wait(&S.bar_w, (unsigned)k & 1u);          // the taps have landed
+            else if (BX) cp_async_wait<0>();                        // (the only cp.async group of the tile)
+            else cp_async_wait<1>();
             __syncwarp();                                           // ... and y is where the coalesced mapping finds it
             if (Du >= 128u) {                                       // warp-uniform
                 const bool inside = Du < (unsigned)CH_TILE;         // some taps are outputs of this very tile
 #pragma unroll
                 for (int c = 0; c < CH_TQ / 32; c++) {
                     const unsigned q = 32u * c + wl;
-                    const float4 t0 = S.w[q], y = xs[ch_qpos(q)];
+                    const float4 t0 = S.w[q], y = xs[XQ(q)];
                     float4 t1 = t0;
                     if (sh) t1 = S.w[q + 1];
                     float4 z;
@@ -548,9 +631,9 @@ dfcomb_kernel(const float* __restrict__ coef, const float* __restrict__ pw, cons
                     }
                 }
             } else if (Du >= 64u) {
-                comb_small<CH_TILE, 2>(reinterpret_cast<const float*>(xs), wf, zout.data, zb, zm, Du, sh, g, wl);
+                comb_small<CH_TILE, 2, SKEW>(reinterpret_cast<const float*>(xs), wf, zout.data, zb, zm, Du, sh, g, wl);
             } else {
-                comb_small<CH_TILE, 1>(reinterpret_cast<const float*>(xs), wf, zout.data, zb, zm, Du, sh, g, wl);
+                comb_small<CH_TILE, 1, SKEW>(reinterpret_cast<const float*>(xs), wf, zout.data, zb, zm, Du, sh, g, wl);
             }
             __syncwarp();                                           // the next tile's taps read these stores
             qb += CH_TILE; zb += CH_TILE;
@@ -582,12 +665,21 @@ cudaError_t launch_dfcomb(const DirectFormDev& df, const FbDelayDev& fb, ChainSt
     if (lo != 0 && lo != st.time) return cudaErrorInvalidValue;    // the renderer restarts recurrences at t = 0 or continues
     const unsigned per_cta = DF_CTA_THREADS / 32;
     const unsigned grid = (df.n_lanes + per_cta - 1) / per_cta;
-    if (exciter)
-        dfcomb_kernel<true><<<grid, DF_CTA_THREADS, 0, stream>>>(df.d_coef, df.d_pow, fb.d_delay, fb.d_gain, d_bufdesc, nullptr,
-                                                                 first_out_buf, st.d_state, df.n_lanes, lo, hi, *exciter, d_exc_voice);
-    else
-        dfcomb_kernel<false><<<grid, DF_CTA_THREADS, 0, stream>>>(df.d_coef, df.d_pow, fb.d_delay, fb.d_gain, d_bufdesc, d_in_bufs,
-                                                                  first_out_buf, st.d_state, df.n_lanes, lo, hi, OscOneSrc{}, nullptr);
+    // measurement knob: FRB_K4_BULK=0 / 1 selects the cp.async (LDGSTS) / bulk-copy (UBLKCP + mbarrier) instance
+    static const int bulk_env = [] { const char* e = getenv("FRB_K4_BULK"); return e ? atoi(e) : -1; }();
+    const int bulk = bulk_env < 0 ? kChainBulkDefault : bulk_env;
+    auto go = [&](auto kernel, const uint32_t* in_bufs, const OscOneSrc& ex, const uint32_t* ev) {
+        kernel<<<grid, DF_CTA_THREADS, 0, stream>>>(df.d_coef, df.d_pow, fb.d_delay, fb.d_gain, d_bufdesc, in_bufs, first_out_buf,
+                                                    st.d_state, df.n_lanes, lo, hi, ex, ev);
+    };
+    if (exciter) {
+        if (bulk == 2) go(dfcomb_kernel<true, 2>, nullptr, *exciter, d_exc_voice);
+        else go(dfcomb_kernel<true, 0>, nullptr, *exciter, d_exc_voice);        // no x tile to copy: 1 == 0
+    } else {
+        if (bulk == 2) go(dfcomb_kernel<false, 2>, d_in_bufs, OscOneSrc{}, nullptr);
+        else if (bulk == 1) go(dfcomb_kernel<false, 1>, d_in_bufs, OscOneSrc{}, nullptr);
+        else go(dfcomb_kernel<false, 0>, d_in_bufs, OscOneSrc{}, nullptr);
+    }
     st.time = hi;
     if (n_launches) *n_launches = 1;
     return cudaGetLastError();
