@@ -164,6 +164,17 @@ def extra_configs(peak_fma, hbm_gbs):
     except Exception as e:      # pragma: no cover
         ex["cfg1"] = {"error": repr(e)}
     try:
+        # the same graph and call pattern from plain C (tools/microbench/cfg1_latency.c, built by __graft_entry__.build()):
+        # what one frb_fill_buffer call costs without a Python binding in the way
+        import subprocess
+        exe = os.path.join(ROOT, "build", "bin", "cfg1_latency")
+        r = subprocess.run([exe, "512", "2000"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+        c = json.loads(r.stdout.strip().splitlines()[-1])
+        ex["cfg1"]["c_abi"] = {"us_per_512_sample_call_median": c["us_per_call_median"], "us_p10": c["us_p10"], "us_p90": c["us_p90"],
+                               "realtime_factor": c["realtime_factor"], "calls": c["calls"], "program": "tools/microbench/cfg1_latency.c"}
+    except Exception as e:      # pragma: no cover
+        ex.setdefault("cfg1", {})["c_abi"] = {"error": repr(e)}
+    try:
         c = case_cfg2()
         ps = 1024 * 480000
         ex["cfg2"] = {"workload": "1,024 harmonic partials x 1 voice, 48 kHz x 10 s, device resident", "ms": c["ms"], "osc_ms": c["osc_ms"],

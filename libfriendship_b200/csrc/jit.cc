@@ -47,6 +47,7 @@ struct Api {
     CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*);
     CUresult (*ModuleUnload)(CUmodule);
     CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**);
+    CUresult (*OccupancyMaxActiveBlocks)(int*, CUfunction, int, size_t);
 };
 
 template <typename T>
@@ -75,7 +76,8 @@ Api& api(bool need_driver) {
             void* lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_LOCAL);
             if (!lib) { a.why = "libcuda.so.1 not found"; return; }
             drv_ok = sym(lib, "cuModuleLoadData", &a.ModuleLoadData) && sym(lib, "cuModuleGetFunction", &a.ModuleGetFunction) &&
-                     sym(lib, "cuModuleUnload", &a.ModuleUnload) && sym(lib, "cuLaunchKernel", &a.LaunchKernel);
+                     sym(lib, "cuModuleUnload", &a.ModuleUnload) && sym(lib, "cuLaunchKernel", &a.LaunchKernel) &&
+                     sym(lib, "cuOccupancyMaxActiveBlocksPerMultiprocessor", &a.OccupancyMaxActiveBlocks);
             if (!drv_ok) a.why = "driver API symbols missing";
         });
     }
@@ -536,6 +538,7 @@ struct JitKernel {
     CUfunction fn = nullptr;
     unsigned* d_tab = nullptr;      // operand table (device)
     unsigned groups_per_thread = 1;
+    int ctas_per_sm = 16;           // resident 128-thread CTAs per SM (register-limited): sizes the grid to ONE wave
 };
 
 JitKernel* jit_build(const Stage& st, std::string* err) {
@@ -556,6 +559,8 @@ JitKernel* jit_load(const std::string& cubin, const std::vector<uint32_t>& table
         if (err) *err = "cuModuleLoadData failed";
         return nullptr;
     }
+    int occ = 0;
+    if (a.OccupancyMaxActiveBlocks(&occ, k->fn, 128, 0) == CUDA_SUCCESS && occ > 0) k->ctas_per_sm = std::min(occ, 16);
     const size_t bytes = std::max<size_t>(table.size(), 1) * sizeof(uint32_t);
     if (cudaMalloc(&k->d_tab, bytes) != cudaSuccess ||
         (!table.empty() && cudaMemcpy(k->d_tab, table.data(), table.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess)) {
@@ -580,7 +585,9 @@ bool jit_launch(JitKernel* k, const InterpParams& p, int sm_count, cudaStream_t 
     if (p.n_groups == 0) return true;
     const unsigned long long per_block = 128ull * k->groups_per_thread;          // every thread gets its two groups when the body walks two
     unsigned long long blocks = (p.n_groups + per_block - 1) / per_block;
-    unsigned long long cap = (unsigned long long)sm_count * 16 / p.n_strands;   // rounded down: never a second wave of a few CTAs
+    // one resident wave, rounded down: never a second wave of a few CTAs (the kernel's register count decides how many
+    // CTAs an SM holds: 16 at 32 registers, 10 at 48)
+    unsigned long long cap = (unsigned long long)sm_count * (unsigned)k->ctas_per_sm / p.n_strands;
     if (cap < 1) cap = 1;
     if (blocks > cap) blocks = cap;
     InterpParams pp = p;

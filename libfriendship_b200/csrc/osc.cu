@@ -70,12 +70,18 @@ struct OscBankDev {
     uint32_t voice_cap = 0;
     char* d_raw = nullptr;          // definition-time scratch (raw parameters, ranks); kept only by a re-defined bank
     size_t raw_cap = 0;
-    mutable float* d_planes = nullptr; // scratch for split > 1: [split][n_voices][plane_len]
-    mutable uint64_t planes_cap = 0;
+    mutable float* d_planes = nullptr; // scratch for split > 1: TWO buffers [split][n_voices][plane_len] (see launch_osc)
+    mutable uint64_t planes_cap = 0;   // floats per buffer
+    // The plane reduce of sub-block k runs on its own stream beside the main kernel of sub-block k + 1 (launch_osc):
+    mutable cudaStream_t red = nullptr;
+    mutable cudaEvent_t ev_main[2] = {nullptr, nullptr}, ev_red[2] = {nullptr, nullptr};
+    mutable bool red_pending[2] = {false, false};
     mutable cudaStream_t side = nullptr;   // the (tiny, slow) attack-ramp kernel runs beside the main kernel
     mutable cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     ~OscBankDev() {
         if (side) cudaStreamDestroy(side);
+        if (red) cudaStreamDestroy(red);
+        for (int i = 0; i < 2; i++) { if (ev_main[i]) cudaEventDestroy(ev_main[i]); if (ev_red[i]) cudaEventDestroy(ev_red[i]); }
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_join) cudaEventDestroy(ev_join);
         cudaFree(d_hot); cudaFree(d_anc); cudaFree(d_ph);
@@ -90,6 +96,8 @@ struct OscBankDev {
         mv(d_raw, src.d_raw); mv(raw_cap, src.raw_cap);
         mv(d_planes, src.d_planes); mv(planes_cap, src.planes_cap);
         mv(side, src.side); mv(ev_fork, src.ev_fork); mv(ev_join, src.ev_join);
+        mv(red, src.red);
+        for (int i = 0; i < 2; i++) { mv(ev_main[i], src.ev_main[i]); mv(ev_red[i], src.ev_red[i]); red_pending[i] = false; }
     }
 };
 
@@ -694,7 +702,8 @@ __global__ void osc_reduce_kernel(OscLaunch p) {
 }
 
 static cudaError_t launch_osc_range(const OscBankDev& b, const BufferDesc* d_bufdesc, uint32_t first_buf, uint64_t lo, uint64_t hi,
-                                    uint32_t anchor, int sm_count, cudaStream_t stream, uint64_t* n_launches);
+                                    uint32_t anchor, int sm_count, cudaStream_t stream, uint64_t* n_launches, unsigned which = 0,
+                                    bool overlap_reduce = false);
 
 // per device, called when a renderer is created on it: the accumulator columns need up to 32 KB of dynamic shared memory
 cudaError_t osc_init_device() {
@@ -717,17 +726,35 @@ cudaError_t launch_osc(const OscBankDev& b, const BufferDesc* d_bufdesc, uint32_
     // ... in sub-blocks whose planes stay under 1 GiB (at least 64 Ki samples)
     uint64_t sub = 1ull << 20;
     while (sub > (1ull << 16) && sub * b.split * b.n_voices > (1ull << 28)) sub >>= 1;
-    for (uint64_t c0 = lo; c0 < hi;) {
+    // The plane reduce is HBM-bound (it reads split x voices x samples x 4 B) and the main kernel FMA-bound, so the reduce
+    // of sub-block k runs on a stream of its own BESIDE the main kernel of sub-block k + 1, the two alternating between two
+    // plane buffers: only the last sub-block's reduce is left on the critical path (8 voices per GPU, split 128: 0.35 ms of
+    // reduce per 31 ms step were all exposed before — the whole of the 8-GPU scaling loss, profiles/r2f_timeline_n8.json).
+    static const bool overlap_env = [] { const char* e = getenv("FRB_OSC_REDUCE_OVERLAP"); return !e || e[0] != '0'; }();   // measurement knob
+    const bool overlap = overlap_env && (lo / sub != (hi - 1) / sub);     // a single sub-block has nothing to overlap with
+    if (overlap && !b.red) {
+        cudaError_t e = cudaStreamCreateWithFlags(&b.red, cudaStreamNonBlocking);
+        for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+            e = cudaEventCreateWithFlags(&b.ev_main[i], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b.ev_red[i], cudaEventDisableTiming);
+        }
+        if (e != cudaSuccess) return e;
+    }
+    unsigned k = 0;
+    for (uint64_t c0 = lo; c0 < hi; k++) {
         const uint64_t c1 = std::min(hi, (c0 / sub + 1) * sub);
-        cudaError_t e = launch_osc_range(b, d_bufdesc, first_buf, c0, c1, anchor, sm_count, stream, n_launches);
+        cudaError_t e = launch_osc_range(b, d_bufdesc, first_buf, c0, c1, anchor, sm_count, stream, n_launches, k & 1u, overlap);
         if (e != cudaSuccess) return e;
         c0 = c1;
     }
-    return cudaSuccess;
+    for (int i = 0; i < 2; i++)                                   // the rings are complete when both reduce chains are
+        if (b.red_pending[i]) { cudaStreamWaitEvent(stream, b.ev_red[i], 0); b.red_pending[i] = false; }
+    return cudaGetLastError();
 }
 
 static cudaError_t launch_osc_range(const OscBankDev& b, const BufferDesc* d_bufdesc, uint32_t first_buf, uint64_t lo, uint64_t hi,
-                                    uint32_t anchor, int sm_count, cudaStream_t stream, uint64_t* n_launches) {
+                                    uint32_t anchor, int sm_count, cudaStream_t stream, uint64_t* n_launches, unsigned which,
+                                    bool overlap_reduce) {
     OscOneSrc one;
     if (osc_one_source(b, &one)) {                           // one-partial voices: their own kernel, anchors every 8 samples
         const uint64_t span0 = lo / ONE_SPAN, n_span = (hi + ONE_SPAN - 1) / ONE_SPAN - span0;
@@ -754,12 +781,18 @@ static cudaError_t launch_osc_range(const OscBankDev& b, const BufferDesc* d_buf
     if (p.split > 1) {
         uint64_t need = (uint64_t)p.split * b.n_voices * p.plane_len;
         if (need > b.planes_cap) {
-            if (b.d_planes) { cudaStreamSynchronize(stream); cudaFree(b.d_planes); b.d_planes = nullptr; }
-            cudaError_t e = cudaMalloc(&b.d_planes, need * sizeof(float));
+            if (b.d_planes) {
+                cudaStreamSynchronize(stream);
+                if (b.red) cudaStreamSynchronize(b.red);
+                cudaFree(b.d_planes); b.d_planes = nullptr; b.planes_cap = 0;
+            }
+            cudaError_t e = cudaMalloc(&b.d_planes, 2 * need * sizeof(float));
             if (e != cudaSuccess) return e;
             b.planes_cap = need;
         }
-        p.planes = b.d_planes;
+        p.planes = b.d_planes + (size_t)which * b.planes_cap;
+        // this buffer was last read by the reduce of two sub-blocks ago
+        if (overlap_reduce && b.red_pending[which]) { cudaStreamWaitEvent(stream, b.ev_red[which], 0); b.red_pending[which] = false; }
     }
     const unsigned threads = OSC_THREADS;
     // L/4 rows of float4 columns: threads + 1 of them for the small-voice kernels (odd stride), threads for K = 16
@@ -828,9 +861,16 @@ static cudaError_t launch_osc_range(const OscBankDev& b, const BufferDesc* d_buf
     if (p.split > 1) {
         unsigned long long n4 = p.plane_len / 4;
         unsigned bx = (unsigned)std::min<unsigned long long>((n4 + 255) / 256, (unsigned long long)sm_count * 4);
-        osc_reduce_kernel<<<dim3(bx, b.n_voices), 256, 0, stream>>>(p);
+        cudaStream_t rs = stream;
+        if (overlap_reduce) {                                        // beside the next sub-block's main kernel
+            cudaEventRecord(b.ev_main[which], stream);
+            cudaStreamWaitEvent(b.red, b.ev_main[which], 0);
+            rs = b.red;
+        }
+        osc_reduce_kernel<<<dim3(bx, b.n_voices), 256, 0, rs>>>(p);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
+        if (overlap_reduce) { cudaEventRecord(b.ev_red[which], b.red); b.red_pending[which] = true; }
         if (n_launches) (*n_launches)++;
     }
     return cudaSuccess;

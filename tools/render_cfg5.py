@@ -63,9 +63,31 @@ def main():
     if world > 1:
         dist.barrier()
     dt = time.perf_counter() - t0
+    parity = None
+    if rank == 0 and os.environ.get("CFG5_CHECK", "1") != "0":
+        # the rendered file against the fp64 oracle evaluated on the FULL bank (every voice, every partial, both delay
+        # taps) in three short windows: the start, past the last voice's delay tap, and the last samples at t ~ 11.5 M,
+        # where an oscillator that accumulated its phase in f32 would be off by a radian
+        from oracle.binding import OracleRenderer
+        from workloads.banks import full_scale
+        tc = time.perf_counter()
+        full, fids = detuned_bank(n_voices, N_PARTIALS, sr=SR, seed=2)
+        orc = OracleRenderer(ext_mode="fp64")
+        build_voice_mix_graph(orc, full, fids)
+        orc.fill_buffer(1, 0, 0)
+        fs = full_scale(full) * n_voices * 1.3
+        nthr = os.cpu_count() or 1
+        width = int(os.environ.get("CFG5_CHECK_WIDTH", 4))
+        wins = [0, 4800 + 37 * (n_voices - 1) + 1, n_samples - width]
+        worst = 0.0
+        for s0 in wins:
+            want, _ = orc.fill_buffer_mt(1, width, s0, nthr)
+            worst = max(worst, float(np.abs(out[0, s0:s0 + width].astype(np.float64) - want[0].astype(np.float64)).max()) / fs)
+        parity = {"max_err_of_full_scale": worst, "tol": 1e-5, "ok": bool(worst <= 1e-5), "windows": [[int(w), width] for w in wins],
+                  "full_scale": fs, "oracle": "fp64, full bank %d x %d, %d host threads, %.1f s" % (n_voices, N_PARTIALS, nthr, time.perf_counter() - tc)}
     if rank == 0:
         ps = n_voices * N_PARTIALS * n_samples
-        print(json.dumps({
+        print(json.dumps({"parity": parity,
             "workload": "cfg5: 2^20 partials x %d voices, 192 kHz x %.1f s (BASELINE.json configs[4])" % (n_voices, n_samples / SR),
             "n_gpus": world, "render_s": dt, "setup_s": t_setup, "partial_samples": ps, "partial_samples_per_s": ps / dt,
             "realtime_factor": (n_samples / SR) / dt, "out_bytes": int(out.nbytes), "block": block,
