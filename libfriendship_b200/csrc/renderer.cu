@@ -825,23 +825,24 @@ void Renderer::fill(float* out, bool out_on_device, uint32_t n_slots, uint64_t n
         // (input_desc, interp_device.inc) — the graph may name any u32 slot, the table stays as small as the history
         const uint32_t nin = (uint32_t)std::min<uint64_t>(sched_.n_input_slots, inputs_.size());
         n_indesc_ = nin;
-        if (nin) {
-            std::vector<InputDesc> h(nin);
+        {
+            std::vector<InputDesc> h((size_t)nin + 1);             // + the null entry every non-existent slot is clamped to
+            h[nin] = InputDesc{nullptr, 0, 0};
             for (uint32_t s = 0; s < nin; s++) {
                 if (s < inputs_.size() && inputs_[s].d_data) h[s] = InputDesc{inputs_[s].d_data, inputs_[s].base, inputs_[s].end};
                 else h[s] = InputDesc{nullptr, 0, 0};
             }
-            if (d_indesc_cap_ < nin) {
+            if (d_indesc_cap_ < (size_t)nin + 1) {
                 if (d_indesc_) { CU(cudaStreamSynchronize(stream_)); CU(cudaFree(d_indesc_)); }
-                d_indesc_cap_ = std::max<size_t>(nin * 2, 16);
+                d_indesc_cap_ = std::max<size_t>(((size_t)nin + 1) * 2, 16);
                 CU(cudaMalloc(&d_indesc_, d_indesc_cap_ * sizeof(InputDesc)));
                 h_indesc_.clear();
             }
             // the table is re-uploaded only when it changed — when streaming, every call (the history's end moves) —
             // from one of two pinned buffers: asynchronous, no wait on the stream
-            if (h_indesc_.size() != nin || memcmp(h_indesc_.data(), h.data(), nin * sizeof(InputDesc)) != 0) {
+            if (h_indesc_.size() != h.size() || memcmp(h_indesc_.data(), h.data(), h.size() * sizeof(InputDesc)) != 0) {
                 h_indesc_ = h;
-                if (h_pin_indesc_cap_ < nin) {
+                if (h_pin_indesc_cap_ < h.size()) {
                     CU(cudaStreamSynchronize(stream_));
                     for (int i = 0; i < 2; i++) {
                         if (h_pin_indesc_[i]) CU(cudaFreeHost(h_pin_indesc_[i]));
@@ -853,8 +854,8 @@ void Renderer::fill(float* out, bool out_on_device, uint32_t n_slots, uint64_t n
                 }
                 const unsigned b = pin_indesc_next_++ & 1u;
                 CU(cudaEventSynchronize(ev_indesc_[b]));                   // the copy that last read this buffer (two uploads ago)
-                memcpy(h_pin_indesc_[b], h.data(), nin * sizeof(InputDesc));
-                CU(cudaMemcpyAsync(d_indesc_, h_pin_indesc_[b], nin * sizeof(InputDesc), cudaMemcpyHostToDevice, stream_));
+                memcpy(h_pin_indesc_[b], h.data(), h.size() * sizeof(InputDesc));
+                CU(cudaMemcpyAsync(d_indesc_, h_pin_indesc_[b], h.size() * sizeof(InputDesc), cudaMemcpyHostToDevice, stream_));
                 CU(cudaEventRecord(ev_indesc_[b], stream_));
             }
         }

@@ -88,3 +88,53 @@ def test_more_devices_than_the_box_has_is_refused():
     from libfriendship_b200 import B200Renderer, RendererError
     with pytest.raises(RendererError):
         B200Renderer(n_devices=64)
+
+
+@needs2
+def test_external_inputs_reach_every_device_and_streaming_matches():
+    """Lanes multiplied by an external envelope (linear in the lanes: shardable), the envelope also read through a Delay:
+    the caller's input rows must reach every device's history, over ragged consecutive calls, and frb_render_stream on
+    several devices must deliver the same blocks as the fill_buffer calls it stands for."""
+    from libfriendship_b200 import B200Renderer, KIND_DELAY, KIND_MULTIPLY, KIND_OSCBANK, KIND_SUM2
+    from workloads.banks import detuned_bank, full_scale
+    from workloads.graphs import GraphBuilder
+    bank, ids = detuned_bank(6, 300)
+
+    def build(r):
+        r.define_oscbank(7, **bank)
+        g = GraphBuilder(r)
+        r.on_add_node(100, KIND_OSCBANK, 7)
+        env_late = g.node(KIND_DELAY, g.input(0), g.const(37.0))
+        total = None
+        for v in range(6):
+            voice = g.node(KIND_MULTIPLY, (100, v), g.input(0) if v % 2 else env_late)
+            total = voice if total is None else g.node(KIND_SUM2, total, voice)
+        g.output(0, total)
+        g.output(1, g.node(KIND_MULTIPLY, (100, 3), g.const(0.25)))
+
+    one, many, strm = B200Renderer(), B200Renderer(n_devices=2), B200Renderer(n_devices=2)
+    for r in (one, many, strm):
+        build(r)
+    assert many.lane_use(2) == 0
+    rng = np.random.RandomState(3)
+    env = np.abs(rng.randn(6000)).astype(np.float32)
+    fs = full_scale(bank) * 6 * float(env.max())
+    outs = {id(one): [], id(many): []}
+    for idx, n in ((0, 2500), (2500, 1501), (4001, 1999)):
+        row = env[idx:idx + n - (7 if idx else 0)]              # ragged: padded with its last value (reference.rs:72-73)
+        for r in (one, many):
+            outs[id(r)].append(r.fill_buffer(2, n, idx, [row]))
+    a, b = np.concatenate(outs[id(one)], axis=1), np.concatenate(outs[id(many)], axis=1)
+    assert float(np.abs(a.astype(np.float64) - b).max()) <= 4e-7 * fs
+    assert float(np.abs(a).max()) > 1e-3 * fs
+    # streaming: three blocks of 2,000 with the same (unragged) envelope
+    want = B200Renderer(n_devices=2)
+    build(want)
+    w = np.concatenate([want.fill_buffer(2, 2000, k * 2000, [env[k * 2000:(k + 1) * 2000]]) for k in range(3)], axis=1)
+    got = np.zeros_like(w)
+
+    def sink(blk, t):
+        got[:, t:t + blk.shape[1]] = blk
+
+    strm.render_stream(2, 0, 6000, 2000, sink, n_in_rows=1, source=lambda t, n: env[None, t:t + n])
+    assert np.array_equal(got.view(np.uint32), w.view(np.uint32))
