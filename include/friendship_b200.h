@@ -218,11 +218,12 @@ int64_t frb_jit_cubin_size(frb_renderer* r, uint32_t n_slots, uint32_t stage);
 /* Statements the compiler sees for that stage.  Runs of like instruction groups in a stage program (the terms of a
  * Sum2 chain, the voices of a mix) are compiled as loops whose trip counts and operands come from a device table, so
  * this is a measure of the program's STRUCTURE, not of its length: a 9,000-node chain is 11.  NVRTC's time grows faster
- * than linearly in it (100: 1 s, 200: 2 s, 400: 8 s), so a stage above FRB_JIT_MAX_CODE is never compiled (interpreted
- * for good), and one above FRB_JIT_MAX_SYNC_CODE is compiled beside the render loop — the interpreter serving meanwhile
- * — rather than on the render thread (unless FRB_FLAG_JIT_EAGER asks for that). */
+ * than linearly in one straight body (100: 1 s, 200: 2 s, 400: 8 s), so a long APERIODIC program is cut into chunk functions
+ * of 64 statements (400: 2 s, 1,000: 6 s, 2,000: 16 s); a stage above FRB_JIT_MAX_CODE is never compiled (interpreted for
+ * good), and one above FRB_JIT_MAX_SYNC_CODE is compiled beside the render loop — the interpreter serving meanwhile —
+ * rather than on the render thread (unless FRB_FLAG_JIT_EAGER asks for that). */
 #define FRB_JIT_MAX_SYNC_CODE 128
-#define FRB_JIT_MAX_CODE 512
+#define FRB_JIT_MAX_CODE 4096
 int64_t frb_jit_code_instructions(frb_renderer* r, uint32_t n_slots, uint32_t stage);
 
 /* Counters since creation: kernel launches, bytes H2D, bytes D2H. */

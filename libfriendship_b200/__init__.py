@@ -152,7 +152,7 @@ class B200Renderer(_cabi.CRendererBase):
 
     def jit_code_instructions(self, n_slots, stage):
         """Statements the compiled stage would hold (loops over repeated groups count once per unrolled copy, one body
-        per distinct strand structure); the renderer compiles a stage only up to FRB_JIT_MAX_CODE = 512 of them."""
+        per distinct strand structure); the renderer compiles a stage only up to FRB_JIT_MAX_CODE = 4096 of them."""
         n = _lib.frb_jit_code_instructions(self._h, n_slots, stage)
         if n < 0:
             self._check(int(n))

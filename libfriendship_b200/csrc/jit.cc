@@ -22,6 +22,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <set>
 #include <sstream>
 #include <thread>
 
@@ -223,6 +224,7 @@ unsigned unroll_of(const Node& loop) {
     const size_t n = std::max<size_t>(count_leaves(loop.iters[0]), 1);
     return (unsigned)std::max<size_t>(1, std::min<size_t>(8, 32 / n));
 }
+size_t code_size_node(const Stage& st, const Node& nd, int W);
 bool is_pure_load(const Instr& in) {
     const uint32_t op = in.w0 & 0xFFu;
     return op == I_LDIN || op == I_LDBUF || op == I_TAP_IN || op == I_TAP_BUF;
@@ -253,6 +255,71 @@ size_t code_size(const Stage& st, const std::vector<Node>& seq, int W) {
         n += (U > 1 ? (U + 1) * body : unroll_of(nd) * body) + 1;         // loads-first form: U copies + the remainder loop
     }
     return n;
+}
+
+// Registers a node reads and writes (a loop: everything its body does, none of it killing — conservative)
+void node_regs(const Stage& st, const Node& nd, std::set<uint32_t>* use, std::set<uint32_t>* def) {
+    if (nd.loop) { for (const Node& b : nd.iters[0]) node_regs(st, b, use, def); return; }
+    const Instr& in = st.program[nd.instr];
+    const uint32_t op = in.w0 & 0xFFu, flags = (in.w0 >> 8) & 0xFFu;
+    if (reads_a_reg(op, flags)) use->insert(in.a);
+    if (reads_b_reg(op, flags)) use->insert(in.b);
+    if (op != I_STBUF && op != I_STOUT) def->insert(in.w0 >> 16);
+}
+
+// A long APERIODIC program (what is left after folding is still hundreds of statements) is cut into chunks that become
+// __noinline__ device functions: the compiler sees a few dozen statements at a time, so NVRTC's time is linear in the
+// program instead of superlinear (400 straight-line statements: 8 s; in chunks of 64: 2.5 s).  Registers that live across
+// a cut travel through a per-thread array in local memory: a chunk loads the ones it reads before writing and stores the
+// ones it wrote that somebody later reads.
+constexpr size_t kInlineMax = 160;      // statements a shape may have as one straight body
+constexpr size_t kChunk = 64;           // statements per chunk function
+
+struct Chunk {
+    size_t first, count;                // top-level nodes [first, first + count)
+    std::set<uint32_t> regs, live_in, store;
+};
+
+std::vector<Chunk> make_chunks(const Stage& st, const std::vector<Node>& code, int W) {
+    std::vector<Chunk> cs;
+    size_t i = 0;
+    while (i < code.size()) {
+        Chunk c{i, 0, {}, {}, {}};
+        size_t sz = 0;
+        while (i < code.size()) {
+            const size_t n = code[i].loop ? code_size_node(st, code[i], W) : 1;
+            if (c.count && sz + n > kChunk) break;
+            sz += n; c.count++; i++;
+        }
+        cs.push_back(std::move(c));
+    }
+    // per chunk: registers read before any (killing) write in the chunk, registers written
+    std::vector<std::set<uint32_t>> use(cs.size()), kill(cs.size()), def(cs.size());
+    for (size_t k = 0; k < cs.size(); k++) {
+        for (size_t j = cs[k].first; j < cs[k].first + cs[k].count; j++) {
+            std::set<uint32_t> u, d;
+            node_regs(st, code[j], &u, &d);
+            for (uint32_t r : u) { cs[k].regs.insert(r); if (!kill[k].count(r)) use[k].insert(r); }
+            for (uint32_t r : d) { cs[k].regs.insert(r); def[k].insert(r); if (!code[j].loop) kill[k].insert(r); }
+        }
+    }
+    std::set<uint32_t> live;
+    for (size_t k = cs.size(); k-- > 0;) {
+        for (uint32_t r : def[k]) if (live.count(r)) cs[k].store.insert(r);
+        for (uint32_t r : kill[k]) live.erase(r);
+        for (uint32_t r : use[k]) live.insert(r);
+        cs[k].live_in = use[k];
+    }
+    return cs;
+}
+
+size_t code_size_node(const Stage& st, const Node& nd, int W) {
+    std::vector<Node> one;
+    Node c;
+    c.loop = nd.loop; c.instr = nd.instr; c.sym = nd.sym;
+    if (nd.loop) c.iters.push_back(nd.iters[0]);
+    one.push_back(std::move(c));
+    return code_size(st, one, W);
 }
 
 struct Emitter {
@@ -321,10 +388,12 @@ struct Emitter {
         }
     }
 
+    void seq(const std::vector<Node>& nodes, const std::string& cur, const std::string& ind) { seq(nodes, 0, nodes.size(), cur, ind); }
     // `cur` is the operand cursor (a `const unsigned*` variable); on return it has been advanced past everything seq read
-    void seq(const std::vector<Node>& nodes, const std::string& cur, const std::string& ind) {
+    void seq(const std::vector<Node>& nodes, size_t first, size_t count, const std::string& cur, const std::string& ind) {
         size_t off = 0;
-        for (const Node& nd : nodes) {
+        for (size_t ni = first; ni < first + count; ni++) {
+            const Node& nd = nodes[ni];
             if (!nd.loop) { leaf(st.program[nd.instr], cur, &off, ind); continue; }
             const std::string id = std::to_string(next_id++);
             o << ind << "const unsigned n_" << id << " = " << cur << "[" << off << "];\n";
@@ -397,8 +466,8 @@ JitProgram jit_generate(const Stage& st) {
         }
     }
 
-    std::ostringstream o;
-    o << kInterpDeviceSource << "\n";
+    std::ostringstream o, funcs;
+    funcs << kInterpDeviceSource << "\n";
     o << "extern \"C\" __global__ void __launch_bounds__(128) frb_stage(const InterpParams p, const unsigned* __restrict__ tab) {\n";
     o << "  const InputDesc no_in = {nullptr, 0ull, 0ull};\n  const BufferDesc no_buf = {nullptr, 0ull};\n";
     o << "  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);\n";
@@ -408,21 +477,47 @@ JitProgram jit_generate(const Stage& st) {
     o << "  switch (tab[2 * strand]) {\n";
     for (size_t k = 0; k < shapes.size(); k++) {
         const Shape& sh = shapes[k];
-        out.code_instrs += code_size(st, sh.code, sh.nreg <= 6 ? 4 : 2);
-        if (k == 0 || (sh.nreg <= 6 ? 2u : 1u) < out.groups_per_thread) out.groups_per_thread = sh.nreg <= 6 ? 2u : 1u;
-        o << "  case " << k << ": {\n";
+        const bool chunked = code_size(st, sh.code, 2) > kInlineMax;
         // A stage is a stream and what bounds it is the bytes it keeps in flight: 12 resident CTAs x 128 threads x two
         // 16-byte loads per input are 6 MB on the whole GPU, ~5 TB/s at the loaded DRAM latency (measured: 5.0).  A small
         // program therefore walks TWO groups of 8 samples per iteration (one grid stride apart, so every load instruction
         // still covers 512 contiguous bytes), instruction by instruction, which puts the second group's loads in front of
         // the first group's stores.  Loads never alias this stage's stores (a stage reads what earlier stages wrote).
-        const int W = sh.nreg <= 6 ? 4 : 2;            // float4 columns per thread and iteration
+        const int W = (sh.nreg <= 6 && !chunked) ? 4 : 2;            // float4 columns per thread and iteration
+        out.code_instrs += code_size(st, sh.code, W);
+        if (k == 0 || (W == 4 ? 2u : 1u) < out.groups_per_thread) out.groups_per_thread = W == 4 ? 2u : 1u;
+        o << "  case " << k << ": {\n";
         o << "  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;\n";
         o << "  for (unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; g < p.n_groups; g += " << (W / 2) << "ull * stride) {\n";
         o << "    const unsigned long long t_0 = p.t_begin + 8ull * g, t_1 = t_0 + 4ull;\n";
         if (W == 4) {
             o << "    const bool two = g + stride < p.n_groups;\n";       // the last iteration may have one group only:
             o << "    const unsigned long long t_2 = p.t_begin + 8ull * (two ? g + stride : g), t_3 = t_2 + 4ull;\n";   // it loads the first twice and stores once
+        }
+        if (chunked) {
+            const std::vector<Chunk> cs = make_chunks(st, sh.code, W);
+            o << "    float4 R[" << std::max<uint32_t>(sh.nreg, 1) * 2 << "];\n";
+            o << "    const unsigned* q = row;\n";
+            for (size_t c = 0; c < cs.size(); c++) {
+                const std::string fn = "frb_c" + std::to_string(k) + "_" + std::to_string(c);
+                o << "    " << fn << "(R, p, q, t_0, t_1);\n";
+                funcs << "static __device__ __noinline__ void " << fn << "(float4* __restrict__ R, const InterpParams& p, const unsigned*& qref, "
+                      << "const unsigned long long t_0, const unsigned long long t_1) {\n";
+                funcs << "  const InputDesc no_in = {nullptr, 0ull, 0ull};\n  const BufferDesc no_buf = {nullptr, 0ull};\n";
+                funcs << "  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);\n  (void)no_in; (void)no_buf; (void)z4;\n";
+                funcs << "  const unsigned* q = qref;\n";
+                for (uint32_t r : cs[c].regs) {
+                    funcs << "  float4 " << reg(r, 0) << ", " << reg(r, 1) << ";\n";
+                    if (cs[c].live_in.count(r)) funcs << "  " << reg(r, 0) << " = R[" << 2 * r << "]; " << reg(r, 1) << " = R[" << 2 * r + 1 << "];\n";
+                }
+                Emitter em{st, funcs, W};
+                em.next_id = (int)(1000 * c);
+                em.seq(sh.code, cs[c].first, cs[c].count, "q", "  ");
+                for (uint32_t r : cs[c].store) funcs << "  R[" << 2 * r << "] = " << reg(r, 0) << "; R[" << 2 * r + 1 << "] = " << reg(r, 1) << ";\n";
+                funcs << "  qref = q;\n}\n";
+            }
+            o << "  }\n  } break;\n";
+            continue;
         }
         for (uint32_t r = 0; r < sh.nreg; r++) {
             o << "    float4 " << reg(r, 0);
@@ -435,7 +530,7 @@ JitProgram jit_generate(const Stage& st) {
         o << "  }\n  } break;\n";
     }
     o << "  default: break;\n  }\n}\n";
-    out.source = o.str();
+    out.source = funcs.str() + o.str();
     return out;
 }
 

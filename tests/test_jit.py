@@ -177,3 +177,25 @@ def test_repeated_groups_fold_on_two_levels():
     assert "const float4 h" in body                                                     # inner loop: loads first, then arithmetic
     assert r.jit_code_instructions(1, 0) < 120                                          # ~1,000 instructions in the program
     assert r.jit_cubin_size(1, 0) > 1000
+
+
+def test_long_aperiodic_program_is_cut_into_chunk_functions():
+    """What folding cannot shorten (no repetition) is compiled in __noinline__ chunks of 64 statements with the live
+    registers handed over through local memory: NVRTC's time stays linear (400 statements: 2 s instead of 8)."""
+    import random
+    import time
+    from libfriendship_b200 import B200Renderer, KIND_MINIMUM, KIND_MULTIPLY, KIND_SUM2
+    from workloads.graphs import GraphBuilder
+    random.seed(77)
+    r = B200Renderer(device=-1)
+    g = GraphBuilder(r)
+    x = g.input(0)
+    for _ in range(420):
+        x = g.node(random.choice([KIND_SUM2, KIND_MULTIPLY, KIND_MINIMUM, KIND_SUM2]), x, g.input(random.randrange(1, 4)))
+    g.output(0, x)
+    assert 400 < r.jit_code_instructions(1, 0) < 4096
+    src = r.jit_source(1, 0)
+    assert src.count("__noinline__ void frb_c0_") >= 6 and "float4 R[" in src
+    t0 = time.time()
+    assert r.jit_cubin_size(1, 0) > 1000
+    assert time.time() - t0 < 30.0

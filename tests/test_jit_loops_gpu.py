@@ -124,3 +124,42 @@ def test_reading_an_input_slot_that_can_never_be_fed_is_zero():
     assert_same_bits(outs[0], outs[2], "interpreter")
     assert_same_bits(outs[1], outs[2], "jit")
     assert np.array_equal(outs[2][0], np.arange(64, dtype=np.float32)) and not outs[2][1].any()
+
+
+def test_long_aperiodic_program_chunked_jit_three_ways():
+    """1,200 nodes with no repetition to fold (random operations over four inputs, a shared side value re-used far
+    downstream so that registers live across chunk boundaries): compiled as chunk functions, bit-exact vs the interpreter
+    and the oracle over ragged consecutive calls."""
+    import random
+    from libfriendship_b200 import (B200Renderer, FLAG_JIT_EAGER, FLAG_NO_JIT, KIND_DIVIDE, KIND_MINIMUM, KIND_MODULO,
+                                    KIND_MULTIPLY, KIND_SUM2)
+    from oracle.binding import OracleRenderer
+    from workloads.graphs import GraphBuilder
+
+    def build(r):
+        rs = random.Random(2024)
+        g = GraphBuilder(r)
+        x = g.input(0)
+        side = g.node(KIND_MULTIPLY, g.input(1), g.const(0.37))
+        kept = []
+        for k in range(1200):
+            kind = rs.choice([KIND_SUM2, KIND_MULTIPLY, KIND_MINIMUM, KIND_SUM2, KIND_MODULO if k % 97 == 0 else KIND_SUM2,
+                              KIND_DIVIDE if k % 89 == 0 else KIND_MULTIPLY])
+            other = rs.choice([g.input(rs.randrange(1, 4)), side, g.const(rs.choice([0.5, -1.25, 2.0, 0.999]))] + kept[-2:])
+            x = g.node(kind, x, other)
+            if k % 150 == 0:
+                kept.append(x)
+        g.output(0, g.node(KIND_MINIMUM, x, g.const(1e6)))
+        g.output(1, g.node(KIND_SUM2, kept[0], kept[-1]))
+
+    jit, itp, orc = B200Renderer(flags=FLAG_JIT_EAGER), B200Renderer(flags=FLAG_NO_JIT), OracleRenderer()
+    for r in (jit, itp, orc):
+        build(r)
+    assert "__noinline__ void frb_c0_" in jit.jit_source(2, 0)
+    rng = np.random.RandomState(5)
+    for idx, n in ((0, 300), (300, 1025)):
+        rows = [(rng.rand(n if k != 2 else n - 5) * 0.9 + 0.05).astype(np.float32) for k in range(4)]
+        a, b, c = (r.fill_buffer(2, n, idx, rows) for r in (jit, itp, orc))
+        assert_same_bits(a, c, f"chunked jit vs oracle idx {idx}")
+        assert_same_bits(b, c, f"interpreter vs oracle idx {idx}")
+    assert jit.stats()["jit_launches"] >= 2 and itp.stats()["jit_launches"] == 0
