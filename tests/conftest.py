@@ -30,6 +30,11 @@ def _has_gpu():
 
 
 def pytest_collection_modifyitems(config, items):
+    # no test may hang a GPU box (or the CPU suite): 10 minutes each at the very most (pytest-timeout, when installed)
+    if config.pluginmanager.hasplugin("timeout"):
+        for item in items:
+            if not any(m.name == "timeout" for m in item.iter_markers()):
+                item.add_marker(pytest.mark.timeout(600))
     # `-m gpu` on a box without a GPU (or vice versa) should skip, not fail.
     if _has_gpu():
         return
