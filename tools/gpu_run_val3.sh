@@ -1,0 +1,5 @@
+set -x
+mkdir -p gpurun_out
+(time timeout 900 python -m pytest tests -m gpu -x -q) > gpurun_out/r2k_pytest.log 2>&1
+tail -4 gpurun_out/r2k_pytest.log
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
