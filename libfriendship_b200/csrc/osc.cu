@@ -74,6 +74,8 @@ struct OscBankDev {
     mutable uint64_t planes_cap = 0;   // floats per buffer
     // The plane reduce of sub-block k runs on its own stream beside the main kernel of sub-block k + 1 (launch_osc):
     mutable cudaStream_t red = nullptr;
+    mutable cudaStream_t main2 = nullptr;          // odd sub-blocks' main kernels: their head fills the even ones' tail
+    mutable cudaEvent_t ev_enter = nullptr;
     mutable cudaEvent_t ev_main[2] = {nullptr, nullptr}, ev_red[2] = {nullptr, nullptr};
     mutable bool red_pending[2] = {false, false};
     mutable cudaStream_t side = nullptr;   // the (tiny, slow) attack-ramp kernel runs beside the main kernel
@@ -81,6 +83,8 @@ struct OscBankDev {
     ~OscBankDev() {
         if (side) cudaStreamDestroy(side);
         if (red) cudaStreamDestroy(red);
+        if (main2) cudaStreamDestroy(main2);
+        if (ev_enter) cudaEventDestroy(ev_enter);
         for (int i = 0; i < 2; i++) { if (ev_main[i]) cudaEventDestroy(ev_main[i]); if (ev_red[i]) cudaEventDestroy(ev_red[i]); }
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_join) cudaEventDestroy(ev_join);
@@ -96,7 +100,7 @@ struct OscBankDev {
         mv(d_raw, src.d_raw); mv(raw_cap, src.raw_cap);
         mv(d_planes, src.d_planes); mv(planes_cap, src.planes_cap);
         mv(side, src.side); mv(ev_fork, src.ev_fork); mv(ev_join, src.ev_join);
-        mv(red, src.red);
+        mv(red, src.red); mv(main2, src.main2); mv(ev_enter, src.ev_enter);
         for (int i = 0; i < 2; i++) { mv(ev_main[i], src.ev_main[i]); mv(ev_red[i], src.ev_red[i]); red_pending[i] = false; }
     }
 };
@@ -730,20 +734,47 @@ cudaError_t launch_osc(const OscBankDev& b, const BufferDesc* d_bufdesc, uint32_
     // of sub-block k runs on a stream of its own BESIDE the main kernel of sub-block k + 1, the two alternating between two
     // plane buffers: only the last sub-block's reduce is left on the critical path (8 voices per GPU, split 128: 0.35 ms of
     // reduce per 31 ms step were all exposed before — the whole of the 8-GPU scaling loss, profiles/r2f_timeline_n8.json).
-    static const bool overlap_env = [] { const char* e = getenv("FRB_OSC_REDUCE_OVERLAP"); return !e || e[0] != '0'; }();   // measurement knob
+    static const bool overlap_env = [] { const char* e = getenv("FRB_OSC_REDUCE_OVERLAP"); return !e || e[0] != '0'; }();   // measurement knobs
+    static const int main_streams = [] { const char* e = getenv("FRB_OSC_MAIN_STREAMS"); return e ? atoi(e) : 2; }();
+    static const uint64_t min_ranges = [] { const char* e = getenv("FRB_OSC_MIN_RANGES"); return e ? strtoull(e, nullptr, 10) : 1ull; }();
+    // (more, shorter sub-blocks would shrink the one reduce left on the critical path, but every launch costs a ramp and a
+    // tail: 8 sub-blocks instead of 2 measured 31.04 vs 30.73 ms on an 8-voice shard; FRB_OSC_MIN_RANGES forces them)
+    if (overlap_env) while (sub > (1ull << 16) && (hi - lo) / sub < min_ranges) sub >>= 1;
     const bool overlap = overlap_env && (lo / sub != (hi - 1) / sub);     // a single sub-block has nothing to overlap with
     if (overlap && !b.red) {
         cudaError_t e = cudaStreamCreateWithFlags(&b.red, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b.main2, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b.ev_enter, cudaEventDisableTiming);
         for (int i = 0; i < 2 && e == cudaSuccess; i++) {
             e = cudaEventCreateWithFlags(&b.ev_main[i], cudaEventDisableTiming);
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b.ev_red[i], cudaEventDisableTiming);
         }
         if (e != cudaSuccess) return e;
     }
+    // Main kernels of consecutive sub-blocks alternate between the caller's stream and a second one (they write different
+    // plane buffers): the head of sub-block k + 1 fills the SMs the last CTAs of sub-block k leave idle, so only the
+    // last launch of a render has a tail.
+    if (overlap) {
+        // both plane buffers up front, for the longest sub-block: nothing is reallocated while another stream uses it
+        int L = anchor ? (int)anchor : 128;
+        L = std::max(16, std::min(OSC_LMAX, (L / 16) * 16));
+        const uint64_t longest = std::min<uint64_t>(sub, hi - lo);
+        const uint64_t need = (uint64_t)b.split * b.n_voices * ((longest + L - 1) / L + 1) * L;
+        if (need > b.planes_cap) {
+            cudaStreamSynchronize(stream); cudaStreamSynchronize(b.red); cudaStreamSynchronize(b.main2);
+            cudaFree(b.d_planes); b.d_planes = nullptr; b.planes_cap = 0;
+            cudaError_t e = cudaMalloc(&b.d_planes, 2 * need * sizeof(float));
+            if (e != cudaSuccess) return e;
+            b.planes_cap = need;
+        }
+    }
+    const bool two_mains = overlap && main_streams >= 2;
+    if (two_mains) { cudaEventRecord(b.ev_enter, stream); cudaStreamWaitEvent(b.main2, b.ev_enter, 0); }
     unsigned k = 0;
     for (uint64_t c0 = lo; c0 < hi; k++) {
         const uint64_t c1 = std::min(hi, (c0 / sub + 1) * sub);
-        cudaError_t e = launch_osc_range(b, d_bufdesc, first_buf, c0, c1, anchor, sm_count, stream, n_launches, k & 1u, overlap);
+        cudaStream_t ms = (two_mains && (k & 1u)) ? b.main2 : stream;
+        cudaError_t e = launch_osc_range(b, d_bufdesc, first_buf, c0, c1, anchor, sm_count, ms, n_launches, k & 1u, overlap);
         if (e != cudaSuccess) return e;
         c0 = c1;
     }
