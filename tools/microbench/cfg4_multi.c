@@ -83,9 +83,9 @@ int main(int argc, char** argv) {
     for (uint64_t i = 0; i < ns; i++) { if (fabs(out[i]) > peak) peak = fabs(out[i]); sum += out[i]; }
     frb_stats st; frb_get_stats(r, &st);
     printf("{\"case\": \"cfg4 through the C ABI, one handle, host output buffer\", \"n_devices\": %u, \"voices\": %u, \"partials\": %llu, \"samples\": %llu, "
-           "\"ms_per_render_best\": %.3f, \"partial_samples_per_s\": %.4e, \"first_call_ms\": %.1f, \"peak\": %.4f, \"checksum\": %.6f, \"kernel_launches\": %llu}\n",
+           "\"ms_per_render_best\": %.3f, \"partial_samples_per_s\": %.4e, \"first_call_ms\": %.1f, \"peak\": %.4f, \"checksum\": %.6f, \"kernel_launches\": %llu, \"jit_launches\": %llu, \"interp_launches\": %llu}\n",
            n_dev, nv, (unsigned long long)np, (unsigned long long)ns, best, (double)nv * (double)np * (double)ns / (best * 1e-3), first, peak, sum,
-           (unsigned long long)st.kernel_launches);
+           (unsigned long long)st.kernel_launches, (unsigned long long)st.jit_launches, (unsigned long long)st.interp_launches);
     frb_destroy(r);
     return 0;
 }
