@@ -119,13 +119,14 @@ class WavClient(Client):
 
 
 class Dispatch:
-    def __init__(self, client=None, device=0, flags=0):
+    def __init__(self, client=None, device=0, flags=0, n_devices=0):
+        """n_devices > 1: the Dispatch's ONE renderer drives devices device .. device + n_devices - 1 (csrc/multi.cu)."""
         self.client = client or Client()
         self._cb_audio = _AUDIO(self._on_audio)
         self._cb_meta = _NODEJSON(lambda u, h, s: self.client.node_meta(h, json.loads(s.decode())))
         self._cb_id = _NODEJSON(lambda u, h, s: self.client.node_id(h, json.loads(s.decode())))
         self._cs = _frd_client(None, self._cb_audio, self._cb_meta, self._cb_id)
-        cfg = _cabi.frb_config(device, flags, 0, 0)
+        cfg = _cabi.frb_config(device, flags, 0, n_devices)
         self._h = _lib.frd_create(C.byref(cfg), C.byref(self._cs))
         if not self._h:
             msg = _lib.frb_last_error(None)

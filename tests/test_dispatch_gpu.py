@@ -11,7 +11,12 @@ pytestmark = pytest.mark.gpu
 KIND_NAME = {0: "Delay", 1: "F32Constant", 2: "Sum2", 3: "Multiply", 4: "Divide", 5: "Modulo", 6: "Minimum"}
 
 
-@pytest.mark.parametrize("via", ["methods", "osc_address"])
+def _n_devices():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("via", ["methods", "osc_address", "two_devices"])
 @pytest.mark.parametrize("test", load_golden(), ids=lambda t: t["name"])
 def test_dispatch_replays_reference_tests(test, via, tmp_path):
     from libfriendship_b200.dispatch import Client, Dispatch, EffectId, sha256_file
@@ -23,7 +28,14 @@ def test_dispatch_replays_reference_tests(test, via, tmp_path):
         def audio_rendered(self, buffer, idx):
             rendered.append(buffer)
 
-    d = Dispatch(MyClient())
+    if via == "two_devices":
+        # the same Dispatch with ITS ONE renderer spanning two B200s (frb_config.n_devices, csrc/multi.cu): the reference's
+        # graphs use no oscillator-bank lane, so the result must stay bit for bit what one device renders
+        if _n_devices() < 2:
+            pytest.skip("needs two CUDA devices")
+        d = Dispatch(MyClient(), n_devices=2)
+    else:
+        d = Dispatch(MyClient())
     if via == "osc_address":
         # the same messages through the one entry point, by address (Dispatch::dispatch, dispatch.rs:109-160)
         disp = d
