@@ -405,11 +405,16 @@ std::shared_ptr<OscBankDev> osc_create(const frb_oscbank_desc* d, cudaStream_t s
                                                            d_phase, d_attack, d_tau, b->d_hot, b->d_anc, b->d_ph);
         OC(cudaGetLastError());
     }
-    OC(cudaStreamSynchronize(stream));
-    lap("setup");
     if (!recycle) {   // a first definition is usually the only one: give the scratch (28 B per partial) back
+        OC(cudaStreamSynchronize(stream));
+        lap("setup");
         cudaFree(b->d_raw); b->d_raw = nullptr; b->raw_cap = 0;
         lap("free raw");
+    } else {
+        // a re-definition (the per-render input of a synthesis graph): the caller's arrays were consumed by the copies
+        // the wait above covered, and the fill / setup kernels are ordered before any render on this stream — the host
+        // goes on to enqueue that render instead of waiting for them
+        lap("setup (enqueued)");
     }
 #undef OC
     return b;

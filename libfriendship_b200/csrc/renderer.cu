@@ -546,15 +546,12 @@ void Renderer::grow_slot(InputSlot& s, uint64_t need_end) {
     s.cap = ncap;
 }
 
-// reference.rs:49-75
-void Renderer::ingest_inputs(uint32_t n_slots, uint64_t n_times, uint64_t idx, const float* in_data, bool in_on_device,
-                             const uint64_t* offs, uint32_t n_rows) {
+void Renderer::validate_inputs(uint32_t n_slots, uint64_t n_times, uint64_t idx, const uint64_t* offs, uint32_t n_rows) const {
     const bool seek = idx != head_;
     const uint64_t buff_len = (uint64_t)n_slots * n_times;                // ndarray len(): element count (:60)
     const uint64_t n_vec_after = std::max(n_slot_vectors_, buff_len);
     const size_t n_fed = (size_t)std::min<uint64_t>(n_rows, n_vec_after); // zip(rows, slots) stops at the shorter (:68)
-
-    // validate everything before touching state (the reference panics half-way; we refuse the call instead)
+    // everything is checked before any state changes (the reference panics half-way; we refuse the call instead)
     for (size_t r = 0; r < n_fed; r++) {
         if (offs[r + 1] < offs[r]) throw Error{FRB_E_INVALID, "in_row_offsets must be non-decreasing"};
         uint64_t row_len = offs[r + 1] - offs[r];
@@ -567,6 +564,15 @@ void Renderer::ingest_inputs(uint32_t n_slots, uint64_t n_times, uint64_t idx, c
         if (len_now != idx) throw Error{FRB_E_INPUT_GAP, "input slot " + std::to_string(r) + " has length " + std::to_string(len_now) + " != idx (reference.rs:69 assert_eq)"};
         if (row_len > n_times) throw Error{FRB_E_INPUT_TOO_LONG, "cannot send inputs ahead of outputs (reference.rs:71 assert)"};
     }
+}
+
+// reference.rs:49-75
+void Renderer::ingest_inputs(uint32_t n_slots, uint64_t n_times, uint64_t idx, const float* in_data, bool in_on_device,
+                             const uint64_t* offs, uint32_t n_rows) {
+    const bool seek = idx != head_;
+    const uint64_t buff_len = (uint64_t)n_slots * n_times;                // ndarray len(): element count (:60)
+    const uint64_t n_vec_after = std::max(n_slot_vectors_, buff_len);
+    const size_t n_fed = (size_t)std::min<uint64_t>(n_rows, n_vec_after); // zip(rows, slots) stops at the shorter (:68)
 
     if (seek) {                                                            // :52-58
         for (auto& s : inputs_) { s.base = idx & ~3ull; s.end = idx; if (s.d_data && s.cap) CU(cudaMemsetAsync(s.d_data, 0, std::min<uint64_t>(s.cap, 8) * sizeof(float), stream_)); }
@@ -810,6 +816,7 @@ void Renderer::fill(float* out, bool out_on_device, uint32_t n_slots, uint64_t n
     // From here on state changes (input history, rings, recurrence carries).  A failure half-way (out of device memory,
     // a launch error) leaves the history ahead of the playhead, so the next call is made a seek whatever its idx: the
     // reference's seek rule (renderer.rs:12-15) then resets every slot and the rings are rebuilt — consistent again.
+    validate_inputs(n_slots, n_times, idx, offs, n_rows);      // a refused call (reference: assert) changes nothing
     struct FailGuard {
         Renderer* r; bool armed = true;
         ~FailGuard() { if (armed) { r->cache_valid_ = false; r->head_ = ~0ull; } }

@@ -79,6 +79,7 @@ private:
     void ensure_rings(uint64_t t_end);
     void ingest_inputs(uint32_t n_slots, uint64_t n_times, uint64_t idx, const float* in_data, bool in_on_device,
                        const uint64_t* offs, uint32_t n_rows);
+    void validate_inputs(uint32_t n_slots, uint64_t n_times, uint64_t idx, const uint64_t* offs, uint32_t n_rows) const;
     void materialise_slot(size_t r);
     void grow_slot(InputSlot& s, uint64_t need_end);
     void run_range(uint64_t lo, uint64_t hi, float* d_out, uint64_t t0, uint64_t t1, uint64_t out_stride);

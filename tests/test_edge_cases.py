@@ -152,3 +152,24 @@ def test_many_long_input_rows_ragged_and_unaligned():
             saved = [rows for rows, _ in got]
         outs.append(np.concatenate([o for _, o in got], axis=1))
     assert_same_bits(outs[0], outs[1], "batched ingest of ragged, unaligned rows")
+
+
+def test_a_refused_call_changes_nothing():
+    """The reference asserts on a row longer than n_times (reference.rs:71) or a slot fed after it was skipped (:69); the
+    C ABI refuses such a call BEFORE any state changes: the next call is still contiguous and still reads the history
+    the earlier calls supplied (here through a Delay of 2)."""
+    from libfriendship_b200 import B200Renderer, KIND_DELAY, RendererError
+    from workloads.graphs import GraphBuilder
+    r = B200Renderer()
+    g = GraphBuilder(r)
+    g.output(0, g.node(KIND_DELAY, g.input(0), g.const(2.0)))
+    a = r.fill_buffer(1, 4, 0, [[1, 2, 3, 4]])
+    assert a[0].tolist() == [0, 0, 1, 2]
+    for bad in ([[9, 9, 9, 9, 9]],):                               # longer than n_times
+        with pytest.raises(RendererError) as e:
+            r.fill_buffer(1, 4, 4, bad)
+        assert e.value.code == -2
+    b = r.fill_buffer(1, 4, 4, [[5, 6, 7, 8]])                     # contiguous: NOT a seek, history intact
+    assert b[0].tolist() == [3, 4, 5, 6]
+    c = r.fill_buffer(1, 4, 100, [[1, 1, 1, 1]])                   # a seek (idx != 8) is legal and forgets the history (renderer.rs:12-15)
+    assert c[0].tolist() == [0, 0, 1, 1]
