@@ -240,8 +240,9 @@ unsigned hoist_unroll(const Stage& st, const Node& loop, int W) {
         if (op == I_STBUF || op == I_STOUT) return 1;
         loads += is_pure_load(in);
     }
-    if (!loads || loads * (size_t)W > 16) return 1;
-    size_t U = std::min<size_t>(8, 16 / (loads * (size_t)W));              // ~16 quads (256 B) in flight per thread
+    static const size_t quads = [] { const char* e = getenv("FRB_JIT_QUADS"); return e ? (size_t)std::max(4, atoi(e)) : (size_t)16; }();   // measurement knob
+    if (!loads || loads * (size_t)W > quads) return 1;
+    size_t U = std::min<size_t>(8, quads / (loads * (size_t)W));           // ~16 quads (256 B) in flight per thread
     U = std::min<size_t>(U, std::max<size_t>(1, 64 / loop.iters[0].size()));   // ... and an unrolled body of a few dozen instructions
     return (unsigned)std::max<size_t>(U, 2);
 }
