@@ -248,6 +248,10 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg4", choices=["cfg4", "cfg5"],
+                    help="cfg4 = the bench (BASELINE.json configs[3]); cfg5 = the offline large render (configs[4]: 2^20 partials x "
+                         "256 voices, 192 kHz x 60 s, meant for 8 GPUs under torchrun), one render through the streaming path with "
+                         "oracle windows on the full bank — tools/render_cfg5.py, its own JSON line")
     ap.add_argument("--voices", type=int, default=N_VOICES, help="debug: shrink the workload (invalidates the number)")
     ap.add_argument("--partials", type=int, default=N_PARTIALS)
     ap.add_argument("--samples", type=int, default=N_SAMPLES)
@@ -265,6 +269,12 @@ def main():
 
     if args.impl == "reference":
         run_reference(args, rank, world, out)
+        return
+    if args.workload == "cfg5":
+        os.dup2(out.fileno(), 1)            # that tool prints its line itself
+        sys.stdout = out
+        from tools import render_cfg5
+        render_cfg5.main()
         return
 
     import torch
