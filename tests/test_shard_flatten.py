@@ -67,3 +67,19 @@ def test_rank_out_of_range_is_refused():
     r = B200Renderer(device=-1)
     with pytest.raises(RendererError):
         r.dump_schedule_shard(1, 3, 2)
+
+
+def test_banks_larger_than_a_launch_can_hold_are_refused_at_definition():
+    """Voices / lanes ride on grid.y: more than 65,535 per bank used to fail in the middle of a render, after the input
+    history had advanced.  Now the definition is refused."""
+    from libfriendship_b200 import B200Renderer, RendererError
+    r = B200Renderer(device=-1)
+    nv = 70000
+    bank = dict(sample_rate=48000.0, voice_offsets=np.arange(nv + 1, dtype=np.uint64), freq_hz=np.full(nv, 440.0),
+                amp=np.ones(nv, np.float32), phase=np.zeros(nv, np.float32), attack=np.zeros(nv, np.float32), tau=np.zeros(nv, np.float32))
+    with pytest.raises(RendererError) as e:
+        r.define_oscbank(3, **bank)
+    assert e.value.code == -7
+    with pytest.raises(RendererError) as e:
+        r.define_fbdelay(4, np.full(nv, 100, np.uint32), np.full(nv, 0.5, np.float32))
+    assert e.value.code == -7
