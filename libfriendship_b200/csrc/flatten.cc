@@ -131,6 +131,7 @@ struct Flattener {
         if (e.from == 0) {
             // reading an input of this graph level
             if (c.parent < 0) {
+                if (e.from_slot >= env.input_slot_cap) return zero();     // no such slot exists (FlattenEnv::input_slot_cap)
                 s.n_input_slots = std::max<uint64_t>(s.n_input_slots, (uint64_t)e.from_slot + 1);
                 return mk(V_INPUT, 0, 0, e.from_slot);
             }

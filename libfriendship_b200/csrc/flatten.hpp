@@ -19,6 +19,11 @@ struct FlattenEnv {
     // is the zero signal, and zeros fold through Sum2 / Multiply / Divide / Delay — so the sum of the ranks' outputs is the
     // whole graph's output wherever that output is linear in the bank lanes (lane_use_of_outputs checks it).
     uint32_t shard_rank = 0, shard_world = 1;
+    // External-input slots at or beyond this number read as the zero signal.  A graph may name any u32 slot (the
+    // reference's RouteGraph does not check toplevel slots and RefRenderer returns 0 for a slot that was never fed,
+    // reference.rs:90-96); the renderer sets the cap above every slot that exists (and re-flattens if a call ever feeds
+    // a slot beyond it), so the device table can cover every slot a program names and kernels index it unchecked.
+    uint32_t input_slot_cap = 1u << 16;
 };
 
 // Throws frb::Error.

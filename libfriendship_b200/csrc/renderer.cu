@@ -303,6 +303,7 @@ FlattenEnv Renderer::flatten_env(uint32_t rank, uint32_t world, bool compact_ban
     env.sparkle_delay = (cfg_.flags & FRB_FLAG_SPARKLE_DELAY) != 0;
     env.shard_rank = rank;
     env.shard_world = world ? world : 1;
+    env.input_slot_cap = (uint32_t)std::min<uint64_t>(0xFFFFFFFFull, std::max<uint64_t>(kMinInputSlotCap, inputs_.size()));
     return env;
 }
 
@@ -318,6 +319,7 @@ const Schedule& Renderer::schedule(uint32_t n_slots) {
         const bool sharded = shard_world_ > 1 && flatten_sharded_;
         FlattenEnv env = flatten_env(sharded ? shard_rank_ : 0, sharded ? shard_world_ : 1, false);
         Schedule s = flatten(graph_, n_slots, env);   // throws on malformed graphs; state unchanged then
+        sched_input_cap_ = env.input_slot_cap;
         if (!host_only_) {
             CU(cudaSetDevice(device_));
             CU(cudaStreamSynchronize(stream_));
@@ -811,6 +813,8 @@ void Renderer::fill(float* out, bool out_on_device, uint32_t n_slots, uint64_t n
     CU(cudaSetDevice(device_));
     if (n_rows && !offs) throw Error{FRB_E_INVALID, "in_row_offsets is NULL"};
     if (idx + n_times < idx) throw Error{FRB_E_INVALID, "idx + n_times overflows"};
+    // the schedule maps input slots beyond its cap to zero: a call that feeds a slot up there (absurd, but legal) re-flattens
+    if (std::max<uint64_t>(inputs_.size(), n_rows) > sched_input_cap_) dirty_ = true;
     ensure_schedule(n_slots);            // may throw on a malformed graph, before any state changes
     if (profiling) { timing = frb_timing{}; CU(cudaEventRecord(ev_[0], stream_)); }
     // From here on state changes (input history, rings, recurrence carries).  A failure half-way (out of device memory,
@@ -828,20 +832,18 @@ void Renderer::fill(float* out, bool out_on_device, uint32_t n_slots, uint64_t n
     uint64_t n_out_host = 0;
     if (n_times > 0 && n_slots > 0) {
         // input descriptor table for the slots the schedule reads
-        // table of the slots that exist: a slot the graph reads but no call ever fed has no entry and reads as 0
-        // (input_desc, interp_device.inc) — the graph may name any u32 slot, the table stays as small as the history
-        const uint32_t nin = (uint32_t)std::min<uint64_t>(sched_.n_input_slots, inputs_.size());
+        // one entry per slot number the schedule names (all below its input-slot cap); slots no call ever fed are null
+        const uint32_t nin = (uint32_t)sched_.n_input_slots;
         n_indesc_ = nin;
-        {
-            std::vector<InputDesc> h((size_t)nin + 1);             // + the null entry every non-existent slot is clamped to
-            h[nin] = InputDesc{nullptr, 0, 0};
+        if (nin) {
+            std::vector<InputDesc> h(nin);
             for (uint32_t s = 0; s < nin; s++) {
                 if (s < inputs_.size() && inputs_[s].d_data) h[s] = InputDesc{inputs_[s].d_data, inputs_[s].base, inputs_[s].end};
                 else h[s] = InputDesc{nullptr, 0, 0};
             }
-            if (d_indesc_cap_ < (size_t)nin + 1) {
+            if (d_indesc_cap_ < (size_t)nin) {
                 if (d_indesc_) { CU(cudaStreamSynchronize(stream_)); CU(cudaFree(d_indesc_)); }
-                d_indesc_cap_ = std::max<size_t>(((size_t)nin + 1) * 2, 16);
+                d_indesc_cap_ = std::max<size_t>((size_t)nin * 2, 16);
                 CU(cudaMalloc(&d_indesc_, d_indesc_cap_ * sizeof(InputDesc)));
                 h_indesc_.clear();
             }

@@ -146,7 +146,9 @@ private:
     uint64_t head_ = 0;                                            // reference.rs:26-28
     InputDesc* d_indesc_ = nullptr;
     size_t d_indesc_cap_ = 0;
-    uint32_t n_indesc_ = 0;                                        // entries of d_indesc_ in use (slots that exist)
+    uint32_t n_indesc_ = 0;                                        // entries of d_indesc_ in use
+    static constexpr uint64_t kMinInputSlotCap = 1u << 16;         // FlattenEnv::input_slot_cap is at least this
+    uint64_t sched_input_cap_ = 0;                                 // ... and this is what the current schedule was flattened with
     float* d_in_stage_ = nullptr;
     size_t d_in_stage_cap_ = 0;
     void* d_ingest_ = nullptr;                  // row descriptors of a batched ingest (renderer.cu ingest_rows_kernel)

@@ -162,10 +162,16 @@ def test_graphs_deeper_than_the_walk_allows_are_refused_not_crashed_on():
     assert e.value.code == FRB_E_UNSUPPORTED
 
 
-def test_input_slot_count_does_not_wrap():
-    """slot 0xFFFFFFFF + 1 used to wrap to 0 in u32: the count is kept in 64 bits and the dump saturates."""
+def test_input_slot_that_cannot_exist_is_the_zero_signal():
+    """slot 0xFFFFFFFF + 1 used to wrap the slot count to 0 in u32 and index the device table out of bounds.
+    Slots at or beyond the flattener's cap (above every slot that exists; at least 65,536) are the zero signal, so the
+    table covers every slot a program names."""
     from libfriendship_b200 import B200Renderer
     r = B200Renderer(device=-1)
     r.on_add_edge((0, 0, 0xFFFFFFFF, 0))
-    w = r.dump_schedule(1)
-    assert int(w[6]) == 0xFFFFFFFF
+    r.on_add_edge((0, 0, 70000, 1))
+    r.on_add_edge((0, 0, 65535, 2))
+    d = parse_dump(r.dump_schedule(3))
+    assert d["n_inputs"] == 65536
+    ops = [d["values"][o][0] for o in d["outputs"]]
+    assert ops == [0, 0, 2]                      # V_ZERO, V_ZERO, V_INPUT
