@@ -169,7 +169,7 @@ def extra_configs(peak_fma, hbm_gbs):
         import subprocess
         exe = os.path.join(ROOT, "build", "bin", "cfg1_latency")
         r = subprocess.run([exe, "512", "2000"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
-        c = json.loads(r.stdout.strip().splitlines()[-1])
+        c = json.loads([l for l in r.stdout.strip().splitlines() if '"us_per_call_median"' in l][-1])
         ex["cfg1"]["c_abi"] = {"us_per_512_sample_call_median": c["us_per_call_median"], "us_p10": c["us_p10"], "us_p90": c["us_p90"],
                                "realtime_factor": c["realtime_factor"], "calls": c["calls"], "program": "tools/microbench/cfg1_latency.c"}
     except Exception as e:      # pragma: no cover

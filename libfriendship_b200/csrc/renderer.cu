@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -807,8 +808,28 @@ void Renderer::run_range(uint64_t lo, uint64_t hi, float* d_out, uint64_t t0, ui
     }
 }
 
+// FRB_TRACE_FILL=1: host-clock time per phase of fill(), summed over calls and printed when the renderer goes away (tuning aid)
+namespace {
+struct FillTrace {
+    bool on = getenv("FRB_TRACE_FILL") != nullptr;
+    double ns[8] = {0}; uint64_t calls = 0;
+    std::chrono::steady_clock::time_point t;
+    void start() { if (on) t = std::chrono::steady_clock::now(); }
+    void lap(int i) { if (!on) return; auto n = std::chrono::steady_clock::now(); if (calls > 2000) ns[i] += std::chrono::duration<double, std::nano>(n - t).count(); t = n; }
+    ~FillTrace() {
+        if (calls > 2000) calls -= 2000;
+        if (on && calls) fprintf(stderr, "[frb] fill x %llu: schedule %.2f ingest %.2f table %.2f rings %.2f run %.2f d2h %.2f wait %.2f us per call\n",
+                                 (unsigned long long)calls, ns[0] / calls / 1e3, ns[1] / calls / 1e3, ns[2] / calls / 1e3, ns[3] / calls / 1e3,
+                                 ns[4] / calls / 1e3, ns[5] / calls / 1e3, ns[6] / calls / 1e3);
+    }
+} g_fill_trace;
+
+}  // namespace
+
 void Renderer::fill(float* out, bool out_on_device, uint32_t n_slots, uint64_t n_times, uint64_t idx,
                     const float* in_data, bool in_on_device, const uint64_t* offs, uint32_t n_rows) {
+    g_fill_trace.start();
+    g_fill_trace.calls++;
     require_device();
     CU(cudaSetDevice(device_));
     if (n_rows && !offs) throw Error{FRB_E_INVALID, "in_row_offsets is NULL"};
@@ -816,6 +837,7 @@ void Renderer::fill(float* out, bool out_on_device, uint32_t n_slots, uint64_t n
     // the schedule maps input slots beyond its cap to zero: a call that feeds a slot up there (absurd, but legal) re-flattens
     if (std::max<uint64_t>(inputs_.size(), n_rows) > sched_input_cap_) dirty_ = true;
     ensure_schedule(n_slots);            // may throw on a malformed graph, before any state changes
+    g_fill_trace.lap(0);
     if (profiling) { timing = frb_timing{}; CU(cudaEventRecord(ev_[0], stream_)); }
     // From here on state changes (input history, rings, recurrence carries).  A failure half-way (out of device memory,
     // a launch error) leaves the history ahead of the playhead, so the next call is made a seek whatever its idx: the
@@ -826,6 +848,7 @@ void Renderer::fill(float* out, bool out_on_device, uint32_t n_slots, uint64_t n
         ~FailGuard() { if (armed) { r->cache_valid_ = false; r->head_ = ~0ull; } }
     } guard{this};
     ingest_inputs(n_slots, n_times, idx, in_data, in_on_device, offs, n_rows);
+    g_fill_trace.lap(1);
 
     const uint64_t t1 = idx + n_times;
     bool pinned_out = false;
@@ -868,7 +891,9 @@ void Renderer::fill(float* out, bool out_on_device, uint32_t n_slots, uint64_t n
                 CU(cudaEventRecord(ev_indesc_[b], stream_));
             }
         }
+        g_fill_trace.lap(2);
         ensure_rings(t1);
+        g_fill_trace.lap(3);
 
         float* d_out = out;
         const uint64_t n_out = (uint64_t)n_slots * n_times;
@@ -887,6 +912,7 @@ void Renderer::fill(float* out, bool out_on_device, uint32_t n_slots, uint64_t n
             run_range(start & ~7ull, idx, nullptr, idx, idx, 0);
         }
         run_range(idx, t1, d_out, idx, t1, n_times);
+        g_fill_trace.lap(4);
         cache_valid_ = true;
         cache_head_ = t1;
         if (!out_on_device) {
@@ -903,10 +929,12 @@ void Renderer::fill(float* out, bool out_on_device, uint32_t n_slots, uint64_t n
         CU(cudaEventSynchronize(ev_[1]));
         CU(cudaEventElapsedTime(&timing.total_ms, ev_[0], ev_[1]));
     }
+    g_fill_trace.lap(5);
     if (!out_on_device) {
         CU(cudaStreamSynchronize(stream_));
         if (pinned_out) memcpy(out, h_pin_out_, n_out_host * sizeof(float));
     }
+    g_fill_trace.lap(6);
     guard.armed = false;
 }
 

@@ -23,6 +23,7 @@ int main(int argc, char** argv) {
     const uint64_t block = argc > 1 ? strtoull(argv[1], 0, 10) : 512;
     const int calls = argc > 2 ? atoi(argv[2]) : 2000;
     frb_config cfg; memset(&cfg, 0, sizeof cfg);
+    if (getenv("CFG1_FLAGS")) cfg.flags = (uint32_t)atoi(getenv("CFG1_FLAGS"));   /* e.g. 2 = FRB_FLAG_NO_JIT, 4 = FRB_FLAG_JIT_EAGER */
     frb_renderer* r = frb_create(&cfg);
     if (!r) { printf("FAIL frb_create: %s\n", frb_last_error(NULL)); return 1; }
     /* handles: 1 = constants, 2 gain, 3 delay, 4 wet gain, 5 sum, 6 min, 7 mod, 8 div (tests/graphs.py build_cfg1_graph) */
@@ -50,11 +51,25 @@ int main(int argc, char** argv) {
         checksum += out[0] + out[block];
         idx += block;
     }
+    /* medians of the four quarters of the run, in call order: shows a tier change (interpreter -> compiled stage) */
+    double quarter[4];
+    for (int k = 0; k < 4; k++) {
+        const int a = calls * k / 4, n = calls * (k + 1) / 4 - a;
+        double* tmp = malloc((n > 0 ? n : 1) * sizeof(double));
+        memcpy(tmp, us + a, n * sizeof(double));
+        qsort(tmp, n, sizeof(double), cmp);
+        quarter[k] = n ? tmp[n / 2] : 0;
+        free(tmp);
+    }
     qsort(us, calls, sizeof(double), cmp);
     printf("{\"case\": \"cfg1 through the C ABI, host buffers\", \"block\": %llu, \"calls\": %d, \"us_per_call_median\": %.2f, "
-           "\"us_p10\": %.2f, \"us_p90\": %.2f, \"realtime_factor\": %.1f, \"checksum\": %.6f}\n",
-           (unsigned long long)block, calls, us[calls / 2], us[calls / 10], us[calls * 9 / 10],
+           "\"us_p10\": %.2f, \"us_p90\": %.2f, \"us_median_by_quarter\": [%.2f, %.2f, %.2f, %.2f], \"realtime_factor\": %.1f, \"checksum\": %.6f}\n",
+           (unsigned long long)block, calls, us[calls / 2], us[calls / 10], us[calls * 9 / 10], quarter[0], quarter[1], quarter[2], quarter[3],
            (double)block / 48000.0 * 1e6 / us[calls / 2], checksum);
+    frb_stats st; frb_get_stats(r, &st);
+    printf("{\"stats\": {\"kernel_launches\": %llu, \"jit_launches\": %llu, \"interp_launches\": %llu, \"h2d_bytes\": %llu, \"d2h_bytes\": %llu, \"schedule_builds\": %llu}}\n",
+           (unsigned long long)st.kernel_launches, (unsigned long long)st.jit_launches, (unsigned long long)st.interp_launches,
+           (unsigned long long)st.h2d_bytes, (unsigned long long)st.d2h_bytes, (unsigned long long)st.schedule_builds);
     frb_destroy(r);
     return 0;
 }
