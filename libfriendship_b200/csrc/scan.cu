@@ -45,7 +45,8 @@ struct FbDelayDev {
     uint64_t min_delay = ~0ull;
     uint32_t* d_delay = nullptr;
     float* d_gain = nullptr;
-    ~FbDelayDev() { cudaFree(d_delay); cudaFree(d_gain); }
+    uint32_t* d_order = nullptr;  // fused chain: which lane the w-th warp of the launch takes (see chain_lane_order)
+    ~FbDelayDev() { cudaFree(d_delay); cudaFree(d_gain); cudaFree(d_order); }
 };
 
 struct ChainStateDev {            // biquad carry of a fused DirectForm -> FbDelay chain: {x[n-1], x[n-2], y[n-1], y[n-2]} at `time`
@@ -91,6 +92,38 @@ std::shared_ptr<DirectFormDev> directform_create(const frb_directform_desc* d, c
     return f;
 }
 
+// The fused chain kernel gives every lane one warp for the whole launch and all its CTAs are resident at once, so a launch
+// lasts as long as the busiest SM.  A comb shorter than a tile costs more per sample (taps out of the tile itself: a
+// barrier per chunk; below 128 narrower chunks), and lanes of one class tend to be neighbours (cfg3: D = 100 + v mod 900
+// puts 156 short combs in a row = 39 whole CTAs, two of them on some SMs and none on others: 3.25 against 3.06 ms with
+// uniform long delays).  Lanes are therefore sorted by cost class and dealt out across the CTAs, warp w of CTA c taking
+// sorted[w * n_ctas + (c - 37 w) mod n_ctas]: every CTA gets at most one lane more of a class than any other.  A lane's
+// arithmetic does not depend on which warp runs it.  cfg3, ring-fed: 3.27 -> 3.125 ms (3.08 with uniform long delays);
+// FRB_K4_LANE_ORDER=0 keeps the identity (measurement knob; profiles/k4_lane_order_ab_r2.jsonl).
+static std::vector<uint32_t> chain_lane_order(const uint32_t* delay, uint32_t n_lanes) {
+    std::vector<uint32_t> order(n_lanes);
+    for (uint32_t i = 0; i < n_lanes; i++) order[i] = i;
+    static const bool on = [] { const char* e = getenv("FRB_K4_LANE_ORDER"); return !(e && e[0] == '0'); }();
+    if (!on || n_lanes == 0) return order;
+    auto cls = [&](uint32_t l) { const uint32_t D = delay[l]; return D < 64 ? 0 : D < 128 ? 1 : D < 256 ? 2 : 3; };
+    bool mixed = false;
+    for (uint32_t i = 1; i < n_lanes && !mixed; i++) mixed = cls(i) != cls(0);
+    if (!mixed) return order;                                      // one class: nothing to balance, neighbours stay together
+    std::vector<uint32_t> sorted = order;
+    std::stable_sort(sorted.begin(), sorted.end(), [&](uint32_t a, uint32_t b) { return cls(a) < cls(b); });
+    const uint32_t per_cta = DF_CTA_THREADS / 32, n_ctas = (n_lanes + per_cta - 1) / per_cta;
+    const uint32_t rot = 37;                                       // a CTA's lanes (their rings) not a power of two apart: 0.5%
+    // slots of the last CTA beyond n_lanes do not exist: walk the (w, c) grid in sorted order and skip them
+    uint32_t i = 0;
+    for (uint32_t w = 0; w < per_cta; w++)
+        for (uint32_t k = 0; k < n_ctas; k++) {
+            const uint32_t c = (k + rot * w) % n_ctas;
+            const uint32_t slot = c * per_cta + w;
+            if (slot < n_lanes) order[slot] = sorted[i++];
+        }
+    return order;
+}
+
 std::shared_ptr<FbDelayDev> fbdelay_create(const frb_fbdelay_desc* d, cudaStream_t stream, std::string* err) {
     auto fail = [&](const std::string& m) { if (err) *err = m; return std::shared_ptr<FbDelayDev>(); };
     if (d->n_lanes && (!d->delay || !d->gain)) return fail("fbdelay: null array");
@@ -102,11 +135,14 @@ std::shared_ptr<FbDelayDev> fbdelay_create(const frb_fbdelay_desc* d, cudaStream
         f->min_delay = std::min<uint64_t>(f->min_delay, d->delay[i]);
     }
     const size_t n = std::max<uint32_t>(d->n_lanes, 1);
-    if (cudaMalloc(&f->d_delay, n * sizeof(uint32_t)) != cudaSuccess || cudaMalloc(&f->d_gain, n * sizeof(float)) != cudaSuccess)
+    if (cudaMalloc(&f->d_delay, n * sizeof(uint32_t)) != cudaSuccess || cudaMalloc(&f->d_gain, n * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&f->d_order, n * sizeof(uint32_t)) != cudaSuccess)
         return fail("fbdelay: out of device memory");
+    const std::vector<uint32_t> order = chain_lane_order(d->delay, d->n_lanes);
     if (d->n_lanes) {
         cudaMemcpyAsync(f->d_delay, d->delay, d->n_lanes * sizeof(uint32_t), cudaMemcpyHostToDevice, stream);
         cudaMemcpyAsync(f->d_gain, d->gain, d->n_lanes * sizeof(float), cudaMemcpyHostToDevice, stream);
+        cudaMemcpyAsync(f->d_order, order.data(), d->n_lanes * sizeof(uint32_t), cudaMemcpyHostToDevice, stream);
     }
     if (cudaStreamSynchronize(stream) != cudaSuccess) return fail("fbdelay: upload failed");
     return f;
@@ -391,7 +427,7 @@ __global__ void __launch_bounds__(DF_CTA_THREADS, 7)
 dfcomb_kernel(const float* __restrict__ coef, const float* __restrict__ pw, const uint32_t* __restrict__ delay,
               const float* __restrict__ gain, const BufferDesc* __restrict__ bufdesc, const uint32_t* __restrict__ in_bufs,
               uint32_t first_out_buf, float4* __restrict__ state, unsigned n_lanes, unsigned long long lo, unsigned long long hi,
-              OscOneSrc exc, const uint32_t* __restrict__ exc_voice) {
+              OscOneSrc exc, const uint32_t* __restrict__ exc_voice, const uint32_t* __restrict__ order) {
     // Samples per thread.  16 halves the per-sample cost of the scan and of everything that happens once per tile, which
     // pays when the kernel is bound by issue slots (EXC: 3.20 -> 2.81 ms on cfg3) and not when it is bound by the LSU
     // pipe (ring input: 3.26 -> 3.43 ms); the biquad's tiles — hence its roundings — therefore differ between the two.
@@ -405,8 +441,9 @@ dfcomb_kernel(const float* __restrict__ coef, const float* __restrict__ pw, cons
     auto XQ = [](unsigned q) { return SKEW ? ch_qpos(q) : q; };
     __shared__ ChainWarpSmem<SPT> s_all[NW];
     const unsigned wl = threadIdx.x & 31, wi = threadIdx.x >> 5;
-    const unsigned lane = blockIdx.x * NW + wi;
-    if (lane >= n_lanes) return;                                   // whole warp exits together
+    const unsigned slot = blockIdx.x * NW + wi;
+    if (slot >= n_lanes) return;                                   // whole warp exits together
+    const unsigned lane = order[slot];                             // chain_lane_order: cost classes dealt out across the CTAs
     ChainWarpSmem<SPT>& S = s_all[wi];
     BufferDesc xin = {nullptr, 0};
     unsigned exc_flags = 0;
@@ -670,7 +707,7 @@ cudaError_t launch_dfcomb(const DirectFormDev& df, const FbDelayDev& fb, ChainSt
     const int bulk = bulk_env < 0 ? kChainBulkDefault : bulk_env;
     auto go = [&](auto kernel, const uint32_t* in_bufs, const OscOneSrc& ex, const uint32_t* ev) {
         kernel<<<grid, DF_CTA_THREADS, 0, stream>>>(df.d_coef, df.d_pow, fb.d_delay, fb.d_gain, d_bufdesc, in_bufs, first_out_buf,
-                                                    st.d_state, df.n_lanes, lo, hi, ex, ev);
+                                                    st.d_state, df.n_lanes, lo, hi, ex, ev, fb.d_order);
     };
     if (exciter) {
         if (bulk == 2) go(dfcomb_kernel<true, 2>, nullptr, *exciter, d_exc_voice);

@@ -10,7 +10,7 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 import numpy as np
 
-import filters
+from workloads import filters
 import bench_kernels
 
 _orig = filters.cfg3_filters
