@@ -33,6 +33,7 @@
 //    depends on the block size); the range planes are summed in fixed order by osc_reduce_kernel.
 #include "osc.cuh"
 #include "osc_one.cuh"
+#include "osc_gemm.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -63,7 +64,10 @@ struct OscBankDev {
     float4* d_hot = nullptr;        // {a, b, cm1, k1}
     float4* d_anc = nullptr;        // {k2, amp, kappa, invA}
     uint4* d_ph = nullptr;          // {inc_lo, inc_hi, ph0_lo, ph0_hi}
-    uint64_t rec_cap = 0;           // records the three arrays above can hold
+    float4* d_rot = nullptr;        // K1G (osc_gemm.cuh): {rho^1024 (cos, sin)(1024 w), rho^8 (cos, sin)(8 w)}
+    uint64_t rec_cap = 0;           // records the four arrays above can hold
+    float2* d_vscale = nullptr;     // K1G: per voice {2^k, 2^-k} with max |amp| 2^k in [0.5, 1)
+    bool gemm = false;              // K1G renders this bank past its attack ramps (osc_gemm_wanted)
     uint32_t* d_grp_begin = nullptr;   // per voice: first group
     uint32_t* d_n_grp0 = nullptr;      // per voice: groups of class 0
     uint32_t* d_n_grp = nullptr;       // per voice: groups in total
@@ -88,14 +92,15 @@ struct OscBankDev {
         for (int i = 0; i < 2; i++) { if (ev_main[i]) cudaEventDestroy(ev_main[i]); if (ev_red[i]) cudaEventDestroy(ev_red[i]); }
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_join) cudaEventDestroy(ev_join);
-        cudaFree(d_hot); cudaFree(d_anc); cudaFree(d_ph);
+        cudaFree(d_hot); cudaFree(d_anc); cudaFree(d_ph); cudaFree(d_rot); cudaFree(d_vscale);
         cudaFree(d_grp_begin); cudaFree(d_n_grp0); cudaFree(d_n_grp); cudaFree(d_planes); cudaFree(d_raw);
     }
     // a bank that replaces `src` under the same key takes over every device allocation of it (cudaMalloc / cudaFree cost
     // milliseconds each beside a busy context; a re-definition per render must not pay them)
     void take_buffers(OscBankDev& src) {
         auto mv = [](auto& a, auto& b2) { a = b2; b2 = {}; };
-        mv(d_hot, src.d_hot); mv(d_anc, src.d_anc); mv(d_ph, src.d_ph); mv(rec_cap, src.rec_cap);
+        mv(d_hot, src.d_hot); mv(d_anc, src.d_anc); mv(d_ph, src.d_ph); mv(d_rot, src.d_rot); mv(rec_cap, src.rec_cap);
+        mv(d_vscale, src.d_vscale);
         mv(d_grp_begin, src.d_grp_begin); mv(d_n_grp0, src.d_n_grp0); mv(d_n_grp, src.d_n_grp); mv(voice_cap, src.voice_cap);
         mv(d_raw, src.d_raw); mv(raw_cap, src.raw_cap);
         mv(d_planes, src.d_planes); mv(planes_cap, src.planes_cap);
@@ -165,11 +170,37 @@ osc_rank_kernel(unsigned n_voices, const unsigned long long* __restrict__ voice_
     if (ln == 0 && my_att > 0.f) atomicMax(max_attack_bits, __float_as_uint(my_att));   // positive floats order like their bits
 }
 
-__global__ void osc_fill_kernel(uint64_t n, float4* __restrict__ hot, float4* __restrict__ anc, uint4* __restrict__ ph) {
+__global__ void osc_fill_kernel(uint64_t n, float4* __restrict__ hot, float4* __restrict__ anc, uint4* __restrict__ ph,
+                                float4* __restrict__ rot) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         hot[i] = make_float4(0.f, 0.f, 0.f, 0.f);           // a resonator that stays at 0
         anc[i] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
         ph[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (rot) rot[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+// K1G: per voice the power of two that brings the largest amplitude into [0.5, 1) (fp16 operands, osc_gemm.cuh)
+__global__ void osc_vscale_kernel(unsigned n_voices, const unsigned long long* __restrict__ voice_offsets,
+                                  const float* __restrict__ amp, float2* __restrict__ vscale) {
+    __shared__ float warp_max[8];
+    for (unsigned v = blockIdx.x; v < n_voices; v += gridDim.x) {
+        float m = 0.f;
+        for (unsigned long long p = voice_offsets[v] + threadIdx.x; p < voice_offsets[v + 1]; p += blockDim.x) {
+            const float a = fabsf(amp[p]);
+            if (isfinite(a)) m = fmaxf(m, a);
+        }
+        for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) warp_max[threadIdx.x >> 5] = m;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int k = 1; k < 8; k++) m = fmaxf(m, warp_max[k]);
+            int e = 0;
+            if (m > 0.f) frexpf(m, &e);                      // m = f 2^e, f in [0.5, 1)
+            e = max(-100, min(100, e));
+            vscale[v] = make_float2(exp2f((float)-e), exp2f((float)e));
+        }
     }
 }
 
@@ -179,7 +210,8 @@ __global__ void osc_setup_kernel(unsigned n_voices, const unsigned long long* __
                                  const unsigned* __restrict__ rank, double sample_rate, const double* __restrict__ freq,
                                  const float* __restrict__ amp, const float* __restrict__ phase,
                                  const float* __restrict__ attack, const float* __restrict__ tau,
-                                 float4* __restrict__ hot, float4* __restrict__ anc, uint4* __restrict__ ph) {
+                                 float4* __restrict__ hot, float4* __restrict__ anc, uint4* __restrict__ ph,
+                                 float4* __restrict__ rot) {
     const double PI = 3.14159265358979323846;
     for (unsigned v = blockIdx.y; v < n_voices; v += gridDim.y) {
     const unsigned long long vlo = voice_offsets[v], vhi = voice_offsets[v + 1];
@@ -229,8 +261,32 @@ __global__ void osc_setup_kernel(unsigned n_voices, const unsigned long long* __
         p0 -= floor(p0);
         const unsigned long long ph0 = __double2ull_rn(p0 * 18446744073709551616.0);
         ph[i] = make_uint4((unsigned)(inc & 0xffffffffull), (unsigned)(inc >> 32), (unsigned)(ph0 & 0xffffffffull), (unsigned)(ph0 >> 32));
+        if (rot) {                                          // K1G: N samples on = a rotation by N w and a decay by rho^N
+            float r4[4];
+            const double steps[2] = {8.0 * 128.0, 8.0};     // rows of a thread are 8 blocks apart, its columns 8 samples
+            for (int k = 0; k < 2; k++) {
+                double fn = fr * steps[k];
+                fn -= floor(fn);
+                const double R = decays ? exp(-steps[k] / (double)tf) : 1.0;
+                double sn, cs;
+                sincos(2.0 * PI * fn, &sn, &cs);
+                r4[2 * k] = (float)(R * cs); r4[2 * k + 1] = (float)(R * sn);
+            }
+            rot[i] = make_float4(r4[0], r4[1], r4[2], r4[3]);
+        }
     }
     }
+}
+
+// Which banks K1G renders (past their attack ramps): a property of the bank alone, so that a sample's value never depends on
+// how a render is cut into calls.  The tensor-core kernel wants a few hundred partials per voice (a step is 8 partials,
+// a tile 16,384 samples of one voice) and enough voices to fill the machine with tiles; everything else stays on the
+// resonator kernel.  FRB_OSC_GEMM=0 never, 2 every bank with the 16-record layout (tests).
+static bool osc_gemm_wanted(int K, uint32_t n_voices, uint64_t n_records) {
+    static const int mode = [] { const char* e = getenv("FRB_OSC_GEMM"); return e ? atoi(e) : 1; }();
+    if (mode == 0 || K != OSC_K || n_voices == 0) return false;
+    if (mode >= 2) return true;
+    return n_voices >= 4 && n_records / n_voices >= 512;
 }
 
 std::shared_ptr<OscBankDev> osc_create(const frb_oscbank_desc* d, cudaStream_t stream, std::string* err,
@@ -375,17 +431,20 @@ std::shared_ptr<OscBankDev> osc_create(const frb_oscbank_desc* d, cudaStream_t s
     }
 
     const uint64_t nn = std::max<uint64_t>(n, 1);
-    if (b->rec_cap < nn) {
-        cudaFree(b->d_hot); cudaFree(b->d_anc); cudaFree(b->d_ph);
-        b->d_hot = b->d_anc = nullptr; b->d_ph = nullptr; b->rec_cap = 0;
+    b->gemm = osc_gemm_wanted(K, nv, n);
+    if (b->rec_cap < nn || (b->gemm && !b->d_rot)) {
+        cudaFree(b->d_hot); cudaFree(b->d_anc); cudaFree(b->d_ph); cudaFree(b->d_rot);
+        b->d_hot = b->d_anc = b->d_rot = nullptr; b->d_ph = nullptr; b->rec_cap = 0;
         OC(cudaMalloc(&b->d_hot, nn * sizeof(float4))); OC(cudaMalloc(&b->d_anc, nn * sizeof(float4))); OC(cudaMalloc(&b->d_ph, nn * sizeof(uint4)));
+        if (b->gemm) OC(cudaMalloc(&b->d_rot, nn * sizeof(float4)));
         b->rec_cap = nn;
     }
     const uint32_t nv1 = std::max<uint32_t>(nv, 1);
-    if (b->voice_cap < nv1) {
-        cudaFree(b->d_grp_begin); cudaFree(b->d_n_grp0); cudaFree(b->d_n_grp);
-        b->d_grp_begin = b->d_n_grp0 = b->d_n_grp = nullptr; b->voice_cap = 0;
+    if (b->voice_cap < nv1 || (b->gemm && !b->d_vscale)) {
+        cudaFree(b->d_grp_begin); cudaFree(b->d_n_grp0); cudaFree(b->d_n_grp); cudaFree(b->d_vscale);
+        b->d_grp_begin = b->d_n_grp0 = b->d_n_grp = nullptr; b->d_vscale = nullptr; b->voice_cap = 0;
         OC(cudaMalloc(&b->d_grp_begin, nv1 * sizeof(uint32_t))); OC(cudaMalloc(&b->d_n_grp0, nv1 * sizeof(uint32_t))); OC(cudaMalloc(&b->d_n_grp, nv1 * sizeof(uint32_t)));
+        if (b->gemm) OC(cudaMalloc(&b->d_vscale, nv1 * sizeof(float2)));
         b->voice_cap = nv1;
     }
     if (nv) {
@@ -396,14 +455,18 @@ std::shared_ptr<OscBankDev> osc_create(const frb_oscbank_desc* d, cudaStream_t s
     lap("alloc records");
     if (n) {
         const unsigned fb = (unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 8);
-        osc_fill_kernel<<<fb, 256, 0, stream>>>(n, b->d_hot, b->d_anc, b->d_ph);
+        osc_fill_kernel<<<fb, 256, 0, stream>>>(n, b->d_hot, b->d_anc, b->d_ph, b->gemm ? b->d_rot : nullptr);
         OC(cudaGetLastError());
         lap("fill");
         const unsigned gy = std::min<uint32_t>(nv, 32768);
         const unsigned gx = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((mx + 255) / 256, std::max<uint64_t>(1, 148ull * 16 / gy)));
         osc_setup_kernel<<<dim3(gx, gy), 256, 0, stream>>>(nv, d_offs, K, b->d_grp_begin, b->d_n_grp0, d_rank, d->sample_rate, d_freq, d_amp,
-                                                           d_phase, d_attack, d_tau, b->d_hot, b->d_anc, b->d_ph);
+                                                           d_phase, d_attack, d_tau, b->d_hot, b->d_anc, b->d_ph, b->gemm ? b->d_rot : nullptr);
         OC(cudaGetLastError());
+        if (b->gemm) {
+            osc_vscale_kernel<<<std::min<uint32_t>(nv, 148 * 4), 256, 0, stream>>>(nv, d_offs, d_amp, b->d_vscale);
+            OC(cudaGetLastError());
+        }
     }
     if (!recycle) {   // a first definition is usually the only one: give the scratch (28 B per partial) back
         OC(cudaStreamSynchronize(stream));
@@ -723,12 +786,49 @@ cudaError_t osc_init_device() {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(osc_kernel<OSC_K_SMALL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(osc_kernel<OSC_K_ONE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(osc_kernel<OSC_K_ONE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(osc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GM_SMEM);
     return e;
 }
+
+static cudaError_t launch_osc_fma(const OscBankDev& b, const BufferDesc* d_bufdesc, uint32_t first_buf, uint64_t lo, uint64_t hi,
+                                  uint32_t anchor, int sm_count, cudaStream_t stream, uint64_t* n_launches);
 
 cudaError_t launch_osc(const OscBankDev& b, const BufferDesc* d_bufdesc, uint32_t first_buf, uint64_t lo, uint64_t hi,
                        uint32_t anchor, int sm_count, cudaStream_t stream, uint64_t* n_launches) {
     if (n_launches) *n_launches = 0;
+    if (hi <= lo || b.n_voices == 0) return cudaSuccess;
+    if (!b.gemm) return launch_osc_fma(b, d_bufdesc, first_buf, lo, hi, anchor, sm_count, stream, n_launches);
+    // K1G from the first 128-sample block past every attack ramp; the resonator kernels (with their ramp instance) before it
+    const uint64_t ramp_end = ((uint64_t)std::ceil((double)std::max(b.max_attack, 0.0f)) + GM_N - 1) / GM_N * GM_N;
+    if (lo < ramp_end) {
+        cudaError_t e = launch_osc_fma(b, d_bufdesc, first_buf, lo, std::min(hi, ramp_end), anchor, sm_count, stream, n_launches);
+        if (e != cudaSuccess) return e;
+    }
+    if (hi > ramp_end) {
+        OscGemmLaunch p;
+        p.anc = b.d_anc; p.ph = b.d_ph; p.rot = b.d_rot;
+        p.grp_begin = b.d_grp_begin; p.n_grp = b.d_n_grp; p.vscale = b.d_vscale;
+        p.bufdesc = d_bufdesc; p.first_buf = first_buf;
+        p.lo = std::max(lo, ramp_end); p.hi = hi;
+        p.K = b.K;
+        const uint64_t tile_len = (uint64_t)GM_M * GM_N;
+        p.tile0 = p.lo / tile_len;
+        const uint64_t n_tiles = (hi + tile_len - 1) / tile_len - p.tile0;
+        for (uint64_t t = 0; t < n_tiles; t += 65535) {                  // (grid.x is the wide dimension: tiles there, voices in y)
+            OscGemmLaunch q = p;
+            q.tile0 = p.tile0 + t;
+            const unsigned nx = (unsigned)std::min<uint64_t>(n_tiles - t, 65535);
+            osc_gemm_kernel<<<dim3(nx, b.n_voices), GM_THREADS, GM_SMEM, stream>>>(q);
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) return e;
+            if (n_launches) (*n_launches)++;
+        }
+    }
+    return cudaSuccess;
+}
+
+static cudaError_t launch_osc_fma(const OscBankDev& b, const BufferDesc* d_bufdesc, uint32_t first_buf, uint64_t lo, uint64_t hi,
+                                  uint32_t anchor, int sm_count, cudaStream_t stream, uint64_t* n_launches) {
     if (hi <= lo || b.n_voices == 0) return cudaSuccess;
     // split banks stage their partial-range planes in scratch: bound it by rendering 64 Ki samples at a time
     if (b.split == 1) return launch_osc_range(b, d_bufdesc, first_buf, lo, hi, anchor, sm_count, stream, n_launches);
