@@ -34,6 +34,7 @@
 #include "osc.cuh"
 #include "osc_one.cuh"
 #include "osc_gemm.cuh"
+#include "osc_tc.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -66,7 +67,7 @@ struct OscBankDev {
     uint4* d_ph = nullptr;          // {inc_lo, inc_hi, ph0_lo, ph0_hi}
     float4* d_rot = nullptr;        // K1G (osc_gemm.cuh): {rho^1024 (cos, sin)(1024 w), rho^8 (cos, sin)(8 w)}
     uint64_t rec_cap = 0;           // records the four arrays above can hold
-    float2* d_vscale = nullptr;     // K1G: per voice {2^k, 2^-k} with max |amp| 2^k in [0.5, 1)
+    float2* d_vscale = nullptr;     // K1G: per voice {2^k, 2^-k} with max |amp| 2^k in [2^13, 2^14)
     bool gemm = false;              // K1G renders this bank past its attack ramps (osc_gemm_wanted)
     uint32_t* d_grp_begin = nullptr;   // per voice: first group
     uint32_t* d_n_grp0 = nullptr;      // per voice: groups of class 0
@@ -180,7 +181,7 @@ __global__ void osc_fill_kernel(uint64_t n, float4* __restrict__ hot, float4* __
     }
 }
 
-// K1G: per voice the power of two that brings the largest amplitude into [0.5, 1) (fp16 operands, osc_gemm.cuh)
+// K1G / K1T: per voice the power of two that brings the largest amplitude into [2^13, 2^14) (fp16 operands, osc_gemm.cuh)
 __global__ void osc_vscale_kernel(unsigned n_voices, const unsigned long long* __restrict__ voice_offsets,
                                   const float* __restrict__ amp, float2* __restrict__ vscale) {
     __shared__ float warp_max[8];
@@ -199,7 +200,7 @@ __global__ void osc_vscale_kernel(unsigned n_voices, const unsigned long long* _
             int e = 0;
             if (m > 0.f) frexpf(m, &e);                      // m = f 2^e, f in [0.5, 1)
             e = max(-100, min(100, e));
-            vscale[v] = make_float2(exp2f((float)-e), exp2f((float)e));
+            vscale[v] = make_float2(exp2f((float)(14 - e)), exp2f((float)(e - 14)));
         }
     }
 }
@@ -282,12 +283,18 @@ __global__ void osc_setup_kernel(unsigned n_voices, const unsigned long long* __
 // how a render is cut into calls.  The tensor-core kernel wants a few hundred partials per voice (a step is 8 partials,
 // a tile 16,384 samples of one voice) and enough voices to fill the machine with tiles; everything else stays on the
 // resonator kernel.  FRB_OSC_GEMM=0 never, 2 every bank with the 16-record layout (tests).
-static bool osc_gemm_wanted(int K, uint32_t n_voices, uint64_t n_records) {
+static int osc_gemm_mode() {
     static const int mode = [] { const char* e = getenv("FRB_OSC_GEMM"); return e ? atoi(e) : 1; }();
+    return mode;
+}
+static bool osc_gemm_wanted(int K, uint32_t n_voices, uint64_t n_records) {
+    const int mode = osc_gemm_mode();
     if (mode == 0 || K != OSC_K || n_voices == 0) return false;
-    if (mode >= 2) return true;
+    if (mode == 2 || mode == 3) return true;
     return n_voices >= 4 && n_records / n_voices >= 512;
 }
+// which of the two matrix-product kernels: mma.sync (K1G, osc_gemm.cuh) or tcgen05 (K1T, osc_tc.cuh); FRB_OSC_GEMM=3 / 4 = K1T
+static bool osc_gemm_tcgen05() { const int m = osc_gemm_mode(); return m == 3 || m == 4; }
 
 std::shared_ptr<OscBankDev> osc_create(const frb_oscbank_desc* d, cudaStream_t stream, std::string* err,
                                        const std::shared_ptr<OscBankDev>& recycle, uint32_t shard_rank, uint32_t shard_world) {
@@ -787,6 +794,7 @@ cudaError_t osc_init_device() {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(osc_kernel<OSC_K_ONE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(osc_kernel<OSC_K_ONE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(osc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GM_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(osc_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM);
     return e;
 }
 
@@ -818,7 +826,8 @@ cudaError_t launch_osc(const OscBankDev& b, const BufferDesc* d_bufdesc, uint32_
             OscGemmLaunch q = p;
             q.tile0 = p.tile0 + t;
             const unsigned nx = (unsigned)std::min<uint64_t>(n_tiles - t, 65535);
-            osc_gemm_kernel<<<dim3(nx, b.n_voices), GM_THREADS, GM_SMEM, stream>>>(q);
+            if (osc_gemm_tcgen05()) osc_tc_kernel<<<dim3(nx, b.n_voices), GT_THREADS, GT_SMEM, stream>>>(q);
+            else osc_gemm_kernel<<<dim3(nx, b.n_voices), GM_THREADS, GM_SMEM, stream>>>(q);
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) return e;
             if (n_launches) (*n_launches)++;

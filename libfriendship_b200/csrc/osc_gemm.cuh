@@ -11,8 +11,9 @@
 // osc_group does it (phase in 64-bit fixed-point turns = exact range reduction, MUFU sin/cos/ex2).
 //   * arithmetic: fp16 x fp16 -> fp32 (mma.sync.m16n8k16, SASS HMMA.16816.F32).  fp16 alone is 11 bits, so every operand
 //     is split x = hi + lo (two fp16: 22 bits) and a step issues lo*hi + hi*lo + hi*hi (the lo*lo term is 2^-22 of the
-//     product).  A is scaled per voice by a power of two so that the largest amplitude is in [0.5, 1): fp16 never
-//     overflows, and what it flushes is 2^-25 of the voice's full scale.
+//     product).  fp16 has a short exponent range too (spacing 2^-24 below 6e-5), so A is scaled per voice by a power of
+//     two that puts the largest amplitude into [2^13, 2^14) and W by 2^10: a partial 2^-20 of the loudest one still has
+//     all 22 bits, nothing overflows (the products add up in fp32), and the write-out multiplies the scale back out.
 //   * accumulation: a tensor-core accumulator takes one rounding per MMA; thousands of them in a row drift.  The MMA
 //     accumulators are therefore added into fp32 sums in shared memory (FADD, round to nearest) every GM_FLUSH steps
 //     (256 partials) and cleared.
@@ -32,6 +33,7 @@ constexpr int GM_N = 128;            // samples per block (GEMM N)
 constexpr int GM_M = 128;            // blocks per CTA tile (GEMM M)
 constexpr int GM_THREADS = 128;      // 4 warps, 2 x 2, warp tile 64 x 64
 constexpr int GM_FLUSH = 32;         // k-steps (8 partials each) between flushes of the MMA accumulators
+constexpr float GM_WSCALE = 1024.0f; // W is generated times 2^10 (see above)
 constexpr int GM_ROW_STRIDE = 8 * GM_N;   // samples between consecutive rows of a thread (rows g, g + 8, ...)
 constexpr size_t GM_SMEM = (size_t)4 * 32 * 32 * sizeof(float4);   // fp32 sums: [warp][quad][lane]
 
@@ -140,7 +142,7 @@ __global__ void __launch_bounds__(GM_THREADS, 2) osc_gemm_kernel(OscGemmLaunch p
             const float kappa = R.anc[tq + 4 * q].z;
             const float4 rt = R.rot[tq + 4 * q];
             float ws, wc;
-            gm_anchor(ph.x, ph.y, 0u, kappa, 1.0f, col0, ws, wc);
+            gm_anchor(ph.x, ph.y, 0u, kappa, GM_WSCALE, col0, ws, wc);
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 gm_split(wc, ws, bh[j][q], bl[j][q]);
@@ -190,7 +192,8 @@ __global__ void __launch_bounds__(GM_THREADS, 2) osc_gemm_kernel(OscGemmLaunch p
             const unsigned long long r = tile * GM_M + 64u * wm + 16u * i + g;
             const unsigned c = 64u * wn + 8u * j + 2u * tq;
             const unsigned long long t0 = r * GM_N + c, t1 = t0 + (unsigned long long)GM_ROW_STRIDE;
-            const float o[4] = {s.x * vs.y, s.y * vs.y, s.z * vs.y, s.w * vs.y};
+            const float un = vs.y * (1.0f / GM_WSCALE);
+            const float o[4] = {s.x * un, s.y * un, s.z * un, s.w * un};
             if (t0 >= p.lo && t0 + 2 <= p.hi) *reinterpret_cast<float2*>(bd.data + (t0 & bd.mask)) = make_float2(o[0], o[1]);
             else { if (t0 >= p.lo && t0 < p.hi) bd.data[t0 & bd.mask] = o[0]; if (t0 + 1 >= p.lo && t0 + 1 < p.hi) bd.data[(t0 + 1) & bd.mask] = o[1]; }
             if (t1 >= p.lo && t1 + 2 <= p.hi) *reinterpret_cast<float2*>(bd.data + (t1 & bd.mask)) = make_float2(o[2], o[3]);
