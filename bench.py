@@ -225,7 +225,7 @@ def workload_config(n_gpus, exchange="NCCL reduce"):
             "voices": N_VOICES, "partials_per_voice": N_PARTIALS, "samples": N_SAMPLES, "sample_rate": SR,
             "partial_samples_per_step": N_VOICES * N_PARTIALS * N_SAMPLES,
             "sharding": f"voices round-robin over {n_gpus} GPU(s), one {exchange} exchange of the [1 x 480000] mix per step",
-            "cache": "compute-bound; per-step parameter stream 201 MB/GPU-shard-of-64 > 126 MB L2, re-read every 64k-sample block",
+            "cache": "compute-bound; per-step parameter stream 201 MB/GPU-shard-of-64 > 126 MB L2, re-read by every 16,384-sample tile of a voice",
             "inputs": "synthesis: the graph's only input is the bank's parameter arrays (24 B per partial, host). "
                       "`value`: uploaded once, resident in HBM when the timed region starts. `e2e`: re-uploaded from pinned "
                       "host memory through frb_define_oscbank every step, inside the timed region"}
@@ -387,18 +387,44 @@ def main():
             traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
         except Exception:
             pass
-        line = {
-            "metric": "rendered partial-samples/sec", "value": value, "unit": "partial-samples/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(world, "NCCL reduce" if args.exchange == "nccl" else "P2P-store + rank-ordered sum (K5)"),
-            "e2e": {"value": e2e_v, "unit": "partial-samples/s", "h2d_bytes_per_step": int(h2d.item()),
-                    "d2h_bytes_per_step": 4 * n_samples, "ms_per_step": ms_e2e / args.steps,
-                    "gpu_launches": int(s3["kernel_launches"] - s2["kernel_launches"]),
-                    "calls": "per step: frb_define_oscbank(pinned host arrays) + frb_fill_buffer(host out)"},
-            "gpu_launches": int(s1["kernel_launches"] - s0["kernel_launches"]),
-            "clocks": sampler.result(),
-            "roofline": {
+        tensor_launches = int(s1.get("osc_tensor_launches", 0) - s0.get("osc_tensor_launches", 0))
+        k1_ms = float(osc_ms.item())
+        share = k1_ms / float(tot_ms.item())
+        if tensor_launches > 0:
+            # K1T / K1G (csrc/osc_tc.cuh, osc_gemm.cuh): the bank past its attack ramps is a matrix product on the tensor cores
+            tile = 128 * 128
+            ramp_end = 384                                          # longest attack ramp of the bench bank (48 * 7 = 336), in 128-sample blocks
+            n_tiles = -(-n_samples // tile) - ramp_end // tile
+            stages = -(-n_partials // 16)
+            issued = len(my_voices) * n_tiles * stages * 6 * 2.0 * 128 * 128 * 16      # six M128 N128 K16 MMAs per 16 partials and tile
+            algorithmic = ps_per_gpu * FMA_SLOTS_PER_PARTIAL_SAMPLE * 2                  # 6 slots = 12 flop per partial-sample
+            peak_tensor = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1369.6))
+            tensor_kernel = os.environ.get("FRB_OSC_GEMM", "1") not in ("2", "5")
+            roofline = {
+                "kernel": "osc_tc_kernel (K1T, tcgen05)" if tensor_kernel else "osc_gemm_kernel (K1G, mma.sync)",
+                "bound": "tensor", "achieved": algorithmic / osc_s / 1e12, "peak": peak_tensor, "unit": "TFLOP/s",
+                "frac": algorithmic / osc_s / 1e12 / peak_tensor,
+                "frac_note": "SURVEY.md 8d's algorithmic 12 flop (6 FMA slots) per partial-sample over the K1 family's time, against the "
+                             "measured dense 16-bit tensor peak.  The kernel ISSUES 12 flop per partial-sample of its tiles too "
+                             "(fp16 hi/lo split: three M128 N128 K16 MMAs per 8 partials, 2 K flop per sample) — issued_frac counts the "
+                             "tiles' padding as well.  What bounds the kernel is generating the operands (FMA / conversion pipes, "
+                             "shared-memory stores), not the tensor pipe: DESIGN.md",
+                "issued_tflops": issued / osc_s / 1e12, "issued_frac": issued / osc_s / 1e12 / peak_tensor,
+                "traffic": None,
+                "traffic_note": "DRAM traffic is the parameter records (48 B per partial and tile, L2 hits after the first tile of a voice) "
+                                "and the output: under 1% of the HBM peak; no ncu capture of this kernel yet",
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16 8192^3 back to back; fp16 runs at the same rate); "
+                               f"burst {peaks.get('bf16_tflops')}",
+                "algorithmic": "12 flop per partial-sample x partial-samples per step (SURVEY.md 8d)",
+                "fp32_fma_equivalent_frac": ps_per_gpu * EXECUTED_OPS_PER_PARTIAL_SAMPLE / osc_s / peak_fma,
+                "k1_family_launches_per_step": int(n_osc_launches), "tensor_launches_per_step": tensor_launches // max(1, args.steps),
+                "k1_ms_per_step": k1_ms,
+                "launches_note": "K1 family = the matrix-product kernel (one launch) + the resonator kernels of the attack-ramp region "
+                                 "(main, ramp instance, plane reduce); time = CUDA events on the renderer's stream",
+                "kernel_share_of_step": share,
+            }
+        else:
+            roofline = {
                 "kernel": "osc_kernel<16,false> (K1)", "bound": "fp32_fma", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved / peak_tf,
                 "frac_note": "issued-op utilisation of the FP32 pipe: K1 issues 4 ops per partial-sample (3 FFMA + 1 FADD: the decay is "
@@ -412,12 +438,26 @@ def main():
                                "tools/microbench/fma_peak.cu measured 3.60e13 FMA/s = 97% of it on this pool",
                 "algorithmic": "issued: 4 FP32 ops (8 flop) per partial-sample x partial-samples per step; SURVEY.md §8d: 6 slots (12 flop)",
                 "executed_frac": ps_per_gpu * EXECUTED_OPS_PER_PARTIAL_SAMPLE / osc_s / peak_fma,
-                "k1_family_launches_per_step": int(n_osc_launches), "k1_ms_per_step": float(osc_ms.item()),
+                "k1_family_launches_per_step": int(n_osc_launches), "k1_ms_per_step": k1_ms,
                 "launches_note": "K1 family = main kernel per sub-block + its plane reduce + one attack-ramp kernel; "
                                  "achieved = algorithmic flop of the step / summed K1 time (CUDA events on the renderer's stream)",
-                "kernel_share_of_step": float(osc_ms.item()) / float(tot_ms.item()),
-            },
+                "kernel_share_of_step": share,
+            }
+        line = {
+            "metric": "rendered partial-samples/sec", "value": value, "unit": "partial-samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(world, "NCCL reduce" if args.exchange == "nccl" else "P2P-store + rank-ordered sum (K5)"),
+            "e2e": {"value": e2e_v, "unit": "partial-samples/s", "h2d_bytes_per_step": int(h2d.item()),
+                    "d2h_bytes_per_step": 4 * n_samples, "ms_per_step": ms_e2e / args.steps,
+                    "gpu_launches": int(s3["kernel_launches"] - s2["kernel_launches"]),
+                    "calls": "per step: frb_define_oscbank(pinned host arrays) + frb_fill_buffer(host out)"},
+            "gpu_launches": int(s1["kernel_launches"] - s0["kernel_launches"]),
+            "clocks": sampler.result(),
+            "roofline": roofline,
         }
+        if tensor_launches > 0:
+            line["dtype"] = "f32 (operands split into 2 x fp16 = 22 bits, products exact, fp32 accumulation; parity below)"
         if not (args.voices == N_VOICES and args.partials == N_PARTIALS and args.samples == N_SAMPLES):
             line["config"]["workload"] = f"DEBUG reduced workload {n_voices}x{n_partials}x{n_samples}: not a valid bench number"
         if world == 1 and not args.no_cpu_baseline:

@@ -237,6 +237,7 @@ typedef struct frb_stats {
     uint64_t scan_launches;
     uint64_t jit_launches;      /* stage launches that ran a JIT-compiled kernel instead of the interpreter */
     uint64_t chain_launches;    /* fused DirectForm -> FbDelay launches (counted in scan_launches too) */
+    uint64_t osc_tensor_launches; /* of osc_launches: the matrix-product oscillator kernels (tensor cores: K1T tcgen05 / K1G mma.sync) */
 } frb_stats;
 int frb_get_stats(const frb_renderer* r, frb_stats* out);
 

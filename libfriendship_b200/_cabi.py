@@ -74,7 +74,7 @@ class frb_fbdelay_desc(C.Structure):
 class frb_stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("kernel_launches", "h2d_bytes", "d2h_bytes", "schedule_builds",
                                            "osc_launches", "interp_launches", "scan_launches", "jit_launches",
-                                           "chain_launches")]
+                                           "chain_launches", "osc_tensor_launches")]
 
 
 class frb_timing(C.Structure):

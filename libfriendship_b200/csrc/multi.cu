@@ -269,6 +269,7 @@ frb_stats MultiRenderer::get_stats() const {
         s.kernel_launches += a.kernel_launches; s.h2d_bytes += a.h2d_bytes; s.d2h_bytes += a.d2h_bytes;
         s.schedule_builds += a.schedule_builds; s.osc_launches += a.osc_launches; s.interp_launches += a.interp_launches;
         s.scan_launches += a.scan_launches; s.jit_launches += a.jit_launches; s.chain_launches += a.chain_launches;
+        s.osc_tensor_launches += a.osc_tensor_launches;
     }
     return s;
 }

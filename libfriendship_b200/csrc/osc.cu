@@ -282,7 +282,8 @@ __global__ void osc_setup_kernel(unsigned n_voices, const unsigned long long* __
 // Which banks K1G renders (past their attack ramps): a property of the bank alone, so that a sample's value never depends on
 // how a render is cut into calls.  The tensor-core kernel wants a few hundred partials per voice (a step is 8 partials,
 // a tile 16,384 samples of one voice) and enough voices to fill the machine with tiles; everything else stays on the
-// resonator kernel.  FRB_OSC_GEMM=0 never, 2 every bank with the 16-record layout (tests).
+// resonator kernel.  FRB_OSC_GEMM (measurement / test knob): unset or 1 = this rule, on tcgen05 (K1T); 0 = never;
+// 2 / 3 = every bank with the 16-record layout, on mma.sync (K1G) / tcgen05; 5 = this rule on mma.sync.
 static int osc_gemm_mode() {
     static const int mode = [] { const char* e = getenv("FRB_OSC_GEMM"); return e ? atoi(e) : 1; }();
     return mode;
@@ -293,8 +294,8 @@ static bool osc_gemm_wanted(int K, uint32_t n_voices, uint64_t n_records) {
     if (mode == 2 || mode == 3) return true;
     return n_voices >= 4 && n_records / n_voices >= 512;
 }
-// which of the two matrix-product kernels: mma.sync (K1G, osc_gemm.cuh) or tcgen05 (K1T, osc_tc.cuh); FRB_OSC_GEMM=3 / 4 = K1T
-static bool osc_gemm_tcgen05() { const int m = osc_gemm_mode(); return m == 3 || m == 4; }
+// which of the two matrix-product kernels: tcgen05 (K1T, osc_tc.cuh) unless the knob asks for mma.sync (K1G, osc_gemm.cuh)
+static bool osc_gemm_tcgen05() { const int m = osc_gemm_mode(); return m != 2 && m != 5; }
 
 std::shared_ptr<OscBankDev> osc_create(const frb_oscbank_desc* d, cudaStream_t stream, std::string* err,
                                        const std::shared_ptr<OscBankDev>& recycle, uint32_t shard_rank, uint32_t shard_world) {
@@ -802,8 +803,9 @@ static cudaError_t launch_osc_fma(const OscBankDev& b, const BufferDesc* d_bufde
                                   uint32_t anchor, int sm_count, cudaStream_t stream, uint64_t* n_launches);
 
 cudaError_t launch_osc(const OscBankDev& b, const BufferDesc* d_bufdesc, uint32_t first_buf, uint64_t lo, uint64_t hi,
-                       uint32_t anchor, int sm_count, cudaStream_t stream, uint64_t* n_launches) {
+                       uint32_t anchor, int sm_count, cudaStream_t stream, uint64_t* n_launches, uint64_t* n_tensor_launches) {
     if (n_launches) *n_launches = 0;
+    if (n_tensor_launches) *n_tensor_launches = 0;
     if (hi <= lo || b.n_voices == 0) return cudaSuccess;
     if (!b.gemm) return launch_osc_fma(b, d_bufdesc, first_buf, lo, hi, anchor, sm_count, stream, n_launches);
     // K1G from the first 128-sample block past every attack ramp; the resonator kernels (with their ramp instance) before it
@@ -831,6 +833,7 @@ cudaError_t launch_osc(const OscBankDev& b, const BufferDesc* d_bufdesc, uint32_
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) return e;
             if (n_launches) (*n_launches)++;
+            if (n_tensor_launches) (*n_tensor_launches)++;
         }
     }
     return cudaSuccess;

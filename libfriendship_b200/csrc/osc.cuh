@@ -40,6 +40,7 @@ bool osc_one_source(const OscBankDev& b, OscOneSrc* out);
 // Renders every voice of the bank over absolute times [lo, hi) into the voices' ring buffers
 // bufdesc[first_buf + v].  `anchor` = samples between exact re-anchors of each partial.
 cudaError_t launch_osc(const OscBankDev& b, const BufferDesc* d_bufdesc, uint32_t first_buf, uint64_t lo, uint64_t hi,
-                       uint32_t anchor, int sm_count, cudaStream_t stream, uint64_t* n_launches);
+                       uint32_t anchor, int sm_count, cudaStream_t stream, uint64_t* n_launches,
+                       uint64_t* n_tensor_launches = nullptr);   // of *n_launches: the matrix-product kernels (osc_gemm.cuh, osc_tc.cuh)
 
 }  // namespace frb

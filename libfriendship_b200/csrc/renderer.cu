@@ -741,12 +741,13 @@ void Renderer::run_range(uint64_t lo, uint64_t hi, float* d_out, uint64_t t0, ui
             const Stage& st = sched_.stages[sg];
             for (uint32_t xi : st.ext) {
                 const ExtInstance& x = sched_.ext[xi];
-                uint64_t nl = 0;
+                uint64_t nl = 0, nt = 0;
                 if (x.kind == EXT_OSCBANK && exc_fused_[xi]) {
                     continue;                                   // evaluated inside the chain kernel that reads it
                 } else if (x.kind == EXT_OSCBANK) {
-                    timed(&frb_timing::osc_ms, [&] { CU(launch_osc(*osc_defs_.at(x.key), d_bufdesc_, x.first_out_buf, c0, c1, cfg_.osc_anchor, sm_count_, stream_, &nl)); });
+                    timed(&frb_timing::osc_ms, [&] { CU(launch_osc(*osc_defs_.at(x.key), d_bufdesc_, x.first_out_buf, c0, c1, cfg_.osc_anchor, sm_count_, stream_, &nl, &nt)); });
                     stats.osc_launches += nl;
+                    stats.osc_tensor_launches += nt;
                 } else if (x.kind == EXT_DIRECTFORM && chained_[xi]) {
                     continue;                                   // runs inside its comb's launch
                 } else if (x.kind == EXT_FBDELAY && chain_of_[xi] >= 0) {
