@@ -2,8 +2,10 @@
 //
 //   out_v(t) = sum_p amp_p * min(t/A_p, 1) * exp(-t/tau_p) * sin(2 pi f_p t / sr + phi_p)
 //
-// Bound: the FP32 FMA pipe (128 lanes/clk/SM; measured 125 on B200 with tools/microbench/fma_peak.cu).
-// There is no dense contraction here, so tensor cores are not used.
+// This file: the resonator kernel K1 (attack ramps of every bank; banks of few or small voices), the definition pipeline and
+// the launch policy.  Past the ramps a bank of big voices is a matrix product and runs on the tensor cores: osc_tc.cuh (K1T,
+// tcgen05) / osc_gemm.cuh (K1G, mma.sync), see osc_gemm_wanted and launch_osc below.
+// K1's bound: the FP32 FMA pipe (128 lanes/clk/SM; measured 125 on B200 with tools/microbench/fma_peak.cu).
 //
 // Design (measured choices: tools/microbench/, profiles/ncu_osc_r1*_summary.txt):
 //  * One thread owns one time SEGMENT of L = 128 consecutive samples of one voice, and walks through the partials of
