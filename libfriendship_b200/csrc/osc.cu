@@ -68,6 +68,7 @@ struct OscBankDev {
     float4* d_anc = nullptr;        // {k2, amp, kappa, invA}
     uint4* d_ph = nullptr;          // {inc_lo, inc_hi, ph0_lo, ph0_hi}
     float4* d_rot = nullptr;        // K1G (osc_gemm.cuh): {rho^1024 (cos, sin)(1024 w), rho^8 (cos, sin)(8 w)}
+    uint32_t* d_tc = nullptr;       // K1T (osc_tc.cuh): per record group 9 words x 16 records (GT_REC_WORDS), what a stage reads
     uint64_t rec_cap = 0;           // records the four arrays above can hold
     float2* d_vscale = nullptr;     // K1G: per voice {2^k, 2^-k} with max |amp| 2^k in [2^13, 2^14)
     bool gemm = false;              // K1G renders this bank past its attack ramps (osc_gemm_wanted)
@@ -87,27 +88,33 @@ struct OscBankDev {
     mutable bool red_pending[2] = {false, false};
     mutable cudaStream_t side = nullptr;   // the (tiny, slow) attack-ramp kernel runs beside the main kernel
     mutable cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    mutable cudaStream_t gside = nullptr;  // K1T / K1G: the resonator kernels of the ramp region run beside the matrix-product kernel
+    mutable cudaEvent_t ev_gfork = nullptr, ev_gjoin = nullptr;
     ~OscBankDev() {
         if (side) cudaStreamDestroy(side);
+        if (gside) cudaStreamDestroy(gside);
+        if (ev_gfork) cudaEventDestroy(ev_gfork);
+        if (ev_gjoin) cudaEventDestroy(ev_gjoin);
         if (red) cudaStreamDestroy(red);
         if (main2) cudaStreamDestroy(main2);
         if (ev_enter) cudaEventDestroy(ev_enter);
         for (int i = 0; i < 2; i++) { if (ev_main[i]) cudaEventDestroy(ev_main[i]); if (ev_red[i]) cudaEventDestroy(ev_red[i]); }
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_join) cudaEventDestroy(ev_join);
-        cudaFree(d_hot); cudaFree(d_anc); cudaFree(d_ph); cudaFree(d_rot); cudaFree(d_vscale);
+        cudaFree(d_hot); cudaFree(d_anc); cudaFree(d_ph); cudaFree(d_rot); cudaFree(d_tc); cudaFree(d_vscale);
         cudaFree(d_grp_begin); cudaFree(d_n_grp0); cudaFree(d_n_grp); cudaFree(d_planes); cudaFree(d_raw);
     }
     // a bank that replaces `src` under the same key takes over every device allocation of it (cudaMalloc / cudaFree cost
     // milliseconds each beside a busy context; a re-definition per render must not pay them)
     void take_buffers(OscBankDev& src) {
         auto mv = [](auto& a, auto& b2) { a = b2; b2 = {}; };
-        mv(d_hot, src.d_hot); mv(d_anc, src.d_anc); mv(d_ph, src.d_ph); mv(d_rot, src.d_rot); mv(rec_cap, src.rec_cap);
+        mv(d_hot, src.d_hot); mv(d_anc, src.d_anc); mv(d_ph, src.d_ph); mv(d_rot, src.d_rot); mv(d_tc, src.d_tc); mv(rec_cap, src.rec_cap);
         mv(d_vscale, src.d_vscale);
         mv(d_grp_begin, src.d_grp_begin); mv(d_n_grp0, src.d_n_grp0); mv(d_n_grp, src.d_n_grp); mv(voice_cap, src.voice_cap);
         mv(d_raw, src.d_raw); mv(raw_cap, src.raw_cap);
         mv(d_planes, src.d_planes); mv(planes_cap, src.planes_cap);
         mv(side, src.side); mv(ev_fork, src.ev_fork); mv(ev_join, src.ev_join);
+        mv(gside, src.gside); mv(ev_gfork, src.ev_gfork); mv(ev_gjoin, src.ev_gjoin);
         mv(red, src.red); mv(main2, src.main2); mv(ev_enter, src.ev_enter);
         for (int i = 0; i < 2; i++) { mv(ev_main[i], src.ev_main[i]); mv(ev_red[i], src.ev_red[i]); red_pending[i] = false; }
     }
@@ -174,12 +181,16 @@ osc_rank_kernel(unsigned n_voices, const unsigned long long* __restrict__ voice_
 }
 
 __global__ void osc_fill_kernel(uint64_t n, float4* __restrict__ hot, float4* __restrict__ anc, uint4* __restrict__ ph,
-                                float4* __restrict__ rot) {
+                                float4* __restrict__ rot, uint32_t* __restrict__ tc) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         hot[i] = make_float4(0.f, 0.f, 0.f, 0.f);           // a resonator that stays at 0
         anc[i] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
         ph[i] = make_uint4(0u, 0u, 0u, 0u);
         if (rot) rot[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tc) {
+#pragma unroll
+            for (int wd = 0; wd < GT_REC_WORDS; wd++) tc[(i / 16) * (GT_REC_WORDS * 16) + wd * 16 + (i % 16)] = 0u;
+        }
     }
 }
 
@@ -214,7 +225,7 @@ __global__ void osc_setup_kernel(unsigned n_voices, const unsigned long long* __
                                  const float* __restrict__ amp, const float* __restrict__ phase,
                                  const float* __restrict__ attack, const float* __restrict__ tau,
                                  float4* __restrict__ hot, float4* __restrict__ anc, uint4* __restrict__ ph,
-                                 float4* __restrict__ rot) {
+                                 float4* __restrict__ rot, uint32_t* __restrict__ tc) {
     const double PI = 3.14159265358979323846;
     for (unsigned v = blockIdx.y; v < n_voices; v += gridDim.y) {
     const unsigned long long vlo = voice_offsets[v], vhi = voice_offsets[v + 1];
@@ -276,6 +287,13 @@ __global__ void osc_setup_kernel(unsigned n_voices, const unsigned long long* __
                 r4[2 * k] = (float)(R * cs); r4[2 * k + 1] = (float)(R * sn);
             }
             rot[i] = make_float4(r4[0], r4[1], r4[2], r4[3]);
+            if (tc) {                                       // the same numbers, word-major per group of 16 records
+                uint32_t* g = tc + (i / 16) * (GT_REC_WORDS * 16) + (i % 16);
+                g[0 * 16] = (unsigned)(inc & 0xffffffffull); g[1 * 16] = (unsigned)(inc >> 32); g[2 * 16] = (unsigned)(ph0 >> 32);
+                g[3 * 16] = __float_as_uint(kappa); g[4 * 16] = __float_as_uint(am);
+                g[5 * 16] = __float_as_uint(r4[0]); g[6 * 16] = __float_as_uint(r4[1]);
+                g[7 * 16] = __float_as_uint(r4[2]); g[8 * 16] = __float_as_uint(r4[3]);
+            }
         }
     }
     }
@@ -443,10 +461,13 @@ std::shared_ptr<OscBankDev> osc_create(const frb_oscbank_desc* d, cudaStream_t s
     const uint64_t nn = std::max<uint64_t>(n, 1);
     b->gemm = osc_gemm_wanted(K, nv, n);
     if (b->rec_cap < nn || (b->gemm && !b->d_rot)) {
-        cudaFree(b->d_hot); cudaFree(b->d_anc); cudaFree(b->d_ph); cudaFree(b->d_rot);
-        b->d_hot = b->d_anc = b->d_rot = nullptr; b->d_ph = nullptr; b->rec_cap = 0;
+        cudaFree(b->d_hot); cudaFree(b->d_anc); cudaFree(b->d_ph); cudaFree(b->d_rot); cudaFree(b->d_tc);
+        b->d_hot = b->d_anc = b->d_rot = nullptr; b->d_ph = nullptr; b->d_tc = nullptr; b->rec_cap = 0;
         OC(cudaMalloc(&b->d_hot, nn * sizeof(float4))); OC(cudaMalloc(&b->d_anc, nn * sizeof(float4))); OC(cudaMalloc(&b->d_ph, nn * sizeof(uint4)));
-        if (b->gemm) OC(cudaMalloc(&b->d_rot, nn * sizeof(float4)));
+        if (b->gemm) {
+            OC(cudaMalloc(&b->d_rot, nn * sizeof(float4)));
+            OC(cudaMalloc(&b->d_tc, ((nn + 15) / 16) * GT_REC_WORDS * 16 * sizeof(uint32_t)));
+        }
         b->rec_cap = nn;
     }
     const uint32_t nv1 = std::max<uint32_t>(nv, 1);
@@ -465,13 +486,13 @@ std::shared_ptr<OscBankDev> osc_create(const frb_oscbank_desc* d, cudaStream_t s
     lap("alloc records");
     if (n) {
         const unsigned fb = (unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 8);
-        osc_fill_kernel<<<fb, 256, 0, stream>>>(n, b->d_hot, b->d_anc, b->d_ph, b->gemm ? b->d_rot : nullptr);
+        osc_fill_kernel<<<fb, 256, 0, stream>>>(n, b->d_hot, b->d_anc, b->d_ph, b->gemm ? b->d_rot : nullptr, b->gemm ? b->d_tc : nullptr);
         OC(cudaGetLastError());
         lap("fill");
         const unsigned gy = std::min<uint32_t>(nv, 32768);
         const unsigned gx = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((mx + 255) / 256, std::max<uint64_t>(1, 148ull * 16 / gy)));
         osc_setup_kernel<<<dim3(gx, gy), 256, 0, stream>>>(nv, d_offs, K, b->d_grp_begin, b->d_n_grp0, d_rank, d->sample_rate, d_freq, d_amp,
-                                                           d_phase, d_attack, d_tau, b->d_hot, b->d_anc, b->d_ph, b->gemm ? b->d_rot : nullptr);
+                                                           d_phase, d_attack, d_tau, b->d_hot, b->d_anc, b->d_ph, b->gemm ? b->d_rot : nullptr, b->gemm ? b->d_tc : nullptr);
         OC(cudaGetLastError());
         if (b->gemm) {
             osc_vscale_kernel<<<std::min<uint32_t>(nv, 148 * 4), 256, 0, stream>>>(nv, d_offs, d_amp, b->d_vscale);
@@ -812,13 +833,27 @@ cudaError_t launch_osc(const OscBankDev& b, const BufferDesc* d_bufdesc, uint32_
     if (!b.gemm) return launch_osc_fma(b, d_bufdesc, first_buf, lo, hi, anchor, sm_count, stream, n_launches);
     // K1G from the first 128-sample block past every attack ramp; the resonator kernels (with their ramp instance) before it
     const uint64_t ramp_end = ((uint64_t)std::ceil((double)std::max(b.max_attack, 0.0f)) + GM_N - 1) / GM_N * GM_N;
-    if (lo < ramp_end) {
-        cudaError_t e = launch_osc_fma(b, d_bufdesc, first_buf, lo, std::min(hi, ramp_end), anchor, sm_count, stream, n_launches);
+    // The ramp region is a few hundred samples — a handful of one-warp CTAs per voice walking every partial, 1.2 ms on cfg4 —
+    // and writes other samples than the matrix-product kernel: it runs on a stream of its own beside it.
+    const bool beside = lo < ramp_end && hi > ramp_end;
+    if (beside && !b.gside) {
+        int lo_prio = 0, hi_prio = 0;
+        cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio);
+        cudaError_t e = cudaStreamCreateWithPriority(&b.gside, cudaStreamNonBlocking, hi_prio);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b.ev_gfork, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b.ev_gjoin, cudaEventDisableTiming);
         if (e != cudaSuccess) return e;
+    }
+    if (lo < ramp_end) {
+        cudaStream_t rs = stream;
+        if (beside) { cudaEventRecord(b.ev_gfork, stream); cudaStreamWaitEvent(b.gside, b.ev_gfork, 0); rs = b.gside; }
+        cudaError_t e = launch_osc_fma(b, d_bufdesc, first_buf, lo, std::min(hi, ramp_end), anchor, sm_count, rs, n_launches);
+        if (e != cudaSuccess) return e;
+        if (beside) cudaEventRecord(b.ev_gjoin, b.gside);
     }
     if (hi > ramp_end) {
         OscGemmLaunch p;
-        p.anc = b.d_anc; p.ph = b.d_ph; p.rot = b.d_rot;
+        p.anc = b.d_anc; p.ph = b.d_ph; p.rot = b.d_rot; p.tc = b.d_tc;
         p.grp_begin = b.d_grp_begin; p.n_grp = b.d_n_grp; p.vscale = b.d_vscale;
         p.bufdesc = d_bufdesc; p.first_buf = first_buf;
         p.lo = std::max(lo, ramp_end); p.hi = hi;
@@ -838,6 +873,7 @@ cudaError_t launch_osc(const OscBankDev& b, const BufferDesc* d_bufdesc, uint32_
             if (n_tensor_launches) (*n_tensor_launches)++;
         }
     }
+    if (beside) cudaStreamWaitEvent(stream, b.ev_gjoin, 0);
     return cudaSuccess;
 }
 

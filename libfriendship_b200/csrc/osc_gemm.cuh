@@ -34,11 +34,13 @@ constexpr int GM_M = 128;            // blocks per CTA tile (GEMM M)
 constexpr int GM_THREADS = 128;      // 4 warps, 2 x 2, warp tile 64 x 64
 constexpr int GM_FLUSH = 32;         // k-steps (8 partials each) between flushes of the MMA accumulators
 constexpr float GM_WSCALE = 1024.0f; // W is generated times 2^10 (see above)
+constexpr int GT_REC_WORDS = 9;      // K1T's record: inc_lo, inc_hi, ph0_hi, kappa, amp, rho^1024 (cos, sin), rho^8 (cos, sin)
 constexpr int GM_ROW_STRIDE = 8 * GM_N;   // samples between consecutive rows of a thread (rows g, g + 8, ...)
 constexpr size_t GM_SMEM = (size_t)4 * 32 * 32 * sizeof(float4);   // fp32 sums: [warp][quad][lane]
 
 struct OscGemmLaunch {
     const float4* anc; const uint4* ph; const float4* rot;
+    const uint32_t* tc;              // K1T: the same record fields word-major per group of 16 (GT_REC_WORDS x 16 words)
     const uint32_t* grp_begin; const uint32_t* n_grp; const float2* vscale;
     const BufferDesc* bufdesc; uint32_t first_buf;
     unsigned long long lo, hi;       // absolute output window [lo, hi)

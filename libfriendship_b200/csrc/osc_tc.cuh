@@ -33,7 +33,9 @@ constexpr int GT_TMEM_COLS = 256;                        // two accumulators of 
 constexpr unsigned GT_FLUSH = 4;                          // stages (6 MMAs each) between drains of the TMEM accumulator
 constexpr size_t GT_SMEM = 2 * (size_t)GT_STAGE_BYTES + 1024;   // + slack to align the buffers to 1 KB
 
-struct GtRecs { uint4 ph[16]; float4 anc[16]; float4 rot[16]; };   // one record group
+struct __align__(16) GtRecs { uint32_t w[GT_REC_WORDS][16]; };           // one record group, word-major: a warp's load of one word is ONE
+                                                          // shared-memory wavefront (a 16-byte record load is four, and the loads
+                                                          // contend with the tensor core's operand reads: ncu, 24% of all wavefronts)
 
 __device__ __forceinline__ unsigned gt_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void gt_wait(unsigned long long* bar, unsigned parity) {
@@ -78,15 +80,11 @@ __global__ void __launch_bounds__(GT_THREADS, 2) osc_tc_kernel(OscGemmLaunch p) 
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(gt_smem_u32(&tmem_base_s)), "r"(GT_TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
-    const size_t rec0 = (size_t)p.grp_begin[v] * p.K;
     const unsigned n_stages = p.n_grp[v];                 // K == 16: one record group per stage
-    auto stage_recs = [&](unsigned s, unsigned b) {       // 48 threads x 16 bytes: the records of stage s
-        if (tid < 48) {
-            const unsigned which = tid >> 4, k = tid & 15;
-            const size_t r = rec0 + 16u * s + k;
-            if (which == 0) gm_cp16(&recs[b].ph[k], p.ph + r);
-            else if (which == 1) gm_cp16(&recs[b].anc[k], p.anc + r);
-            else gm_cp16(&recs[b].rot[k], p.rot + r);
+    auto stage_recs = [&](unsigned s, unsigned b) {       // 36 threads x 16 bytes: the records of stage s
+        if (tid < GT_REC_WORDS * 4) {
+            const uint32_t* src = p.tc + ((size_t)p.grp_begin[v] + s) * (GT_REC_WORDS * 16) + 4u * tid;
+            gm_cp16(&recs[b].w[0][0] + 4u * tid, src);
         }
         asm volatile("cp.async.commit_group;\n" ::: "memory");
     };
@@ -132,9 +130,10 @@ __global__ void __launch_bounds__(GT_THREADS, 2) osc_tc_kernel(OscGemmLaunch p) 
         if (s >= 2) gt_wait(&bar_done[b], ((s >> 1) - 1u) & 1u);       // the MMAs that read this buffer two stages ago are done
         unsigned char* const base = buf0 + (size_t)b * GT_STAGE_BYTES + step_off + el_off;
         const unsigned P = tq + 4u * hh;
-        const uint4 ph = recs[b].ph[P];
-        const float4 an = recs[b].anc[P];
-        const float4 rt = recs[b].rot[P];
+        const uint4 ph = make_uint4(recs[b].w[0][P], recs[b].w[1][P], 0u, recs[b].w[2][P]);
+        const float4 an = make_float4(0.f, __uint_as_float(recs[b].w[4][P]), __uint_as_float(recs[b].w[3][P]), 0.f);
+        const float4 rt = make_float4(__uint_as_float(recs[b].w[5][P]), __uint_as_float(recs[b].w[6][P]),
+                                      __uint_as_float(recs[b].w[7][P]), __uint_as_float(recs[b].w[8][P]));
         {   // A: (sin, cos) at rows 64 half64 + g + 8 i
             float zs, zc;
             gm_anchor(ph.x, ph.y, ph.w, an.z, an.y * vs.x, nA, zs, zc);
