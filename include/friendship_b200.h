@@ -84,6 +84,11 @@ typedef struct frb_config {
 #define FRB_FLAG_SPARKLE_MIN  32u  /* Minimum as the reference's JIT renderer computes it, select(a ULT b, a, b): a NaN in either
                                       operand yields a (reference sparkle.rs:492-498), instead of f32::min = minNum, which
                                       yields the operand that is not NaN (reference.rs:242-248, the default) */
+#define FRB_FLAG_NO_TENSOR_OSC 64u /* oscillator banks never take the matrix-product (tensor-core) kernels.  Those work in tiles of
+                                    * 16,384 samples of a voice: the right unit for long renders of big banks (cfg4: 7.6x the
+                                    * resonator kernel), the wrong one for a big bank streamed in short real-time calls, where every
+                                    * call computes whole tiles and keeps a slice.  Which kernel renders a sample is a property of
+                                    * the bank and this flag only — never of how a render is cut into calls. */
 #define FRB_FLAG_NO_JIT        2u  /* always interpret stage programs; never compile them (see frb_jit_cubin_size) */
 #define FRB_FLAG_JIT_EAGER     4u  /* compile a stage program the first time it runs (default: once it is hot) */
 #define FRB_FLAG_NO_CHAIN_FUSION 8u /* run DirectForm -> FbDelay chains as two kernels (16 B per lane-sample) even where the

@@ -11,7 +11,7 @@ import os as _os
 from . import _cabi
 from ._cabi import (  # noqa: F401
     KIND_DELAY, KIND_F32CONSTANT, KIND_SUM2, KIND_MULTIPLY, KIND_DIVIDE, KIND_MODULO, KIND_MINIMUM, KIND_EFFECT,
-    KIND_OSCBANK, KIND_DIRECTFORM, KIND_FBDELAY, FLAG_SPARKLE_DELAY, FLAG_NO_JIT, FLAG_JIT_EAGER, FLAG_NO_CHAIN_FUSION, FLAG_NO_EXCITER_FUSION, FLAG_SPARKLE_MIN,
+    KIND_OSCBANK, KIND_DIRECTFORM, KIND_FBDELAY, FLAG_SPARKLE_DELAY, FLAG_NO_JIT, FLAG_JIT_EAGER, FLAG_NO_CHAIN_FUSION, FLAG_NO_EXCITER_FUSION, FLAG_SPARKLE_MIN, FLAG_NO_TENSOR_OSC,
     RendererError,
 )
 

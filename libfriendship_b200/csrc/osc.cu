@@ -318,7 +318,8 @@ static bool osc_gemm_wanted(int K, uint32_t n_voices, uint64_t n_records) {
 static bool osc_gemm_tcgen05() { const int m = osc_gemm_mode(); return m != 2 && m != 5; }
 
 std::shared_ptr<OscBankDev> osc_create(const frb_oscbank_desc* d, cudaStream_t stream, std::string* err,
-                                       const std::shared_ptr<OscBankDev>& recycle, uint32_t shard_rank, uint32_t shard_world) {
+                                       const std::shared_ptr<OscBankDev>& recycle, uint32_t shard_rank, uint32_t shard_world,
+                                       bool allow_tensor) {
     std::shared_ptr<OscBankDev> b;
     bool stolen = false;
     auto fail = [&](const std::string& m) {
@@ -459,7 +460,7 @@ std::shared_ptr<OscBankDev> osc_create(const frb_oscbank_desc* d, cudaStream_t s
     }
 
     const uint64_t nn = std::max<uint64_t>(n, 1);
-    b->gemm = osc_gemm_wanted(K, nv, n);
+    b->gemm = allow_tensor && osc_gemm_wanted(K, nv, n);
     if (b->rec_cap < nn || (b->gemm && !b->d_rot)) {
         cudaFree(b->d_hot); cudaFree(b->d_anc); cudaFree(b->d_ph); cudaFree(b->d_rot); cudaFree(b->d_tc);
         b->d_hot = b->d_anc = b->d_rot = nullptr; b->d_ph = nullptr; b->d_tc = nullptr; b->rec_cap = 0;

@@ -26,7 +26,8 @@ struct OscBankInfo {
 // `recycle` is left hollow; on failure it gets its allocations back (check osc_usable: a failed reallocation loses them).
 std::shared_ptr<OscBankDev> osc_create(const frb_oscbank_desc* d, cudaStream_t stream, std::string* err,
                                        const std::shared_ptr<OscBankDev>& recycle = nullptr,
-                                       uint32_t shard_rank = 0, uint32_t shard_world = 1);
+                                       uint32_t shard_rank = 0, uint32_t shard_world = 1,
+                                       bool allow_tensor = true);   // false: FRB_FLAG_NO_TENSOR_OSC
 OscBankInfo osc_info(const OscBankDev& b);
 bool osc_usable(const OscBankDev& b);   // false for a bank whose allocations were lost to a failed re-definition
 

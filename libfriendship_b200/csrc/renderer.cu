@@ -195,7 +195,7 @@ void Renderer::define_oscbank(uint64_t key, const frb_oscbank_desc* d) {
     std::shared_ptr<OscBankDev> old;
     if (auto it = osc_defs_.find(key); it != osc_defs_.end()) old = it->second;
     const uint32_t old_voices = old ? osc_info(*old).n_voices : 0;
-    auto b = osc_create(d, stream_, &err, old, shard_rank_, shard_world_);
+    auto b = osc_create(d, stream_, &err, old, shard_rank_, shard_world_, (cfg_.flags & FRB_FLAG_NO_TENSOR_OSC) == 0);
     if (!b) {
         if (old && !osc_usable(*old)) { osc_defs_.erase(key); dirty_ = true; }   // its allocations went into the failed attempt
         throw Error{FRB_E_INVALID, err};

@@ -165,3 +165,19 @@ print(json.dumps(r.stats()))
     for start in (0, 300, 16384 - 16, 20000 - 32):
         w = o.fill_buffer(4, 32, start)
         assert (np.abs(out[:, start:start + 32].astype(np.float64) - w) / fs).max() <= TOL, start
+
+
+def test_no_tensor_flag_keeps_a_big_bank_on_the_resonator_kernel():
+    """FRB_FLAG_NO_TENSOR_OSC: a creation flag for callers that stream a big bank in short real-time calls."""
+    from libfriendship_b200 import B200Renderer, FLAG_NO_TENSOR_OSC
+    nv, npart, n = 4, 512, 20000
+    bank, _ = bank_with_levels(nv, npart)
+    plain = B200Renderer(flags=FLAG_NO_TENSOR_OSC)
+    a = render_voices(plain, bank, nv, n)
+    assert plain.stats()["osc_tensor_launches"] == 0 and plain.stats()["osc_launches"] > 0
+    if "FRB_OSC_GEMM" not in os.environ:                  # the default policy picks the tensor-core kernel for this bank
+        tensor = B200Renderer()
+        b = render_voices(tensor, bank, nv, n)
+        assert tensor.stats()["osc_tensor_launches"] > 0
+        fs = voice_full_scales(bank, nv)[:, None]
+        assert (np.abs(a.astype(np.float64) - b) / fs).max() <= 4e-6
