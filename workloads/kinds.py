@@ -21,3 +21,4 @@ FLAG_JIT_EAGER = 4
 FLAG_NO_CHAIN_FUSION = 8
 FLAG_NO_EXCITER_FUSION = 16
 FLAG_SPARKLE_MIN = 32
+FLAG_NO_TENSOR_OSC = 64
