@@ -8,7 +8,8 @@ One "step" = one full 10 s render of the whole graph (2.013e12 partial-samples o
   e2e   : the same through the host-facing calls, every step: frb_define_oscbank from PINNED HOST parameter arrays (the
           synthesis graph's only input: host->device copy + device-side regroup/setup) + frb_fill_buffer into a host
           buffer (device->host copy of the mixed block on rank 0), all inside the timed region
-  roofline : dominant kernel (K1 osc_kernel) against the FP32 FMA pipe
+  roofline : dominant kernel: K1T osc_tc_kernel (the bank as a matrix product, tcgen05) against the measured dense tensor peak;
+             the resonator kernel K1 against the FP32 FMA pipe when FRB_OSC_GEMM=0 keeps the bank on it
   cpu_baseline : the CPU oracle (restatement of the reference's per-sample renderer) on the box's host cores
   parity   : after the timed regions (outside them), rank 0's rendered block — device path and host path — against the
              fp64 oracle evaluated on the FULL 64 x 65,536 bank in five windows; the run fails (rc 3) above 1e-5 of full scale
